@@ -1,0 +1,142 @@
+/* phi3_b200.h — C ABI of libphi3b200.so (sm_100a only).
+ *
+ * The reference (JosefAlbers/Phi-3-Vision-MLX) has no FFI/plugin layer: its hot path calls
+ * mlx==0.15 ops from Python. Each entry below replaces one of those MLX call
+ * sites; the cited lines are in /root/reference/phi.py (phi:) and
+ * /root/reference/phi_3_vision_mlx.py (pv:). INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions: plain device pointers + sizes, caller-owned memory and workspaces, no
+ * allocation and no host synchronisation inside, stream-ordered and CUDA-graph capturable.
+ * Every function returns 0 on success, <0 on error; p3_last_error() gives the message
+ * (thread-local). bf16 = __nv_bfloat16 storage. "Rows" are tokens (B*L flattened).
+ */
+#ifndef PHI3_B200_H
+#define PHI3_B200_H
+#include <stdint.h>
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* GEMM epilogues (p3_gemm, p3_gemm_skinny) */
+#define P3_EPI_NONE 0       /* out bf16 = acc (+bias) */
+#define P3_EPI_QGELU 1      /* bias + x*sigmoid(1.702x)         nn.gelu_fast_approx, phi:154 */
+#define P3_EPI_GELU 2       /* bias + exact erf GELU            nn.GELU(), phi:391 */
+#define P3_EPI_RESIDUAL 3   /* out = resid + bf16(acc+bias)     phi:170-171, 483, 485 */
+#define P3_EPI_SWIGLU 4     /* out[:, N/2] = silu(gate)*up      phi:470-471, interleaved W (see p3_gemm) */
+#define P3_EPI_F32 5        /* out fp32 = acc (+bias)           lm_head logits, phi:608 */
+#define P3_EPI_RESIDUAL_F32 6 /* out fp32 = resid fp32 + acc+bias  CLIP residual stream (fp32 in the reference) */
+
+#define P3_PAGE_TOKENS 64   /* tokens per KV page */
+
+const char* p3_last_error(void);
+int p3_version(void);
+
+/* nn.Embedding phi:568,577 — ids<0 (image placeholders, phi:270) read row 0 */
+int p3_embed_gather(const void* table, const int32_t* ids, void* out, int64_t T, int H, int vocab, cudaStream_t st);
+
+/* nn.RMSNorm / mx.fast.rms_norm phi:478-479,571 */
+int p3_rmsnorm(const void* x, const void* w, void* y, int64_t T, int H, float eps, cudaStream_t st);
+
+/* nn.LayerNorm / mx.fast.layer_norm phi:165,167,212. x fp32 (CLIP residual stream);
+ * y bf16 (out_f32 = 0, feeds a GEMM) or fp32 (out_f32 = 1, pre_layrnorm phi:218). */
+int p3_layernorm(const float* x, const void* w, const void* b, void* y, int64_t T, int H, float eps, int out_f32,
+                 cudaStream_t st);
+
+/* _rotate_half + SuRoPE table + KVCache slice-assign: phi:418-423, 487-507, 542-548.
+ * qkv [B*L, (n_heads+2*n_kv)*hd] bf16 roped in place; cos/sin fp32 [Bt, L_all, hd/2];
+ * tab_bstride = 0 for a shared table, else elements between table rows; row b uses
+ * table/cache row b/row_div (row_div = n_beam, phi:447-450). pool = this layer's page pool
+ * [page][2][n_kv][64][hd]; block_table int32 [n_seq, bt_stride]. past_dev (device int32, may be
+ * NULL) overrides `past` at run time so a captured CUDA graph can be replayed every step. */
+int p3_rope_kvwrite(void* qkv, const float* cosT, const float* sinT, int64_t tab_bstride, int B, int L, int n_heads,
+                    int n_kv, int hd, int past, int row_div, void* pool, const int32_t* block_table, int bt_stride,
+                    int write_cache, const int32_t* past_dev, cudaStream_t st);
+
+/* mx.argmax pv:386,392,506,559; nn.log_softmax + gathers pv:476,541-547,571-573;
+ * mx.argpartition top-n pv:507 — one pass per logits row. Any output pointer may be NULL. */
+int p3_row_stats(const float* logits, int64_t R, int64_t ld, int V, int32_t* argmax_out, float* max_out,
+                 float* lse_out, int n_top, int32_t* topk_ids, float* topk_lp, int n_gather,
+                 const int32_t* gather_ids, float* gather_lp, cudaStream_t st);
+
+/* Greedy-loop bookkeeping on the device (pv:390-398 without the two host syncs per token):
+ * history[b][*step] = tok[b]; eos_seen[b] |= (tok[b]==32007); ++*step; ++*past (past may be NULL). */
+int p3_decode_advance(const int32_t* tok, int32_t* history, int64_t ld, int B, int32_t* step, int32_t* past,
+                      int32_t* eos_seen, cudaStream_t st);
+
+/* nn.Linear at decode (M<=16 tokens): phi:437-438,465-466,604. Optional fused RMSNorm prologue
+ * (norm_w != NULL: X is the raw hidden state). epi in {NONE, RESIDUAL, SWIGLU, F32}. */
+int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, void* out, int64_t ldo,
+                   const void* resid, int M, int N, int K, int epi, cudaStream_t st);
+
+/* nn.Linear for prefill / ViT / projector (phi:140-143,155-156,391,437-438,465-466,604) and the
+ * patch-embed conv as GEMM (phi:186-192): out[M,N] = X[M,K] . W[N,K]^T on tcgen05 tensor cores
+ * (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue). bias bf16 [N] or NULL. row_map int32 [M] or
+ * NULL scatters output rows (image-feature splice, phi:412-415). For P3_EPI_SWIGLU W must be in
+ * the interleaved layout (per 256 rows: 128 gate rows then the matching 128 up rows) and out is
+ * [M, N/2]. impl: 0 = tcgen05 (product path), 1 = mma.sync cross-check kernel (tests only). */
+int p3_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
+            const void* resid, const int32_t* row_map, int64_t M, int N, int K, int epi, int impl, cudaStream_t st);
+
+/* Prefill / ViT flash attention: phi:454-457 (causal + left-pad predicate instead of Mask4D
+ * phi:550-563) and mx.fast.scaled_dot_product_attention phi:148 (causal=0).
+ * q/k/v point into the (roped) qkv buffer; row strides in elements; head h at +h*hd.
+ * Keys [0,past) come from the paged pool (cache row b/row_div), keys [past,past+L) from k/v.
+ * kv_start int32 [B] (left-pad length; NULL = 0). Pad queries produce zeros. */
+int p3_attention_prefill(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* out,
+                         int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale, int causal, int past,
+                         const int32_t* kv_start, const void* pool, const int32_t* block_table, int bt_stride,
+                         int row_div, cudaStream_t st);
+
+/* Decode-time attention for L<=16 new tokens per row over a paged KV cache (split-KV):
+ * phi:454-457 with KVCache reads phi:523-527 (n_beam shared prefix: row_div) / phi:548.
+ * workspace: fp32, p3_attention_decode_workspace() bytes. */
+int64_t p3_attention_decode_workspace(int B, int L, int n_heads, int hd, int n_splits);
+int p3_attention_decode(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* out,
+                        int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale, int past,
+                        const int32_t* kv_start, const void* pool, const int32_t* block_table, int bt_stride,
+                        int row_div, int n_splits, void* workspace, const int32_t* past_dev, cudaStream_t st);
+
+/* 4-bit g32 KV-cache quantisation (mx.quantize/dequantize, phi:532,536-537). Quantises the
+ * first n_tokens positions of the bf16 pool pages of each cache row in place into a q4 pool
+ * ([page][2][n_kv][64][hd/2 bytes] codes + [page][2][n_kv][64][hd/32][2] bf16 scale,bias). */
+int p3_kv_quantize_q4g32(const void* pool, void* qcodes, void* qmeta, const int32_t* block_table, int bt_stride,
+                         int n_seq, int n_tokens, int n_kv, int hd, cudaStream_t st);
+int p3_attention_decode_q4(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                           void* out, int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale, int past,
+                           int n_quant, const int32_t* kv_start, const void* pool, const void* qcodes,
+                           const void* qmeta, const int32_t* block_table, int bt_stride, int row_div, int n_splits,
+                           void* workspace, const int32_t* past_dev, cudaStream_t st);
+
+/* Vision front end. */
+/* PIL BILINEAR resize (phi:299), white pad to x336 (phi:300-306), (x/255-mean)/std (phi:309):
+ * src uint8 HWC with element strides (sx, sy) so a transposed view needs no copy (phi:295,308).
+ * coefficient tables are built on the host exactly as Pillow's precompute_coeffs does. */
+int p3_hd_resize_h(const uint8_t* src, int64_t sy, int64_t sx, int in_w, int in_h, uint8_t* tmp, int out_w,
+                   const int32_t* bounds, const int32_t* kk, int ksize, cudaStream_t st);
+/* vertical pass + white pad (pad_top rows above, to padded_h) + optional un-transpose; writes the
+ * padded uint8 HWC image ([padded_h, tmp_w, 3], or [tmp_w, padded_h, 3] when transposed). */
+int p3_hd_resize_v_pad(const uint8_t* tmp, int tmp_w, int tmp_h, int out_h, const int32_t* bounds, const int32_t* kk,
+                       int ksize, int pad_top, int padded_h, int transposed, uint8_t* out_hwc, cudaStream_t st);
+/* normalise through a 256x3 float64 LUT ((v/255-mean)/std, phi:309), sub-crop tiling (phi:322-326)
+ * and the reference's 2-tap interpolate_336 global crop (phi:331-372, float64 accumulate) into
+ * pixel_values [n_crops+1, 3, 336, 336] fp32 (crop 0 = global). idx/wgt tables are [336][2]. */
+int p3_hd_tile_crops(const uint8_t* img_hwc, int H, int W, const double* lut, float* pixel_values,
+                     const int32_t* h_idx, const float* h_wgt, const int32_t* w_idx, const float* w_wgt,
+                     cudaStream_t st);
+/* im2col for the 14x14/14 patch conv (phi:186-192,199): pixel_values [N,3,336,336] fp32 ->
+ * A [N*576, Kpad] bf16, k = (ky*14+kx)*3 + c (NHWC weight order, pv:374), zero padded. */
+int p3_patch_im2col(const float* pixel_values, void* A, int N, int Kpad, cudaStream_t st);
+/* cat[class_emb, patches] + position_embedding (phi:202-205): patches fp32 [N*576, D] -> fp32 [N,577,D] */
+int p3_clip_embed(const float* patches, const void* cls, const void* pos, float* out, int N, int D, cudaStream_t st);
+/* drop CLS (phi:221) + 2x2 token merge + sub_GN/glb_GN separators (phi:403-407):
+ * feats fp32 [n_crops+1, 577, C] (crop 0 = global) -> bf16 [(hc*wc+1)*144 + 1 + (hc+1)*12, 4*C] */
+int p3_gn_assemble(const float* feats, const void* sub_GN, const void* glb_GN, void* out, int hc, int wc, int C,
+                   cudaStream_t st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,76 @@
+"""ctypes binding of libphi3b200.so (the C ABI declared in include/phi3_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, this
+module raises. Build with `python -c "import __graft_entry__ as g; g.build()"` or
+`make -C phi-3-vision-mlx_b200/csrc`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libphi3b200.so')
+
+EPI_NONE, EPI_QGELU, EPI_GELU, EPI_RESIDUAL, EPI_SWIGLU, EPI_F32, EPI_RESIDUAL_F32 = range(7)
+PAGE = 64
+
+_p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_SIGS = {
+    'p3_embed_gather': [_p, _p, _p, _l, _i, _i, _p],
+    'p3_rmsnorm': [_p, _p, _p, _l, _i, _f, _p],
+    'p3_layernorm': [_p, _p, _p, _p, _l, _i, _f, _i, _p],
+    'p3_rope_kvwrite': [_p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p],
+    'p3_row_stats': [_p, _l, _l, _i, _p, _p, _p, _i, _p, _p, _i, _p, _p, _p],
+    'p3_gemm_skinny': [_p, _l, _p, _f, _p, _p, _l, _p, _i, _i, _i, _i, _p],
+    'p3_gemm': [_p, _l, _p, _l, _p, _p, _l, _p, _p, _l, _i, _i, _i, _i, _p],
+    'p3_attention_prefill': [_p, _p, _p, _l, _l, _l, _p, _l, _i, _i, _i, _i, _i, _f, _i, _i, _p, _p, _p, _i, _i, _p],
+    'p3_attention_decode': [_p, _p, _p, _l, _l, _l, _p, _l, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p],
+    'p3_attention_decode_q4': [_p, _p, _p, _l, _l, _l, _p, _l, _i, _i, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p, _i,
+                               _i, _i, _p, _p, _p],
+    'p3_kv_quantize_q4g32': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    'p3_decode_advance': [_p, _p, _l, _i, _p, _p, _p],
+    'p3_hd_resize_h': [_p, _l, _l, _i, _i, _p, _i, _p, _p, _i, _p],
+    'p3_hd_resize_v_pad': [_p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p],
+    'p3_hd_tile_crops': [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    'p3_patch_im2col': [_p, _p, _i, _i, _p],
+    'p3_clip_embed': [_p, _p, _p, _p, _i, _i, _p],
+    'p3_gn_assemble': [_p, _p, _p, _p, _i, _i, _i, _p],
+}
+
+_lib = None
+launches = 0          # number of p3_* kernel-launching calls issued (bench.py reports it)
+
+
+def exported_symbols():
+    return sorted(list(_SIGS) + ['p3_last_error', 'p3_version', 'p3_attention_decode_workspace'])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: the CUDA extension must be built (no CPU fallback exists). '
+                               'Run __graft_entry__.build().')
+        L = C.CDLL(LIB_PATH)
+        for name, sig in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes, fn.restype = sig, C.c_int
+        L.p3_last_error.restype = C.c_char_p
+        L.p3_version.restype = C.c_int
+        L.p3_attention_decode_workspace.argtypes = [_i, _i, _i, _i, _i]
+        L.p3_attention_decode_workspace.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor, None -> NULL."""
+    return None if t is None else t.data_ptr()
+
+
+def call(name, *args):
+    global launches
+    L = lib()
+    rc = getattr(L, name)(*args)
+    launches += 1
+    if rc != 0:
+        raise RuntimeError(f'{name} failed ({rc}): {L.p3_last_error().decode()}')

@@ -1,0 +1,448 @@
+"""Public inference API with the reference's signatures:
+load / generate / choose / constrain (/root/reference/phi_3_vision_mlx.py:1279, 1324, 1376, 1425)
+and the decode drivers behind them (_generate pv:376-409, _choose_from pv:466-487,
+_constrain/_get_beam pv:500-619, Streamer/LogitStopper/TokenStopper pv:45-117,
+_apply_chat_template pv:341-357). Control flow lives here in Python; every tensor op is a
+kernel of libphi3b200.so.
+
+Differences a caller can see (all opt-in or forced by the offline environment):
+  * `load()` accepts tokenizer=, weights= (dict or safetensors dir), cfg=, random_init=,
+    num_crops=, device= through **kwargs — there are no checkpoint / tokenizer files offline;
+  * quantize_model / use_adapter raise NotImplementedError;
+  * constrain(..., n_beam=3) exposes the beam width the reference hard-codes (pv:505);
+  * images may be PIL images or uint8 HWC arrays (no URL fetching offline).
+"""
+import os
+import time
+import glob
+import torch
+from . import _lib
+from ._lib import call, ptr
+from .configs import PHI35_MINI, PHI35_VISION, ID_EOS, with_overrides
+from .model import Phi3B200, _stream
+from .processor import Phi3FProcessor, Phi3VProcessor, ByteTokenizer
+from .weights import random_weights
+
+PATH_ORIGINAL_PHI3_VISION = 'models/phi3_v'             # pv:38-41
+PATH_ORIGINAL_PHI3_BLIND = 'models/phi3_mini_128k'
+
+
+class Tic:                                              # phi.py:16-24
+    def __init__(self):
+        self.last = time.perf_counter()
+
+    def __call__(self):
+        now = time.perf_counter()
+        d, self.last = now - self.last, now
+        return d
+
+
+# ------------------------------------------------------------------------------------- load
+def _read_safetensors(path):
+    from safetensors.torch import load_file
+    w = {}
+    for f in sorted(glob.glob(os.path.join(path, '*.safetensors'))):
+        w.update(load_file(f))
+    if not w:
+        raise FileNotFoundError(f'no *.safetensors under {path}')
+    key = 'model.vision_embed_tokens.img_processor.vision_model.embeddings.patch_embedding.weight'
+    if key in w and w[key].shape[1] == 3:               # HF [O,I,kh,kw] -> reference layout [O,kh,kw,I] (pv:374)
+        w[key] = w[key].permute(0, 2, 3, 1).contiguous()
+    return w
+
+
+def load(blind_model=False, quantize_model=False, quantize_cache=False, use_adapter=False, **kwargs):
+    """pv:1279-1322. Returns (model, processor)."""
+    if quantize_model:
+        raise NotImplementedError('quantize_model (4-bit weights) is outside the B200 hot-path scope (SURVEY §8f N3)')
+    if use_adapter:
+        raise NotImplementedError('use_adapter (LoRA) is outside the B200 hot-path scope (SURVEY §8f N4)')
+    device = kwargs.pop('device', 'cuda')
+    cfg = kwargs.pop('cfg', None) or (PHI35_MINI if blind_model else PHI35_VISION)
+    cfg = with_overrides(cfg, use_quantized_cache=quantize_cache)          # pv:1322 -> phi.py:512,572
+    tokenizer = kwargs.pop('tokenizer', None)
+    weights = kwargs.pop('weights', None)
+    clip_cfg = kwargs.pop('clip_cfg', None)
+    num_crops = kwargs.pop('num_crops', 16)
+    if weights is None:
+        path = kwargs.pop('model_path', PATH_ORIGINAL_PHI3_BLIND if blind_model else PATH_ORIGINAL_PHI3_VISION)
+        if kwargs.pop('random_init', False):
+            weights = random_weights(cfg, seed=kwargs.pop('seed', 0), device=device, clip_cfg=clip_cfg)
+        elif os.path.isdir(path):
+            weights = _read_safetensors(path)
+        else:
+            raise FileNotFoundError(f'{path} not found and no network to fetch it (reference: _setup, pv:247-255); '
+                                    'pass weights=..., or random_init=True')
+    elif isinstance(weights, str):
+        weights = _read_safetensors(weights)
+    if tokenizer is None:
+        path = PATH_ORIGINAL_PHI3_BLIND if blind_model else PATH_ORIGINAL_PHI3_VISION
+        if os.path.isdir(path):
+            from transformers import AutoTokenizer
+            tokenizer = AutoTokenizer.from_pretrained(path)
+        else:
+            tokenizer = ByteTokenizer()
+    for k, v in kwargs.items():                                            # remaining kwargs override cfg (pv:359-363)
+        setattr(cfg, k, v)
+    model = Phi3B200(cfg, weights, device=device, clip_cfg=clip_cfg)
+    processor = Phi3FProcessor(tokenizer) if blind_model else Phi3VProcessor(tokenizer, num_crops=num_crops, device=device)
+    return model, processor
+
+
+# ------------------------------------------------------------------------------------- helpers
+def _apply_chat_template(prompt, images, verbose, apply_chat_template=True):
+    """pv:341-357 (image loading from URL/file is host glue; PIL images / arrays pass through)."""
+    if apply_chat_template is False:
+        if verbose:
+            print(f'*** Prompt ***\n{prompt}\n*** Images ***\n{images}\n*** Output ***')
+        return prompt, images
+    if images is not None:
+        images = list(images) if isinstance(images, (list, tuple)) else [images]
+        images = [_load_image(i) for i in images]
+        img_prompt = '\n'.join([f'<|image_{i+1}|>' for i in range(len(images))]) + '\n'
+    else:
+        img_prompt = ''
+    prompt = [prompt] if isinstance(prompt, str) else prompt
+    prompt = [f"<|user|>\n{img_prompt}{i.strip()}<|end|>\n<|assistant|>\n" for i in prompt]
+    if verbose:
+        prompt_str = "\n".join(map(str.strip, prompt)).strip()
+        images_str = "\n".join(f'<image {getattr(i, "size", getattr(i, "shape", ""))}>' for i in images) if images else "None"
+        print(f'*** Prompt ***\n{prompt_str}\n*** Images ***\n{images_str}\n*** Output ***')
+    prompt = prompt[0] if len(prompt) == 1 else prompt
+    return prompt, images
+
+
+def _load_image(x):
+    if isinstance(x, str):
+        from PIL import Image
+        if x.startswith('http://') or x.startswith('https://'):
+            raise ValueError('no network in this environment: pass a local path, PIL image or uint8 array')
+        return Image.open(x)
+    return x
+
+
+def _preprocess(s):                                                        # pv:489-493
+    for i in ['<|system|>', '<|user|>', '<|end|>']:
+        s = s.replace(f'{i} ', f'{i}\n').replace(f'{i}\n\n', f'{i}\n')
+    return s.replace('<|end|><|assistant|>', '<|end|>\n<|assistant|>')
+
+
+def _row_stats(model, logits2d, n_top=0, gather=None):
+    """One p3_row_stats launch over fp32 logits [R,V]. Returns dict of device tensors."""
+    R, V = logits2d.shape
+    dev = logits2d.device
+    out = dict(argmax=torch.empty(R, dtype=torch.int32, device=dev), max=torch.empty(R, dtype=torch.float32, device=dev),
+               lse=torch.empty(R, dtype=torch.float32, device=dev))
+    if n_top:
+        out['top_ids'] = torch.empty((R, n_top), dtype=torch.int32, device=dev)
+        out['top_lp'] = torch.empty((R, n_top), dtype=torch.float32, device=dev)
+    ng = 0
+    if gather is not None:
+        gather = gather.to(dev, torch.int32).contiguous()
+        ng = gather.shape[1]
+        out['gather_lp'] = torch.empty((R, ng), dtype=torch.float32, device=dev)
+    call('p3_row_stats', ptr(logits2d), R, logits2d.stride(0), V, ptr(out['argmax']), ptr(out['max']), ptr(out['lse']),
+         n_top, ptr(out.get('top_ids')), ptr(out.get('top_lp')), ng, ptr(gather), ptr(out.get('gather_lp')), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------- generate
+class Streamer:
+    """pv:45-77, fed from the device-side token history."""
+
+    def __init__(self, processor, stream, mute):
+        self.tokenizer = processor.tokenizer
+        self.mute = mute
+        self.stream = stream and (not mute)
+        self.list_tokens = []
+        self.idx_sofar = 0
+
+    def stream_token(self, tok):
+        self.list_tokens.append(tok)
+        txt = self.tokenizer.decode(self.list_tokens)
+        idx_split = txt.rfind(' ', self.idx_sofar)
+        if idx_split > 0:
+            print(txt[self.idx_sofar:idx_split], end='', flush=True)
+            self.idx_sofar = idx_split
+
+    def end(self, hist):
+        rows = hist.tolist()
+        if self.stream:
+            txt = self.tokenizer.decode(self.list_tokens)
+            print(txt[self.idx_sofar:], '\n', flush=True)
+            return txt, len(self.list_tokens)
+        list_txt = self.tokenizer.batch_decode([(r[:r.index(ID_EOS) + 1] if ID_EOS in r else r) for r in rows])
+        if not self.mute:
+            for i, gen in enumerate(list_txt):
+                print(f'\n< Generated text for prompt #{i} >\n{gen}')
+        return list_txt, hist.numel()
+
+
+class LogitStopper:
+    """pv:79-104 (B=1 early-stop heuristic on the EOS log-prob)."""
+
+    def __init__(self, max_tokens, early_stop):
+        self.step = 0
+        self.early_stop = early_stop if isinstance(early_stop, int) and not isinstance(early_stop, bool) \
+            and (early_stop < max_tokens) else False
+        self.log_prob_sum = 0.0
+        self.best_eos_sofar = -float('inf')
+        self.log_prob_sum_at_best_eos = 0.0
+
+    def __call__(self, log_prob_best, log_prob_eos):
+        if not self.early_stop:
+            return False
+        if log_prob_eos > self.best_eos_sofar:
+            since = self.log_prob_sum - self.log_prob_sum_at_best_eos
+            if since < self.best_eos_sofar and self.step > self.early_stop:
+                return True
+            self.best_eos_sofar = log_prob_eos
+            self.log_prob_sum_at_best_eos = self.log_prob_sum
+        self.log_prob_sum += log_prob_best
+        self.step += 1
+        return False
+
+
+def _generate(model, processor, prompt, images=None, max_tokens=512, verbose=True, return_tps=False, early_stop=False,
+              stream=True, mute=False, return_tokens=False, eos_check_every=16):
+    """pv:376-409. The loop body is one CUDA-graph replay per token; EOS for all rows
+    (TokenStopper, pv:106-117) is polled every `eos_check_every` steps instead of twice per token —
+    rows are truncated at their first EOS afterwards exactly as the reference does (pv:73)."""
+    if images is not None and isinstance(prompt, list):
+        raise ValueError('Images cannot be provided when prompt is a list')
+    streamer = Streamer(processor, stream, mute)
+    dict_input = processor(prompt, images)
+    B = dict_input['input_ids'].shape[0]
+    logit_stopper = LogitStopper(max_tokens, early_stop if B == 1 else False)
+    per_token_sync = (streamer.stream and B == 1) or bool(logit_stopper.early_stop)
+    tic = Tic()
+    logits, cache = model(**dict_input, max_tokens=max_tokens, logits_rows='last')
+    st = _row_stats(model, logits[:, -1, :])
+    token = st['argmax']
+    if per_token_sync:
+        if streamer.stream:
+            streamer.stream_token(int(token[0].item()))
+    torch.cuda.synchronize()
+    prompt_time = tic()
+    ses = model.decode_session(token, cache, max_tokens - 1, use_graph=not bool(logit_stopper.early_stop))
+    for i in range(max_tokens - 1):
+        if logit_stopper.early_stop:
+            # un-graphed step so the EOS log-prob of this step can be read (pv:395)
+            lg = model._forward_tokens(ses.tok, B, 1, cache, 1, True, cache.offset + i, 'last', past_dev=ses.past_dev,
+                                       n_splits=ses.n_splits)
+            s2 = _row_stats(model, lg[:, -1, :], gather=torch.full((B, 1), ID_EOS))
+            ses.tok.copy_(s2['argmax'])
+            call('p3_decode_advance', ptr(ses.tok), ptr(ses.hist), ses.hist.stride(0), B, ptr(ses.step_dev),
+                 ptr(ses.past_dev), ptr(ses.eos), _stream())
+            ses.steps_run += 1
+            if streamer.stream:
+                streamer.stream_token(int(ses.tok[0].item()))
+            if logit_stopper(float((s2['max'] - s2['lse'])[0].item()), float(s2['gather_lp'][0, 0].item())):
+                break
+            if ses.all_eos():
+                break
+            continue
+        ses.step()
+        if per_token_sync:
+            t = int(ses.tok[0].item())
+            streamer.stream_token(t)
+            if t == ID_EOS:
+                break
+        elif eos_check_every and (i + 1) % eos_check_every == 0 and ses.all_eos():
+            break
+    hist = ses.finish()
+    torch.cuda.synchronize()
+    result, gen_len = streamer.end(hist)
+    gen_time = tic()
+    prompt_len = dict_input['input_ids'].numel()
+    prompt_tps = prompt_len / prompt_time
+    gen_tps = (gen_len - 1) / gen_time if gen_time > 0 else float('inf')
+    if verbose:
+        print(f"\nPrompt: {prompt_tps:.2f} tokens-per-sec ({prompt_len} tokens / {prompt_time:.1f} sec)")
+        print(f"Generate: {gen_tps:.2f} tokens-per-sec ({gen_len} tokens / {gen_time:.1f} sec)")
+    if return_tokens:
+        return hist
+    if return_tps:
+        return prompt_tps, gen_tps
+    return result
+
+
+def generate(prompt, images=None, preload=None, blind_model=False, quantize_model=False, quantize_cache=False,
+             use_adapter=False, max_tokens=512, verbose=True, return_tps=False, early_stop=False, stream=True,
+             apply_chat_template=True, enable_api=False):
+    """pv:1324-1374."""
+    if enable_api:
+        raise NotImplementedError('enable_api (remote tool calls) is outside the hot-path scope')
+    if preload is None:
+        preload = load(blind_model=blind_model, quantize_model=quantize_model, quantize_cache=quantize_cache,
+                       use_adapter=use_adapter)
+    prompt, images = _apply_chat_template(prompt, images, verbose, apply_chat_template)
+    return _generate(*preload, prompt, images, max_tokens, verbose, return_tps, early_stop, stream)
+
+
+# ------------------------------------------------------------------------------------- choose
+def _choose_from(model, processor, prompt, choices='ABCDE', mute=False):
+    """pv:466-487: last-position log-softmax restricted to the option tokens, argmax."""
+    was_str = isinstance(prompt, str)
+    options = processor([f' {i}' for i in choices])['input_ids'][:, -1]
+    dict_input = processor(prompt)
+    logits, _ = model(**dict_input, max_tokens=0, logits_rows='last')
+    B = logits.shape[0]
+    st = _row_stats(model, logits[:, -1, :], gather=options[None].expand(B, -1))
+    indices = torch.argmax(st['gather_lp'], dim=-1).tolist()
+    output = [choices[i] for i in indices]
+    if not mute:
+        if was_str:
+            print(output[0])
+        else:
+            for i, o in enumerate(output):
+                print(f'\n< Chosen option for prompt #{i} >\n{o}')
+    return output[0] if was_str else output
+
+
+def choose(prompt, choices='ABCDE', images=None, preload=None, blind_model=False, quantize_model=False,
+           quantize_cache=False, use_adapter=False, verbose=True, apply_chat_template=True):
+    """pv:1376-1423."""
+    if preload is None:
+        preload = load(blind_model=blind_model, quantize_model=quantize_model, quantize_cache=quantize_cache,
+                       use_adapter=use_adapter)
+    prompt, images = _apply_chat_template(prompt, images, verbose, apply_chat_template)
+    return _choose_from(*preload, prompt, choices)
+
+
+# ------------------------------------------------------------------------------------- constrain
+def _constrain(model, processor, prompt, constraints, return_full_text=False, mute=False, use_beam=False, verbose=True,
+               log_norm=False, n_beam=3, return_ids=False):
+    """pv:500-619. Scores are means of log-probs over [tokens so far + constraint]; only the
+    gathered log-probs are ever materialised (p3_row_stats) instead of full-vocab log-softmax."""
+    import math
+
+    def mean_lp(x):                                                        # _log_mean pv:501-504
+        return x.sum(-1) / (math.log(x.shape[-1]) if log_norm else x.shape[-1])
+
+    was_str = isinstance(prompt, str)
+    prompt = [prompt] if was_str else list(prompt)
+    tic = Tic()
+    prompt_time = constrain_time = 0.0
+    prompt = [_preprocess(s) for s in prompt]
+    len_ps = [len(p) for p in prompt]
+    B = len(prompt)
+    V = model.V
+    ids_trace = []
+
+    def beam_step(row_logits, cache, ids_c):
+        """_get_beam pv:505-517 on logits rows [B,V] of the position that predicts the beam token."""
+        C = len(ids_c)
+        st = _row_stats(model, row_logits, n_top=n_beam)
+        cand, cand_lp = st['top_ids'], st['top_lp']                          # [B,nb]
+        seq = torch.cat([cand.reshape(-1, 1).long().cpu(), torch.tensor(ids_c).repeat(B * n_beam, 1)], 1)   # [B*nb,1+C]
+        lg, _ = model(seq, cache=cache, n_beam=n_beam, advance_offset=0)
+        g = torch.full((B * n_beam, 1 + C), -1, dtype=torch.int32)
+        g[:, :C] = seq[:, 1:].to(torch.int32)
+        s2 = _row_stats(model, lg.reshape(-1, V), gather=g.reshape(-1, 1))
+        rest = s2['gather_lp'].reshape(B * n_beam, 1 + C)[:, :C]
+        bs = torch.cat([cand_lp.reshape(-1, 1), rest], 1).cpu()              # [B*nb, 1+C]
+        k = torch.argmax(bs.mean(1).reshape(B, n_beam), dim=-1)
+        ar = torch.arange(B)
+        return st['argmax'].cpu().long(), cand.cpu().long()[ar, k], bs.reshape(B, n_beam, -1)[ar, k]
+
+    for constraint in constraints:
+        if isinstance(constraint, str):                                      # pv:531-536
+            out = _choose_from(model, processor, prompt, constraint, True)
+            prompt = [' '.join([p, o]) for p, o in zip(prompt, out)]
+            output = prompt
+            continue
+        max_new, text = constraint
+        ids_c = list(processor.tokenizer.encode(text, add_special_tokens=False)[1:])   # pv:538
+        C = len(ids_c)
+        dict_input = processor(prompt)
+        S = dict_input['input_ids'].shape[1]
+        logits, cache = model(**dict_input, max_tokens=max_new + C + 10, logits_rows='last')
+        last = logits[:, -1, :]
+        st = _row_stats(model, last, gather=torch.full((B, 1), ids_c[0]))
+        s0 = st['gather_lp'].cpu()                                           # [B,1]
+        running = (st['max'] - st['lse']).cpu()[:, None]                     # pv:548
+        tiled = torch.tensor(ids_c).repeat(B, 1)
+        lr, _ = model(tiled, cache=cache, advance_offset=0)                  # peek, pv:545
+        g = torch.full((B, C), -1, dtype=torch.int32)
+        g[:, :C - 1] = tiled[:, 1:].to(torch.int32)
+        s1 = _row_stats(model, lr.reshape(-1, V), gather=g.reshape(-1, 1))['gather_lp'].reshape(B, C)[:, :C - 1].cpu()
+        eos_col = torch.full((B, 1), ID_EOS, dtype=torch.long)
+        pre_score = mean_lp(torch.cat([s0, s1], 1))
+        pre_synth = torch.cat([tiled, eos_col], 1)
+        if use_beam and max_new > 0:                                         # pv:551-557
+            token, beam_tok, beam_sc = beam_step(last, cache, ids_c)
+            post_score = mean_lp(beam_sc)
+            post_synth = torch.cat([beam_tok[:, None], tiled], 1)
+            win = pre_score > post_score
+            score_sofar = torch.where(win, pre_score, post_score)
+            synth_sofar = torch.where(win[:, None], pre_synth, post_synth)
+        else:
+            token = st['argmax'].cpu().long()
+            score_sofar, synth_sofar = pre_score, pre_synth
+        tokens = []
+        alive = torch.ones(B)
+        prompt_time += tic()
+        for i in range(max_new):                                             # pv:567-597
+            tokens.append(token[:, None])
+            tp = torch.cat([token[:, None], tiled], 1)                       # [B,1+C]
+            lg, cache = model(tp, cache=cache, advance_offset=1)
+            g = torch.full((B, 1 + C), -1, dtype=torch.int32)
+            g[:, :C] = tp[:, 1:].to(torch.int32)
+            stp = _row_stats(model, lg.reshape(-1, V), gather=g.reshape(-1, 1))
+            glp = stp['gather_lp'].reshape(B, 1 + C)[:, :C].cpu()
+            pre_score = mean_lp(torch.cat([running, glp], 1))
+            pre_synth = torch.cat(tokens + [tiled, eos_col], 1)
+            first_max_lp = (stp['max'] - stp['lse']).reshape(B, 1 + C)[:, 0].cpu()
+            if use_beam:
+                token, beam_tok, beam_sc = beam_step(lg[:, 0, :], cache, ids_c)
+                post_score = mean_lp(torch.cat([running, beam_sc], 1))
+                post_synth = torch.cat(tokens + [beam_tok[:, None], tiled], 1)
+                win = pre_score > post_score
+                score = torch.where(win, pre_score, post_score)
+                synth = torch.where(win[:, None], pre_synth, post_synth)
+            else:
+                token = stp['argmax'].reshape(B, 1 + C)[:, 0].cpu().long()
+                score, synth = pre_score, pre_synth
+            synth_sofar = torch.cat([synth_sofar, eos_col], 1)
+            toks = torch.cat(tokens, 1)
+            if toks.shape[1] >= C:                                           # _already pv:495-498
+                alive = alive * (~(toks[:, -C:] == torch.tensor(ids_c)).all(1)).float()
+            upd = (score > score_sofar) & (alive > 0)
+            synth_sofar = torch.where(upd[:, None], synth, synth_sofar)
+            score_sofar = torch.where(upd, score, score_sofar)
+            running = torch.cat([running, first_max_lp[:, None]], 1)         # lp of the greedy token (pv:592)
+            alive = alive * (token != ID_EOS).float()
+            if alive.sum() < 1:
+                break
+        constrain_time += tic()
+        out_ids = torch.cat([dict_input['input_ids'], synth_sofar], 1).tolist()
+        out_ids = [(r[:r.index(ID_EOS, S)] if ID_EOS in r[S:] else r) for r in out_ids]
+        out_ids = [[t for t in r if t not in (0, 1)] for r in out_ids]
+        ids_trace.append(out_ids)
+        output = [_preprocess(s) for s in processor.tokenizer.batch_decode(out_ids)]
+        prompt = output
+    if return_ids:
+        return ids_trace
+    if not return_full_text:
+        output = [o[l:] for o, l in zip(output, len_ps)]
+    if not mute:
+        if was_str:
+            print(output[0])
+        else:
+            for i, o in enumerate(output):
+                print(f'\n< Constrained text for prompt #{i} >\n{o}')
+    if verbose:
+        print(f'Prompt: {prompt_time:.2f} sec\nConstrain: {constrain_time:.2f} sec')
+    return output[0] if was_str else output
+
+
+def constrain(prompt, constraints=[(0, '\nThe'), (100, ' The correct answer is'), 'ABCDE'], images=None, preload=None,
+              blind_model=False, quantize_model=False, quantize_cache=False, use_adapter=False, verbose=True,
+              apply_chat_template=True, use_beam=False, n_beam=3):
+    """pv:1425-1487 (+ n_beam, an extension: the reference hard-codes 3, pv:505)."""
+    if preload is None:
+        preload = load(blind_model=blind_model, quantize_model=quantize_model, quantize_cache=quantize_cache,
+                       use_adapter=use_adapter)
+    prompt, images = _apply_chat_template(prompt, images, verbose, apply_chat_template)
+    return _constrain(*preload, prompt, constraints, use_beam=use_beam, verbose=verbose, n_beam=n_beam)

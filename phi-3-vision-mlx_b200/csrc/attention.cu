@@ -1,0 +1,558 @@
+// Attention kernels.
+//  * attn_prefill_kernel : flash-style tiled softmax(QK^T)V for many query rows (prefill, ViT).
+//    Replaces the explicit scores/softmax/PV of phi.py:454-457 and the dense Mask4D of
+//    phi.py:550-563 (predicate: causal + per-row left-pad start) and
+//    mx.fast.scaled_dot_product_attention of phi.py:148 (causal = 0).
+//  * attn_decode_kernel  : memory-bound split-KV attention for <=16 new tokens per row over the
+//    paged bf16 KV pool (phi.py:454-457 + KVCache reads phi.py:523-527,548). 16-byte coalesced
+//    cp.async loads of whole 12 KB page slices into a 4-stage shared-memory ring, warp-shuffle
+//    softmax reductions, tensor-core (mma.sync) dot products so L<=16 queries cost one pass.
+//  * attn_merge_kernel   : combines split partials.
+// Keys [0,past) are read from the paged pool, keys [past,past+L) from the freshly roped
+// qkv buffer ("dual source"), which is what makes the read-only beam step of phi.py:523-527 a
+// plain call with row_div = n_beam.
+#include "common.cuh"
+#include "../../include/phi3_b200.h"
+
+template <int D> struct Swz;
+template <> struct Swz<96> { static __device__ __forceinline__ int f(int c, int r) { return c ^ ((r >> 1) & 3); } };
+template <> struct Swz<64> { static __device__ __forceinline__ int f(int c, int r) { return c ^ (r & 7); } };
+
+// byte offset of 16B chunk c of row r inside a [rows][D] bf16 tile
+template <int D>
+__device__ __forceinline__ uint32_t tile_off(int r, int c) { return (uint32_t)(r * (D * 2) + Swz<D>::f(c, r) * 16); }
+
+struct AttnParams {
+    const bf16 *q, *k, *v;
+    int64_t ldq, ldk, ldv;
+    bf16* out; int64_t ldo;
+    int B, L, n_heads, n_kv, hd;
+    float scale_log2;
+    int causal, past;
+    int past_host; const int32_t* past_dev;   // decode: past read from device memory when past_dev != NULL (CUDA-graph replay)
+    const int32_t* kv_start;
+    const bf16* pool;
+    const int32_t* block_table; int bt_stride;
+    int row_div;
+    // decode only
+    int n_splits, tiles_per_split;
+    float* ws_o; float* ws_ml;
+    // quantised-cache decode: positions [0, n_quant) (multiple of 64) live in the q4 pools
+    int n_quant;
+    const uint8_t* qcodes;      // [page][2][n_kv][64][D/2]
+    const bf16* qmeta;          // [page][2][n_kv][64][D/32][2] (scale, bias)
+};
+
+// Load a 64-key K tile and V tile (absolute key positions [64n, 64n+64)) into shared memory.
+template <int D, int THREADS>
+__device__ __forceinline__ void load_kv_tile(const AttnParams& p, int b, int kvh, int n, int s_total, uint32_t sk, uint32_t sv) {
+    constexpr int CPR = D / 8;
+    const int crow = b / p.row_div;
+    const bf16 *kpage = nullptr, *vpage = nullptr;
+    if (n * P3_PAGE < p.past) {
+        int page = p.block_table[(size_t)crow * p.bt_stride + n];
+        kpage = kv_tile_ptr(p.pool, page, 0, kvh, p.n_kv, D);
+        vpage = kv_tile_ptr(p.pool, page, 1, kvh, p.n_kv, D);
+    }
+    for (int idx = threadIdx.x; idx < 64 * CPR; idx += THREADS) {
+        int r = idx / CPR, c = idx % CPR;
+        int j = n * P3_PAGE + r;
+        const bf16 *ks, *vs;
+        int bytes = 16;
+        if (j < p.past) {
+            ks = kpage + idx * 8; vs = vpage + idx * 8;
+        } else if (j < s_total) {
+            size_t tok = (size_t)b * p.L + (j - p.past);
+            ks = p.k + tok * p.ldk + kvh * D + c * 8;
+            vs = p.v + tok * p.ldv + kvh * D + c * 8;
+        } else {
+            ks = p.k; vs = p.v; bytes = 0;                      // zero fill
+        }
+        cp_async16(sk + tile_off<D>(r, c), ks, bytes);
+        cp_async16(sv + tile_off<D>(r, c), vs, bytes);
+    }
+}
+
+// One warp: S(16 x NK*8 keys) = Q K^T for keys [key0, key0 + 8*NK) of the tile at sk.
+template <int D, int NK>
+__device__ __forceinline__ void qk_mma(const uint32_t (*qf)[4], uint32_t sk, int key0, float (*s)[4], int lane) {
+#pragma unroll
+    for (int nt = 0; nt < NK; nt++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) s[nt][j] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ks++) {
+#pragma unroll
+        for (int np = 0; np < NK / 2; np++) {
+            int r = key0 + np * 16 + (lane >> 4) * 8 + (lane & 7);
+            int c = ks * 2 + ((lane >> 3) & 1);
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(b0, b1, b2, b3, sk + tile_off<D>(r, c));
+            mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+            mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+        }
+    }
+}
+
+// One warp: O(16 x D) += P(16 x NK*8 keys) V
+template <int D, int NK>
+__device__ __forceinline__ void pv_mma(const float (*s)[4], uint32_t sv, int key0, float (*o)[4], int lane) {
+#pragma unroll
+    for (int kk = 0; kk < NK / 2; kk++) {
+        uint32_t a[4] = {pack_bf16(s[2 * kk][0], s[2 * kk][1]), pack_bf16(s[2 * kk][2], s[2 * kk][3]),
+                         pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+#pragma unroll
+        for (int dp = 0; dp < D / 16; dp++) {
+            int r = key0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            int c = dp * 2 + (lane >> 4);
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4_trans(b0, b1, b2, b3, sv + tile_off<D>(r, c));
+            mma_bf16_16816(o[2 * dp], a, b0, b1);
+            mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+        }
+    }
+}
+
+// Online-softmax update for one warp's 16 x (NK*8) score block. Rows g (idx 0) and g+8 (idx 1).
+template <int D, int NK>
+__device__ __forceinline__ void softmax_update(float (*s)[4], float* m, float* l, float (*o)[4]) {
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < NK; nt++) {
+        mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+        mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+    }
+    float corr[2], mu[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        float mn = fmaxf(m[i], mx[i]);
+        mu[i] = (mn == -INFINITY) ? 0.f : mn;
+        corr[i] = exp2f(m[i] - mu[i]);                        // m = -inf -> 0
+        m[i] = mn;
+        l[i] *= corr[i];
+    }
+#pragma unroll
+    for (int nt = 0; nt < NK; nt++) {
+        s[nt][0] = exp2f(s[nt][0] - mu[0]); s[nt][1] = exp2f(s[nt][1] - mu[0]);
+        s[nt][2] = exp2f(s[nt][2] - mu[1]); s[nt][3] = exp2f(s[nt][3] - mu[1]);
+        l[0] += s[nt][0] + s[nt][1];
+        l[1] += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int dt = 0; dt < D / 8; dt++) {
+        o[dt][0] *= corr[0]; o[dt][1] *= corr[0]; o[dt][2] *= corr[1]; o[dt][3] *= corr[1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// prefill / ViT
+// ------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) attn_prefill_kernel(AttnParams p) {
+    constexpr int CPR = D / 8, TILE = 64 * D * 2;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sq = smem_u32(smem), skv = sq + TILE;       // skv: [2 stages][K,V]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int i0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+    const int kvh = h / (p.n_heads / p.n_kv);
+    const int s_total = p.past + p.L;
+    const int kv0 = p.kv_start ? p.kv_start[b / p.row_div] : 0;
+
+    // Q tile
+    for (int idx = tid; idx < 64 * CPR; idx += 128) {
+        int r = idx / CPR, c = idx % CPR;
+        int i = i0 + r;
+        const bf16* src = p.q + ((size_t)b * p.L + (i < p.L ? i : 0)) * p.ldq + h * D + c * 8;
+        cp_async16(sq + tile_off<D>(r, c), src, i < p.L ? 16 : 0);
+    }
+    int n_begin = kv0 / 64;
+    int n_end = (s_total + 63) / 64;
+    if (p.causal) n_end = min(n_end, (p.past + min(i0 + 63, p.L - 1)) / 64 + 1);
+    if (n_begin < n_end) load_kv_tile<D, 128>(p, b, kvh, n_begin, s_total, skv, skv + TILE);
+    cp_async_commit();
+
+    uint32_t qf[D / 16][4];
+    float o[D / 8][4];
+#pragma unroll
+    for (int dt = 0; dt < D / 8; dt++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[dt][j] = 0.f;
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    const int qi0 = p.past + i0 + warp * 16 + g, qi1 = qi0 + 8;   // absolute query positions of rows g, g+8
+
+    for (int n = n_begin; n < n_end; n++) {
+        const int buf = (n - n_begin) & 1;
+        if (n + 1 < n_end) {
+            load_kv_tile<D, 128>(p, b, kvh, n + 1, s_total, skv + (buf ^ 1) * 2 * TILE, skv + (buf ^ 1) * 2 * TILE + TILE);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (n == n_begin) {
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ks++) {
+                int r = warp * 16 + (lane & 15), c = ks * 2 + (lane >> 4);
+                ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], sq + tile_off<D>(r, c));
+            }
+        }
+        const uint32_t sk = skv + buf * 2 * TILE, sv = sk + TILE;
+        float s[8][4];
+        qk_mma<D, 8>(qf, sk, 0, s, lane);
+        const int j0 = n * 64;
+        const bool need_mask = (j0 < kv0) || (j0 + 63 >= s_total) || (p.causal && j0 + 63 > p.past + i0);
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float v = s[nt][e] * p.scale_log2;
+                if (need_mask) {
+                    int j = j0 + nt * 8 + 2 * t + (e & 1);
+                    int qi = (e & 2) ? qi1 : qi0;
+                    bool ok = (j >= kv0) && (j < s_total) && (!p.causal || j <= qi);
+                    if (!ok) v = -INFINITY;
+                }
+                s[nt][e] = v;
+            }
+        softmax_update<D, 8>(s, m, l, o);
+        pv_mma<D, 8>(s, sv, 0, o, lane);
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        l[i] += __shfl_xor_sync(0xffffffffu, l[i], 1);
+        l[i] += __shfl_xor_sync(0xffffffffu, l[i], 2);
+    }
+    const float inv0 = l[0] > 0.f ? 1.f / l[0] : 0.f, inv1 = l[1] > 0.f ? 1.f / l[1] : 0.f;
+    const int r0 = i0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int dt = 0; dt < D / 8; dt++) {
+        int d = dt * 8 + 2 * t;
+        if (r0 < p.L)
+            *reinterpret_cast<uint32_t*>(p.out + ((size_t)b * p.L + r0) * p.ldo + h * D + d) = pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
+        if (r1 < p.L)
+            *reinterpret_cast<uint32_t*>(p.out + ((size_t)b * p.L + r1) * p.ldo + h * D + d) = pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// decode (L <= 16 new tokens per row), split-KV over cached pages
+// ------------------------------------------------------------------------------------------
+#define DEC_STAGES 4
+template <int D, bool Q4>
+__global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
+    constexpr int CPR = D / 8, TILE = 64 * D * 2;
+    constexpr int QC = 64 * D / 2, QM = 64 * (D / 32) * 4;      // bytes of codes / meta per (page, kv, head)
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sq = smem_u32(smem);                         // 16 x D query tile
+    const uint32_t skv = sq + 16 * D * 2;                       // [DEC_STAGES][K,V]
+    const uint32_t sdq = skv + DEC_STAGES * 2 * TILE;           // Q4: dequantised bf16 K,V tile
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int kvh = h / (p.n_heads / p.n_kv);
+    const int past = p.past_dev ? *p.past_dev : p.past_host;
+    const int kv0 = p.kv_start ? p.kv_start[b / p.row_div] : 0;
+    const int s_total = past + p.L;
+
+    for (int idx = tid; idx < 16 * CPR; idx += 128) {
+        int r = idx / CPR, c = idx % CPR;
+        const bf16* src = p.q + ((size_t)b * p.L + (r < p.L ? r : 0)) * p.ldq + h * D + c * 8;
+        cp_async16(sq + tile_off<D>(r, c), src, r < p.L ? 16 : 0);
+    }
+    // cached tiles of this split, then (last split only) one "present" tile holding the L new keys
+    const int tiles_total = (past + 63) / 64;
+    const int tps = p.past_dev ? max((tiles_total + p.n_splits - 1) / p.n_splits, 1) : p.tiles_per_split;
+    int n_lo = max(split * tps, kv0 / 64);
+    int n_hi = min((split + 1) * tps, tiles_total);
+    if (n_hi < n_lo) n_hi = n_lo;
+    const bool has_present = (split == p.n_splits - 1);
+    const int n_iter = (n_hi - n_lo) + (has_present ? 1 : 0);
+
+    auto issue = [&](int it) {
+        if (it < n_iter) {
+            const uint32_t sk = skv + (it % DEC_STAGES) * 2 * TILE, sv = sk + TILE;
+            if (Q4 && it < n_hi - n_lo && (n_lo + it) * 64 < p.n_quant) {
+                // stage layout: [K codes | V codes | K meta | V meta]
+                const int n = n_lo + it;
+                int page = p.block_table[(size_t)(b / p.row_div) * p.bt_stride + n];
+                const uint8_t* kc = p.qcodes + ((size_t)page * 2 * p.n_kv + kvh) * QC;
+                const uint8_t* vc = kc + (size_t)p.n_kv * QC;
+                const uint8_t* km = reinterpret_cast<const uint8_t*>(p.qmeta) + ((size_t)page * 2 * p.n_kv + kvh) * QM;
+                const uint8_t* vm = km + (size_t)p.n_kv * QM;
+                for (int idx = tid; idx < QC / 16; idx += 128) {
+                    cp_async16(sk + idx * 16, kc + idx * 16);
+                    cp_async16(sk + QC + idx * 16, vc + idx * 16);
+                }
+                for (int idx = tid; idx < QM / 16; idx += 128) {
+                    cp_async16(sk + 2 * QC + idx * 16, km + idx * 16);
+                    cp_async16(sk + 2 * QC + QM + idx * 16, vm + idx * 16);
+                }
+            } else if (it < n_hi - n_lo) {
+                const int n = n_lo + it;
+                int page = p.block_table[(size_t)(b / p.row_div) * p.bt_stride + n];
+                const bf16* kp = kv_tile_ptr(p.pool, page, 0, kvh, p.n_kv, D);
+                const bf16* vp = kv_tile_ptr(p.pool, page, 1, kvh, p.n_kv, D);
+                for (int idx = tid; idx < 64 * CPR; idx += 128) {
+                    int r = idx / CPR, c = idx % CPR;
+                    cp_async16(sk + tile_off<D>(r, c), kp + idx * 8);
+                    cp_async16(sv + tile_off<D>(r, c), vp + idx * 8);
+                }
+            } else {                                            // present tile: 16 rows from the qkv buffer
+                for (int idx = tid; idx < 16 * CPR; idx += 128) {
+                    int r = idx / CPR, c = idx % CPR;
+                    size_t tok = (size_t)b * p.L + (r < p.L ? r : 0);
+                    cp_async16(sk + tile_off<D>(r, c), p.k + tok * p.ldk + kvh * D + c * 8, r < p.L ? 16 : 0);
+                    cp_async16(sv + tile_off<D>(r, c), p.v + tok * p.ldv + kvh * D + c * 8, r < p.L ? 16 : 0);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < DEC_STAGES - 1; i++) issue(i);          // group 0 also carries the Q tile
+
+    uint32_t qf[D / 16][4];
+    float o[D / 8][4];
+#pragma unroll
+    for (int dt = 0; dt < D / 8; dt++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[dt][j] = 0.f;
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+
+    for (int it = 0; it < n_iter; it++) {
+        cp_async_wait<DEC_STAGES - 2>();
+        __syncthreads();
+        issue(it + DEC_STAGES - 1);
+        if (it == 0) {
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ks++) {
+                int r = lane & 15, c = ks * 2 + (lane >> 4);
+                ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], sq + tile_off<D>(r, c));
+            }
+        }
+        uint32_t sk = skv + (it % DEC_STAGES) * 2 * TILE, sv = sk + TILE;
+        const bool present = it >= n_hi - n_lo;
+        if (Q4 && !present && (n_lo + it) * 64 < p.n_quant) {
+            // dequantise codes -> bf16 swizzled tiles: deq = bf16(q*scale + bias) (mx.dequantize, phi.py:536-537)
+            const uint8_t* st = smem + (sk - smem_u32(smem));
+            for (int idx = tid; idx < 2 * 64 * CPR; idx += 128) {
+                int kv = idx / (64 * CPR), rem = idx % (64 * CPR);
+                int r = rem / CPR, c = rem % CPR;
+                uint32_t codes = *reinterpret_cast<const uint32_t*>(st + kv * QC + r * (D / 2) + c * 4);
+                uint32_t meta = *reinterpret_cast<const uint32_t*>(st + 2 * QC + kv * QM + (r * (D / 32) + c / 4) * 4);
+                float2 sb = unpack_bf16(meta);
+                uint4 o;
+                uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float lo = __fadd_rn(__fmul_rn((float)((codes >> (8 * j)) & 15), sb.x), sb.y);
+                    float hi = __fadd_rn(__fmul_rn((float)((codes >> (8 * j + 4)) & 15), sb.x), sb.y);
+                    ou[j] = pack_bf16(lo, hi);
+                }
+                *reinterpret_cast<uint4*>(smem + (sdq - smem_u32(smem)) + kv * TILE + tile_off<D>(r, c)) = o;
+            }
+            __syncthreads();
+            sk = sdq; sv = sdq + TILE;
+        }
+        if (present && warp != 0) continue;                     // 16 keys: one warp
+        float s[2][4];
+        qk_mma<D, 2>(qf, sk, present ? 0 : warp * 16, s, lane);
+        const int j0 = present ? past : (n_lo + it) * 64 + warp * 16;
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int j = j0 + nt * 8 + 2 * t + (e & 1);
+                bool ok;
+                if (present) {
+                    int qi = past + ((e & 2) ? g + 8 : g);
+                    ok = (j < s_total) && (j <= qi) && (j >= kv0);
+                } else {
+                    ok = (j >= kv0) && (j < past);
+                }
+                s[nt][e] = ok ? s[nt][e] * p.scale_log2 : -INFINITY;
+            }
+        softmax_update<D, 2>(s, m, l, o);
+        pv_mma<D, 2>(s, sv, present ? 0 : warp * 16, o, lane);
+    }
+    cp_async_wait<0>();
+    __syncthreads();                                            // ring is free: reuse it for the warp merge
+
+    float* sm_o = reinterpret_cast<float*>(smem + 16 * D * 2);  // [4][16][D]
+    float* sm_m = sm_o + 4 * 16 * D;                            // [4][16]
+    float* sm_l = sm_m + 64;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        l[i] += __shfl_xor_sync(0xffffffffu, l[i], 1);
+        l[i] += __shfl_xor_sync(0xffffffffu, l[i], 2);
+    }
+    if (t == 0) {
+        sm_m[warp * 16 + g] = m[0]; sm_m[warp * 16 + g + 8] = m[1];
+        sm_l[warp * 16 + g] = l[0]; sm_l[warp * 16 + g + 8] = l[1];
+    }
+#pragma unroll
+    for (int dt = 0; dt < D / 8; dt++) {
+        int d = dt * 8 + 2 * t;
+        *reinterpret_cast<float2*>(sm_o + (warp * 16 + g) * D + d) = make_float2(o[dt][0], o[dt][1]);
+        *reinterpret_cast<float2*>(sm_o + (warp * 16 + g + 8) * D + d) = make_float2(o[dt][2], o[dt][3]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < p.L * D; idx += 128) {
+        int r = idx / D, d = idx % D;
+        float mm = fmaxf(fmaxf(sm_m[r], sm_m[16 + r]), fmaxf(sm_m[32 + r], sm_m[48 + r]));
+        float mu = (mm == -INFINITY) ? 0.f : mm;
+        float acc = 0.f, ll = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            float f = exp2f(sm_m[w * 16 + r] - mu);
+            acc += f * sm_o[(w * 16 + r) * D + d];
+            ll += f * sm_l[w * 16 + r];
+        }
+        if (p.n_splits == 1) {
+            p.out[((size_t)b * p.L + r) * p.ldo + h * D + d] = __float2bfloat16_rn(ll > 0.f ? acc / ll : 0.f);
+        } else {
+            size_t base = (((size_t)b * p.n_heads + h) * p.n_splits + split) * 16 + r;
+            p.ws_o[base * D + d] = acc;
+            if (d == 0) { p.ws_ml[base * 2] = mm; p.ws_ml[base * 2 + 1] = ll; }
+        }
+    }
+}
+
+template <int D>
+__global__ void attn_merge_kernel(AttnParams p) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    for (int idx = threadIdx.x; idx < p.L * D; idx += blockDim.x) {
+        int r = idx / D, d = idx % D;
+        size_t base0 = (((size_t)b * p.n_heads + h) * p.n_splits) * 16 + r;
+        float mm = -INFINITY;
+        for (int s = 0; s < p.n_splits; s++) mm = fmaxf(mm, p.ws_ml[(base0 + (size_t)s * 16) * 2]);
+        float mu = (mm == -INFINITY) ? 0.f : mm;
+        float acc = 0.f, ll = 0.f;
+        for (int s = 0; s < p.n_splits; s++) {
+            size_t bs = base0 + (size_t)s * 16;
+            float f = exp2f(p.ws_ml[bs * 2] - mu);
+            acc += f * p.ws_o[bs * D + d];
+            ll += f * p.ws_ml[bs * 2 + 1];
+        }
+        p.out[((size_t)b * p.L + r) * p.ldo + h * D + d] = __float2bfloat16_rn(ll > 0.f ? acc / ll : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host entry points
+// ------------------------------------------------------------------------------------------
+static int fill_params(AttnParams& p, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                       void* out, int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale, int causal,
+                       int past, const int32_t* kv_start, const void* pool, const int32_t* block_table, int bt_stride,
+                       int row_div) {
+    P3_CHECK_ARG(hd == 96 || hd == 64, "attention: head_dim must be 96 or 64 (got %d)", hd);
+    P3_CHECK_ARG(n_kv >= 1 && n_heads % n_kv == 0, "attention: n_heads must be a multiple of n_kv");
+    P3_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "attention: strides must keep 16 B alignment");
+    P3_CHECK_ARG(past == 0 || (pool && block_table), "attention: past > 0 needs a KV pool and block table");
+    P3_CHECK_ARG(row_div >= 1, "attention: row_div must be >= 1");
+    p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v;
+    p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.out = (bf16*)out; p.ldo = ldo;
+    p.B = B; p.L = L; p.n_heads = n_heads; p.n_kv = n_kv; p.hd = hd;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.causal = causal; p.past = past; p.past_host = past; p.past_dev = nullptr; p.kv_start = kv_start;
+    p.pool = (const bf16*)pool; p.block_table = block_table; p.bt_stride = bt_stride; p.row_div = row_div;
+    p.n_splits = 1; p.tiles_per_split = 0; p.ws_o = nullptr; p.ws_ml = nullptr;
+    p.n_quant = 0; p.qcodes = nullptr; p.qmeta = nullptr;
+    return 0;
+}
+
+extern "C" int p3_attention_prefill(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                                    void* out, int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale,
+                                    int causal, int past, const int32_t* kv_start, const void* pool,
+                                    const int32_t* block_table, int bt_stride, int row_div, cudaStream_t st) {
+    AttnParams p;
+    if (fill_params(p, q, k, v, ldq, ldk, ldv, out, ldo, B, L, n_heads, n_kv, hd, scale, causal, past, kv_start, pool,
+                    block_table, bt_stride, row_div)) return -1;
+    if (B == 0 || L == 0) return 0;
+    dim3 grid((L + 63) / 64, n_heads, B);
+    int smem = 5 * 64 * hd * 2;
+    if (hd == 96) {
+        static bool set = false;
+        if (!set) { cudaFuncSetAttribute(attn_prefill_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+        attn_prefill_kernel<96><<<grid, 128, smem, st>>>(p);
+    } else {
+        static bool set = false;
+        if (!set) { cudaFuncSetAttribute(attn_prefill_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+        attn_prefill_kernel<64><<<grid, 128, smem, st>>>(p);
+    }
+    P3_CHECK_LAUNCH("attention_prefill");
+    return 0;
+}
+
+extern "C" int64_t p3_attention_decode_workspace(int B, int L, int n_heads, int hd, int n_splits) {
+    (void)L;
+    return (int64_t)B * n_heads * n_splits * 16 * (hd + 2) * 4;
+}
+
+template <int D, bool Q4>
+static int launch_decode(AttnParams& p, cudaStream_t st) {
+    dim3 grid(p.n_splits, p.n_heads, p.B);
+    int smem = 16 * D * 2 + DEC_STAGES * 2 * 64 * D * 2 + (Q4 ? 2 * 64 * D * 2 : 0);
+    static bool set = false;
+    if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<D, Q4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        P3_CHECK_ARG(e == cudaSuccess, "attention_decode: smem attribute: %s", cudaGetErrorString(e));
+        set = true;
+    }
+    attn_decode_kernel<D, Q4><<<grid, 128, smem, st>>>(p);
+    P3_CHECK_LAUNCH("attention_decode");
+    if (p.n_splits > 1) {
+        attn_merge_kernel<D><<<dim3(p.n_heads, p.B), 128, 0, st>>>(p);
+        P3_CHECK_LAUNCH("attention_merge");
+    }
+    return 0;
+}
+
+static int decode_common(AttnParams& p, int L, int past, int n_splits, void* workspace, bool q4, cudaStream_t st) {
+    P3_CHECK_ARG(L >= 1 && L <= 16, "attention_decode: L must be in [1,16] (got %d)", L);
+    P3_CHECK_ARG(n_splits >= 1 && (n_splits == 1 || workspace), "attention_decode: n_splits>1 needs a workspace");
+    if (p.B == 0) return 0;
+    int tiles_total = (past + 63) / 64;
+    if (!p.past_dev && n_splits > tiles_total) n_splits = tiles_total > 0 ? tiles_total : 1;
+    p.n_splits = n_splits;
+    p.tiles_per_split = (tiles_total + n_splits - 1) / n_splits;
+    if (p.tiles_per_split == 0) p.tiles_per_split = 1;
+    p.ws_o = (float*)workspace;
+    p.ws_ml = p.ws_o ? p.ws_o + (size_t)p.B * p.n_heads * n_splits * 16 * p.hd : nullptr;
+    if (p.hd == 96) return q4 ? launch_decode<96, true>(p, st) : launch_decode<96, false>(p, st);
+    return q4 ? launch_decode<64, true>(p, st) : launch_decode<64, false>(p, st);
+}
+
+extern "C" int p3_attention_decode(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                                   void* out, int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale,
+                                   int past, const int32_t* kv_start, const void* pool, const int32_t* block_table,
+                                   int bt_stride, int row_div, int n_splits, void* workspace, const int32_t* past_dev,
+                                   cudaStream_t st) {
+    AttnParams p;
+    if (fill_params(p, q, k, v, ldq, ldk, ldv, out, ldo, B, L, n_heads, n_kv, hd, scale, 1, past, kv_start, pool,
+                    block_table, bt_stride, row_div)) return -1;
+    p.past_dev = past_dev;
+    return decode_common(p, L, past, n_splits, workspace, false, st);
+}
+
+extern "C" int p3_attention_decode_q4(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                                      void* out, int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale,
+                                      int past, int n_quant, const int32_t* kv_start, const void* pool, const void* qcodes,
+                                      const void* qmeta, const int32_t* block_table, int bt_stride, int row_div,
+                                      int n_splits, void* workspace, const int32_t* past_dev, cudaStream_t st) {
+    AttnParams p;
+    if (fill_params(p, q, k, v, ldq, ldk, ldv, out, ldo, B, L, n_heads, n_kv, hd, scale, 1, past, kv_start, pool,
+                    block_table, bt_stride, row_div)) return -1;
+    P3_CHECK_ARG(n_quant % 64 == 0 && n_quant <= past, "attention_decode_q4: n_quant must be a multiple of 64 and <= past");
+    P3_CHECK_ARG(n_quant == 0 || (qcodes && qmeta), "attention_decode_q4: q4 pools missing");
+    p.n_quant = n_quant; p.qcodes = (const uint8_t*)qcodes; p.qmeta = (const bf16*)qmeta;
+    p.past_dev = past_dev;
+    return decode_common(p, L, past, n_splits, workspace, true, st);
+}

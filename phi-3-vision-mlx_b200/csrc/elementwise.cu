@@ -1,0 +1,335 @@
+// HBM-bound row kernels: embedding gather, RMSNorm, LayerNorm, SuRoPE + paged-KV write,
+// argmax / log-prob / top-k row statistics. Each cites the reference op it replaces.
+#include "common.cuh"
+#include "../../include/phi3_b200.h"
+
+// ------------------------------------------------------------------------------------------
+// embed_gather: nn.Embedding (phi.py:568,577). Negative placeholder ids (phi.py:270) and
+// out-of-range ids are clamped to row 0; those rows are overwritten by the image scatter.
+// ------------------------------------------------------------------------------------------
+__global__ void embed_gather_kernel(const bf16* __restrict__ table, const int32_t* __restrict__ ids,
+                                    bf16* __restrict__ out, int64_t T, int H, int vocab) {
+    int64_t t = blockIdx.x;
+    int id = ids[t];
+    if (id < 0 || id >= vocab) id = 0;
+    const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)id * H);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)t * H);
+    for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+extern "C" int p3_embed_gather(const void* table, const int32_t* ids, void* out, int64_t T, int H, int vocab,
+                               cudaStream_t st) {
+    P3_CHECK_ARG(H % 8 == 0, "embed_gather: H must be a multiple of 8");
+    if (T == 0) return 0;
+    embed_gather_kernel<<<(unsigned)T, 128, 0, st>>>((const bf16*)table, ids, (bf16*)out, T, H, vocab);
+    P3_CHECK_LAUNCH("embed_gather");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// rmsnorm: nn.RMSNorm -> mx.fast.rms_norm (phi.py:478-479,571): fp32 accumulate, one rounding.
+// One warp per row, row held in registers (H <= 8192).
+// ------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                               int64_t T, int H, float eps) {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= T) return;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * H);
+    const uint4* wr = reinterpret_cast<const uint4*>(w);
+    uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * H);
+    int nv = H / 8;
+    uint4 v[MAXV];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; i++) {
+        int c = lane + i * 32;
+        if (c < nv) {
+            v[i] = xr[c];
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { float2 f = unpack_bf16(u[j]); ss += f.x * f.x + f.y * f.y; }
+        }
+    }
+    ss = warp_sum(ss);
+    float rs = rsqrtf(ss / (float)H + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; i++) {
+        int c = lane + i * 32;
+        if (c < nv) {
+            uint4 wv = __ldg(wr + c), o;
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[i]);
+            const uint32_t* uw = reinterpret_cast<const uint32_t*>(&wv);
+            uint32_t* uo = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float2 f = unpack_bf16(u[j]), g = unpack_bf16(uw[j]);
+                uo[j] = pack_bf16(f.x * rs * g.x, f.y * rs * g.y);
+            }
+            yr[c] = o;
+        }
+    }
+}
+
+extern "C" int p3_rmsnorm(const void* x, const void* w, void* y, int64_t T, int H, float eps, cudaStream_t st) {
+    P3_CHECK_ARG(H % 8 == 0 && H <= 8192, "rmsnorm: H must be a multiple of 8 and <= 8192");
+    if (T == 0) return 0;
+    unsigned grid = (unsigned)((T + 3) / 4);
+    if (H <= 4096)
+        rmsnorm_kernel<16><<<grid, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, T, H, eps);
+    else
+        rmsnorm_kernel<32><<<grid, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, T, H, eps);
+    P3_CHECK_LAUNCH("rmsnorm");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// layernorm: nn.LayerNorm -> mx.fast.layer_norm (phi.py:165,167,212), eps 1e-5, with bias.
+// Input is the fp32 CLIP residual stream (the reference runs CLIP activations in fp32);
+// output bf16 (feeds a GEMM) or fp32 (pre_layrnorm, phi.py:218). One warp per row, H <= 1024.
+// ------------------------------------------------------------------------------------------
+template <bool OUT_F32>
+__global__ void layernorm_kernel(const float* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                 void* __restrict__ y, int64_t T, int H, float eps) {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= T) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * H);
+    int nv = H / 4;
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int c = lane + i * 32;
+        if (c < nv) { v[i] = xr[c]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+    }
+    float mean = warp_sum(s) / (float)H;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int c = lane + i * 32;
+        if (c < nv) {
+            float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+            ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+        }
+    }
+    float rs = rsqrtf(warp_sum(ss) / (float)H + eps);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int c = lane + i * 32;
+        if (c < nv) {
+            uint2 wv = __ldg(reinterpret_cast<const uint2*>(w) + c), bv = __ldg(reinterpret_cast<const uint2*>(b) + c);
+            float2 w0 = unpack_bf16(wv.x), w1 = unpack_bf16(wv.y), b0 = unpack_bf16(bv.x), b1 = unpack_bf16(bv.y);
+            float o0 = (v[i].x - mean) * rs * w0.x + b0.x, o1 = (v[i].y - mean) * rs * w0.y + b0.y;
+            float o2 = (v[i].z - mean) * rs * w1.x + b1.x, o3 = (v[i].w - mean) * rs * w1.y + b1.y;
+            if (OUT_F32) {
+                reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (size_t)row * H)[c] = make_float4(o0, o1, o2, o3);
+            } else {
+                reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(y) + (size_t)row * H)[c] = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+            }
+        }
+    }
+}
+
+extern "C" int p3_layernorm(const float* x, const void* w, const void* b, void* y, int64_t T, int H, float eps,
+                            int out_f32, cudaStream_t st) {
+    P3_CHECK_ARG(H % 4 == 0 && H <= 1024, "layernorm: H must be a multiple of 4 and <= 1024");
+    if (T == 0) return 0;
+    unsigned grid = (unsigned)((T + 3) / 4);
+    if (out_f32) layernorm_kernel<true><<<grid, 128, 0, st>>>(x, (const bf16*)w, (const bf16*)b, y, T, H, eps);
+    else layernorm_kernel<false><<<grid, 128, 0, st>>>(x, (const bf16*)w, (const bf16*)b, y, T, H, eps);
+    P3_CHECK_LAUNCH("layernorm");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// rope_kvwrite: _rotate_half on q,k (phi.py:418-423,451-452) with the SuRoPE table
+// (phi.py:487-507) + KVCache slice-assign (phi.py:542-548) into the paged pool.
+// qkv: [B*L, (n_heads + 2*n_kv)*hd] bf16, roped in place. cos/sin: fp32 [Bt, L_all, hd/2]
+// (half table: the reference concatenates [freqs, freqs]); row b uses table row (b / row_div)
+// when tab_bstride != 0. Token i of row b sits at absolute position past + i.
+// ------------------------------------------------------------------------------------------
+__global__ void rope_kvwrite_kernel(bf16* __restrict__ qkv, const float* __restrict__ cosT, const float* __restrict__ sinT,
+                                    int64_t tab_bstride, int B, int L, int n_heads, int n_kv, int hd, int past,
+                                    int row_div, bf16* __restrict__ pool, const int32_t* __restrict__ block_table,
+                                    int bt_stride, int write_cache, const int32_t* __restrict__ past_dev) {
+    if (past_dev) past = *past_dev;
+    const int half = hd / 2, cpr = half / 8;                  // 8-elem chunks per half head
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)B * L * n_heads * cpr;
+    if (idx >= total) return;
+    int c = (int)(idx % cpr);
+    int h = (int)((idx / cpr) % n_heads);
+    int64_t tok = idx / ((int64_t)cpr * n_heads);
+    int b = (int)(tok / L), i = (int)(tok % L);
+    int pos = past + i;
+    int qkv_dim = (n_heads + 2 * n_kv) * hd;
+    const float* cr = cosT + (size_t)(b / row_div) * tab_bstride + (size_t)pos * half + c * 8;
+    const float* sr = sinT + (size_t)(b / row_div) * tab_bstride + (size_t)pos * half + c * 8;
+    float cs[8], sn[8];
+    *reinterpret_cast<float4*>(cs) = *reinterpret_cast<const float4*>(cr);
+    *reinterpret_cast<float4*>(cs + 4) = *reinterpret_cast<const float4*>(cr + 4);
+    *reinterpret_cast<float4*>(sn) = *reinterpret_cast<const float4*>(sr);
+    *reinterpret_cast<float4*>(sn + 4) = *reinterpret_cast<const float4*>(sr + 4);
+    bf16* row = qkv + (size_t)tok * qkv_dim;
+
+    auto rope8 = [&](bf16* p, uint4& o1, uint4& o2) {
+        uint4 a = *reinterpret_cast<uint4*>(p + c * 8), bb = *reinterpret_cast<uint4*>(p + half + c * 8);
+        const uint32_t* ua = reinterpret_cast<const uint32_t*>(&a);
+        const uint32_t* ub = reinterpret_cast<const uint32_t*>(&bb);
+        uint32_t* u1 = reinterpret_cast<uint32_t*>(&o1);
+        uint32_t* u2 = reinterpret_cast<uint32_t*>(&o2);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float2 x1 = unpack_bf16(ua[j]), x2 = unpack_bf16(ub[j]);
+            // out[:half] = x1*cos - x2*sin ; out[half:] = x2*cos + x1*sin
+            u1[j] = pack_bf16(x1.x * cs[2 * j] - x2.x * sn[2 * j], x1.y * cs[2 * j + 1] - x2.y * sn[2 * j + 1]);
+            u2[j] = pack_bf16(x2.x * cs[2 * j] + x1.x * sn[2 * j], x2.y * cs[2 * j + 1] + x1.y * sn[2 * j + 1]);
+        }
+        *reinterpret_cast<uint4*>(p + c * 8) = o1;
+        *reinterpret_cast<uint4*>(p + half + c * 8) = o2;
+    };
+    uint4 o1, o2;
+    rope8(row + h * hd, o1, o2);                              // q head h
+    if (h < n_kv) {
+        rope8(row + (n_heads + h) * hd, o1, o2);              // k head h
+        if (write_cache) {
+            int page = block_table[(size_t)(b / row_div) * bt_stride + pos / P3_PAGE];
+            int slot = pos % P3_PAGE;
+            bf16* kd = pool + (size_t)page * kv_page_elems(n_kv, hd) + ((size_t)h * P3_PAGE + slot) * hd;
+            bf16* vd = kd + (size_t)n_kv * P3_PAGE * hd;
+            *reinterpret_cast<uint4*>(kd + c * 8) = o1;
+            *reinterpret_cast<uint4*>(kd + half + c * 8) = o2;
+            const bf16* vs = row + (n_heads + n_kv + h) * hd;
+            *reinterpret_cast<uint4*>(vd + c * 8) = *reinterpret_cast<const uint4*>(vs + c * 8);
+            *reinterpret_cast<uint4*>(vd + half + c * 8) = *reinterpret_cast<const uint4*>(vs + half + c * 8);
+        }
+    }
+}
+
+extern "C" int p3_rope_kvwrite(void* qkv, const float* cosT, const float* sinT, int64_t tab_bstride, int B, int L,
+                               int n_heads, int n_kv, int hd, int past, int row_div, void* pool,
+                               const int32_t* block_table, int bt_stride, int write_cache, const int32_t* past_dev,
+                               cudaStream_t st) {
+    P3_CHECK_ARG(hd % 16 == 0, "rope_kvwrite: head_dim must be a multiple of 16");
+    P3_CHECK_ARG(n_kv <= n_heads && row_div >= 1, "rope_kvwrite: bad head counts / row_div");
+    int64_t total = (int64_t)B * L * n_heads * (hd / 16);
+    if (total == 0) return 0;
+    rope_kvwrite_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (bf16*)qkv, cosT, sinT, tab_bstride, B, L, n_heads, n_kv, hd, past, row_div, (bf16*)pool, block_table,
+        bt_stride, write_cache, past_dev);
+    P3_CHECK_LAUNCH("rope_kvwrite");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// row_stats: mx.argmax (pv:386,392,506,559), nn.log_softmax + gathers (pv:476,541-547,571-573),
+// mx.argpartition top-n (pv:507) in ONE pass over each logits row.
+// Per row r of logits[R, V] (fp32, row stride ld):
+//   argmax[r] (first index on ties), maxv[r], lse[r] = log sum exp
+//   topk_ids[r, k], topk_lp[r, k]  (k < n_top, descending; log-probs)
+//   gather_lp[r, g] = logits[r, gather_ids[r, g]] - lse[r]
+// ------------------------------------------------------------------------------------------
+#define RS_THREADS 256
+__global__ void row_stats_kernel(const float* __restrict__ logits, int64_t ld, int V, int32_t* __restrict__ argmax_out,
+                                 float* __restrict__ max_out, float* __restrict__ lse_out, int n_top,
+                                 int32_t* __restrict__ topk_ids, float* __restrict__ topk_lp, int n_gather,
+                                 const int32_t* __restrict__ gather_ids, float* __restrict__ gather_lp) {
+    __shared__ float s_val[RS_THREADS / 32];
+    __shared__ int s_idx[RS_THREADS / 32];
+    __shared__ float s_sum[RS_THREADS / 32];
+    __shared__ int s_taken[8];
+    __shared__ float s_bval;
+    __shared__ int s_bidx;
+    int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* row = logits + (size_t)r * ld;
+    float lse = 0.f, rowmax = 0.f;
+    for (int k = 0; k < (n_top > 0 ? n_top : 1); k++) {
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < V; i += RS_THREADS) {
+            float v = row[i];
+            bool taken = false;
+            for (int j = 0; j < k; j++) taken |= (s_taken[j] == i);
+            if (!taken && (v > best || (v == best && i < bi))) { best = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < RS_THREADS / 32; w++)
+                if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
+            s_bval = best; s_bidx = bi;
+            if (k < 8) s_taken[k] = bi;
+        }
+        __syncthreads();
+        best = s_bval; bi = s_bidx;
+        if (k == 0) {
+            rowmax = best;
+            float sum = 0.f;
+            for (int i = tid; i < V; i += RS_THREADS) sum += __expf(row[i] - rowmax);
+            sum = warp_sum(sum);
+            if (lane == 0) s_sum[warp] = sum;
+            __syncthreads();
+            sum = 0.f;
+            for (int w = 0; w < RS_THREADS / 32; w++) sum += s_sum[w];
+            lse = rowmax + logf(sum);
+            if (tid == 0) {
+                if (argmax_out) argmax_out[r] = bi;
+                if (max_out) max_out[r] = rowmax;
+                if (lse_out) lse_out[r] = lse;
+            }
+        }
+        if (n_top > 0 && tid == 0) {
+            topk_ids[(size_t)r * n_top + k] = bi;
+            topk_lp[(size_t)r * n_top + k] = best - lse;
+        }
+        __syncthreads();
+    }
+    for (int g = tid; g < n_gather; g += RS_THREADS) {
+        int id = gather_ids[(size_t)r * n_gather + g];
+        gather_lp[(size_t)r * n_gather + g] = (id >= 0 && id < V) ? row[id] - lse : -INFINITY;
+    }
+}
+
+extern "C" int p3_row_stats(const float* logits, int64_t R, int64_t ld, int V, int32_t* argmax_out, float* max_out,
+                            float* lse_out, int n_top, int32_t* topk_ids, float* topk_lp, int n_gather,
+                            const int32_t* gather_ids, float* gather_lp, cudaStream_t st) {
+    P3_CHECK_ARG(n_top >= 0 && n_top <= 8, "row_stats: n_top must be in [0,8]");
+    P3_CHECK_ARG(n_top == 0 || (topk_ids && topk_lp), "row_stats: top-k outputs missing");
+    P3_CHECK_ARG(n_gather == 0 || (gather_ids && gather_lp), "row_stats: gather buffers missing");
+    if (R == 0) return 0;
+    row_stats_kernel<<<(unsigned)R, RS_THREADS, 0, st>>>(logits, ld, V, argmax_out, max_out, lse_out, n_top, topk_ids,
+                                                         topk_lp, n_gather, gather_ids, gather_lp);
+    P3_CHECK_LAUNCH("row_stats");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// decode_advance: greedy-loop bookkeeping kept on the device so a whole decode step replays as
+// one CUDA graph with no host sync (the reference syncs twice per token, pv:393,397).
+//   history[b][*step] = tok[b];  eos_seen[b] |= tok[b]==eos;  (*step)++;  (*past)++
+// ------------------------------------------------------------------------------------------
+__global__ void decode_advance_kernel(const int32_t* __restrict__ tok, int32_t* __restrict__ history, int64_t ld, int B,
+                                      int32_t* step, int32_t* past, int32_t* eos_seen) {
+    int s = *step;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        history[(size_t)b * ld + s] = tok[b];
+        if (eos_seen && tok[b] == 32007) eos_seen[b] = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *step = s + 1; if (past) *past = *past + 1; }
+}
+
+extern "C" int p3_decode_advance(const int32_t* tok, int32_t* history, int64_t ld, int B, int32_t* step, int32_t* past,
+                                 int32_t* eos_seen, cudaStream_t st) {
+    decode_advance_kernel<<<1, 128, 0, st>>>(tok, history, ld, B, step, past, eos_seen);
+    P3_CHECK_LAUNCH("decode_advance");
+    return 0;
+}

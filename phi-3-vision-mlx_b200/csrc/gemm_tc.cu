@@ -1,0 +1,473 @@
+// Dense bf16 GEMM on 5th-gen tensor cores: out[M,N] = X[M,K] . W[N,K]^T (+ fused epilogue).
+// Replaces every prefill / ViT / projector nn.Linear and the patch-embed conv of the reference
+// (phi.py:140-143,155-156,186-192,391,437-438,465-466,604).
+//
+// Structure (one CTA per SM, persistent over output tiles, 128 x BN tile, BK = 64):
+//   warp 0   : TMA producer  — cp.async.bulk.tensor 2D, 128B swizzle, STAGES-deep mbarrier ring
+//   warp 1   : MMA issuer    — one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//                              (UMMA 128 x BN x 16), accumulators in TMEM (2 x BN columns, double buffered)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      — tcgen05.ld 32x32b, fused bias / GELU / residual / SwiGLU / fp32 / row scatter
+// Both operands are K-major (activations [M,K] and nn.Linear weights [N,K]), so no transposes.
+#include "common.cuh"
+#include "../../include/phi3_b200.h"
+#include <cuda.h>
+#include <mutex>
+
+struct GemmEpi {
+    const bf16* bias;
+    void* out;
+    int64_t ldo;
+    const void* resid;
+    const int32_t* row_map;
+    int kind;
+};
+
+__device__ __forceinline__ float epi_act(int kind, float x) {
+    // CLIP fc1 and the projector run in fp32 in the reference (fp32 activations x bf16 weights
+    // promote to fp32), so the activation is applied to the unrounded accumulator.
+    if (kind == P3_EPI_QGELU) return x / (1.f + __expf(-1.702f * x));
+    if (kind == P3_EPI_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major) | SBO>>4 [32,46) = 1024B between
+// 8-row groups | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int BN>
+struct TcCfg {
+    static constexpr int BM = 128, BK = 64;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+    // kind::f16 instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+// epilogue for 32 consecutive accumulator columns of one output row
+__device__ __forceinline__ void epi_store32(const GemmEpi& ep, int64_t orow, int n0, int N, const uint32_t* acc) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(acc[i]);
+    if (ep.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) if (n0 + i < N) v[i] += __bfloat162float(ep.bias[n0 + i]);
+    }
+    if (ep.kind == P3_EPI_F32 || ep.kind == P3_EPI_RESIDUAL_F32) {
+        float* o = reinterpret_cast<float*>(ep.out) + orow * ep.ldo + n0;
+        if (ep.kind == P3_EPI_RESIDUAL_F32) {
+            const float* r = reinterpret_cast<const float*>(ep.resid) + orow * ep.ldo + n0;
+            if (n0 + 32 <= N && (ep.ldo & 3) == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    float4 f = reinterpret_cast<const float4*>(r)[i];
+                    v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+                }
+            } else {
+                for (int i = 0; i < 32; i++) if (n0 + i < N) v[i] += r[i];
+            }
+        }
+        if (n0 + 32 <= N && (ep.ldo & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+            for (int i = 0; i < 32; i++) if (n0 + i < N) o[i] = v[i];
+        }
+        return;
+    }
+    bf16* o = reinterpret_cast<bf16*>(ep.out) + orow * ep.ldo + n0;
+    const bool full = (n0 + 32 <= N) && ((ep.ldo & 7) == 0);
+    if (ep.kind == P3_EPI_RESIDUAL) {
+        const bf16* r = reinterpret_cast<const bf16*>(ep.resid) + orow * ep.ldo + n0;
+        if (full) {
+            uint4 rv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) rv[i] = reinterpret_cast<const uint4*>(r)[i];
+            const uint32_t* ru = reinterpret_cast<const uint32_t*>(rv);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                float2 f = unpack_bf16(ru[i]);
+                v[2 * i] = f.x + bf16_round(v[2 * i]);
+                v[2 * i + 1] = f.y + bf16_round(v[2 * i + 1]);
+            }
+        } else {
+            for (int i = 0; i < 32; i++) if (n0 + i < N) v[i] = __bfloat162float(r[i]) + bf16_round(v[i]);
+        }
+    } else if (ep.kind == P3_EPI_QGELU || ep.kind == P3_EPI_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = epi_act(ep.kind, v[i]);
+    }
+    if (full) {
+        uint4 ov[4];
+        uint32_t* ou = reinterpret_cast<uint32_t*>(ov);
+#pragma unroll
+        for (int i = 0; i < 16; i++) ou[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(o)[i] = ov[i];
+    } else {
+        for (int i = 0; i < 32; i++) if (n0 + i < N) o[i] = __float2bfloat16_rn(v[i]);
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpi ep,
+               int M, int N, int K) {
+    using C = TcCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
+    const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+        smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (M + C::BM - 1) / C::BM, n_tiles = (N + BN - 1) / BN;
+    const int total = m_tiles * n_tiles, kb = (K + C::BK - 1) / C::BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int m_idx = (tile % m_tiles) * C::BM, n_idx = (tile / m_tiles) * BN;
+                for (int k = 0; k < kb; k++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, full_bar(stage), k * C::BK, m_idx);
+                    tma_load_2d(sa + C::A_BYTES, &tmB, full_bar(stage), k * C::BK, n_idx);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int k = 0; k < kb; k++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + C::A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < C::BK / 16; kk++)   // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
+                        tc_mma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, C::IDESC, (k | kk) ? 1u : 0u);
+                    tc_commit(empty_bar(stage));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int m_idx = (tile % m_tiles) * C::BM, n_idx = (tile / m_tiles) * BN;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row = m_idx + q * 32 + lane;
+            const bool row_ok = row < M;
+            const int64_t orow = row_ok ? (ep.row_map ? (int64_t)ep.row_map[row] : (int64_t)row) : 0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            if (ep.kind == P3_EPI_SWIGLU) {
+                // interleaved weights: columns [0,BN/2) gate, [BN/2,BN) matching up
+                for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+                    uint32_t g[32], u[32];
+                    tc_ld32(taddr + c0, g);
+                    tc_ld32(taddr + BN / 2 + c0, u);
+                    const int on0 = n_idx / 2 + c0;
+                    if (row_ok && on0 < N / 2) {
+                        uint4 ov[4];
+                        uint32_t* ou = reinterpret_cast<uint32_t*>(ov);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            float g0 = bf16_round(__uint_as_float(g[2 * i])), g1 = bf16_round(__uint_as_float(g[2 * i + 1]));
+                            float u0 = bf16_round(__uint_as_float(u[2 * i])), u1 = bf16_round(__uint_as_float(u[2 * i + 1]));
+                            float a0 = bf16_round(g0 / (1.f + __expf(-g0))), a1 = bf16_round(g1 / (1.f + __expf(-g1)));
+                            ou[i] = pack_bf16(a0 * u0, a1 * u1);
+                        }
+                        bf16* o = reinterpret_cast<bf16*>(ep.out) + orow * ep.ldo + on0;
+                        if (on0 + 32 <= N / 2 && (ep.ldo & 7) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(o)[i] = ov[i];
+                        } else {
+                            const bf16* ob = reinterpret_cast<const bf16*>(ov);
+                            for (int i = 0; i < 32; i++) if (on0 + i < N / 2) o[i] = ob[i];
+                        }
+                    }
+                }
+            } else {
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + c0, v);
+                    if (row_ok && n_idx + c0 < N) epi_store32(ep, orow, n_idx + c0, N, v);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// mma.sync cross-check GEMM (tests / bring-up only; not the product path)
+// ------------------------------------------------------------------------------------------
+#define FB_BM 64
+#define FB_BN 64
+#define FB_BK 32
+__global__ void __launch_bounds__(128) gemm_mma_kernel(const bf16* __restrict__ X, int64_t ldx, const bf16* __restrict__ W,
+                                                       int64_t ldw, GemmEpi ep, int M, int N, int K) {
+    __shared__ __align__(16) bf16 sA[FB_BM][FB_BK + 8];
+    __shared__ __align__(16) bf16 sB[FB_BN][FB_BK + 8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int m0 = blockIdx.y * FB_BM;
+    const bool swiglu = ep.kind == P3_EPI_SWIGLU;
+    // SwiGLU: this CTA produces 64 output columns; gate rows then (second pass) the matching up rows
+    const int o0 = blockIdx.x * FB_BN;
+    const int passes = swiglu ? 2 : 1;
+    float acc[2][2][4][4];
+    for (int pass = 0; pass < passes; pass++) {
+        const int nrow0 = swiglu ? ((o0 / 128) * 256 + (o0 % 128) + pass * 128) : o0;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[pass][i][j][c] = 0.f;
+        for (int k0 = 0; k0 < K; k0 += FB_BK) {
+            for (int i = tid; i < FB_BM * FB_BK / 8; i += 128) {
+                int r = i / (FB_BK / 8), c = (i % (FB_BK / 8)) * 8;
+                uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+                if (m0 + r < M && k0 + c < K) va = *reinterpret_cast<const uint4*>(X + (size_t)(m0 + r) * ldx + k0 + c);
+                if (nrow0 + r < N && k0 + c < K) vb = *reinterpret_cast<const uint4*>(W + (size_t)(nrow0 + r) * ldw + k0 + c);
+                *reinterpret_cast<uint4*>(&sA[r][c]) = va;
+                *reinterpret_cast<uint4*>(&sB[r][c]) = vb;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int ks = 0; ks < FB_BK; ks += 16) {
+                uint32_t a[2][4], b[4][2];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    a[i][0] = *reinterpret_cast<const uint32_t*>(&sA[wm + i * 16 + g][ks + 2 * t]);
+                    a[i][1] = *reinterpret_cast<const uint32_t*>(&sA[wm + i * 16 + g + 8][ks + 2 * t]);
+                    a[i][2] = *reinterpret_cast<const uint32_t*>(&sA[wm + i * 16 + g][ks + 2 * t + 8]);
+                    a[i][3] = *reinterpret_cast<const uint32_t*>(&sA[wm + i * 16 + g + 8][ks + 2 * t + 8]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    b[j][0] = *reinterpret_cast<const uint32_t*>(&sB[wn + j * 8 + g][ks + 2 * t]);
+                    b[j][1] = *reinterpret_cast<const uint32_t*>(&sB[wn + j * 8 + g][ks + 2 * t + 8]);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) mma_bf16_16816(acc[pass][i][j], a[i], b[j][0], b[j][1]);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int row = m0 + wm + i * 16 + g + (c >> 1) * 8;
+                int col = o0 + wn + j * 8 + 2 * t + (c & 1);
+                if (row >= M) continue;
+                int64_t orow = ep.row_map ? ep.row_map[row] : row;
+                if (swiglu) {
+                    if (col >= N / 2) continue;
+                    float gb = bf16_round(acc[0][i][j][c]), ub = bf16_round(acc[1][i][j][c]);
+                    float a = bf16_round(gb / (1.f + __expf(-gb)));
+                    reinterpret_cast<bf16*>(ep.out)[orow * ep.ldo + col] = __float2bfloat16_rn(a * ub);
+                    continue;
+                }
+                if (col >= N) continue;
+                float v = acc[0][i][j][c] + (ep.bias ? __bfloat162float(ep.bias[col]) : 0.f);
+                if (ep.kind == P3_EPI_F32) { reinterpret_cast<float*>(ep.out)[orow * ep.ldo + col] = v; continue; }
+                if (ep.kind == P3_EPI_RESIDUAL_F32) {
+                    reinterpret_cast<float*>(ep.out)[orow * ep.ldo + col] = v + reinterpret_cast<const float*>(ep.resid)[orow * ep.ldo + col];
+                    continue;
+                }
+                if (ep.kind == P3_EPI_RESIDUAL) v = __bfloat162float(reinterpret_cast<const bf16*>(ep.resid)[orow * ep.ldo + col]) + bf16_round(v);
+                else if (ep.kind == P3_EPI_QGELU || ep.kind == P3_EPI_GELU) v = epi_act(ep.kind, v);
+                reinterpret_cast<bf16*>(ep.out)[orow * ep.ldo + col] = __float2bfloat16_rn(v);
+            }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    P3_CHECK_ARG(enc, "gemm: cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    P3_CHECK_ARG(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld", (int)r,
+                 (long long)rows, (long long)K, (long long)ld);
+    return 0;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+    return n;
+}
+
+template <int BN>
+static int launch_tc(const void* X, int64_t ldx, const void* W, int64_t ldw, const GemmEpi& ep, int64_t M, int N, int K,
+                     cudaStream_t st) {
+    using C = TcCfg<BN>;
+    CUtensorMap ta, tb;
+    if (make_tmap(&ta, X, M, K, ldx, C::BM)) return -1;
+    if (make_tmap(&tb, W, N, K, ldw, BN)) return -1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        P3_CHECK_ARG(e == cudaSuccess, "gemm: cannot set %d B dynamic smem: %s", C::SMEM, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    int64_t tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
+    unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
+    gemm_tc_kernel<BN><<<grid, 256, C::SMEM, st>>>(ta, tb, ep, (int)M, N, K);
+    P3_CHECK_LAUNCH("gemm_tc");
+    return 0;
+}
+
+extern "C" int p3_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                       const void* resid, const int32_t* row_map, int64_t M, int N, int K, int epi, int impl,
+                       cudaStream_t st) {
+    P3_CHECK_ARG(epi >= P3_EPI_NONE && epi <= P3_EPI_RESIDUAL_F32, "gemm: unknown epilogue %d", epi);
+    P3_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0, "gemm: ldx/ldw must be multiples of 8 elements (16 B)");
+    P3_CHECK_ARG(((uintptr_t)X & 15) == 0 && ((uintptr_t)W & 15) == 0, "gemm: X/W must be 16-byte aligned");
+    P3_CHECK_ARG((epi != P3_EPI_RESIDUAL && epi != P3_EPI_RESIDUAL_F32) || resid, "gemm: residual epilogue needs resid");
+    P3_CHECK_ARG(epi != P3_EPI_SWIGLU || (N % 256 == 0 && !bias), "gemm: SwiGLU needs N %% 256 == 0 and no bias");
+    P3_CHECK_ARG(M < (1ll << 31), "gemm: M too large");
+    if (M == 0) return 0;
+    GemmEpi ep{(const bf16*)bias, out, ldo, resid, row_map, epi};
+    if (impl == 1) {
+        int ncols = epi == P3_EPI_SWIGLU ? N / 2 : N;
+        dim3 grid((ncols + FB_BN - 1) / FB_BN, (unsigned)((M + FB_BM - 1) / FB_BM));
+        gemm_mma_kernel<<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, ep, (int)M, N, K);
+        P3_CHECK_LAUNCH("gemm_mma");
+        return 0;
+    }
+    int64_t m_tiles = (M + 127) / 128;
+    bool small = m_tiles * ((N + 255) / 256) < 2 * num_sms();
+    if (epi == P3_EPI_SWIGLU || !small) return launch_tc<256>(X, ldx, W, ldw, ep, M, N, K, st);
+    return launch_tc<128>(X, ldx, W, ldw, ep, M, N, K, st);
+}

@@ -1,0 +1,416 @@
+"""Phi-3.5 (mini / vision) on B200 — host-side mirror of the reference model call protocol.
+
+`Phi3B200.__call__` keeps the signature of Phi3ForCausalLM.__call__ (/root/reference/phi.py:606):
+    model(input_ids, pixel_values=None, image_sizes=None, positions=None, cache=None, pids=None,
+          mask=None, max_tokens=0, advance_offset=None, n_beam=1) -> (logits[B,L,V], cache)
+All arithmetic runs in the sm_100a kernels of libphi3b200.so through the C ABI (`_lib.call`);
+PyTorch only owns device memory and streams. There is no CPU path.
+
+HBM layout
+  weights        bf16, nn.Linear layout [N,K] (K-major for both TMA operands); gate_up_proj rows
+                 interleaved per 256 rows as [128 gate | 128 up] so SwiGLU fuses into the epilogue
+  hidden state   bf16 [B*L, H] (the reference keeps bf16 activations between modules)
+  KV cache       paged: pool[layer][page][K|V][head][64 tokens][head_dim] bf16 (zero-initialised),
+                 block_table int32 [B, pages]; left-padded rows keep the reference's absolute
+                 indices and carry kv_start[b] = pad length (replaces Mask4D, phi:550-563)
+  quantised KV   full prompt pages as 4-bit codes + bf16 (scale,bias) per 32 values (phi:528-540)
+"""
+import math
+import torch
+from . import _lib
+from ._lib import call, ptr, PAGE
+from .configs import CLIP_VIT_L14_336
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def interleave_gate_up(w):
+    """[2I, K] (gate rows then up rows, phi:470) -> per 256-row block [128 gate | 128 up]."""
+    I = w.shape[0] // 2
+    assert I % 128 == 0, 'intermediate_size must be a multiple of 128'
+    g, u = w[:I].reshape(I // 128, 128, -1), w[I:].reshape(I // 128, 128, -1)
+    return torch.stack([g, u], dim=1).reshape(2 * I, -1).contiguous()
+
+
+class KVCacheB200(list):
+    """Opaque cache handle returned to the decode drivers (the reference returns a list of
+    per-layer KVCache objects, phi:581; drivers only pass it back). `self[0].offset` works."""
+
+    def __init__(self, cfg, B, L, max_tokens, dev, quantized):
+        super().__init__([self])
+        nl, nkv = cfg.num_hidden_layers, cfg.num_key_value_heads
+        hd = cfg.hidden_size // cfg.num_attention_heads
+        self.B, self.S_max, self.max_tokens = B, L + max_tokens, max_tokens
+        self.offset = 0
+        self.quantized, self.n_quant = quantized, 0
+        self.pages_per_seq = (self.S_max + PAGE - 1) // PAGE
+        n_pages = B * self.pages_per_seq
+        # zero-initialised: masked slots must hold finite values (0 * NaN would poison P.V)
+        self.pool = torch.zeros((nl, n_pages, 2, nkv, PAGE, hd), dtype=torch.bfloat16, device=dev)
+        self.block_table = torch.arange(n_pages, dtype=torch.int32, device=dev).reshape(B, self.pages_per_seq)
+        self.kv_start = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.cos = self.sin = None
+        self.tab_bstride = 0
+        self.qcodes = self.qmeta = None
+        self.past_dev = None                 # device copy of offset (CUDA-graph decode)
+
+
+class Phi3B200:
+    def __init__(self, cfg, weights, device='cuda', clip_cfg=None, gemm_impl=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError('Phi3B200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        _lib.lib()
+        self.cfg, self.dev = cfg, torch.device(device)
+        self.clip_cfg = clip_cfg or CLIP_VIT_L14_336
+        self.gemm_impl = gemm_impl
+        self.H = cfg.hidden_size
+        self.n_heads, self.n_kv = cfg.num_attention_heads, cfg.num_key_value_heads
+        self.hd = self.H // self.n_heads
+        self.qkv_dim = (self.n_heads + 2 * self.n_kv) * self.hd
+        self.I = cfg.intermediate_size
+        self.V = cfg.vocab_size
+        self.eps = float(cfg.rms_norm_eps)
+        self.scale = self.hd ** -0.5
+        self.use_quantized_cache = bool(getattr(cfg, 'use_quantized_cache', False))
+        d = lambda t: t.to(self.dev, torch.bfloat16).contiguous()
+        w = weights
+        self.embed = d(w['model.embed_tokens.weight'])
+        self.layers = []
+        for i in range(cfg.num_hidden_layers):
+            p = f'model.layers.{i}.'
+            self.layers.append(dict(
+                ln1=d(w[p + 'input_layernorm.weight']), qkv=d(w[p + 'self_attn.qkv_proj.weight']),
+                o=d(w[p + 'self_attn.o_proj.weight']), ln2=d(w[p + 'post_attention_layernorm.weight']),
+                gu=interleave_gate_up(d(w[p + 'mlp.gate_up_proj.weight'])), down=d(w[p + 'mlp.down_proj.weight'])))
+        self.norm = d(w['model.norm.weight'])
+        self.lm_head = d(w['lm_head.weight'])
+        self.vision = None
+        if any(k.startswith('model.vision_embed_tokens') for k in w):
+            self._load_vision(w, d)
+        self._masker_roper = None
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ vision weights
+    def _load_vision(self, w, d):
+        cc = self.clip_cfg
+        P = 'model.vision_embed_tokens.img_processor.vision_model.'
+        D = cc.hidden_size
+        kp = 640                                         # 588 padded to a multiple of the 64-wide K block
+        pw = torch.zeros((D, kp), dtype=torch.bfloat16, device=self.dev)
+        pw[:, :588] = d(w[P + 'embeddings.patch_embedding.weight']).reshape(D, -1)     # [O,kh,kw,I] (pv:374)
+        v = dict(kpad=kp, patch_w=pw, cls=d(w[P + 'embeddings.class_embedding']),
+                 pos=d(w[P + 'embeddings.position_embedding.weight']),
+                 pre_w=d(w[P + 'pre_layrnorm.weight']), pre_b=d(w[P + 'pre_layrnorm.bias']), layers=[])
+        for j in range(cc.num_hidden_layers - 1):        # the reference runs layers[:-1] (phi:219)
+            L = P + f'encoder.layers.{j}.'
+            v['layers'].append(dict(
+                ln1w=d(w[L + 'layer_norm1.weight']), ln1b=d(w[L + 'layer_norm1.bias']),
+                qkv_w=torch.cat([d(w[L + f'self_attn.{n}_proj.weight']) for n in 'qkv'], 0).contiguous(),
+                qkv_b=torch.cat([d(w[L + f'self_attn.{n}_proj.bias']) for n in 'qkv'], 0).contiguous(),
+                out_w=d(w[L + 'self_attn.out_proj.weight']), out_b=d(w[L + 'self_attn.out_proj.bias']),
+                ln2w=d(w[L + 'layer_norm2.weight']), ln2b=d(w[L + 'layer_norm2.bias']),
+                fc1_w=d(w[L + 'mlp.fc1.weight']), fc1_b=d(w[L + 'mlp.fc1.bias']),
+                fc2_w=d(w[L + 'mlp.fc2.weight']), fc2_b=d(w[L + 'mlp.fc2.bias'])))
+        Vp = 'model.vision_embed_tokens.'
+        v.update(glb_GN=d(w[Vp + 'glb_GN']).reshape(-1), sub_GN=d(w[Vp + 'sub_GN']).reshape(-1),
+                 p0_w=d(w[Vp + 'img_projection.0.weight']), p0_b=d(w[Vp + 'img_projection.0.bias']),
+                 p2_w=d(w[Vp + 'img_projection.2.weight']), p2_b=d(w[Vp + 'img_projection.2.bias']))
+        self.vision = v
+
+    # ------------------------------------------------------------------ thin kernel wrappers
+    def gemm(self, x, w, out, epi=_lib.EPI_NONE, bias=None, resid=None, row_map=None, N=None):
+        M, K = x.shape
+        N = w.shape[0] if N is None else N
+        call('p3_gemm', ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), ptr(resid),
+             ptr(row_map), M, N, K, epi, self.gemm_impl, _stream())
+        return out
+
+    def skinny(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None):
+        M, K = x.shape
+        call('p3_gemm_skinny', ptr(x), x.stride(0), ptr(norm_w), self.eps, ptr(w), ptr(out), out.stride(0),
+             ptr(resid), M, w.shape[0], K, epi, _stream())
+        return out
+
+    def linear(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None):
+        """Route by token count: <=16 rows is a weight stream (skinny), else tensor-core GEMM."""
+        if x.shape[0] <= 16:
+            return self.skinny(x, w, out, epi, norm_w, resid)
+        if norm_w is not None:
+            xn = torch.empty_like(x)
+            call('p3_rmsnorm', ptr(x), ptr(norm_w), ptr(xn), x.shape[0], x.shape[1], self.eps, _stream())
+            x = xn
+        return self.gemm(x, w, out, epi, resid=resid)
+
+    # ------------------------------------------------------------------ rope table (phi:487-507)
+    def _rope_table(self, L_all, pids):
+        cfg = self.cfg
+        sf = math.sqrt(1 + math.log(cfg.max_position_embeddings / cfg.original_max_position_embeddings)
+                       / math.log(cfg.original_max_position_embeddings))
+        fac = cfg.rope_scaling['long_factor'] if L_all > cfg.original_max_position_embeddings \
+            else cfg.rope_scaling['short_factor']                                  # static switch (H7)
+        if pids is None:
+            pos = torch.arange(L_all, dtype=torch.float32)[None]
+        else:
+            pids = torch.as_tensor(pids).to('cpu', torch.float32)
+            ext = pids[:, -1][:, None] + 1 + torch.arange(L_all - pids.shape[1], dtype=torch.float32)[None, :]
+            pos = torch.cat([pids, ext], dim=1)                                    # pad slots carry pid 1 (H8)
+        inv_freq = 1.0 / (torch.tensor(fac, dtype=torch.float32)
+                          * cfg.rope_theta ** (torch.arange(0, self.hd, 2, dtype=torch.float32) / self.hd))
+        freqs = pos[:, :, None] * inv_freq[None, None, :]
+        cos = (torch.cos(freqs) * sf).contiguous().to(self.dev)
+        sin = (torch.sin(freqs) * sf).contiguous().to(self.dev)
+        return cos, sin, (0 if cos.shape[0] == 1 else cos.shape[1] * cos.shape[2])
+
+    # ------------------------------------------------------------------ vision tower (phi:135-226, 393-416)
+    def _vision_embed(self, h, L, pixel_values, image_sizes, positions):
+        v, cc = self.vision, self.clip_cfg
+        D, nh = cc.hidden_size, cc.num_attention_heads
+        st = _stream()
+        sizes = (torch.as_tensor(image_sizes).cpu() // 336).tolist()
+        positions = torch.as_tensor(positions).cpu().tolist()
+        pv = torch.as_tensor(pixel_values).to(self.dev, torch.float32)
+        # only crops 0..hc*wc of each image reach the output (phi:405-406); zero-pad crops are skipped
+        used = [pv[b, :hw[0] * hw[1] + 1] for b, hw in enumerate(sizes)]
+        px = torch.cat(used, 0).contiguous()
+        N = px.shape[0]
+        T = N * 577
+        A = torch.empty((N * 576, v['kpad']), dtype=torch.bfloat16, device=self.dev)
+        call('p3_patch_im2col', ptr(px), ptr(A), N, v['kpad'], st)
+        patches = torch.empty((N * 576, D), dtype=torch.float32, device=self.dev)
+        self.gemm(A, v['patch_w'], patches, _lib.EPI_F32)
+        x = torch.empty((T, D), dtype=torch.float32, device=self.dev)
+        call('p3_clip_embed', ptr(patches), ptr(v['cls']), ptr(v['pos']), ptr(x), N, D, st)
+        call('p3_layernorm', ptr(x), ptr(v['pre_w']), ptr(v['pre_b']), ptr(x), T, D, 1e-5, 1, st)
+        xn = torch.empty((T, D), dtype=torch.bfloat16, device=self.dev)
+        qkv = torch.empty((T, 3 * D), dtype=torch.bfloat16, device=self.dev)
+        att = torch.empty((T, D), dtype=torch.bfloat16, device=self.dev)
+        mid = torch.empty((T, cc.intermediate_size), dtype=torch.bfloat16, device=self.dev)
+        hd = D // nh
+        for lw in v['layers']:
+            call('p3_layernorm', ptr(x), ptr(lw['ln1w']), ptr(lw['ln1b']), ptr(xn), T, D, cc.layer_norm_eps, 0, st)
+            self.gemm(xn, lw['qkv_w'], qkv, _lib.EPI_NONE, bias=lw['qkv_b'])
+            call('p3_attention_prefill', ptr(qkv), qkv.data_ptr() + 2 * D, qkv.data_ptr() + 4 * D, 3 * D, 3 * D, 3 * D,
+                 ptr(att), D, N, 577, nh, nh, hd, hd ** -0.5, 0, 0, None, None, None, 0, 1, st)
+            self.gemm(att, lw['out_w'], x, _lib.EPI_RESIDUAL_F32, bias=lw['out_b'], resid=x)
+            call('p3_layernorm', ptr(x), ptr(lw['ln2w']), ptr(lw['ln2b']), ptr(xn), T, D, cc.layer_norm_eps, 0, st)
+            self.gemm(xn, lw['fc1_w'], mid, _lib.EPI_QGELU, bias=lw['fc1_b'])
+            self.gemm(mid, lw['fc2_w'], x, _lib.EPI_RESIDUAL_F32, bias=lw['fc2_b'], resid=x)
+        # token assembly + projector + splice (phi:400-415)
+        crop0, idx = 0, 0
+        for b, (hc, wc) in enumerate(sizes):
+            cnt = (hc * wc + 1) * 144 + 1 + (hc + 1) * 12
+            feats = x[crop0 * 577:(crop0 + hc * wc + 1) * 577]
+            tok = torch.empty((cnt, 4 * D), dtype=torch.bfloat16, device=self.dev)
+            call('p3_gn_assemble', ptr(feats), ptr(v['sub_GN']), ptr(v['glb_GN']), ptr(tok), hc, wc, D, st)
+            p1 = torch.empty((cnt, self.H), dtype=torch.bfloat16, device=self.dev)
+            self.gemm(tok, v['p0_w'], p1, _lib.EPI_GELU, bias=v['p0_b'])
+            r, c = positions[idx]
+            row_map = (torch.arange(cnt, dtype=torch.int32, device=self.dev) + (r * L + c)).contiguous()
+            self.gemm(p1, v['p2_w'], h, _lib.EPI_NONE, bias=v['p2_b'], row_map=row_map)
+            crop0 += hc * wc + 1
+            idx += cnt
+        return h
+
+    # ------------------------------------------------------------------ one decoder pass
+    def _forward_tokens(self, ids_dev, B, L, cache, n_beam, write_cache, past, logits_rows, past_dev=None,
+                        n_splits=None, h=None):
+        """ids_dev int32 [B*L] on device. Returns fp32 logits [B, R, V] (R = L or 1)."""
+        st = _stream()
+        T, H = B * L, self.H
+        dev = self.dev
+        if h is None:
+            h = torch.empty((T, H), dtype=torch.bfloat16, device=dev)
+            call('p3_embed_gather', ptr(self.embed), ptr(ids_dev), ptr(h), T, H, self.V, st)
+        qkv = torch.empty((T, self.qkv_dim), dtype=torch.bfloat16, device=dev)
+        att = torch.empty((T, self.n_heads * self.hd), dtype=torch.bfloat16, device=dev)
+        act = torch.empty((T, self.I), dtype=torch.bfloat16, device=dev)
+        use_decode_attn = L <= 16 and cache is not None
+        ws = None
+        if use_decode_attn:
+            if n_splits is None:
+                tiles = max(1, (past + PAGE - 1) // PAGE)
+                n_splits = max(1, min((4 * 148 + B * self.n_heads - 1) // (B * self.n_heads), (tiles + 3) // 4))
+            if n_splits > 1:
+                ws = torch.empty(_lib.lib().p3_attention_decode_workspace(B, L, self.n_heads, self.hd, n_splits) // 4,
+                                 dtype=torch.float32, device=dev)
+        qoff, koff, voff = 0, self.n_heads * self.hd * 2, (self.n_heads + self.n_kv) * self.hd * 2
+        if cache is not None:
+            cosT, sinT, tbs = cache.cos, cache.sin, cache.tab_bstride
+            bt, bts, kvs = cache.block_table, cache.block_table.stride(0), cache.kv_start
+        else:
+            cosT, sinT, tbs, bt, bts, kvs = self._nc_cos, self._nc_sin, self._nc_tbs, None, 0, self._nc_kvs
+        for li, lw in enumerate(self.layers):
+            pool = cache.pool[li] if cache is not None else None
+            self.linear(h, lw['qkv'], qkv, _lib.EPI_NONE, norm_w=lw['ln1'])
+            call('p3_rope_kvwrite', ptr(qkv), ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads, self.n_kv, self.hd, past,
+                 n_beam, ptr(pool), ptr(bt), bts, 1 if (write_cache and cache is not None) else 0, ptr(past_dev), st)
+            qp = qkv.data_ptr()
+            if use_decode_attn:
+                if cache.quantized and cache.n_quant > 0:
+                    call('p3_attention_decode_q4', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim,
+                         self.qkv_dim, ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale,
+                         past, cache.n_quant, ptr(kvs), ptr(pool), ptr(cache.qcodes[li]), ptr(cache.qmeta[li]), ptr(bt),
+                         bts, n_beam, n_splits, ptr(ws), ptr(past_dev), st)
+                else:
+                    call('p3_attention_decode', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim,
+                         self.qkv_dim, ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale,
+                         past, ptr(kvs), ptr(pool), ptr(bt), bts, n_beam, n_splits, ptr(ws), ptr(past_dev), st)
+            else:
+                call('p3_attention_prefill', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim, self.qkv_dim,
+                     ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale, 1, past, ptr(kvs),
+                     ptr(pool), ptr(bt), bts, n_beam, st)
+            self.linear(att, lw['o'], h, _lib.EPI_RESIDUAL, resid=h)
+            self.linear(h, lw['gu'], act, _lib.EPI_SWIGLU, norm_w=lw['ln2'])
+            self.linear(act, lw['down'], h, _lib.EPI_RESIDUAL, resid=h)
+        if logits_rows == 'last':
+            hl = h.view(B, L, H)[:, -1, :]
+            R = 1
+        else:
+            hl, R = h, L
+        hl = hl.reshape(B * R, H) if hl.is_contiguous() else hl.contiguous().reshape(B * R, H)
+        logits = torch.empty((B * R, self.V), dtype=torch.float32, device=dev)
+        self.linear(hl, self.lm_head, logits, _lib.EPI_F32, norm_w=self.norm)
+        return logits.view(B, R, self.V)
+
+    # ------------------------------------------------------------------ reference call protocol (phi:606, 576-592)
+    def __call__(self, input_ids, pixel_values=None, image_sizes=None, positions=None, cache=None, pids=None,
+                 mask=None, max_tokens=0, advance_offset=None, n_beam=1, logits_rows='all'):
+        ids = torch.as_tensor(input_ids)
+        if ids.dim() == 1:
+            ids = ids[None]
+        B, L = ids.shape
+        ids_dev = ids.to(self.dev, torch.int32).contiguous().reshape(-1)
+        h = None
+        if pixel_values is not None and self.vision is not None:
+            h = torch.empty((B * L, self.H), dtype=torch.bfloat16, device=self.dev)
+            call('p3_embed_gather', ptr(self.embed), ptr(ids_dev), ptr(h), B * L, self.H, self.V, _stream())
+            h = self._vision_embed(h, L, pixel_values, image_sizes, positions)
+        if cache is None:
+            L_all = L + max_tokens
+            cos, sin, tbs = self._rope_table(L_all, pids)
+            kvs = torch.zeros(B, dtype=torch.int32, device=self.dev)
+            if mask is not None:
+                m = torch.as_tensor(mask).cpu()
+                kvs = (m.shape[1] - m.sum(dim=1)).to(self.dev, torch.int32)      # left-pad length per row
+            if max_tokens < 1:                                                   # KVCache passthrough (phi:521-522)
+                self._nc_cos, self._nc_sin, self._nc_tbs, self._nc_kvs = cos, sin, tbs, kvs
+                logits = self._forward_tokens(ids_dev, B, L, None, 1, False, 0, logits_rows, h=h)
+                return logits, None
+            cache = KVCacheB200(self.cfg, B, L, max_tokens, self.dev, self.use_quantized_cache)
+            cache.cos, cache.sin, cache.tab_bstride, cache.kv_start = cos, sin, tbs, kvs
+        if n_beam > 1 and cache.quantized and not getattr(self.cfg, 'allow_beam_with_quantized_cache', False):
+            raise NotImplementedError('Beam Search is not yet compatible with Quantized Cache')   # phi:524-525
+        past = cache.offset
+        if past + L > cache.S_max:
+            raise ValueError(f'KV cache overflow: {past}+{L} > {cache.S_max}')
+        write = n_beam == 1
+        first_fill = write and past == 0
+        logits = self._forward_tokens(ids_dev, B, L, cache, n_beam, write, past, logits_rows, h=h)
+        if write:
+            cache.offset = past + L                                               # phi:544-547
+        if first_fill and cache.quantized:
+            self._quantize_prompt(cache, L)
+        if advance_offset is not None:
+            cache.offset = past + advance_offset                                  # phi:589-591
+        return logits, cache
+
+    def _quantize_prompt(self, cache, n_tokens):
+        """mx.quantize of the prompt K,V (phi:531-533): later steps read the 4-bit image."""
+        nl, n_pages = cache.pool.shape[0], cache.pool.shape[1]
+        cache.qcodes = torch.zeros((nl, n_pages, 2, self.n_kv, PAGE, self.hd // 2), dtype=torch.uint8, device=self.dev)
+        cache.qmeta = torch.zeros((nl, n_pages, 2, self.n_kv, PAGE, self.hd // 32, 2), dtype=torch.bfloat16,
+                                  device=self.dev)
+        for li in range(nl):
+            call('p3_kv_quantize_q4g32', ptr(cache.pool[li]), ptr(cache.qcodes[li]), ptr(cache.qmeta[li]),
+                 ptr(cache.block_table), cache.block_table.stride(0), cache.B, n_tokens, self.n_kv, self.hd, _stream())
+        cache.n_quant = (n_tokens // PAGE) * PAGE
+
+    # ------------------------------------------------------------------ device-resident greedy loop (pv:390-398)
+    def decode_session(self, first_token, cache, max_steps, use_graph=True):
+        return DecodeSession(self, first_token, cache, max_steps, use_graph)
+
+    def greedy_decode(self, first_token, cache, n_steps, use_graph=True, eos_check_every=0):
+        """n_steps decode steps from `first_token` [B] with no per-token host sync.
+        Returns int32 history [B, steps_run+1] (first_token then every generated token)."""
+        ses = DecodeSession(self, first_token, cache, n_steps, use_graph)
+        for i in range(n_steps):
+            ses.step()
+            if eos_check_every and (i + 1) % eos_check_every == 0 and ses.all_eos():
+                break
+        return ses.finish()
+
+
+class DecodeSession:
+    """One CUDA graph = one greedy decode step (embed -> 32 layers -> lm_head -> argmax -> bookkeeping).
+    `past`, the step counter, the current token and the token history live on the device, so
+    replaying the graph advances generation with zero host synchronisation (the reference syncs
+    at mx.eval and `eos_id in token` every token, pv:393,397,113)."""
+
+    def __init__(self, model, first_token, cache, max_steps, use_graph=True):
+        self.m, self.cache, self.max_steps = model, cache, max_steps
+        B = cache.B
+        dev = model.dev
+        self.B = B
+        self.hist = torch.zeros((B, max_steps + 1), dtype=torch.int32, device=dev)
+        first_token = first_token.to(dev, torch.int32).reshape(B).contiguous()
+        self.hist[:, 0] = first_token
+        self.tok = first_token.clone()
+        self.step_dev = torch.ones(1, dtype=torch.int32, device=dev)
+        self.past_dev = torch.full((1,), cache.offset, dtype=torch.int32, device=dev)
+        self.eos = (first_token == 32007).to(torch.int32)
+        self.steps_run = 0
+        self.graph = None
+        self.launches_per_step = 0
+        if max_steps <= 0:
+            return
+        if cache.offset + max_steps > cache.S_max:
+            raise ValueError('KV cache overflow: decode session longer than the cache was sized for')
+        tiles = (cache.offset + max_steps + PAGE - 1) // PAGE
+        self.n_splits = max(1, min((4 * 148 + B * model.n_heads - 1) // (B * model.n_heads), (tiles + 3) // 4))
+        if use_graph and B <= 16:
+            cur = torch.cuda.current_stream()
+            s = torch.cuda.Stream()
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                self._one_step()                              # warm-up: smem attributes, allocator pools
+            cur.wait_stream(s)
+            torch.cuda.synchronize()
+            # the warm-up step really executed; roll the device state back before capture
+            self.step_dev.fill_(1); self.past_dev.fill_(cache.offset); self.tok.copy_(first_token)
+            self.eos.copy_((first_token == 32007).to(torch.int32))
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launches
+            with torch.cuda.graph(self.graph):
+                self._one_step()
+            self.launches_per_step = _lib.launches - n0
+
+    def _one_step(self):
+        m = self.m
+        logits = m._forward_tokens(self.tok, self.B, 1, self.cache, 1, True, self.cache.offset, 'last',
+                                   past_dev=self.past_dev, n_splits=self.n_splits)
+        call('p3_row_stats', ptr(logits), self.B, m.V, m.V, ptr(self.tok), None, None, 0, None, None, 0, None, None,
+             _stream())
+        call('p3_decode_advance', ptr(self.tok), ptr(self.hist), self.hist.stride(0), self.B, ptr(self.step_dev),
+             ptr(self.past_dev), ptr(self.eos), _stream())
+
+    def step(self):
+        if self.steps_run >= self.max_steps:
+            raise ValueError('decode session exhausted')
+        if self.graph is not None:
+            self.graph.replay()
+            _lib.launches += self.launches_per_step
+        else:
+            self._one_step()
+        self.steps_run += 1
+
+    def all_eos(self):
+        return bool(self.eos.all().item())                    # host sync (off the per-token path)
+
+    def last_token(self):
+        return self.tok
+
+    def finish(self):
+        self.cache.offset = self.cache.offset + self.steps_run
+        return self.hist[:, :self.steps_run + 1]

@@ -1,0 +1,344 @@
+"""-m gpu: every C-ABI kernel against a plain torch fp32 restatement of the same op
+(floating-point kernels; tolerance stated per test) — the oracle-level parity tests are in
+test_model_gpu.py."""
+import math
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    import phi3_b200  # noqa
+    from phi3_b200 import _lib
+    return _lib
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def test_rmsnorm(dev):
+    L = _mods()
+    torch.manual_seed(0)
+    for T, H in [(5, 384), (33, 3072), (7, 8192)]:
+        x = bf(torch.randn(T, H, device=dev) * 3)
+        w = bf(1 + 0.1 * torch.randn(H, device=dev))
+        y = torch.empty_like(x)
+        L.call('p3_rmsnorm', x.data_ptr(), w.data_ptr(), y.data_ptr(), T, H, 1e-5, st())
+        xf = x.float()
+        ref = bf(xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * w.float())
+        assert (y.float() - ref.float()).abs().max() <= 2 ** -7 * ref.float().abs().max()   # <= 1 bf16 ulp
+        assert (y != ref).float().mean() < 0.01
+
+
+def test_layernorm(dev):
+    L = _mods()
+    torch.manual_seed(0)
+    T, H = 37, 1024
+    x = torch.randn(T, H, device=dev) * 2 + 0.5
+    w, b = bf(1 + 0.1 * torch.randn(H, device=dev)), bf(0.1 * torch.randn(H, device=dev))
+    ref = torch.nn.functional.layer_norm(x, (H,), w.float(), b.float(), 1e-5)
+    y = torch.empty(T, H, device=dev, dtype=torch.bfloat16)
+    L.call('p3_layernorm', x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), T, H, 1e-5, 0, st())
+    assert (y.float() - ref).abs().max() < 3e-2
+    y32 = torch.empty(T, H, device=dev)
+    L.call('p3_layernorm', x.data_ptr(), w.data_ptr(), b.data_ptr(), y32.data_ptr(), T, H, 1e-5, 1, st())
+    assert (y32 - ref).abs().max() < 1e-4
+
+
+def test_embed_gather_negative_ids(dev):
+    L = _mods()
+    tab = bf(torch.randn(100, 64, device=dev))
+    ids = torch.tensor([3, -1, 99, 0, -7, 250], dtype=torch.int32, device=dev)
+    out = torch.empty(6, 64, device=dev, dtype=torch.bfloat16)
+    L.call('p3_embed_gather', tab.data_ptr(), ids.data_ptr(), out.data_ptr(), 6, 64, 100, st())
+    exp = tab[torch.tensor([3, 0, 99, 0, 0, 0], device=dev)]
+    assert torch.equal(out, exp)
+
+
+EPIS = ['none', 'bias', 'qgelu', 'gelu', 'resid', 'swiglu', 'f32', 'resid_f32', 'rowmap']
+
+
+def _gemm_ref(x, w, epi, bias, resid):
+    acc = x.float() @ w.float().T
+    if bias is not None:
+        acc = acc + bias.float()
+    if epi == 'qgelu':
+        return bf(acc * torch.sigmoid(1.702 * acc))
+    if epi == 'gelu':
+        return bf(torch.nn.functional.gelu(acc))
+    if epi == 'resid':
+        return bf(resid.float() + bf(acc).float())
+    if epi == 'resid_f32':
+        return resid + acc
+    if epi == 'f32':
+        return acc
+    return bf(acc)
+
+
+def _run_gemm(L, dev, M, N, K, epi, impl):
+    torch.manual_seed(1)
+    x = bf(torch.randn(M, K, device=dev))
+    w = bf(torch.randn(N, K, device=dev) * K ** -0.5)
+    bias = bf(torch.randn(N, device=dev)) if epi in ('bias', 'qgelu', 'gelu', 'resid_f32') else None
+    code = dict(none=0, bias=0, qgelu=1, gelu=2, resid=3, swiglu=4, f32=5, resid_f32=6, rowmap=0)[epi]
+    resid = row_map = None
+    if epi == 'swiglu':
+        from phi3_b200.model import interleave_gate_up
+        out = torch.zeros(M, N // 2, device=dev, dtype=torch.bfloat16)
+        wi = interleave_gate_up(w)
+        L.call('p3_gemm', x.data_ptr(), K, wi.data_ptr(), K, None, out.data_ptr(), N // 2, None, None, M, N, K, 4, impl, st())
+        acc = x.float() @ w.float().T
+        g, u = bf(acc[:, :N // 2]).float(), bf(acc[:, N // 2:]).float()
+        ref = bf(bf(torch.nn.functional.silu(g)).float() * u)
+        return out, ref
+    if epi in ('f32', 'resid_f32'):
+        out = torch.zeros(M, N, device=dev)
+        if epi == 'resid_f32':
+            resid = torch.randn(M, N, device=dev)
+            out.copy_(resid)
+    else:
+        out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        if epi == 'resid':
+            resid = bf(torch.randn(M, N, device=dev))
+            out.copy_(resid)
+    ref = _gemm_ref(x, w, epi, bias, resid)
+    nrows = M
+    if epi == 'rowmap':
+        perm = torch.randperm(M + 5, device=dev)[:M].to(torch.int32)
+        row_map = perm
+        out = torch.zeros(M + 5, N, device=dev, dtype=torch.bfloat16)
+    L.call('p3_gemm', x.data_ptr(), K, w.data_ptr(), K, None if bias is None else bias.data_ptr(), out.data_ptr(), N,
+           out.data_ptr() if resid is not None else None, None if row_map is None else row_map.data_ptr(), M, N, K, code,
+           impl, st())
+    if epi == 'rowmap':
+        out = out[row_map.long()]
+    return out, ref
+
+
+def _check(out, ref, tol=2e-2):
+    torch.cuda.synchronize()
+    err = (out.float() - ref.float()).abs().max().item()
+    scale = ref.float().abs().max().item()
+    assert math.isfinite(err) and err <= tol * scale, f'err {err} scale {scale}'
+
+
+@pytest.mark.parametrize('epi', EPIS)
+def test_gemm_mma_crosscheck(dev, epi):
+    L = _mods()
+    out, ref = _run_gemm(L, dev, 150, 512, 320, epi, impl=1)
+    _check(out, ref)
+
+
+@pytest.mark.parametrize('shape', [(128, 256, 64), (128, 256, 256), (300, 512, 384), (1000, 1024, 640),
+                                   (257, 32064, 384), (2885, 3072, 1024), (64, 9216, 3072), (4096, 3072, 8192)])
+def test_gemm_tcgen05_shapes(dev, shape):
+    L = _mods()
+    M, N, K = shape
+    out, ref = _run_gemm(L, dev, M, N, K, 'none', impl=0)
+    _check(out, ref)
+
+
+@pytest.mark.parametrize('epi', EPIS)
+def test_gemm_tcgen05_epilogues(dev, epi):
+    L = _mods()
+    out, ref = _run_gemm(L, dev, 333, 1024, 512, epi, impl=0)
+    _check(out, ref)
+    out, ref = _run_gemm(L, dev, 2000, 8192 if epi == 'swiglu' else 3072, 384, epi, impl=0)   # BN=256 path
+    _check(out, ref)
+
+
+@pytest.mark.parametrize('M', [1, 4, 8, 11, 16])
+@pytest.mark.parametrize('mode', ['plain', 'norm', 'resid', 'swiglu', 'f32'])
+def test_gemm_skinny(dev, M, mode):
+    L = _mods()
+    torch.manual_seed(2)
+    K = 3072 if mode != 'resid' else 8192
+    N = {'plain': 9216, 'norm': 9216, 'resid': 3072, 'swiglu': 4096, 'f32': 32064}[mode]
+    x = bf(torch.randn(M, K, device=dev))
+    w = bf(torch.randn(N, K, device=dev) * K ** -0.5)
+    nw = bf(1 + 0.1 * torch.randn(K, device=dev))
+    xin = x
+    if mode in ('norm', 'swiglu', 'f32'):
+        xf = x.float()
+        xin = bf(xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * nw.float())
+    acc = xin.float() @ w.float().T
+    if mode == 'swiglu':
+        from phi3_b200.model import interleave_gate_up
+        out = torch.zeros(M, N // 2, device=dev, dtype=torch.bfloat16)
+        L.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr(), 1e-5, interleave_gate_up(w).data_ptr(), out.data_ptr(),
+               N // 2, None, M, N, K, 4, st())
+        g, u = bf(acc[:, :N // 2]).float(), bf(acc[:, N // 2:]).float()
+        ref = bf(bf(torch.nn.functional.silu(g)).float() * u)
+    elif mode == 'f32':
+        out = torch.zeros(M, N, device=dev)
+        L.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr(), 1e-5, w.data_ptr(), out.data_ptr(), N, None, M, N, K, 5, st())
+        ref = acc
+    elif mode == 'resid':
+        out = bf(torch.randn(M, N, device=dev))
+        ref = bf(out.float() + bf(acc).float())
+        L.call('p3_gemm_skinny', x.data_ptr(), K, None, 1e-5, w.data_ptr(), out.data_ptr(), N, out.data_ptr(), M, N, K, 3, st())
+    else:
+        out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        L.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr() if mode == 'norm' else None, 1e-5, w.data_ptr(),
+               out.data_ptr(), N, None, M, N, K, 0, st())
+        ref = bf(acc)
+    _check(out, ref, tol=1e-2)
+
+
+def _paged(kc, vc, dev):
+    """dense [B,H,S,D] -> pool [pages,2,H,64,D], block_table"""
+    B, H, S, D = kc.shape
+    pps = (S + 63) // 64
+    pool = torch.zeros(B * pps, 2, H, 64, D, device=dev, dtype=torch.bfloat16)
+    bt = torch.arange(B * pps, dtype=torch.int32, device=dev).reshape(B, pps)
+    bt = bt.flip(1).contiguous()               # non-trivial page order
+    for b in range(B):
+        for p in range(pps):
+            n = min(64, S - p * 64)
+            pool[bt[b, p], 0, :, :n] = kc[b, :, p * 64:p * 64 + n]
+            pool[bt[b, p], 1, :, :n] = vc[b, :, p * 64:p * 64 + n]
+    return pool, bt
+
+
+def _attn_ref(q, k, v, scale, causal, past, kv_start):
+    """q [B,H,L,D], k/v [B,H,S,D] (S = past+L)."""
+    B, H, Lq, D = q.shape
+    S = k.shape[2]
+    s = (q.float() * scale) @ k.float().transpose(-1, -2)
+    qi = past + torch.arange(Lq, device=q.device)[:, None]
+    kj = torch.arange(S, device=q.device)[None, :]
+    allow = torch.ones(Lq, S, dtype=torch.bool, device=q.device)
+    if causal:
+        allow = kj <= qi
+    allow = allow[None, None] & (kj[None, None] >= kv_start[:, None, None, None])
+    s = s.masked_fill(~allow, float('-inf'))
+    dead = (~allow).all(-1, keepdim=True)
+    p = torch.softmax(s.masked_fill(dead, 0), -1).masked_fill(dead, 0)
+    return p @ v.float()
+
+
+@pytest.mark.parametrize('cfg', [(2, 4, 96, 200, 0, True), (1, 16, 64, 577, 0, False), (3, 2, 96, 64, 0, True),
+                                 (2, 3, 96, 130, 100, True), (1, 2, 96, 1100, 0, True)])
+def test_attention_prefill(dev, cfg):
+    L = _mods()
+    B, H, D, Lq, past, causal = cfg
+    torch.manual_seed(3)
+    qkv = bf(torch.randn(B * Lq, 3 * H * D, device=dev))
+    kc, vc = bf(torch.randn(B, H, past, D, device=dev)), bf(torch.randn(B, H, past, D, device=dev))
+    kv_start = torch.tensor([0, 17, 70][:B], dtype=torch.int32, device=dev) if causal else torch.zeros(B, dtype=torch.int32, device=dev)
+    out = torch.zeros(B * Lq, H * D, device=dev, dtype=torch.bfloat16)
+    pool, bt = _paged(kc, vc, dev) if past else (None, None)
+    p = qkv.data_ptr()
+    L.call('p3_attention_prefill', p, p + H * D * 2, p + 2 * H * D * 2, 3 * H * D, 3 * H * D, 3 * H * D, out.data_ptr(),
+           H * D, B, Lq, H, H, D, D ** -0.5, int(causal), past, kv_start.data_ptr(),
+           None if pool is None else pool.data_ptr(), None if bt is None else bt.data_ptr(), 0 if bt is None else bt.stride(0), 1, st())
+    x = qkv.view(B, Lq, 3, H, D).permute(2, 0, 3, 1, 4)
+    q, k, v = x[0], torch.cat([kc, x[1]], 2), torch.cat([vc, x[2]], 2)
+    ref = _attn_ref(q, k, v, D ** -0.5, causal, past, kv_start.long()).transpose(1, 2).reshape(B * Lq, H * D)
+    _check(out, ref, tol=2e-2)
+
+
+@pytest.mark.parametrize('cfg', [(2, 4, 96, 1, 300, 1, 1), (2, 4, 96, 1, 300, 3, 1), (3, 2, 96, 5, 1000, 4, 1),
+                                 (4, 2, 96, 6, 257, 2, 2), (1, 32, 96, 1, 2100, 5, 1), (2, 2, 96, 16, 64, 1, 1),
+                                 (2, 2, 96, 3, 0, 1, 1), (2, 4, 64, 2, 130, 2, 1)])
+def test_attention_decode(dev, cfg):
+    L = _mods()
+    B, H, D, Lq, past, n_splits, n_beam = cfg
+    torch.manual_seed(4)
+    nseq = B // n_beam
+    qkv = bf(torch.randn(B * Lq, 3 * H * D, device=dev))
+    kc, vc = bf(torch.randn(nseq, H, past, D, device=dev)), bf(torch.randn(nseq, H, past, D, device=dev))
+    kv_start = torch.tensor([0, 9, 70, 3][:nseq], dtype=torch.int32, device=dev).clamp(max=max(past - 1, 0))
+    pool, bt = _paged(kc, vc, dev) if past else (torch.zeros(1, 2, H, 64, D, device=dev, dtype=torch.bfloat16),
+                                                 torch.zeros(nseq, 1, dtype=torch.int32, device=dev))
+    out = torch.zeros(B * Lq, H * D, device=dev, dtype=torch.bfloat16)
+    nb = L.lib().p3_attention_decode_workspace(B, Lq, H, D, n_splits)
+    ws = torch.empty(nb // 4, device=dev)
+    p = qkv.data_ptr()
+    L.call('p3_attention_decode', p, p + H * D * 2, p + 2 * H * D * 2, 3 * H * D, 3 * H * D, 3 * H * D, out.data_ptr(),
+           H * D, B, Lq, H, H, D, D ** -0.5, past, kv_start.data_ptr(), pool.data_ptr(), bt.data_ptr(), bt.stride(0),
+           n_beam, n_splits, ws.data_ptr(), None, st())
+    x = qkv.view(B, Lq, 3, H, D).permute(2, 0, 3, 1, 4)
+    kr, vr = kc.repeat_interleave(n_beam, 0), vc.repeat_interleave(n_beam, 0)
+    q, k, v = x[0], torch.cat([kr, x[1]], 2), torch.cat([vr, x[2]], 2)
+    ref = _attn_ref(q, k, v, D ** -0.5, True, past, kv_start.long().repeat_interleave(n_beam)).transpose(1, 2).reshape(B * Lq, H * D)
+    _check(out, ref, tol=2e-2)
+
+
+def test_rope_kvwrite(dev):
+    L = _mods()
+    torch.manual_seed(5)
+    B, Lq, H, D, past, S = 2, 5, 4, 96, 70, 160
+    qkv = bf(torch.randn(B * Lq, 3 * H * D, device=dev))
+    orig = qkv.clone()
+    ang = torch.rand(B, S, D // 2, device=dev) * 6
+    cos, sin = (torch.cos(ang) * 1.19).contiguous(), (torch.sin(ang) * 1.19).contiguous()
+    pps = (S + 63) // 64
+    pool = torch.zeros(B * pps, 2, H, 64, D, device=dev, dtype=torch.bfloat16)
+    bt = torch.arange(B * pps, dtype=torch.int32, device=dev).reshape(B, pps)
+    L.call('p3_rope_kvwrite', qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), S * (D // 2), B, Lq, H, H, D, past, 1,
+           pool.data_ptr(), bt.data_ptr(), pps, 1, None, st())
+    x = orig.view(B, Lq, 3, H, D).float()
+    c = torch.cat([cos, cos], -1)[:, past:past + Lq, None, :]
+    s_ = torch.cat([sin, sin], -1)[:, past:past + Lq, None, :]
+    rot = lambda t: t * c + torch.cat([-t[..., D // 2:], t[..., :D // 2]], -1) * s_
+    qr, kr = bf(rot(x[:, :, 0])), bf(rot(x[:, :, 1]))
+    got = qkv.view(B, Lq, 3, H, D)
+    assert (got[:, :, 0].float() - qr.float()).abs().max() <= 2 ** -6 * qr.float().abs().max()
+    assert (got[:, :, 1].float() - kr.float()).abs().max() <= 2 ** -6 * kr.float().abs().max()
+    assert torch.equal(got[:, :, 2], orig.view(B, Lq, 3, H, D)[:, :, 2])
+    for b in range(B):
+        for i in range(Lq):
+            pos = past + i
+            pg = bt[b, pos // 64]
+            assert torch.equal(pool[pg, 0, :, pos % 64], got[b, i, 1])
+            assert torch.equal(pool[pg, 1, :, pos % 64], got[b, i, 2])
+
+
+def test_row_stats(dev):
+    L = _mods()
+    torch.manual_seed(6)
+    R, V = 7, 32064
+    lg = torch.randn(R, V, device=dev) * 3
+    lg[2, 100] = lg[2, 50] = 20.0                      # tie -> first index
+    from phi3_b200.api import _row_stats
+
+    class M:
+        pass
+    g = torch.randint(0, V, (R, 5))
+    out = _row_stats(M(), lg, n_top=4, gather=g)
+    lp = torch.log_softmax(lg, -1)
+    assert torch.equal(out['argmax'].long().cpu(), lg.argmax(-1).cpu())
+    assert out['argmax'][2].item() == 50
+    assert (out['lse'] - torch.logsumexp(lg, -1)).abs().max() < 1e-3
+    tv, ti = lp.topk(4, -1)
+    assert torch.equal(out['top_ids'].long().sort(-1).values, ti.sort(-1).values)
+    assert (out['top_lp'] - tv).abs().max() < 1e-3
+    assert (out['gather_lp'] - lp.gather(1, g.to(dev))).abs().max() < 1e-3
+
+
+def test_kv_quant_roundtrip_matches_oracle(dev):
+    L = _mods()
+    from oracle.phi3_oracle import quantize_q4g32, dequantize_q4g32
+    torch.manual_seed(7)
+    nseq, H, D, S = 2, 3, 96, 150
+    kc, vc = bf(torch.randn(nseq, H, S, D, device=dev) * 2), bf(torch.randn(nseq, H, S, D, device=dev))
+    pool, bt = _paged(kc, vc, dev)
+    qc = torch.zeros(pool.shape[0], 2, H, 64, D // 2, dtype=torch.uint8, device=dev)
+    qm = torch.zeros(pool.shape[0], 2, H, 64, D // 32, 2, dtype=torch.bfloat16, device=dev)
+    L.call('p3_kv_quantize_q4g32', pool.data_ptr(), qc.data_ptr(), qm.data_ptr(), bt.data_ptr(), bt.stride(0), nseq, S, H, D, st())
+    torch.cuda.synchronize()
+    for src, kv in ((kc, 0), (vc, 1)):
+        flat = src.float().cpu().reshape(nseq * H, -1)
+        deq = dequantize_q4g32(*quantize_q4g32(flat, 'b200'), (nseq, H, S, D)).to(torch.bfloat16)
+        for b in range(nseq):
+            for p in range((S + 63) // 64):
+                n = min(64, S - p * 64)
+                got = pool[bt[b, p], kv, :, :n].cpu()
+                assert torch.equal(got, deq[b, :, p * 64:p * 64 + n]), (kv, b, p)

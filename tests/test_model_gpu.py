@@ -1,0 +1,188 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs
+and random-init weights. Tolerance (BASELINE.json north_star): logits within 2e-2 relative
+(max abs error / max abs logit), teacher-forced greedy tokens agree on >= 99 % of positions."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _setup(vision=False, layers=2, seed=0, **kw):
+    import phi3_b200  # noqa
+    from phi3_b200 import configs, weights
+    from phi3_b200.model import Phi3B200
+    from oracle.phi3_oracle import Phi3Oracle
+    cfg = configs.tiny(vision=vision, layers=layers, **kw)
+    clip = configs.tiny_clip(3) if vision else None
+    w = weights.random_weights(cfg, seed=seed, clip_cfg=clip)
+    return cfg, w, Phi3B200(cfg, w, clip_cfg=clip), Phi3Oracle(cfg, w, prec='b200', clip_cfg=clip)
+
+
+def rel(a, b):
+    return ((a.float().cpu() - b.float()).abs().max() / b.float().abs().max()).item()
+
+
+def _ids(B, L, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(3, 32000, (B, L), generator=g)
+    ids[:, 0] = 1
+    return ids
+
+
+def test_prefill_and_decode_equal_length(dev):
+    cfg, w, m, o = _setup()
+    ids = _ids(4, 32)
+    lo, co = o(ids, max_tokens=8)
+    lg, cg = m(ids, max_tokens=8)
+    assert rel(lg, lo) < TOL
+    tok = lo[:, -1].argmax(-1)
+    for _ in range(6):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        assert rel(lg, lo) < TOL
+        tok = lo[:, -1].argmax(-1)
+
+
+def test_left_padded_batch(dev):
+    from phi3_b200.processor import Phi3FProcessor
+    cfg, w, m, o = _setup()
+
+    class Tok:
+        def __call__(self, texts):
+            class E:
+                pass
+            e = E()
+            g = torch.Generator().manual_seed(5)
+            e.input_ids = [[1] + torch.randint(3, 32000, (n - 1,), generator=g).tolist() for n in (17, 23, 29, 32)]
+            return e
+    inp = Phi3FProcessor(Tok())(['a', 'b', 'c', 'd'])
+    lo, co = o(**inp, max_tokens=4)
+    lg, cg = m(**inp, max_tokens=4)
+    valid = inp['mask'].bool()
+    assert ((lg.cpu() - lo).abs()[valid].max() / lo[valid].abs().max()).item() < TOL
+    tok = lo[:, -1].argmax(-1)
+    for _ in range(3):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        assert rel(lg, lo) < TOL
+        tok = lo[:, -1].argmax(-1)
+
+
+def test_long_prefill_then_graph_decode(dev):
+    cfg, w, m, o = _setup()
+    ids = _ids(2, 200, seed=3)
+    n_new = 24
+    lo, co = o(ids, max_tokens=n_new)
+    lg, cg = m(ids, max_tokens=n_new, logits_rows='last')
+    assert rel(lg[:, -1], lo[:, -1]) < TOL
+    first = lo[:, -1].argmax(-1)
+    # oracle greedy rollout
+    toks = [first]
+    for _ in range(n_new - 1):
+        lo, co = o(toks[-1][:, None], cache=co)
+        toks.append(lo[:, -1].argmax(-1))
+    ref = torch.stack(toks, 1)
+    hist = m.greedy_decode(first.to(dev), cg, n_new - 1).cpu().long()
+    agree = (hist == ref).float().mean().item()
+    # free-running greedy may diverge after a near-tie; the first tokens must match and most of the rest
+    assert torch.equal(hist[:, :4], ref[:, :4])
+    assert agree >= 0.8, agree
+    assert cg.offset == 200 + n_new - 1
+
+
+def test_teacher_forced_agreement(dev):
+    cfg, w, m, o = _setup(layers=4)
+    ids = _ids(4, 48, seed=9)
+    n = 40
+    lo, co = o(ids, max_tokens=n)
+    lg, cg = m(ids, max_tokens=n)
+    hit = tot = 0
+    tok = lo[:, -1].argmax(-1)
+    for _ in range(n - 1):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        hit += (lg[:, -1].argmax(-1).cpu() == lo[:, -1].argmax(-1)).sum().item()
+        tot += tok.numel()
+        tok = lo[:, -1].argmax(-1)
+    assert hit / tot >= 0.99, (hit, tot)
+
+
+def test_peek_and_beam_protocol(dev):
+    """advance_offset / n_beam semantics of phi.py:523-527, 589-591 used by constrain."""
+    cfg, w, m, o = _setup()
+    ids = _ids(3, 40, seed=4)
+    lo, co = o(ids, max_tokens=20)
+    lg, cg = m(ids, max_tokens=20)
+    cons = torch.tensor([[11, 12, 13]]).repeat(3, 1)
+    lo1, _ = o(cons, cache=co, advance_offset=0)
+    lg1, _ = m(cons, cache=cg, advance_offset=0)
+    assert rel(lg1, lo1) < TOL and cg.offset == 40 and co[0].offset == 40
+    step = torch.cat([lo[:, -1].argmax(-1)[:, None], cons], 1)
+    lo2, _ = o(step, cache=co, advance_offset=1)
+    lg2, _ = m(step, cache=cg, advance_offset=1)
+    assert rel(lg2, lo2) < TOL and cg.offset == 41
+    beams = torch.cat([torch.randint(3, 32000, (9, 1), generator=torch.Generator().manual_seed(1)), cons.repeat(3, 1)], 1)
+    lo3, _ = o(beams, cache=co, n_beam=3, advance_offset=0)
+    lg3, _ = m(beams, cache=cg, n_beam=3, advance_offset=0)
+    assert rel(lg3, lo3) < TOL and cg.offset == 41
+
+
+def test_quantized_cache_decode(dev):
+    cfg, w, m, o = _setup(use_quantized_cache=True)
+    ids = _ids(2, 150, seed=6)
+    lo, co = o(ids, max_tokens=8)
+    lg, cg = m(ids, max_tokens=8)
+    assert rel(lg, lo) < TOL
+    assert cg.n_quant == 128
+    tok = lo[:, -1].argmax(-1)
+    for _ in range(5):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        assert rel(lg, lo) < TOL
+        tok = lo[:, -1].argmax(-1)
+
+
+def test_no_cache_choose_path(dev):
+    cfg, w, m, o = _setup()
+    ids = _ids(3, 21, seed=8)
+    lo, _ = o(ids, max_tokens=0)
+    lg, c = m(ids, max_tokens=0)
+    assert c is None and rel(lg, lo) < TOL
+
+
+def test_vision_splice(dev):
+    cfg, w, m, o = _setup(vision=True)
+    g = torch.Generator().manual_seed(2)
+    pv = torch.randn(1, 5, 3, 336, 336, generator=g)
+    sizes = torch.tensor([[672, 672]])
+    n_img = (2 * 2 + 1) * 144 + 1 + (2 + 1) * 12
+    ids = torch.cat([torch.tensor([1, 50, 60]), torch.full((n_img,), -1), torch.tensor([1, 70, 80, 90])])[None]
+    pos = torch.nonzero(ids < 0)
+    lo, _ = o(ids, pixel_values=pv, image_sizes=sizes, positions=pos, max_tokens=2)
+    lg, _ = m(ids, pixel_values=pv, image_sizes=sizes, positions=pos, max_tokens=2)
+    assert rel(lg, lo) < TOL
+
+
+def test_full_size_config1(dev):
+    """BASELINE config 1 shapes: Phi-3.5-mini, 4 prompts x 32 tokens, random-init, a few decode steps."""
+    import phi3_b200  # noqa
+    from phi3_b200 import configs, weights
+    from phi3_b200.model import Phi3B200
+    from oracle.phi3_oracle import Phi3Oracle
+    cfg = configs.PHI35_MINI
+    w = weights.random_weights(cfg, seed=0)
+    m = Phi3B200(cfg, w)
+    o = Phi3Oracle(cfg, w, prec='b200')
+    ids = _ids(4, 32, seed=11)
+    lo, co = o(ids, max_tokens=4)
+    lg, cg = m(ids, max_tokens=4)
+    assert rel(lg, lo) < TOL
+    tok = lo[:, -1].argmax(-1)
+    agree = (lg[:, -1].argmax(-1).cpu() == tok).float().mean().item()
+    for _ in range(2):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        assert rel(lg, lo) < TOL
+        tok = lo[:, -1].argmax(-1)
+    assert agree >= 0.75
