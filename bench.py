@@ -1,0 +1,323 @@
+"""bench.py — headline benchmark of the B200 hot path (contract: see task statement / DESIGN.md §5).
+
+Workload (BASELINE.json configs[2], the batched data-parallel config the metric is quoted on,
+sharded 8 prompts per GPU — weak scaling; at N=8 it is exactly the 64-prompt config):
+  per GPU and per step: 8 image+text prompts (one 672x672 image each, HD transform num_crops=4 ->
+  5 crops, 757 image tokens) padded with random text to a 2048-token context, 256 greedy tokens.
+  One step = HD transform -> CLIP ViT-L/14-336 + projector -> 32-layer prefill -> 255 decode
+  steps (CUDA-graph replays) on Phi-3.5-vision, random-init bf16 weights, synthetic inputs.
+`value` = batched decode tokens/s summed over all ranks, device-timed with inputs resident in HBM
+(decode phase only, the reference's gen_tps definition pv:403); `e2e` = new tokens / wall time of
+the whole public-API call from HOST buffers (H2D of images+ids and D2H of tokens inside).
+`vqa_prefill_ms` = BASELINE configs[1]: single-image VQA (336px HD crops, num_crops=4) time to
+first token at batch 1.  `--impl reference` times the CPU oracle (the reference's arithmetic,
+MLX itself is not installable here) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'batched_decode_tok_per_s'
+B_PER_GPU, CTX, NEW, IMG = 8, 2048, 256, 672
+KV_BYTES_PER_POS = 2 * 32 * 96 * 2          # per layer per sequence (K+V, bf16)
+WEIGHT_BYTES_PER_STEP = 7_445_157_888       # SURVEY.md §8 header (decoder + lm_head, bf16)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    def __init__(self, idx):
+        self.idx, self.rows, self.proc = idx, [], None
+
+    def start(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), f'--query-gpu={q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith('Active') for r in self.rows)]
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def make_inputs(seed, B, ctx, n_img_tok):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    imgs = torch.randint(0, 256, (B, IMG, IMG, 3), generator=g, dtype=torch.uint8)
+    n_text = ctx - n_img_tok
+    head, tail = 6, n_text - 6
+    ids = torch.randint(3, 32000, (B, ctx), generator=g)
+    ids[:, 0] = 1
+    ids[:, head:head + n_img_tok] = -1                      # <|image_1|> placeholders (phi.py:270)
+    ids[:, head + n_img_tok] = 1                            # each text chunk restarts with BOS (phi.py:265)
+    assert tail > 0
+    return imgs, ids
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import phi3_b200  # noqa
+    from phi3_b200 import configs, weights, _lib
+    from phi3_b200.model import Phi3B200
+    from phi3_b200.processor import Phi3VImageProcessor, hd_geometry
+    from phi3_b200.api import _row_stats
+    dev = torch.device('cuda', local)
+    cfg = configs.PHI35_VISION
+    w = weights.random_weights(cfg, seed=0, device=dev)     # same seed on every rank: replicated weights
+    model = Phi3B200(cfg, w, device=dev)
+    del w
+    ip = Phi3VImageProcessor(num_crops=4, device=dev)
+    geo = hd_geometry(IMG, IMG, 4)
+    n_img_tok = geo['num_img_tokens']
+    imgs_h, ids_h = make_inputs(1000 + rank, B_PER_GPU, CTX, n_img_tok)
+    imgs_h, ids_h = imgs_h.pin_memory(), ids_h.pin_memory()
+    positions = torch.nonzero(ids_h < 0)
+    sizes = torch.tensor([[geo['H'], geo['W']]] * B_PER_GPU)
+
+    def step(imgs, ids, timing=None, instrument=False):
+        """one pass of the hot path over one batch; returns token history [B, NEW] on device"""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        pv = ip([imgs[i] for i in range(B_PER_GPU)])['pixel_values']
+        ev[1].record()
+        logits, cache = model(ids, pixel_values=pv, image_sizes=sizes, positions=positions, max_tokens=NEW,
+                              logits_rows='last')
+        tok = _row_stats(model, logits[:, -1, :])['argmax']
+        ev[2].record()
+        model.profile = [] if instrument else None
+        hist = model.greedy_decode(tok, cache, NEW - 1, use_graph=not instrument)
+        ev[3].record()
+        if timing is not None:
+            timing.append(ev)
+        return hist, cache
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    imgs_d, ids_d = imgs_h.to(dev), ids_h.to(dev)
+    for _ in range(args.warmup):
+        step(imgs_d, ids_d)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launches
+    timing = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(imgs_d, ids_d, timing)
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = _lib.launches - n0
+    clocks = sampler.stop() if rank == 0 else None
+    hd_ms = sum(e[0].elapsed_time(e[1]) for e in timing) / args.steps
+    pre_ms = sum(e[1].elapsed_time(e[2]) for e in timing) / args.steps
+    dec_ms = sum(e[2].elapsed_time(e[3]) for e in timing) / args.steps
+    step_ms = sum(e[0].elapsed_time(e[3]) for e in timing) / args.steps
+
+    # ---- e2e through the public call path from host buffers (H2D + D2H inside the timed region)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hist, _ = step(imgs_h.to(dev, non_blocking=True), ids_h.to(dev, non_blocking=True))
+        out_h = hist.cpu()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+
+    # ---- instrumented step: CUDA events around every decode-attention / skinny-GEMM launch
+    roof = gemv = None
+    if rank == 0:
+        hist, cache = step(imgs_d, ids_d, instrument=True)
+        torch.cuda.synchronize()
+        peak, peak_src = peaks()
+        att = [(a.elapsed_time(b), meta) for kind, a, b, meta in model.profile if kind == 'attn']
+        sk = [(a.elapsed_time(b), meta) for kind, a, b, meta in model.profile if kind == 'skinny']
+        model.profile = None
+        if att:
+            byts = sum(m for _, m in att)
+            ms = sum(t for t, _ in att)
+            ach = byts / (ms * 1e-3) / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get('attn_decode_kernel_bytes_per_launch')
+            roof = {'kernel': 'attn_decode_kernel<96,false> (paged bf16 KV, split-KV)', 'bound': 'hbm',
+                    'achieved': round(ach, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4),
+                    'traffic': traffic, 'peak_source': peak_src, 'launches': len(att),
+                    'avg_us': round(1e3 * ms / len(att), 2),
+                    'algorithmic_bytes_per_launch': int(byts / len(att))}
+        if sk:
+            byts = sum(m for _, m in sk)
+            ms = sum(t for t, _ in sk)
+            ach = byts / (ms * 1e-3) / 1e9
+            gemv = {'kernel': 'gemm_skinny_kernel (weight stream)', 'bound': 'hbm', 'achieved': round(ach, 1),
+                    'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4), 'launches': len(sk)}
+
+    # ---- BASELINE configs[1]: single-image VQA prefill at batch 1
+    vqa_ms = None
+    if rank == 0:
+        ids1 = ids_d[:1, :n_img_tok + 30].contiguous()
+        ids1[:, n_img_tok + 6:] = torch.randint(3, 32000, (1, 24), device=dev)
+        pos1 = torch.nonzero(ids1.cpu() < 0)
+        ts = []
+        for i in range(5):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            pv = ip([imgs_d[0]])['pixel_values']
+            lg, c = model(ids1, pixel_values=pv, image_sizes=sizes[:1], positions=pos1, max_tokens=128, logits_rows='last')
+            t1 = _row_stats(model, lg[:, -1, :])['argmax']
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        vqa_ms = min(ts[2:])
+
+    # ---- max over ranks
+    vals = torch.tensor([dec_ms, step_ms, e2e_s, pre_ms, hd_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    dec_ms, step_ms, e2e_s, pre_ms, hd_ms = vals.tolist()
+    tokens = world * B_PER_GPU * (NEW - 1)                  # decode-phase tokens per step (first token comes from prefill)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(steps=2)
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': round(tokens / (dec_ms * 1e-3), 1), 'unit': 'tok/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(dec_ms, 3), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'data': 'synthetic (random-init bf16 weights, random uint8 images and token ids; no network)',
+            'config': {'workload': 'Phi-3.5-vision batched generation: 8 image+text prompts per GPU x 2048 context x 256 '
+                                   'new tokens, 672x672 image, HD transform num_crops=4 (BASELINE configs[2], 64 prompts at 8 GPUs)',
+                       'per_gpu_batch': B_PER_GPU, 'context': CTX, 'new_tokens': NEW, 'parallelism': f'dp{world}',
+                       'l2_policy': 'inputs larger than L2: 7.4 GB weights + 6.8 GB KV streamed per decode step'},
+            'whole_step_ms': round(step_ms, 2), 'hd_transform_ms': round(hd_ms, 3),
+            'vision_prefill_ms': round(pre_ms, 2), 'decode_ms_per_token': round(dec_ms / (NEW - 1), 4),
+            'vqa_prefill_ms': None if vqa_ms is None else round(vqa_ms, 3),
+            'e2e': {'value': round(world * B_PER_GPU * NEW / e2e_s, 1), 'unit': 'tok/s (new tokens / whole generate call)',
+                    'h2d_bytes_per_step': int(imgs_h.numel() + ids_h.numel() * 8),
+                    'd2h_bytes_per_step': int(B_PER_GPU * NEW * 4), 's_per_step': round(e2e_s, 4)},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_skinny_gemm': gemv,
+            'cpu_baseline': cpu, 'wall_s_timed_region': round(wall, 3),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(steps=2, threads=None):
+    """The CPU oracle (op-for-op restatement of the reference, fp32) on the host cores: B=8 decode
+    steps against a 2048-token synthetic KV cache (bounded sample of the same workload)."""
+    import torch
+    from phi3_b200 import configs
+    from oracle.phi3_oracle import Phi3Oracle, KVCache, Mask4D, SuRoPE
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = configs.PHI35_MINI
+    t0 = time.perf_counter()
+    from phi3_b200.weights import _names
+    w = {}
+    g = torch.Generator().manual_seed(0)
+    for name, shape, kind in _names(cfg, None, False):
+        t = torch.empty(shape, dtype=torch.float32)
+        t.normal_(0, 0.02, generator=g) if kind in ('lin', 'res') else t.normal_(1.0 if kind == 'norm' else 0.0, 0.1 if kind == 'norm' else 1.0, generator=g)
+        w[name] = t
+    o = Phi3Oracle(cfg, w, prec='fp32')
+    B, S = B_PER_GPU, CTX
+    cache = [KVCache(cfg, B, S, NEW, 'fp32') for _ in range(cfg.num_hidden_layers)]
+    for c in cache:
+        c.k = torch.randn(c.shape) * 0.5
+        c.v = torch.randn(c.shape) * 0.5
+        c.offset, c.prompt_done = S, True
+    o._masker = Mask4D(S + NEW, None)
+    o._roper = SuRoPE(cfg, S + NEW, None)
+    setup = time.perf_counter() - t0
+    tok = torch.randint(3, 32000, (B, 1))
+    ts = []
+    for i in range(steps + 1):
+        t1 = time.perf_counter()
+        lg, cache = o(tok, cache=cache)
+        tok = lg[:, -1].argmax(-1)[:, None]
+        ts.append(time.perf_counter() - t1)
+    s = min(ts[1:])
+    return {'value': round(B / s, 3), 'unit': 'tok/s', 'cores': threads, 'kind': 'port',
+            'sample': f'Phi-3.5-mini decoder, batch {B}, {steps} greedy decode steps at a {S}-token synthetic fp32 KV cache '
+                      f'(dense mask, all-position lm_head as the reference); setup {setup:.0f}s excluded',
+            's_per_step': round(s, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    cb = cpu_baseline(steps=max(1, args.steps))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': 'tok/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', 1)),
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(1e3 * cb['s_per_step'], 1),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'CPU oracle (restatement of the reference; MLX not installable offline) on the bounded '
+                                   'decode sample of the bench workload', 'sample': cb['sample']},
+            'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'tok/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.gpus > 1 and world == 1:
+        # convenience: self-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_cuda(args)
+
+
+if __name__ == '__main__':
+    main()

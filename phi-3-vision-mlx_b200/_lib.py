@@ -27,7 +27,7 @@ _SIGS = {
     'p3_attention_decode_q4': [_p, _p, _p, _l, _l, _l, _p, _l, _i, _i, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p, _i,
                                _i, _i, _p, _p, _p],
     'p3_kv_quantize_q4g32': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
-    'p3_decode_advance': [_p, _p, _l, _i, _p, _p, _p],
+    'p3_decode_advance': [_p, _p, _l, _i, _p, _p, _p, _p],
     'p3_hd_resize_h': [_p, _l, _l, _i, _i, _p, _i, _p, _p, _i, _p],
     'p3_hd_resize_v_pad': [_p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p],
     'p3_hd_tile_crops': [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p],
@@ -70,6 +70,8 @@ def ptr(t):
 def call(name, *args):
     global launches
     L = lib()
+    if len(args) != len(_SIGS[name]):
+        raise TypeError(f'{name}: expected {len(_SIGS[name])} arguments, got {len(args)}')
     rc = getattr(L, name)(*args)
     launches += 1
     if rc != 0:

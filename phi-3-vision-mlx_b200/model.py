@@ -89,8 +89,7 @@ class Phi3B200:
         self.vision = None
         if any(k.startswith('model.vision_embed_tokens') for k in w):
             self._load_vision(w, d)
-        self._masker_roper = None
-        self._graphs = {}
+        self.profile = None      # bench.py: list of (kind, ev0, ev1, algorithmic_bytes) when instrumenting
 
     # ------------------------------------------------------------------ vision weights
     def _load_vision(self, w, d):
@@ -129,9 +128,20 @@ class Phi3B200:
 
     def skinny(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None):
         M, K = x.shape
+        ev = self._ev()
         call('p3_gemm_skinny', ptr(x), x.stride(0), ptr(norm_w), self.eps, ptr(w), ptr(out), out.stride(0),
              ptr(resid), M, w.shape[0], K, epi, _stream())
+        self._ev(ev, 'skinny', w.shape[0] * K * 2)
         return out
+
+    def _ev(self, start=None, kind=None, nbytes=0):
+        if self.profile is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        if start is not None:
+            self.profile.append((kind, start, e, nbytes))
+        return e
 
     def linear(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None):
         """Route by token count: <=16 rows is a weight stream (skinny), else tensor-core GEMM."""
@@ -247,6 +257,7 @@ class Phi3B200:
             call('p3_rope_kvwrite', ptr(qkv), ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads, self.n_kv, self.hd, past,
                  n_beam, ptr(pool), ptr(bt), bts, 1 if (write_cache and cache is not None) else 0, ptr(past_dev), st)
             qp = qkv.data_ptr()
+            ev = self._ev() if use_decode_attn else None
             if use_decode_attn:
                 if cache.quantized and cache.n_quant > 0:
                     call('p3_attention_decode_q4', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim,
@@ -261,6 +272,8 @@ class Phi3B200:
                 call('p3_attention_prefill', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim, self.qkv_dim,
                      ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale, 1, past, ptr(kvs),
                      ptr(pool), ptr(bt), bts, n_beam, st)
+            if ev is not None:
+                self._ev(ev, 'attn', B * past * 2 * self.n_kv * self.hd * 2)
             self.linear(att, lw['o'], h, _lib.EPI_RESIDUAL, resid=h)
             self.linear(h, lw['gu'], act, _lib.EPI_SWIGLU, norm_w=lw['ln2'])
             self.linear(act, lw['down'], h, _lib.EPI_RESIDUAL, resid=h)
@@ -388,7 +401,7 @@ class DecodeSession:
 
     def _one_step(self):
         m = self.m
-        logits = m._forward_tokens(self.tok, self.B, 1, self.cache, 1, True, self.cache.offset, 'last',
+        logits = m._forward_tokens(self.tok, self.B, 1, self.cache, 1, True, self.cache.offset + self.steps_run, 'last',
                                    past_dev=self.past_dev, n_splits=self.n_splits)
         call('p3_row_stats', ptr(logits), self.B, m.V, m.V, ptr(self.tok), None, None, 0, None, None, 0, None, None,
              _stream())

@@ -20,9 +20,9 @@ def _names(cfg, clip_cfg, vision):
     for i in range(cfg.num_hidden_layers):
         p = f'model.layers.{i}.'
         out += [(p + 'input_layernorm.weight', (H,), 'norm'), (p + 'self_attn.qkv_proj.weight', (qkv, H), 'lin'),
-                (p + 'self_attn.o_proj.weight', (H, cfg.num_attention_heads * hd), 'lin'),
+                (p + 'self_attn.o_proj.weight', (H, cfg.num_attention_heads * hd), 'res'),
                 (p + 'post_attention_layernorm.weight', (H,), 'norm'),
-                (p + 'mlp.gate_up_proj.weight', (2 * I, H), 'lin'), (p + 'mlp.down_proj.weight', (H, I), 'lin')]
+                (p + 'mlp.gate_up_proj.weight', (2 * I, H), 'lin'), (p + 'mlp.down_proj.weight', (H, I), 'res')]
     out += [('model.norm.weight', (H,), 'norm'), ('lm_head.weight', (V, H), 'lin')]
     if vision:
         c = clip_cfg
@@ -36,11 +36,12 @@ def _names(cfg, clip_cfg, vision):
         for j in range(c.num_hidden_layers):
             L = P + f'encoder.layers.{j}.'
             for n in ('q_proj', 'k_proj', 'v_proj', 'out_proj'):
-                out += [(L + f'self_attn.{n}.weight', (D, D), 'lin'), (L + f'self_attn.{n}.bias', (D,), 'b')]
+                out += [(L + f'self_attn.{n}.weight', (D, D), 'cres' if n == 'out_proj' else 'lin'),
+                        (L + f'self_attn.{n}.bias', (D,), 'b')]
             out += [(L + 'layer_norm1.weight', (D,), 'norm'), (L + 'layer_norm1.bias', (D,), 'b'),
                     (L + 'layer_norm2.weight', (D,), 'norm'), (L + 'layer_norm2.bias', (D,), 'b'),
                     (L + 'mlp.fc1.weight', (F, D), 'lin'), (L + 'mlp.fc1.bias', (F,), 'b'),
-                    (L + 'mlp.fc2.weight', (D, F), 'lin'), (L + 'mlp.fc2.bias', (D,), 'b')]
+                    (L + 'mlp.fc2.weight', (D, F), 'cres'), (L + 'mlp.fc2.bias', (D,), 'b')]
         out += [(P + 'post_layernorm.weight', (D,), 'norm'), (P + 'post_layernorm.bias', (D,), 'b')]
         E = cfg.img_processor['image_dim_out'] * 4
         Vp = 'model.vision_embed_tokens.'
@@ -51,9 +52,12 @@ def _names(cfg, clip_cfg, vision):
 
 
 def random_weights(cfg, seed=0, device='cpu', clip_cfg=None, vision=None):
-    """N(0,sigma) bf16 tensors: linear 0.02, embedding 1.0, norm gains 1+0.1*N, biases/pos 0.1*N,
-    GN separators N(0,1). Scales are chosen so the 32-layer residual stream stays O(1..10) and the
-    logits have O(1) spread (SURVEY.md §7 hard part 1)."""
+    """N(0,sigma) bf16 tensors, GPT-2-style: linear 0.02, residual-writing projections (o_proj,
+    down_proj, CLIP out_proj/fc2) 0.02/sqrt(2*n_layers), embedding 1.0, norm gains 1+0.1*N,
+    biases/pos 0.1*N, GN separators N(0,1). With the residual scaling the residual stream stays
+    O(1) over 32 layers and the random network is not chaotic (a plain 0.02 init amplifies a 1e-3
+    perturbation ~25x by layer 32, which says nothing about kernel accuracy); logits have O(1)
+    spread (SURVEY.md §7 hard part 1)."""
     if vision is None:
         vision = 'V' in cfg.architectures[0]
     clip_cfg = clip_cfg or CLIP_VIT_L14_336
@@ -63,6 +67,10 @@ def random_weights(cfg, seed=0, device='cpu', clip_cfg=None, vision=None):
         t = torch.randn(shape, generator=g, device=device, dtype=torch.float32)
         if kind == 'lin':
             t.mul_(0.02)
+        elif kind == 'res':
+            t.mul_(0.02 / (2 * cfg.num_hidden_layers) ** 0.5)
+        elif kind == 'cres':
+            t.mul_(0.02 / (2 * clip_cfg.num_hidden_layers) ** 0.5)
         elif kind == 'norm':
             t.mul_(0.1).add_(1.0)
         elif kind == 'b':
