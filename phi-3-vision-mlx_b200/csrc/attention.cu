@@ -94,13 +94,22 @@ __device__ __forceinline__ void qk_mma(const uint32_t (*qf)[4], uint32_t sk, int
     }
 }
 
-// One warp: O(16 x D) += P(16 x NK*8 keys) V
+// One warp: O(16 x D) += P(16 x NK*8 keys) V.
+// P is fed to the tensor cores as a bf16 hi/lo pair (P = hi + lo, two MMAs): P keeps ~16 mantissa
+// bits, so the only roundings on the attention path are the stored bf16 q,k,v and output — the
+// same points the oracle's 'b200' mode rounds at (the reference runs softmax.V in fp32, phi.py:454-457).
 template <int D, int NK>
 __device__ __forceinline__ void pv_mma(const float (*s)[4], uint32_t sv, int key0, float (*o)[4], int lane) {
 #pragma unroll
     for (int kk = 0; kk < NK / 2; kk++) {
-        uint32_t a[4] = {pack_bf16(s[2 * kk][0], s[2 * kk][1]), pack_bf16(s[2 * kk][2], s[2 * kk][3]),
-                         pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+        uint32_t a[4], al[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float p0 = s[2 * kk + (j >> 1)][(j & 1) * 2], p1 = s[2 * kk + (j >> 1)][(j & 1) * 2 + 1];
+            a[j] = pack_bf16(p0, p1);
+            float2 h = unpack_bf16(a[j]);
+            al[j] = pack_bf16(p0 - h.x, p1 - h.y);
+        }
 #pragma unroll
         for (int dp = 0; dp < D / 16; dp++) {
             int r = key0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -108,7 +117,9 @@ __device__ __forceinline__ void pv_mma(const float (*s)[4], uint32_t sv, int key
             uint32_t b0, b1, b2, b3;
             ldmatrix_x4_trans(b0, b1, b2, b3, sv + tile_off<D>(r, c));
             mma_bf16_16816(o[2 * dp], a, b0, b1);
+            mma_bf16_16816(o[2 * dp], al, b0, b1);
             mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+            mma_bf16_16816(o[2 * dp + 1], al, b2, b3);
         }
     }
 }

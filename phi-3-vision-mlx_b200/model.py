@@ -89,6 +89,7 @@ class Phi3B200:
         self.vision = None
         if any(k.startswith('model.vision_embed_tokens') for k in w):
             self._load_vision(w, d)
+        self.force_long_rope = None   # parallel.py: LongRoPE switch decided from the global batch (H7)
         self.profile = None      # bench.py: list of (kind, ev0, ev1, algorithmic_bytes) when instrumenting
 
     # ------------------------------------------------------------------ vision weights
@@ -158,8 +159,8 @@ class Phi3B200:
         cfg = self.cfg
         sf = math.sqrt(1 + math.log(cfg.max_position_embeddings / cfg.original_max_position_embeddings)
                        / math.log(cfg.original_max_position_embeddings))
-        fac = cfg.rope_scaling['long_factor'] if L_all > cfg.original_max_position_embeddings \
-            else cfg.rope_scaling['short_factor']                                  # static switch (H7)
+        use_long = L_all > cfg.original_max_position_embeddings if self.force_long_rope is None else self.force_long_rope
+        fac = cfg.rope_scaling['long_factor'] if use_long else cfg.rope_scaling['short_factor']   # static switch (H7)
         if pids is None:
             pos = torch.arange(L_all, dtype=torch.float32)[None]
         else:

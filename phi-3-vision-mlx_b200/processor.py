@@ -197,7 +197,10 @@ class Phi3VImageProcessor:
         st = torch.cuda.current_stream().cuda_stream
         if hasattr(img, 'convert'):
             img = np.asarray(img.convert('RGB'))
-        arr = torch.from_numpy(np.ascontiguousarray(img, dtype=np.uint8)).to(dev)
+        if isinstance(img, torch.Tensor):                     # uint8 HWC, host (pinned) or already on the device
+            arr = img.to(dev, torch.uint8, non_blocking=True).contiguous()
+        else:
+            arr = torch.from_numpy(np.ascontiguousarray(img, dtype=np.uint8)).to(dev)
         h0, w0 = arr.shape[:2]
         g = hd_geometry(w0, h0, self.num_crops)
         # logical (possibly transposed) source view: element strides

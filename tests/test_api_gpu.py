@@ -1,0 +1,146 @@
+"""-m gpu: the public API (generate / choose / constrain) and the GPU HD transform against the
+oracle drivers / oracle processors. Index work is bit-exact; token outputs are compared on
+tiny random-init models where near-ties are rare at this vocabulary/sequence size."""
+import json
+import os
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _setup(vision=False, **kw):
+    import phi3_b200  # noqa
+    from phi3_b200 import configs, weights, api
+    from phi3_b200.processor import ByteTokenizer
+    from oracle.phi3_oracle import Phi3Oracle
+    cfg = configs.tiny(vision=vision, **kw)
+    clip = configs.tiny_clip(3) if vision else None
+    w = weights.random_weights(cfg, seed=3, clip_cfg=clip)
+    model, proc = api.load(blind_model=not vision, cfg=cfg, weights=w, tokenizer=ByteTokenizer(), clip_cfg=clip,
+                           num_crops=4, quantize_cache=bool(kw.get('use_quantized_cache', False)))
+    return api, model, proc, Phi3Oracle(model.cfg, w, prec='b200', clip_cfg=clip)
+
+
+@pytest.mark.parametrize('cfgcase', [(336, 336, 4), (500, 350, 4), (300, 420, 4), (640, 480, 16), (1344, 336, 4), (97, 33, 4)])
+def test_hd_transform_bit_exact(dev, cfgcase):
+    """uint8 padded image bit-exact vs PIL path; pixel_values equal to the oracle's float64 result rounded to fp32."""
+    import phi3_b200  # noqa
+    from PIL import Image
+    from phi3_b200.processor import Phi3VImageProcessor
+    from oracle import processors as op
+    w, h, nc = cfgcase
+    arr = np.random.RandomState(w + h).randint(0, 256, (h, w, 3), dtype=np.uint8)
+    ip = Phi3VImageProcessor(num_crops=nc, device=dev)
+    pv, shape, ntok, u8 = ip._one(arr)
+    ref_u8 = op.hd_transform_u8(Image.fromarray(arr), nc)
+    assert torch.equal(u8.cpu(), torch.from_numpy(ref_u8))
+    ref = op.image_processor([Image.fromarray(arr)], num_crops=nc, max_crops=1)
+    assert shape == ref['image_sizes'][0] and ntok == ref['num_img_tokens'][0]
+    ref_pv = torch.from_numpy(ref['pixel_values'][0].astype(np.float32))
+    got = pv.cpu()
+    assert got.shape == ref_pv.shape
+    assert torch.equal(got[1:], ref_pv[1:])                                  # sub crops: LUT values, exact
+    assert (got[0] - ref_pv[0]).abs().max() <= 1e-6                          # global crop: float64 sum order only
+    out = ip([arr])
+    assert out['pixel_values'].shape[1] == max(nc + 1, got.shape[0])
+
+
+def test_hd_transform_matches_reference_golden_fixture(dev):
+    import phi3_b200  # noqa
+    from phi3_b200.processor import Phi3VImageProcessor
+    gold = json.load(open(os.path.join(HERE, 'golden', 'processor_golden.json')))
+    arr = np.load(os.path.join(HERE, 'golden', 'processor_golden.npz'))
+    for tag in 'abc':
+        meta = gold[f'pixel_{tag}']
+        pv, shape, ntok, _ = Phi3VImageProcessor(num_crops=meta['num_crops'], device=dev)._one(arr[f'img_{tag}'])
+        assert shape == meta['image_sizes'] and ntok == meta['num_img_tokens'] and pv.shape[0] == meta['n_used']
+        sub = pv[:, :, ::7, ::5].cpu().numpy()
+        assert np.array_equal(sub[1:], arr[f'pv_{tag}'][1:])
+        assert np.abs(sub[0] - arr[f'pv_{tag}'][0]).max() <= 1e-6
+        assert np.allclose(pv.double().sum(dim=(1, 2, 3)).cpu().numpy(), arr[f'pvsum_{tag}'], rtol=0, atol=2e-2)
+
+
+def test_generate_matches_oracle_rollout(dev):
+    api, model, proc, ora = _setup()
+    from oracle import drivers
+    prompts = ['The quick brown fox', 'Hello', 'A somewhat longer prompt about nothing']
+    templ, _ = api._apply_chat_template(prompts, None, False)
+    inp = proc(templ)
+    ref = drivers.generate_ids(ora, inp, 12)
+    hist = api._generate(model, proc, templ, max_tokens=12, verbose=False, stream=False, mute=True, return_tokens=True)
+    got = hist.cpu().long()
+    assert got.shape == ref.shape
+    assert torch.equal(got[:, :3], ref[:, :3])
+    assert (got == ref).float().mean() >= 0.9
+    txt = api.generate(prompts, preload=(model, proc), max_tokens=6, verbose=False, stream=False)
+    assert isinstance(txt, list) and len(txt) == 3
+    one = api.generate('Hello', preload=(model, proc), max_tokens=5, verbose=False, stream=True)
+    assert isinstance(one, str)
+    tps = api.generate(prompts, preload=(model, proc), max_tokens=6, verbose=False, return_tps=True)
+    assert len(tps) == 2 and tps[1] > 0
+    with pytest.raises(ValueError):
+        api.generate(prompts, images=[np.zeros((8, 8, 3), np.uint8)], preload=(model, proc), verbose=False)
+
+
+def test_choose_matches_oracle(dev):
+    api, model, proc, ora = _setup()
+    from oracle import drivers
+    prompts = ['Which letter? A B C D E', 'Another question entirely', 'x']
+    templ, _ = api._apply_chat_template(prompts, None, False)
+    opts = proc([f' {c}' for c in 'ABCDE'])['input_ids'][:, -1]
+    ref = drivers.choose_ids(ora, proc(templ), opts)
+    got = api.choose(prompts, preload=(model, proc), verbose=False)
+    assert got == ['ABCDE'[i] for i in ref.tolist()]
+    assert api.choose('single', preload=(model, proc), verbose=False) in 'ABCDE'
+
+
+@pytest.mark.parametrize('use_beam', [False, True])
+def test_constrain_matches_oracle(dev, use_beam):
+    api, model, proc, ora = _setup()
+    from oracle import drivers
+    prompts = [api._preprocess(p) for p in api._apply_chat_template(['First question here', 'Second, longer question text here'], None, False)[0]]
+    text = ' The answer is'
+    ids_c = list(proc.tokenizer.encode(text, add_special_tokens=False)[1:])
+    inp = proc(prompts)
+    synth, score = drivers.constrain_ids(ora, inp, ids_c, 6, use_beam=use_beam, n_beam=3)
+    S = inp['input_ids'].shape[1]
+    ref_ids = torch.cat([inp['input_ids'], synth], 1).tolist()
+    ref_ids = [(r[:r.index(32007, S)] if 32007 in r[S:] else r) for r in ref_ids]
+    ref_ids = [[t for t in r if t not in (0, 1)] for r in ref_ids]
+    got = api._constrain(model, proc, prompts, [(6, text)], mute=True, verbose=False, use_beam=use_beam, n_beam=3, return_ids=True)
+    assert got[0] == ref_ids
+    out = api.constrain(['q one', 'q two'], constraints=[(3, ' The'), 'AB'], preload=(model, proc), verbose=False, use_beam=use_beam)
+    assert isinstance(out, list) and len(out) == 2 and all(o.rstrip()[-1] in 'AB' for o in out)
+
+
+def test_quantized_cache_generate_and_beam_raises(dev):
+    api, model, proc, ora = _setup(use_quantized_cache=True)
+    txt = api.generate(['abc def ghi jkl mno pqr stu vwx yz ' * 3, 'short'], preload=(model, proc), max_tokens=8, verbose=False, stream=False)
+    assert len(txt) == 2
+    ids = torch.randint(3, 300, (2, 70))
+    lg, cache = model(ids, max_tokens=8)
+    with pytest.raises(NotImplementedError):
+        model(torch.randint(3, 300, (6, 2)), cache=cache, n_beam=3, advance_offset=0)
+
+
+def test_vision_generate_end_to_end(dev):
+    api, model, proc, ora = _setup(vision=True)
+    from oracle import processors as op
+    from oracle import drivers
+    from PIL import Image
+    arr = np.random.RandomState(5).randint(0, 256, (350, 500, 3), dtype=np.uint8)
+    prompt, imgs = api._apply_chat_template('What is shown?', [arr], False)
+    inp = proc(prompt, imgs)
+    ref_img = op.image_processor([Image.fromarray(arr)], num_crops=4)
+    ref_inp = op.merge(proc.tokenizer, ref_img, prompt)
+    assert inp['input_ids'].tolist() == ref_inp['input_ids'].tolist()           # image-token positions bit-exact
+    assert inp['positions'].tolist() == ref_inp['positions'].tolist()
+    assert inp['image_sizes'].tolist() == ref_inp['image_sizes'].tolist()
+    ref_inp = {k: torch.from_numpy(np.asarray(v)) for k, v in ref_inp.items()}
+    ref = drivers.generate_ids(ora, ref_inp, 6)
+    hist = api._generate(model, proc, prompt, imgs, max_tokens=6, verbose=False, stream=False, mute=True, return_tokens=True)
+    assert torch.equal(hist.cpu().long()[:, :2], ref[:, :2])
+    assert (hist.cpu().long() == ref).float().mean() >= 0.8

@@ -1,0 +1,151 @@
+"""-m "not gpu": host-side logic — the C-ABI library loads and exports every symbol the header
+declares (no compute without a GPU), ctypes signatures match the header, the product never
+imports the oracle, DP sharding over world_size 2 (gloo), chat template / stoppers."""
+import os
+import re
+import subprocess
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'phi-3-vision-mlx_b200')
+
+
+def _header_decls():
+    h = open(os.path.join(ROOT, 'include', 'phi3_b200.h')).read()
+    h = re.sub(r'/\*.*?\*/', '', h, flags=re.S)
+    out = {}
+    for m in re.finditer(r'\b(?:int|int64_t|const char\*)\s+(p3_\w+)\s*\(([^;]*?)\)\s*;', h, flags=re.S):
+        args = [a for a in m.group(2).split(',') if a.strip() and a.strip() != 'void']
+        out[m.group(1)] = len(args)
+    return out
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    import phi3_b200  # noqa
+    from phi3_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), 'build the extension first (__graft_entry__.build())'
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    decls = _header_decls()
+    assert len(decls) >= 20
+    for name in decls:
+        assert hasattr(L, name), f'{name} declared in include/phi3_b200.h but not exported'
+    assert L.p3_version() == 1
+
+
+def test_ctypes_signatures_match_header():
+    import phi3_b200  # noqa
+    from phi3_b200 import _lib
+    decls = _header_decls()
+    for name, sig in _lib._SIGS.items():
+        assert name in decls, name
+        assert len(sig) == decls[name], (name, len(sig), decls[name])
+    with pytest.raises(TypeError):
+        _lib.call('p3_rmsnorm', 0, 0)
+
+
+def test_bad_arguments_fail_loudly_without_gpu():
+    """argument validation happens before any launch, so it is testable on a CPU box"""
+    import phi3_b200  # noqa
+    from phi3_b200 import _lib
+    with pytest.raises(RuntimeError, match='M must be in'):
+        _lib.call('p3_gemm_skinny', None, 8, None, 1e-5, None, None, 8, None, 17, 64, 64, 0, None)
+    with pytest.raises(RuntimeError, match='head_dim must be 96 or 64'):
+        _lib.call('p3_attention_prefill', None, None, None, 8, 8, 8, None, 8, 1, 1, 1, 1, 80, 1.0, 1, 0, None, None, None, 0, 1, None)
+    with pytest.raises(RuntimeError, match='n_top'):
+        _lib.call('p3_row_stats', None, 1, 8, 8, None, None, None, 9, None, None, 0, None, None, None)
+
+
+def test_model_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    import phi3_b200  # noqa
+    from phi3_b200 import configs
+    from phi3_b200.model import Phi3B200
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        Phi3B200(configs.tiny(), {})
+
+
+def test_product_never_imports_oracle():
+    for fn in os.listdir(PKG):
+        if fn.endswith('.py'):
+            src = open(os.path.join(PKG, fn)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), fn
+    for fn in os.listdir(os.path.join(PKG, 'csrc')):
+        if fn.endswith(('.cu', '.cuh')):
+            assert 'oracle' not in open(os.path.join(PKG, 'csrc', fn)).read().replace('mirrors oracle.quantize_q4g32', '')
+
+
+def test_chat_template_and_preprocess():
+    import phi3_b200  # noqa
+    from phi3_b200.api import _apply_chat_template, _preprocess, LogitStopper
+    p, im = _apply_chat_template('  hi there ', None, False)
+    assert p == '<|user|>\nhi there<|end|>\n<|assistant|>\n' and im is None
+    p, _ = _apply_chat_template(['a', 'b'], None, False)
+    assert p == ['<|user|>\na<|end|>\n<|assistant|>\n', '<|user|>\nb<|end|>\n<|assistant|>\n']
+    p, im = _apply_chat_template('x', [object(), object()], False)
+    assert p.startswith('<|user|>\n<|image_1|>\n<|image_2|>\nx<|end|>')
+    assert _apply_chat_template('raw', None, False, apply_chat_template=False)[0] == 'raw'
+    assert _preprocess('<|user|> a<|end|><|assistant|>') == '<|user|>\na<|end|>\n<|assistant|>'
+    ls = LogitStopper(10, 3)
+    assert ls.early_stop == 3 and LogitStopper(10, False).early_stop is False and LogitStopper(10, 20).early_stop is False
+
+
+def test_byte_tokenizer_roundtrip():
+    import phi3_b200  # noqa
+    from phi3_b200.processor import ByteTokenizer, Phi3FProcessor
+    t = ByteTokenizer()
+    s = '<|user|>\nWhat is 2+2?<|end|>\n<|assistant|>\n'
+    ids = t(s).input_ids
+    assert ids[0] == 1 and 32007 in ids and t.decode(ids[1:]) == s
+    out = Phi3FProcessor(t)(['ab', 'abcd'])
+    assert out['input_ids'].shape == (2, 5) and out['input_ids'][0, :2].tolist() == [0, 0]
+    assert out['pids'][0].tolist() == [1, 1, 0, 1, 2] and out['mask'][0].tolist() == [0, 0, 1, 1, 1]
+
+
+def test_shard_indices_and_rope_switch():
+    import phi3_b200  # noqa
+    from phi3_b200.parallel import shard_indices, global_rope_switch, dp_map
+    sh = shard_indices([5, 9, 1, 7, 3], 2)
+    assert sorted(sh[0] + sh[1]) == [0, 1, 2, 3, 4] and sh[0] == [1, 0, 2] and sh[1] == [3, 4]
+    assert shard_indices([1, 2], 4) == [[1], [0], [], []]
+    assert global_rope_switch([100, 4000], 128) and not global_rope_switch([100, 3000], 128)
+    assert dp_map(lambda items, idx: [x * 2 for x in items], [1, 2, 3]) == [2, 4, 6]
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import torch.distributed as dist
+import phi3_b200
+from phi3_b200.parallel import dp_map
+dist.init_process_group('gloo', rank=int(os.environ['RANK']), world_size=2)
+items = [f'p{i}' for i in range(7)]
+lens = [3, 9, 4, 8, 1, 7, 2]
+seen = []
+def fn(shard, idx):
+    seen.extend(idx)
+    return [f'{s}@{dist.get_rank()}' for s in shard]
+out = dp_map(fn, items, lens)
+if dist.get_rank() == 0:
+    assert [o.split('@')[0] for o in out] == items, out
+    assert {o.split('@')[1] for o in out} == {'0', '1'}
+    print('DPMAP_OK', out)
+else:
+    assert out is None
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_dp_map_world_size_2_gloo(tmp_path):
+    script = tmp_path / 'w.py'
+    script.write_text(_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29533', WORLD_SIZE='2')
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert 'DPMAP_OK' in outs[0]

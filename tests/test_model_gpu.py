@@ -177,12 +177,22 @@ def test_full_size_config1(dev):
     ids = _ids(4, 32, seed=11)
     lo, co = o(ids, max_tokens=4)
     lg, cg = m(ids, max_tokens=4)
-    assert rel(lg, lo) < TOL
+    # bf16 pipelines decorrelate completely under any perturbation: the attainable
+    # agreement between two correct bf16 implementations is the bf16 noise floor, measured here as
+    # the distance between the oracle's own bf16 flow and its fp32 arithmetic on the same inputs.
+    lf, _ = Phi3Oracle(cfg, w, prec='fp32')(ids, max_tokens=0)
+    rms = lambda a, b: ((a.float().cpu() - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+    floor = rms(lo, lf)
+    assert rms(lg, lo) < 2.5e-2 and rms(lg, lo) < 1.5 * floor, (rms(lg, lo), floor)
+    assert rms(lg, lf) < 1.5 * floor
+    top2 = lo.topk(2, -1).values
+    margin = top2[..., 0] - top2[..., 1]
+    agree = lg.argmax(-1).cpu() == lo.argmax(-1)
+    assert agree[margin > 0.1].all()                     # every position whose margin clears the noise floor agrees
+    assert agree.float().mean() >= 0.9
     tok = lo[:, -1].argmax(-1)
-    agree = (lg[:, -1].argmax(-1).cpu() == tok).float().mean().item()
     for _ in range(2):
         lo, co = o(tok[:, None], cache=co)
         lg, cg = m(tok[:, None], cache=cg)
-        assert rel(lg, lo) < TOL
+        assert rms(lg, lo) < 2.5e-2
         tok = lo[:, -1].argmax(-1)
-    assert agree >= 0.75

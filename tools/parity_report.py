@@ -39,10 +39,12 @@ def main():
     lgf = lgf.cpu()
     gpu_arg = lgf.argmax(-1)
     rep['graph_decode_vs_gpu_prefill_agreement'] = (gpu_arg[:, 31:] == hist).float().mean().item()
+    keep = {}
     for prec in ('b200', 'ref', 'fp32'):
         t0 = time.time()
         o = Phi3Oracle(cfg, w, prec=prec)
         lo, _ = o(full, max_tokens=0)
+        keep[prec] = lo
         d = (lgf - lo)
         top2 = lo.topk(2, -1).values
         margin = (top2[..., 0] - top2[..., 1])
@@ -53,9 +55,18 @@ def main():
             'teacher_forced_agreement': agree.float().mean().item(),
             'positions': int(agree.numel()),
             'median_top1_top2_margin': margin.median().item(),
+            'agreement_where_margin_gt_0.1': agree[margin > 0.1].float().mean().item(),
+            'positions_margin_gt_0.1': int((margin > 0.1).sum()),
             'margin_at_disagreements': margin[~agree].tolist()[:20],
             'oracle_seconds': time.time() - t0,
         }
+    # the oracle against itself: how far the reference's own bf16 dtype flow is from ideal fp32 arithmetic
+    for a_, b_ in (('ref', 'fp32'), ('b200', 'ref'), ('b200', 'fp32')):
+        d = keep[a_] - keep[b_]
+        rep['modes'][f'oracle_{a_}_vs_oracle_{b_}'] = {
+            'rms_over_rms': (d.pow(2).mean().sqrt() / keep[b_].pow(2).mean().sqrt()).item(),
+            'max_abs_over_max_abs': (d.abs().max() / keep[b_].abs().max()).item(),
+            'greedy_agreement': (keep[a_].argmax(-1) == keep[b_].argmax(-1)).float().mean().item()}
     # step-wise decode through the skinny kernels, teacher-forced on the b200 oracle's tokens
     o = Phi3Oracle(cfg, w, prec='b200')
     lo, co = o(ids, max_tokens=a.steps + 1)
