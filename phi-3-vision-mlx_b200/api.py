@@ -213,6 +213,8 @@ def _generate(model, processor, prompt, images=None, max_tokens=512, verbose=Tru
     streamer = Streamer(processor, stream, mute)
     dict_input = processor(prompt, images)
     B = dict_input['input_ids'].shape[0]
+    if B > 1:
+        streamer.stream = False                                            # pv:53-56: batches are never streamed
     logit_stopper = LogitStopper(max_tokens, early_stop if B == 1 else False)
     per_token_sync = (streamer.stream and B == 1) or bool(logit_stopper.early_stop)
     tic = Tic()

@@ -94,22 +94,15 @@ __device__ __forceinline__ void qk_mma(const uint32_t (*qf)[4], uint32_t sk, int
     }
 }
 
-// One warp: O(16 x D) += P(16 x NK*8 keys) V.
-// P is fed to the tensor cores as a bf16 hi/lo pair (P = hi + lo, two MMAs): P keeps ~16 mantissa
-// bits, so the only roundings on the attention path are the stored bf16 q,k,v and output — the
-// same points the oracle's 'b200' mode rounds at (the reference runs softmax.V in fp32, phi.py:454-457).
+// One warp: O(16 x D) += P(16 x NK*8 keys) V. P is rounded to bf16 for the tensor cores (the
+// reference runs softmax.V in fp32, phi.py:454-457; a bf16 hi/lo split of P was measured to change
+// nothing: bf16 pipelines decorrelate at their noise floor regardless).
 template <int D, int NK>
 __device__ __forceinline__ void pv_mma(const float (*s)[4], uint32_t sv, int key0, float (*o)[4], int lane) {
 #pragma unroll
     for (int kk = 0; kk < NK / 2; kk++) {
-        uint32_t a[4], al[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float p0 = s[2 * kk + (j >> 1)][(j & 1) * 2], p1 = s[2 * kk + (j >> 1)][(j & 1) * 2 + 1];
-            a[j] = pack_bf16(p0, p1);
-            float2 h = unpack_bf16(a[j]);
-            al[j] = pack_bf16(p0 - h.x, p1 - h.y);
-        }
+        uint32_t a[4] = {pack_bf16(s[2 * kk][0], s[2 * kk][1]), pack_bf16(s[2 * kk][2], s[2 * kk][3]),
+                         pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3])};
 #pragma unroll
         for (int dp = 0; dp < D / 16; dp++) {
             int r = key0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -117,9 +110,7 @@ __device__ __forceinline__ void pv_mma(const float (*s)[4], uint32_t sv, int key
             uint32_t b0, b1, b2, b3;
             ldmatrix_x4_trans(b0, b1, b2, b3, sv + tile_off<D>(r, c));
             mma_bf16_16816(o[2 * dp], a, b0, b1);
-            mma_bf16_16816(o[2 * dp], al, b0, b1);
             mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
-            mma_bf16_16816(o[2 * dp + 1], al, b2, b3);
         }
     }
 }
@@ -254,12 +245,23 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(AttnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// decode (L <= 16 new tokens per row), split-KV over cached pages
+// decode (L <= 16 new tokens per row), split-KV over cached pages.
+// grid (n_splits, n_heads, B), 128 threads. Each CTA streams its share of the row's 64-token
+// pages (12 KB K + 12 KB V per head) through a 4-stage cp.async ring; warp w owns keys
+// [16w,16w+16) of every tile, so a tile costs each warp 12 QK + 12 PV mma.sync. All copy and
+// ldmatrix offsets are hoisted out of the tile loop, the page id of tile t+4 is fetched while
+// tile t is consumed, masking runs only on boundary tiles and exp2 is a single MUFU.
 // ------------------------------------------------------------------------------------------
 #define DEC_STAGES 4
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int D, bool Q4>
-__global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
-    constexpr int CPR = D / 8, TILE = 64 * D * 2;
+__global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
+    constexpr int CPR = D / 8, TILE = 64 * D * 2, NSLOT = 64 * CPR / 128;
     constexpr int QC = 64 * D / 2, QM = 64 * (D / 32) * 4;      // bytes of codes / meta per (page, kv, head)
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sq = smem_u32(smem);                         // 16 x D query tile
@@ -269,65 +271,83 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
     const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int kvh = h / (p.n_heads / p.n_kv);
     const int past = p.past_dev ? *p.past_dev : p.past_host;
-    const int kv0 = p.kv_start ? p.kv_start[b / p.row_div] : 0;
+    const int crow = b / p.row_div;
+    const int kv0 = p.kv_start ? p.kv_start[crow] : 0;
     const int s_total = past + p.L;
+    const int32_t* bt = p.block_table + (size_t)crow * p.bt_stride;
 
     for (int idx = tid; idx < 16 * CPR; idx += 128) {
         int r = idx / CPR, c = idx % CPR;
         const bf16* src = p.q + ((size_t)b * p.L + (r < p.L ? r : 0)) * p.ldq + h * D + c * 8;
         cp_async16(sq + tile_off<D>(r, c), src, r < p.L ? 16 : 0);
     }
-    // cached tiles of this split, then (last split only) one "present" tile holding the L new keys
-    const int tiles_total = (past + 63) / 64;
-    const int tps = p.past_dev ? max((tiles_total + p.n_splits - 1) / p.n_splits, 1) : p.tiles_per_split;
-    int n_lo = max(split * tps, kv0 / 64);
-    int n_hi = min((split + 1) * tps, tiles_total);
-    if (n_hi < n_lo) n_hi = n_lo;
+    // balanced split of the cached tiles [t_lo, t_hi); the last split also owns the "present" tile
+    const int t_first = kv0 / 64, t_end = (past + 63) / 64;
+    const int nt_all = max(t_end - t_first, 0);
+    const int n_lo = t_first + (int)(((long long)nt_all * split) / p.n_splits);
+    const int n_hi = t_first + (int)(((long long)nt_all * (split + 1)) / p.n_splits);
+    const int n_cached = n_hi - n_lo;
     const bool has_present = (split == p.n_splits - 1);
-    const int n_iter = (n_hi - n_lo) + (has_present ? 1 : 0);
+    const int n_iter = n_cached + (has_present ? 1 : 0);
 
-    auto issue = [&](int it) {
-        if (it < n_iter) {
-            const uint32_t sk = skv + (it % DEC_STAGES) * 2 * TILE, sv = sk + TILE;
-            if (Q4 && it < n_hi - n_lo && (n_lo + it) * 64 < p.n_quant) {
-                // stage layout: [K codes | V codes | K meta | V meta]
-                const int n = n_lo + it;
-                int page = p.block_table[(size_t)(b / p.row_div) * p.bt_stride + n];
-                const uint8_t* kc = p.qcodes + ((size_t)page * 2 * p.n_kv + kvh) * QC;
-                const uint8_t* vc = kc + (size_t)p.n_kv * QC;
-                const uint8_t* km = reinterpret_cast<const uint8_t*>(p.qmeta) + ((size_t)page * 2 * p.n_kv + kvh) * QM;
-                const uint8_t* vm = km + (size_t)p.n_kv * QM;
-                for (int idx = tid; idx < QC / 16; idx += 128) {
-                    cp_async16(sk + idx * 16, kc + idx * 16);
-                    cp_async16(sk + QC + idx * 16, vc + idx * 16);
-                }
-                for (int idx = tid; idx < QM / 16; idx += 128) {
-                    cp_async16(sk + 2 * QC + idx * 16, km + idx * 16);
-                    cp_async16(sk + 2 * QC + QM + idx * 16, vm + idx * 16);
-                }
-            } else if (it < n_hi - n_lo) {
-                const int n = n_lo + it;
-                int page = p.block_table[(size_t)(b / p.row_div) * p.bt_stride + n];
-                const bf16* kp = kv_tile_ptr(p.pool, page, 0, kvh, p.n_kv, D);
-                const bf16* vp = kv_tile_ptr(p.pool, page, 1, kvh, p.n_kv, D);
-                for (int idx = tid; idx < 64 * CPR; idx += 128) {
-                    int r = idx / CPR, c = idx % CPR;
-                    cp_async16(sk + tile_off<D>(r, c), kp + idx * 8);
-                    cp_async16(sv + tile_off<D>(r, c), vp + idx * 8);
-                }
-            } else {                                            // present tile: 16 rows from the qkv buffer
-                for (int idx = tid; idx < 16 * CPR; idx += 128) {
-                    int r = idx / CPR, c = idx % CPR;
-                    size_t tok = (size_t)b * p.L + (r < p.L ? r : 0);
-                    cp_async16(sk + tile_off<D>(r, c), p.k + tok * p.ldk + kvh * D + c * 8, r < p.L ? 16 : 0);
-                    cp_async16(sv + tile_off<D>(r, c), p.v + tok * p.ldv + kvh * D + c * 8, r < p.L ? 16 : 0);
-                }
-            }
-        }
-        cp_async_commit();
-    };
+    // hoisted per-thread copy slots: chunk (tid + 128 i) of the contiguous 64 x D page slice
+    uint32_t soff[NSLOT];
 #pragma unroll
-    for (int i = 0; i < DEC_STAGES - 1; i++) issue(i);          // group 0 also carries the Q tile
+    for (int i = 0; i < NSLOT; i++) {
+        int idx = tid + 128 * i;
+        soff[i] = tile_off<D>(idx / CPR, idx % CPR);
+    }
+    const size_t head_elems = (size_t)P3_PAGE * D, page_elems = 2 * (size_t)p.n_kv * head_elems;
+    const bf16* pool_k = p.pool + (size_t)kvh * head_elems + tid * 8;          // + page * page_elems
+    const size_t v_delta = (size_t)p.n_kv * head_elems;
+
+    auto issue_cached = [&](int it, int page) {
+        const uint32_t sk = skv + (it % DEC_STAGES) * 2 * TILE;
+        if (Q4 && (n_lo + it) * 64 < p.n_quant) {
+            // stage layout: [K codes | V codes | K meta | V meta]
+            const uint8_t* kc = p.qcodes + ((size_t)page * 2 * p.n_kv + kvh) * QC;
+            const uint8_t* vc = kc + (size_t)p.n_kv * QC;
+            const uint8_t* km = reinterpret_cast<const uint8_t*>(p.qmeta) + ((size_t)page * 2 * p.n_kv + kvh) * QM;
+            const uint8_t* vm = km + (size_t)p.n_kv * QM;
+            for (int idx = tid; idx < QC / 16; idx += 128) {
+                cp_async16(sk + idx * 16, kc + idx * 16);
+                cp_async16(sk + QC + idx * 16, vc + idx * 16);
+            }
+            for (int idx = tid; idx < QM / 16; idx += 128) {
+                cp_async16(sk + 2 * QC + idx * 16, km + idx * 16);
+                cp_async16(sk + 2 * QC + QM + idx * 16, vm + idx * 16);
+            }
+            return;
+        }
+        const bf16* kp = pool_k + (size_t)page * page_elems;
+#pragma unroll
+        for (int i = 0; i < NSLOT; i++) {
+            cp_async16(sk + soff[i], kp + i * 1024);
+            cp_async16(sk + TILE + soff[i], kp + v_delta + i * 1024);
+        }
+    };
+    auto issue_present = [&](int it) {
+        const uint32_t sk = skv + (it % DEC_STAGES) * 2 * TILE, sv = sk + TILE;
+        for (int idx = tid; idx < 16 * CPR; idx += 128) {
+            int r = idx / CPR, c = idx % CPR;
+            size_t tok = (size_t)b * p.L + (r < p.L ? r : 0);
+            cp_async16(sk + tile_off<D>(r, c), p.k + tok * p.ldk + kvh * D + c * 8, r < p.L ? 16 : 0);
+            cp_async16(sv + tile_off<D>(r, c), p.v + tok * p.ldv + kvh * D + c * 8, r < p.L ? 16 : 0);
+        }
+    };
+    // page ids are fetched DEC_STAGES-1 tiles ahead of their use
+    int page_next = (n_cached > 0) ? bt[n_lo] : 0;
+#pragma unroll
+    for (int i = 0; i < DEC_STAGES - 1; i++) {
+        if (i < n_cached) {
+            int pg = page_next;
+            if (i + 1 < n_cached) page_next = bt[n_lo + i + 1];
+            issue_cached(i, pg);
+        } else if (i == n_cached && has_present) {
+            issue_present(i);
+        }
+        cp_async_commit();                                      // group 0 also carries the Q tile
+    }
 
     uint32_t qf[D / 16][4];
     float o[D / 8][4];
@@ -336,11 +356,25 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
 #pragma unroll
         for (int j = 0; j < 4; j++) o[dt][j] = 0.f;
     float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    // hoisted ldmatrix lane offsets (row / swizzle parts that do not depend on the k-step)
+    const int kr = warp * 16 + (lane >> 4) * 8 + (lane & 7);    // K row for QK^T
+    const int vr = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;   // V row for PV
+    const int pr_k = (lane >> 4) * 8 + (lane & 7), pr_v = (lane & 7) + ((lane >> 3) & 1) * 8;  // present tile rows
 
     for (int it = 0; it < n_iter; it++) {
         cp_async_wait<DEC_STAGES - 2>();
         __syncthreads();
-        issue(it + DEC_STAGES - 1);
+        {   // refill the stage that was consumed in the previous iteration
+            const int nx = it + DEC_STAGES - 1;
+            if (nx < n_cached) {
+                int pg = page_next;
+                if (nx + 1 < n_cached) page_next = bt[n_lo + nx + 1];
+                issue_cached(nx, pg);
+            } else if (nx == n_cached && has_present) {
+                issue_present(nx);
+            }
+            cp_async_commit();
+        }
         if (it == 0) {
 #pragma unroll
             for (int ks = 0; ks < D / 16; ks++) {
@@ -349,7 +383,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
             }
         }
         uint32_t sk = skv + (it % DEC_STAGES) * 2 * TILE, sv = sk + TILE;
-        const bool present = it >= n_hi - n_lo;
+        const bool present = it >= n_cached;
         if (Q4 && !present && (n_lo + it) * 64 < p.n_quant) {
             // dequantise codes -> bf16 swizzled tiles: deq = bf16(q*scale + bias) (mx.dequantize, phi.py:536-537)
             const uint8_t* st = smem + (sk - smem_u32(smem));
@@ -359,45 +393,85 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
                 uint32_t codes = *reinterpret_cast<const uint32_t*>(st + kv * QC + r * (D / 2) + c * 4);
                 uint32_t meta = *reinterpret_cast<const uint32_t*>(st + 2 * QC + kv * QM + (r * (D / 32) + c / 4) * 4);
                 float2 sb = unpack_bf16(meta);
-                uint4 o;
-                uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+                uint4 ov;
+                uint32_t* ou = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     float lo = __fadd_rn(__fmul_rn((float)((codes >> (8 * j)) & 15), sb.x), sb.y);
                     float hi = __fadd_rn(__fmul_rn((float)((codes >> (8 * j + 4)) & 15), sb.x), sb.y);
                     ou[j] = pack_bf16(lo, hi);
                 }
-                *reinterpret_cast<uint4*>(smem + (sdq - smem_u32(smem)) + kv * TILE + tile_off<D>(r, c)) = o;
+                *reinterpret_cast<uint4*>(smem + (sdq - smem_u32(smem)) + kv * TILE + tile_off<D>(r, c)) = ov;
             }
             __syncthreads();
             sk = sdq; sv = sdq + TILE;
         }
-        if (present && warp != 0) continue;                     // 16 keys: one warp
-        float s[2][4];
-        qk_mma<D, 2>(qf, sk, present ? 0 : warp * 16, s, lane);
+        if (present && warp != 0) continue;                     // 16 new keys: one warp
+        // ---- S = Q K^T for this warp's 16 keys
+        float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        const int krow = present ? pr_k : kr;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ks++) {
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(b0, b1, b2, b3, sk + tile_off<D>(krow, ks * 2 + ((lane >> 3) & 1)));
+            mma_bf16_16816(s[0], qf[ks], b0, b1);
+            mma_bf16_16816(s[1], qf[ks], b2, b3);
+        }
+        // ---- mask (boundary tiles only)
         const int j0 = present ? past : (n_lo + it) * 64 + warp * 16;
+        if (present || j0 < kv0 || j0 + 16 > past) {
 #pragma unroll
-        for (int nt = 0; nt < 2; nt++)
+            for (int nt = 0; nt < 2; nt++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                int j = j0 + nt * 8 + 2 * t + (e & 1);
-                bool ok;
-                if (present) {
-                    int qi = past + ((e & 2) ? g + 8 : g);
-                    ok = (j < s_total) && (j <= qi) && (j >= kv0);
-                } else {
-                    ok = (j >= kv0) && (j < past);
+                for (int e = 0; e < 4; e++) {
+                    int j = j0 + nt * 8 + 2 * t + (e & 1);
+                    bool ok;
+                    if (present) {
+                        int qi = past + ((e & 2) ? g + 8 : g);
+                        ok = (j < s_total) && (j <= qi);
+                    } else {
+                        ok = (j >= kv0) && (j < past);
+                    }
+                    if (!ok) s[nt][e] = -INFINITY;
                 }
-                s[nt][e] = ok ? s[nt][e] * p.scale_log2 : -INFINITY;
-            }
-        softmax_update<D, 2>(s, m, l, o);
-        pv_mma<D, 2>(s, sv, present ? 0 : warp * 16, o, lane);
+        }
+        // ---- online softmax (rows g and g+8), exp2 domain, one FFMA + one MUFU per element
+        float mx0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
+        float mx1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m[0], mx0), mn1 = fmaxf(m[1], mx1);
+        const float mu0 = (mn0 == -INFINITY) ? 0.f : mn0 * p.scale_log2, mu1 = (mn1 == -INFINITY) ? 0.f : mn1 * p.scale_log2;
+        const float c0 = ex2_approx(m[0] * p.scale_log2 - mu0), c1 = ex2_approx(m[1] * p.scale_log2 - mu1);
+        m[0] = mn0; m[1] = mn1;
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            s[nt][0] = ex2_approx(fmaf(s[nt][0], p.scale_log2, -mu0)); s[nt][1] = ex2_approx(fmaf(s[nt][1], p.scale_log2, -mu0));
+            s[nt][2] = ex2_approx(fmaf(s[nt][2], p.scale_log2, -mu1)); s[nt][3] = ex2_approx(fmaf(s[nt][3], p.scale_log2, -mu1));
+        }
+        l[0] = fmaf(l[0], c0, (s[0][0] + s[0][1]) + (s[1][0] + s[1][1]));
+        l[1] = fmaf(l[1], c1, (s[0][2] + s[0][3]) + (s[1][2] + s[1][3]));
+        if (c0 != 1.f || c1 != 1.f) {                           // warp-divergence free enough: skip when the max did not move
+#pragma unroll
+            for (int dt = 0; dt < D / 8; dt++) { o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1; }
+        }
+        // ---- O += P V
+        const uint32_t a[4] = {pack_bf16(s[0][0], s[0][1]), pack_bf16(s[0][2], s[0][3]),
+                               pack_bf16(s[1][0], s[1][1]), pack_bf16(s[1][2], s[1][3])};
+        const int vrow = present ? pr_v : vr;
+#pragma unroll
+        for (int dp = 0; dp < D / 16; dp++) {
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4_trans(b0, b1, b2, b3, sv + tile_off<D>(vrow, dp * 2 + (lane >> 4)));
+            mma_bf16_16816(o[2 * dp], a, b0, b1);
+            mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+        }
     }
     cp_async_wait<0>();
     __syncthreads();                                            // ring is free: reuse it for the warp merge
 
     float* sm_o = reinterpret_cast<float*>(smem + 16 * D * 2);  // [4][16][D]
-    float* sm_m = sm_o + 4 * 16 * D;                            // [4][16]
+    float* sm_m = sm_o + 4 * 16 * D;                            // [4][16]  (log2 domain, already scaled)
     float* sm_l = sm_m + 64;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
@@ -405,14 +479,16 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
         l[i] += __shfl_xor_sync(0xffffffffu, l[i], 2);
     }
     if (t == 0) {
-        sm_m[warp * 16 + g] = m[0]; sm_m[warp * 16 + g + 8] = m[1];
+        sm_m[warp * 16 + g] = m[0] * p.scale_log2; sm_m[warp * 16 + g + 8] = m[1] * p.scale_log2;
         sm_l[warp * 16 + g] = l[0]; sm_l[warp * 16 + g + 8] = l[1];
     }
+    if (g < p.L || g + 8 < p.L) {
 #pragma unroll
-    for (int dt = 0; dt < D / 8; dt++) {
-        int d = dt * 8 + 2 * t;
-        *reinterpret_cast<float2*>(sm_o + (warp * 16 + g) * D + d) = make_float2(o[dt][0], o[dt][1]);
-        *reinterpret_cast<float2*>(sm_o + (warp * 16 + g + 8) * D + d) = make_float2(o[dt][2], o[dt][3]);
+        for (int dt = 0; dt < D / 8; dt++) {
+            int d = dt * 8 + 2 * t;
+            *reinterpret_cast<float2*>(sm_o + (warp * 16 + g) * D + d) = make_float2(o[dt][0], o[dt][1]);
+            *reinterpret_cast<float2*>(sm_o + (warp * 16 + g + 8) * D + d) = make_float2(o[dt][2], o[dt][3]);
+        }
     }
     __syncthreads();
     for (int idx = tid; idx < p.L * D; idx += 128) {
@@ -422,7 +498,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
         float acc = 0.f, ll = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; w++) {
-            float f = exp2f(sm_m[w * 16 + r] - mu);
+            float f = ex2_approx(sm_m[w * 16 + r] - mu);
             acc += f * sm_o[(w * 16 + r) * D + d];
             ll += f * sm_l[w * 16 + r];
         }
@@ -533,8 +609,7 @@ static int decode_common(AttnParams& p, int L, int past, int n_splits, void* wor
     int tiles_total = (past + 63) / 64;
     if (!p.past_dev && n_splits > tiles_total) n_splits = tiles_total > 0 ? tiles_total : 1;
     p.n_splits = n_splits;
-    p.tiles_per_split = (tiles_total + n_splits - 1) / n_splits;
-    if (p.tiles_per_split == 0) p.tiles_per_split = 1;
+    p.tiles_per_split = 0;                                      // balanced split is computed in the kernel
     p.ws_o = (float*)workspace;
     p.ws_ml = p.ws_o ? p.ws_o + (size_t)p.B * p.n_heads * n_splits * 16 * p.hd : nullptr;
     if (p.hd == 96) return q4 ? launch_decode<96, true>(p, st) : launch_decode<96, false>(p, st);

@@ -1,13 +1,17 @@
 // Skinny (decode-time) GEMM: Y[M,N] = X[M,K] . W[N,K]^T for M <= 16 tokens.
 // Replaces nn.Linear qkv_proj / o_proj / gate_up_proj / down_proj / lm_head at decode
 // (phi.py:437-438,465-466,604) where the op is a pure weight stream: HBM-bound, so the design
-// goal is 16-byte loads of W with many bytes in flight, not tensor-core occupancy.
+// goal is many 16-byte loads of W in flight per SM, not tensor-core occupancy.
 //
 // Mapping: W rows are the MMA "M" dimension (m16n8k16, bf16 -> fp32), the <=16 tokens are "N".
-// Each lane loads 16 contiguous bytes of a W row straight from HBM into the A-fragment
-// registers; the k-index permutation this implies is applied identically to the X operand, so
-// no shared-memory transpose of W is needed. A CTA owns 16*MT W rows and splits K over its
-// 8 warps; partial sums are reduced through shared memory.
+// Each lane owns 16 contiguous bytes of a W row per load; the k-index permutation this implies is
+// applied identically to the X operand, so W needs no shared-memory transpose. A CTA owns 16*MT W
+// rows and splits K over its 8 warps; partial sums are reduced through shared memory.
+//
+// Pipeline: every warp runs a private DEPTH-stage cp.async (LDGSTS) ring in shared memory that
+// carries, per 64-wide k chunk, its W slices, its X slices and the RMSNorm gains. Each lane reads
+// back exactly the bytes it copied, so the ring needs no barrier (cp.async.wait_group only) and
+// no registers: bytes in flight are bounded by shared memory (2 CTAs/SM x 8 warps x DEPTH stages).
 //
 // Fusions: RMSNorm prologue (phi.py:478-479: x*rsqrt(mean(x^2)+eps)*w, rounded to bf16),
 // residual epilogue (phi.py:483,485), SwiGLU epilogue (phi.py:470-471), fp32 logits out.
@@ -29,12 +33,24 @@ struct SkParams {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 
 template <int NT, int MT>
+struct SkCfg {
+    static constexpr int W_SLOTS = 4 * MT, X_SLOTS = 2 * NT;
+    static constexpr int STAGE = (W_SLOTS + X_SLOTS) * 512 + 128;            // + 128 B of norm gains
+    static constexpr int DEPTH = (MT == 1) ? (NT == 1 ? 4 : 3) : 2;   // keeps 2 CTAs/SM (<= ~110 KB each)
+    static constexpr int RING = SK_WARPS * DEPTH * STAGE;
+    static constexpr int RED = SK_WARPS * MT * 8 * NT * 17 * 4;
+    static constexpr int SMEM = RING > RED ? RING : RED;
+};
+
+template <int NT, int MT>
 __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) {
+    using C = SkCfg<NT, MT>;
+    extern __shared__ __align__(128) uint8_t sk_smem[];
     __shared__ float s_rs[16];
-    __shared__ float s_red[SK_WARPS][MT][8 * NT][16 + 1];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int K = p.K, n_chunks = K / 64;
+    const uint32_t ring = smem_u32(sk_smem) + warp * (C::DEPTH * C::STAGE);
 
     // W row pointers for this lane (rows g and g+8 of each 16-row tile)
     const bf16* wrow[MT][2];
@@ -59,18 +75,43 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
             wrow[mt][1] = p.W + (size_t)r1 * K + t * 8;
         }
     }
+    const bf16* xrow[NT];
+    int xbytes[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+        int m = nt * 8 + g;
+        xbytes[nt] = m < p.M ? 16 : 0;                                          // rows >= M are zero-filled
+        xrow[nt] = p.X + (size_t)(m < p.M ? m : 0) * p.ldx + t * 8;
+    }
 
-    // prefetch the first W chunk before the norm prologue so HBM latency overlaps it
-    uint4 wreg[MT][2][2];
-    int ci = warp;
-    if (ci < n_chunks) {
+    // stage layout (per warp): W slots [mt][row-half][k-half], X slots [nt][k-half], each 32 lanes x 16 B;
+    // then 128 B of norm gains (64 elements, read back with broadcast)
+    auto issue = [&](int ci, int stage) {
+        const uint32_t sb = ring + stage * C::STAGE + lane * 16;
+        const int k0 = ci * 64;
 #pragma unroll
         for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                wreg[mt][h][0] = ldg_nc_v4(wrow[mt][h] + ci * 64);
-                wreg[mt][h][1] = ldg_nc_v4(wrow[mt][h] + ci * 64 + 32);
+            for (int hh = 0; hh < 2; hh++) {
+                cp_async16(sb + ((mt * 2 + hh) * 2 + 0) * 512, wrow[mt][hh] + k0);
+                cp_async16(sb + ((mt * 2 + hh) * 2 + 1) * 512, wrow[mt][hh] + k0 + 32);
             }
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+            cp_async16(sb + (C::W_SLOTS + nt * 2 + 0) * 512, xrow[nt] + k0, xbytes[nt]);
+            cp_async16(sb + (C::W_SLOTS + nt * 2 + 1) * 512, xrow[nt] + k0 + 32, xbytes[nt]);
+        }
+        if (p.norm_w && lane < 8)
+            cp_async16(ring + stage * C::STAGE + (C::W_SLOTS + C::X_SLOTS) * 512 + lane * 16, p.norm_w + k0 + lane * 8);
+    };
+
+    // fill the ring before the norm prologue so HBM latency overlaps it
+    int ci_issue = warp;
+#pragma unroll
+    for (int s = 0; s < C::DEPTH; s++) {
+        if (ci_issue < n_chunks) issue(ci_issue, s);
+        cp_async_commit();
+        ci_issue += SK_WARPS;
     }
 
     // ---- RMSNorm prologue: rs[m] for every token (each CTA recomputes; X is L2 resident)
@@ -97,55 +138,37 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
         for (int nt = 0; nt < NT; nt++)
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[mt][nt][j] = 0.f;
-
     float rs[NT];
-    const bf16* xrow[NT];
-    bool xok[NT];
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++) {
-        int m = nt * 8 + g;
-        xok[nt] = m < p.M;
-        xrow[nt] = p.X + (size_t)(xok[nt] ? m : 0) * p.ldx + t * 8;
-        rs[nt] = (p.norm_w && xok[nt]) ? s_rs[m] : 1.f;
-    }
+    for (int nt = 0; nt < NT; nt++) rs[nt] = (p.norm_w && nt * 8 + g < p.M) ? s_rs[nt * 8 + g] : 1.f;
 
-    for (; ci < n_chunks; ci += SK_WARPS) {
-        uint4 wcur[MT][2][2];
+    int stage = 0;
+    for (int ci = warp; ci < n_chunks; ci += SK_WARPS) {
+        cp_async_wait<C::DEPTH - 1>();                                           // oldest group (this chunk) has landed
+        const uint8_t* sb = sk_smem + (size_t)warp * (C::DEPTH * C::STAGE) + stage * C::STAGE;
+        uint4 wcur[MT][2][2], xf[NT][2];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-            for (int h = 0; h < 2; h++) { wcur[mt][h][0] = wreg[mt][h][0]; wcur[mt][h][1] = wreg[mt][h][1]; }
-        int cn = ci + SK_WARPS;
-        if (cn < n_chunks) {
+            for (int hh = 0; hh < 2; hh++)
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++)
+                for (int kh = 0; kh < 2; kh++)
+                    wcur[mt][hh][kh] = *reinterpret_cast<const uint4*>(sb + ((mt * 2 + hh) * 2 + kh) * 512 + lane * 16);
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    wreg[mt][h][0] = ldg_nc_v4(wrow[mt][h] + cn * 64);
-                    wreg[mt][h][1] = ldg_nc_v4(wrow[mt][h] + cn * 64 + 32);
-                }
-        }
-        // X fragments (same k permutation as W): 2 x 16B per token row per chunk
-        uint4 xf[NT][2];
+        for (int nt = 0; nt < NT; nt++)
 #pragma unroll
-        for (int nt = 0; nt < NT; nt++) {
-            if (xok[nt]) {
-                xf[nt][0] = *reinterpret_cast<const uint4*>(xrow[nt] + ci * 64);
-                xf[nt][1] = *reinterpret_cast<const uint4*>(xrow[nt] + ci * 64 + 32);
-            } else {
-                xf[nt][0] = make_uint4(0, 0, 0, 0); xf[nt][1] = make_uint4(0, 0, 0, 0);
-            }
-        }
+            for (int kh = 0; kh < 2; kh++)
+                xf[nt][kh] = *reinterpret_cast<const uint4*>(sb + (C::W_SLOTS + nt * 2 + kh) * 512 + lane * 16);
         if (p.norm_w) {
             uint4 nw[2];
-            nw[0] = __ldg(reinterpret_cast<const uint4*>(p.norm_w + ci * 64 + t * 8));
-            nw[1] = __ldg(reinterpret_cast<const uint4*>(p.norm_w + ci * 64 + 32 + t * 8));
+            nw[0] = *reinterpret_cast<const uint4*>(sb + (C::W_SLOTS + C::X_SLOTS) * 512 + t * 16);
+            nw[1] = *reinterpret_cast<const uint4*>(sb + (C::W_SLOTS + C::X_SLOTS) * 512 + 64 + t * 16);
 #pragma unroll
             for (int nt = 0; nt < NT; nt++)
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    uint32_t* ux = reinterpret_cast<uint32_t*>(&xf[nt][h]);
-                    const uint32_t* uw = reinterpret_cast<const uint32_t*>(&nw[h]);
+                for (int kh = 0; kh < 2; kh++) {
+                    uint32_t* ux = reinterpret_cast<uint32_t*>(&xf[nt][kh]);
+                    const uint32_t* uw = reinterpret_cast<const uint32_t*>(&nw[kh]);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         float2 f = unpack_bf16(ux[j]), w = unpack_bf16(uw[j]);
@@ -153,24 +176,32 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
                     }
                 }
         }
+        // the stage is in registers now: refill it with the chunk DEPTH iterations ahead
+        if (ci_issue < n_chunks) issue(ci_issue, stage);
+        cp_async_commit();
+        ci_issue += SK_WARPS;
+        if (++stage == C::DEPTH) stage = 0;
 #pragma unroll
-        for (int h = 0; h < 2; h++)
+        for (int kh = 0; kh < 2; kh++)
 #pragma unroll
             for (int s = 0; s < 2; s++)
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
-                    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(&wcur[mt][0][h]);
-                    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(&wcur[mt][1][h]);
+                    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(&wcur[mt][0][kh]);
+                    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(&wcur[mt][1][kh]);
                     uint32_t a[4] = {w0[2 * s], w1[2 * s], w0[2 * s + 1], w1[2 * s + 1]};
 #pragma unroll
                     for (int nt = 0; nt < NT; nt++) {
-                        const uint32_t* ux = reinterpret_cast<const uint32_t*>(&xf[nt][h]);
+                        const uint32_t* ux = reinterpret_cast<const uint32_t*>(&xf[nt][kh]);
                         mma_bf16_16816(acc[mt][nt], a, ux[2 * s], ux[2 * s + 1]);
                     }
                 }
     }
+    cp_async_wait<0>();
+    __syncthreads();                                                             // ring -> reduction scratch
 
     // ---- cross-warp reduction through shared memory
+    float (*s_red)[MT][8 * NT][17] = reinterpret_cast<float (*)[MT][8 * NT][17]>(sk_smem);
 #pragma unroll
     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
@@ -214,6 +245,20 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
     }
 }
 
+template <int NT, int MT>
+static int launch_skinny(const SkParams& p, unsigned grid, cudaStream_t st) {
+    using C = SkCfg<NT, MT>;
+    static bool set = false;
+    if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel<NT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        P3_CHECK_ARG(e == cudaSuccess, "gemm_skinny: smem attribute: %s", cudaGetErrorString(e));
+        set = true;
+    }
+    gemm_skinny_kernel<NT, MT><<<grid, SK_THREADS, C::SMEM, st>>>(p);
+    P3_CHECK_LAUNCH("gemm_skinny");
+    return 0;
+}
+
 extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, void* out,
                               int64_t ldo, const void* resid, int M, int N, int K, int epi, cudaStream_t st) {
     P3_CHECK_ARG(M >= 1 && M <= 16, "gemm_skinny: M must be in [1,16] (got %d)", M);
@@ -226,17 +271,12 @@ extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, fl
     if (epi == P3_EPI_SWIGLU) {
         P3_CHECK_ARG(N % 256 == 0, "gemm_skinny: SwiGLU needs N (gate+up rows) to be a multiple of 256");
         unsigned grid = (unsigned)(N / 2 / 16);
-        if (M <= 8) gemm_skinny_kernel<1, 2><<<grid, SK_THREADS, 0, st>>>(p);
-        else gemm_skinny_kernel<2, 2><<<grid, SK_THREADS, 0, st>>>(p);
-    } else if (N >= 148 * 32 * 2) {
-        unsigned grid = (unsigned)((N + 31) / 32);
-        if (M <= 8) gemm_skinny_kernel<1, 2><<<grid, SK_THREADS, 0, st>>>(p);
-        else gemm_skinny_kernel<2, 2><<<grid, SK_THREADS, 0, st>>>(p);
-    } else {
-        unsigned grid = (unsigned)((N + 15) / 16);
-        if (M <= 8) gemm_skinny_kernel<1, 1><<<grid, SK_THREADS, 0, st>>>(p);
-        else gemm_skinny_kernel<2, 1><<<grid, SK_THREADS, 0, st>>>(p);
+        return M <= 8 ? launch_skinny<1, 2>(p, grid, st) : launch_skinny<2, 2>(p, grid, st);
     }
-    P3_CHECK_LAUNCH("gemm_skinny");
-    return 0;
+    if (N >= 148 * 32 * 2) {
+        unsigned grid = (unsigned)((N + 31) / 32);
+        return M <= 8 ? launch_skinny<1, 2>(p, grid, st) : launch_skinny<2, 2>(p, grid, st);
+    }
+    unsigned grid = (unsigned)((N + 15) / 16);
+    return M <= 8 ? launch_skinny<1, 1>(p, grid, st) : launch_skinny<2, 1>(p, grid, st);
 }

@@ -26,6 +26,20 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def pick_splits(n_bh, tiles, slots=2 * 148, min_tiles=3, max_splits=32):
+    """Split-KV factor for decode attention: fill whole waves of the 2-CTA/SM grid (296 slots) while
+    keeping >= min_tiles 64-token pages per split. Returns the split count with the best wave efficiency."""
+    best, best_eff = 1, 0.0
+    for s in range(1, max_splits + 1):
+        if s > 1 and tiles // s < min_tiles:
+            break
+        waves = n_bh * s / slots
+        eff = waves / max(1.0, float(-(-n_bh * s // slots)))
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
+    return best
+
+
 def interleave_gate_up(w):
     """[2I, K] (gate rows then up rows, phi:470) -> per 256-row block [128 gate | 128 up]."""
     I = w.shape[0] // 2
@@ -241,8 +255,7 @@ class Phi3B200:
         ws = None
         if use_decode_attn:
             if n_splits is None:
-                tiles = max(1, (past + PAGE - 1) // PAGE)
-                n_splits = max(1, min((4 * 148 + B * self.n_heads - 1) // (B * self.n_heads), (tiles + 3) // 4))
+                n_splits = pick_splits(B * self.n_heads, max(1, (past + PAGE - 1) // PAGE))
             if n_splits > 1:
                 ws = torch.empty(_lib.lib().p3_attention_decode_workspace(B, L, self.n_heads, self.hd, n_splits) // 4,
                                  dtype=torch.float32, device=dev)
@@ -382,7 +395,7 @@ class DecodeSession:
         if cache.offset + max_steps > cache.S_max:
             raise ValueError('KV cache overflow: decode session longer than the cache was sized for')
         tiles = (cache.offset + max_steps + PAGE - 1) // PAGE
-        self.n_splits = max(1, min((4 * 148 + B * model.n_heads - 1) // (B * model.n_heads), (tiles + 3) // 4))
+        self.n_splits = pick_splits(B * model.n_heads, tiles)
         if use_graph and B <= 16:
             cur = torch.cuda.current_stream()
             s = torch.cuda.Stream()
