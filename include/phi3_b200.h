@@ -34,8 +34,10 @@ extern "C" {
 const char* p3_last_error(void);
 int p3_version(void);
 
-/* nn.Embedding phi:568,577 — ids<0 (image placeholders, phi:270) read row 0 */
-int p3_embed_gather(const void* table, const int32_t* ids, void* out, int64_t T, int H, int vocab, cudaStream_t st);
+/* nn.Embedding phi:568,577 — ids<0 (image placeholders, phi:270) read row 0. ss_out (fp32 [T], may be
+ * NULL) receives each row's sum of squares for the RMSNorm fused into the next p3_gemm_skinny. */
+int p3_embed_gather(const void* table, const int32_t* ids, void* out, int64_t T, int H, int vocab, float* ss_out,
+                    cudaStream_t st);
 
 /* nn.RMSNorm / mx.fast.rms_norm phi:478-479,571 */
 int p3_rmsnorm(const void* x, const void* w, void* y, int64_t T, int H, float eps, cudaStream_t st);
@@ -67,9 +69,13 @@ int p3_decode_advance(const int32_t* tok, int32_t* history, int64_t ld, int B, i
                       int32_t* eos_seen, cudaStream_t st);
 
 /* nn.Linear at decode (M<=16 tokens): phi:437-438,465-466,604. Optional fused RMSNorm prologue
- * (norm_w != NULL: X is the raw hidden state). epi in {NONE, RESIDUAL, SWIGLU, F32}. */
+ * (norm_w != NULL: X is the raw hidden state). epi in {NONE, RESIDUAL, SWIGLU, F32}.
+ * ss_in (fp32 [n_ss_in][16], may be NULL): per-token partial sums of squares of X written by the
+ * kernel that produced X (p3_embed_gather / a RESIDUAL p3_gemm_skinny via ss_out, which writes
+ * [ceil(N/16)][16]); without it the RMSNorm statistic is recomputed from X. */
 int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, void* out, int64_t ldo,
-                   const void* resid, int M, int N, int K, int epi, cudaStream_t st);
+                   const void* resid, int M, int N, int K, int epi, const float* ss_in, int n_ss_in, float* ss_out,
+                   cudaStream_t st);
 
 /* nn.Linear for prefill / ViT / projector (phi:140-143,155-156,391,437-438,465-466,604) and the
  * patch-embed conv as GEMM (phi:186-192): out[M,N] = X[M,K] . W[N,K]^T on tcgen05 tensor cores

@@ -270,6 +270,8 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int kvh = h / (p.n_heads / p.n_kv);
+    pdl_trigger();
+    pdl_wait();                                                 // q/k/v, past and the cache come from earlier kernels
     const int past = p.past_dev ? *p.past_dev : p.past_host;
     const int crow = b / p.row_div;
     const int kv0 = p.kv_start ? p.kv_start[crow] : 0;
@@ -514,6 +516,8 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
 
 template <int D>
 __global__ void attn_merge_kernel(AttnParams p) {
+    pdl_trigger();
+    pdl_wait();
     const int h = blockIdx.x, b = blockIdx.y;
     for (int idx = threadIdx.x; idx < p.L * D; idx += blockDim.x) {
         int r = idx / D, d = idx % D;
@@ -593,10 +597,10 @@ static int launch_decode(AttnParams& p, cudaStream_t st) {
         P3_CHECK_ARG(e == cudaSuccess, "attention_decode: smem attribute: %s", cudaGetErrorString(e));
         set = true;
     }
-    attn_decode_kernel<D, Q4><<<grid, 128, smem, st>>>(p);
+    p3_launch_pdl(attn_decode_kernel<D, Q4>, grid, dim3(128), (size_t)smem, st, p);
     P3_CHECK_LAUNCH("attention_decode");
     if (p.n_splits > 1) {
-        attn_merge_kernel<D><<<dim3(p.n_heads, p.B), 128, 0, st>>>(p);
+        p3_launch_pdl(attn_merge_kernel<D>, dim3(p.n_heads, p.B), dim3(128), 0, st, p);
         P3_CHECK_LAUNCH("attention_merge");
     }
     return 0;

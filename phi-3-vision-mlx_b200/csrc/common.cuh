@@ -78,6 +78,30 @@ __device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, uint
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may start while its
+// stream predecessor drains; everything that reads the predecessor's output must come after
+// pdl_wait(). Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#include <cstdlib>
+inline bool p3_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("P3_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+// launch with the programmatic-stream-serialization attribute (decode-path kernels)
+template <typename... KArgs, typename... Args>
+inline cudaError_t p3_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = p3_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Paged KV pool addressing. One pool per layer:
 //   pool[page][kv(0=K,1=V)][head][slot(0..PAGE-1)][head_dim]   bf16
 #define P3_PAGE 64

@@ -8,20 +8,36 @@
 // out-of-range ids are clamped to row 0; those rows are overwritten by the image scatter.
 // ------------------------------------------------------------------------------------------
 __global__ void embed_gather_kernel(const bf16* __restrict__ table, const int32_t* __restrict__ ids,
-                                    bf16* __restrict__ out, int64_t T, int H, int vocab) {
+                                    bf16* __restrict__ out, int64_t T, int H, int vocab, float* __restrict__ ss_out) {
+    __shared__ float s_part[4];
+    pdl_trigger();
+    pdl_wait();
     int64_t t = blockIdx.x;
     int id = ids[t];
     if (id < 0 || id >= vocab) id = 0;
     const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)id * H);
     uint4* dst = reinterpret_cast<uint4*>(out + (size_t)t * H);
-    for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+        uint4 v = __ldg(src + i);
+        dst[i] = v;
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { float2 f = unpack_bf16(u[j]); ss += f.x * f.x + f.y * f.y; }
+    }
+    if (ss_out) {                                            // sum of squares of the row, for the fused RMSNorm
+        ss = warp_sum(ss);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ss;
+        __syncthreads();
+        if (threadIdx.x == 0) ss_out[t] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+    }
 }
 
 extern "C" int p3_embed_gather(const void* table, const int32_t* ids, void* out, int64_t T, int H, int vocab,
-                               cudaStream_t st) {
+                               float* ss_out, cudaStream_t st) {
     P3_CHECK_ARG(H % 8 == 0, "embed_gather: H must be a multiple of 8");
     if (T == 0) return 0;
-    embed_gather_kernel<<<(unsigned)T, 128, 0, st>>>((const bf16*)table, ids, (bf16*)out, T, H, vocab);
+    p3_launch_pdl(embed_gather_kernel, dim3((unsigned)T), dim3(128), 0, st, (const bf16*)table, ids, (bf16*)out, T, H, vocab, ss_out);
     P3_CHECK_LAUNCH("embed_gather");
     return 0;
 }
@@ -154,6 +170,8 @@ __global__ void rope_kvwrite_kernel(bf16* __restrict__ qkv, const float* __restr
                                     int64_t tab_bstride, int B, int L, int n_heads, int n_kv, int hd, int past,
                                     int row_div, bf16* __restrict__ pool, const int32_t* __restrict__ block_table,
                                     int bt_stride, int write_cache, const int32_t* __restrict__ past_dev) {
+    pdl_trigger();
+    pdl_wait();
     if (past_dev) past = *past_dev;
     const int half = hd / 2, cpr = half / 8;                  // 8-elem chunks per half head
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -216,9 +234,9 @@ extern "C" int p3_rope_kvwrite(void* qkv, const float* cosT, const float* sinT, 
     P3_CHECK_ARG(n_kv <= n_heads && row_div >= 1, "rope_kvwrite: bad head counts / row_div");
     int64_t total = (int64_t)B * L * n_heads * (hd / 16);
     if (total == 0) return 0;
-    rope_kvwrite_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        (bf16*)qkv, cosT, sinT, tab_bstride, B, L, n_heads, n_kv, hd, past, row_div, (bf16*)pool, block_table,
-        bt_stride, write_cache, past_dev);
+    p3_launch_pdl(rope_kvwrite_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+                  (bf16*)qkv, cosT, sinT, tab_bstride, B, L, n_heads, n_kv, hd, past, row_div, (bf16*)pool, block_table,
+                  bt_stride, write_cache, past_dev);
     P3_CHECK_LAUNCH("rope_kvwrite");
     return 0;
 }
@@ -242,6 +260,8 @@ __global__ void row_stats_kernel(const float* __restrict__ logits, int64_t ld, i
     __shared__ int s_taken[8];
     __shared__ float s_bval;
     __shared__ int s_bidx;
+    pdl_trigger();
+    pdl_wait();
     int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* row = logits + (size_t)r * ld;
     float lse = 0.f, rowmax = 0.f;
@@ -305,8 +325,8 @@ extern "C" int p3_row_stats(const float* logits, int64_t R, int64_t ld, int V, i
     P3_CHECK_ARG(n_top == 0 || (topk_ids && topk_lp), "row_stats: top-k outputs missing");
     P3_CHECK_ARG(n_gather == 0 || (gather_ids && gather_lp), "row_stats: gather buffers missing");
     if (R == 0) return 0;
-    row_stats_kernel<<<(unsigned)R, RS_THREADS, 0, st>>>(logits, ld, V, argmax_out, max_out, lse_out, n_top, topk_ids,
-                                                         topk_lp, n_gather, gather_ids, gather_lp);
+    p3_launch_pdl(row_stats_kernel, dim3((unsigned)R), dim3(RS_THREADS), 0, st, logits, ld, V, argmax_out, max_out, lse_out,
+                  n_top, topk_ids, topk_lp, n_gather, gather_ids, gather_lp);
     P3_CHECK_LAUNCH("row_stats");
     return 0;
 }
@@ -318,6 +338,8 @@ extern "C" int p3_row_stats(const float* logits, int64_t R, int64_t ld, int V, i
 // ------------------------------------------------------------------------------------------
 __global__ void decode_advance_kernel(const int32_t* __restrict__ tok, int32_t* __restrict__ history, int64_t ld, int B,
                                       int32_t* step, int32_t* past, int32_t* eos_seen) {
+    pdl_trigger();
+    pdl_wait();
     int s = *step;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         history[(size_t)b * ld + s] = tok[b];
@@ -329,7 +351,7 @@ __global__ void decode_advance_kernel(const int32_t* __restrict__ tok, int32_t* 
 
 extern "C" int p3_decode_advance(const int32_t* tok, int32_t* history, int64_t ld, int B, int32_t* step, int32_t* past,
                                  int32_t* eos_seen, cudaStream_t st) {
-    decode_advance_kernel<<<1, 128, 0, st>>>(tok, history, ld, B, step, past, eos_seen);
+    p3_launch_pdl(decode_advance_kernel, dim3(1), dim3(128), 0, st, tok, history, ld, B, step, past, eos_seen);
     P3_CHECK_LAUNCH("decode_advance");
     return 0;
 }

@@ -28,6 +28,8 @@ struct SkParams {
     void* out; int64_t ldo;
     const bf16* resid;
     int M, N, K, epi;
+    const float* ss_in; int n_ss_in;     // per-token sum-of-squares partials [n_ss_in][16] written by the producer of X
+    float* ss_out;                       // RESIDUAL epilogue: partial[blockIdx.x][16] of the rows this CTA produced
 };
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
 
     // stage layout (per warp): W slots [mt][row-half][k-half], X slots [nt][k-half], each 32 lanes x 16 B;
     // then 128 B of norm gains (64 elements, read back with broadcast)
-    auto issue = [&](int ci, int stage) {
+    auto issue_w = [&](int ci, int stage) {                                      // weights + norm gains: immutable
         const uint32_t sb = ring + stage * C::STAGE + lane * 16;
         const int k0 = ci * 64;
 #pragma unroll
@@ -96,26 +98,47 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
                 cp_async16(sb + ((mt * 2 + hh) * 2 + 0) * 512, wrow[mt][hh] + k0);
                 cp_async16(sb + ((mt * 2 + hh) * 2 + 1) * 512, wrow[mt][hh] + k0 + 32);
             }
+        if (p.norm_w && lane < 8)
+            cp_async16(ring + stage * C::STAGE + (C::W_SLOTS + C::X_SLOTS) * 512 + lane * 16, p.norm_w + k0 + lane * 8);
+    };
+    auto issue_x = [&](int ci, int stage) {                                      // activations: produced by the previous kernel
+        const uint32_t sb = ring + stage * C::STAGE + lane * 16;
+        const int k0 = ci * 64;
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
             cp_async16(sb + (C::W_SLOTS + nt * 2 + 0) * 512, xrow[nt] + k0, xbytes[nt]);
             cp_async16(sb + (C::W_SLOTS + nt * 2 + 1) * 512, xrow[nt] + k0 + 32, xbytes[nt]);
         }
-        if (p.norm_w && lane < 8)
-            cp_async16(ring + stage * C::STAGE + (C::W_SLOTS + C::X_SLOTS) * 512 + lane * 16, p.norm_w + k0 + lane * 8);
     };
 
-    // fill the ring before the norm prologue so HBM latency overlaps it
+    // Fill the ring with weights first: they do not depend on the previous kernel, so under
+    // programmatic dependent launch this HBM traffic overlaps the predecessor's tail.
+    pdl_trigger();
+#pragma unroll
+    for (int s = 0; s < C::DEPTH; s++) {
+        if (warp + s * SK_WARPS < n_chunks) issue_w(warp + s * SK_WARPS, s);
+        cp_async_commit();
+    }
+    pdl_wait();
     int ci_issue = warp;
 #pragma unroll
     for (int s = 0; s < C::DEPTH; s++) {
-        if (ci_issue < n_chunks) issue(ci_issue, s);
+        if (ci_issue < n_chunks) issue_x(ci_issue, s);
         cp_async_commit();
         ci_issue += SK_WARPS;
     }
 
-    // ---- RMSNorm prologue: rs[m] for every token (each CTA recomputes; X is L2 resident)
-    if (p.norm_w) {
+    // ---- RMSNorm prologue: rs[m] = rsqrt(mean(x^2) + eps), from the producer's partial sums when
+    // available (fixed summation order: deterministic), else recomputed from X (L2 resident)
+    if (p.norm_w && p.ss_in) {
+        for (int m = warp; m < p.M; m += SK_WARPS) {
+            float ss = 0.f;
+            for (int c = lane; c < p.n_ss_in; c += 32) ss += p.ss_in[c * 16 + m];
+            ss = warp_sum(ss);
+            if (lane == 0) s_rs[m] = rsqrtf(ss / (float)K + p.eps);
+        }
+        __syncthreads();
+    } else if (p.norm_w) {
         for (int m = warp; m < p.M; m += SK_WARPS) {
             const uint4* xr = reinterpret_cast<const uint4*>(p.X + (size_t)m * p.ldx);
             float ss = 0.f;
@@ -145,6 +168,7 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
     int stage = 0;
     for (int ci = warp; ci < n_chunks; ci += SK_WARPS) {
         cp_async_wait<C::DEPTH - 1>();                                           // oldest group (this chunk) has landed
+        __syncwarp();                                                            // norm gains were copied by lanes 0-7
         const uint8_t* sb = sk_smem + (size_t)warp * (C::DEPTH * C::STAGE) + stage * C::STAGE;
         uint4 wcur[MT][2][2], xf[NT][2];
 #pragma unroll
@@ -177,7 +201,8 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
                 }
         }
         // the stage is in registers now: refill it with the chunk DEPTH iterations ahead
-        if (ci_issue < n_chunks) issue(ci_issue, stage);
+        __syncwarp();
+        if (ci_issue < n_chunks) { issue_w(ci_issue, stage); issue_x(ci_issue, stage); }
         cp_async_commit();
         ci_issue += SK_WARPS;
         if (++stage == C::DEPTH) stage = 0;
@@ -225,21 +250,30 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
             reinterpret_cast<bf16*>(p.out)[(size_t)tok * p.ldo + out_col0 + r] = __float2bfloat16_rn(a * ub);
         }
     } else {
-        for (int o = tid; o < MT * 8 * NT * 16; o += SK_THREADS) {
+        for (int o = tid; o < MT * 8 * NT * 16; o += SK_THREADS) {                  // whole warps enter (128|256|512 outputs)
             int r = o & 15, mt = (o >> 4) % MT, tok = o / (16 * MT);
             int n = out_col0 + mt * 16 + r;
-            if (tok >= p.M || n >= p.N) continue;
-            float s = 0.f;
+            const bool ok = tok < p.M && n < p.N;
+            float s = 0.f, sq = 0.f;
 #pragma unroll
             for (int w = 0; w < SK_WARPS; w++) s += s_red[w][mt][tok][r];
             size_t off = (size_t)tok * p.ldo + n;
-            if (p.epi == P3_EPI_F32) {
-                reinterpret_cast<float*>(p.out)[off] = s;
-            } else if (p.epi == P3_EPI_RESIDUAL) {
-                float rv = __bfloat162float(p.resid[off]);
-                reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16_rn(rv + bf16_round(s));
-            } else {
-                reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16_rn(s);
+            if (ok) {
+                if (p.epi == P3_EPI_F32) {
+                    reinterpret_cast<float*>(p.out)[off] = s;
+                } else if (p.epi == P3_EPI_RESIDUAL) {
+                    float rv = __bfloat162float(p.resid[off]);
+                    bf16 hv = __float2bfloat16_rn(rv + bf16_round(s));
+                    reinterpret_cast<bf16*>(p.out)[off] = hv;
+                    sq = __bfloat162float(hv) * __bfloat162float(hv);
+                } else {
+                    reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16_rn(s);
+                }
+            }
+            if (p.ss_out && MT == 1) {                                             // 16 lanes = one token's 16 new columns
+#pragma unroll
+                for (int d = 8; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+                if (r == 0 && tok < 16) p.ss_out[(size_t)blockIdx.x * 16 + tok] = (tok < p.M) ? sq : 0.f;
             }
         }
     }
@@ -254,20 +288,23 @@ static int launch_skinny(const SkParams& p, unsigned grid, cudaStream_t st) {
         P3_CHECK_ARG(e == cudaSuccess, "gemm_skinny: smem attribute: %s", cudaGetErrorString(e));
         set = true;
     }
-    gemm_skinny_kernel<NT, MT><<<grid, SK_THREADS, C::SMEM, st>>>(p);
+    p3_launch_pdl(gemm_skinny_kernel<NT, MT>, dim3(grid), dim3(SK_THREADS), (size_t)C::SMEM, st, p);
     P3_CHECK_LAUNCH("gemm_skinny");
     return 0;
 }
 
 extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, void* out,
-                              int64_t ldo, const void* resid, int M, int N, int K, int epi, cudaStream_t st) {
+                              int64_t ldo, const void* resid, int M, int N, int K, int epi, const float* ss_in,
+                              int n_ss_in, float* ss_out, cudaStream_t st) {
     P3_CHECK_ARG(M >= 1 && M <= 16, "gemm_skinny: M must be in [1,16] (got %d)", M);
     P3_CHECK_ARG(K % 64 == 0, "gemm_skinny: K must be a multiple of 64 (got %d)", K);
     P3_CHECK_ARG(epi == P3_EPI_NONE || epi == P3_EPI_RESIDUAL || epi == P3_EPI_SWIGLU || epi == P3_EPI_F32,
                  "gemm_skinny: unsupported epilogue %d", epi);
     P3_CHECK_ARG(epi != P3_EPI_RESIDUAL || resid, "gemm_skinny: residual epilogue needs resid");
     P3_CHECK_ARG(ldx % 8 == 0, "gemm_skinny: ldx must be a multiple of 8");
-    SkParams p{(const bf16*)X, ldx, (const bf16*)norm_w, eps, (const bf16*)W, out, ldo, (const bf16*)resid, M, N, K, epi};
+    P3_CHECK_ARG(!ss_out || (epi == P3_EPI_RESIDUAL && N < 148 * 32 * 2), "gemm_skinny: ss_out needs the 16-row residual configuration");
+    SkParams p{(const bf16*)X, ldx, (const bf16*)norm_w, eps, (const bf16*)W, out, ldo, (const bf16*)resid, M, N, K, epi,
+               ss_in, n_ss_in, ss_out};
     if (epi == P3_EPI_SWIGLU) {
         P3_CHECK_ARG(N % 256 == 0, "gemm_skinny: SwiGLU needs N (gate+up rows) to be a multiple of 256");
         unsigned grid = (unsigned)(N / 2 / 16);

@@ -141,11 +141,12 @@ class Phi3B200:
              ptr(row_map), M, N, K, epi, self.gemm_impl, _stream())
         return out
 
-    def skinny(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None):
+    def skinny(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None, ss_in=None, ss_out=None):
         M, K = x.shape
         ev = self._ev()
+        n_ss = 0 if ss_in is None else ss_in.shape[0]
         call('p3_gemm_skinny', ptr(x), x.stride(0), ptr(norm_w), self.eps, ptr(w), ptr(out), out.stride(0),
-             ptr(resid), M, w.shape[0], K, epi, _stream())
+             ptr(resid), M, w.shape[0], K, epi, ptr(ss_in), n_ss, ptr(ss_out), _stream())
         self._ev(ev, 'skinny', w.shape[0] * K * 2)
         return out
 
@@ -158,10 +159,10 @@ class Phi3B200:
             self.profile.append((kind, start, e, nbytes))
         return e
 
-    def linear(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None):
+    def linear(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None, ss_in=None, ss_out=None):
         """Route by token count: <=16 rows is a weight stream (skinny), else tensor-core GEMM."""
         if x.shape[0] <= 16:
-            return self.skinny(x, w, out, epi, norm_w, resid)
+            return self.skinny(x, w, out, epi, norm_w, resid, ss_in, ss_out)
         if norm_w is not None:
             xn = torch.empty_like(x)
             call('p3_rmsnorm', ptr(x), ptr(norm_w), ptr(xn), x.shape[0], x.shape[1], self.eps, _stream())
@@ -245,9 +246,18 @@ class Phi3B200:
         st = _stream()
         T, H = B * L, self.H
         dev = self.dev
+        # decode (T <= 16): per-token sum-of-squares partials travel with the residual stream so the
+        # RMSNorm fused into the next skinny GEMM never re-reads X: ss[c][16] written by the producer
+        ssA = ssB = None
+        if T <= 16:
+            n_part = (H + 15) // 16
+            ssA = torch.zeros((n_part, 16), dtype=torch.float32, device=dev)
+            ssB = torch.zeros((n_part, 16), dtype=torch.float32, device=dev)
+        ss_cur = None
         if h is None:
             h = torch.empty((T, H), dtype=torch.bfloat16, device=dev)
-            call('p3_embed_gather', ptr(self.embed), ptr(ids_dev), ptr(h), T, H, self.V, st)
+            call('p3_embed_gather', ptr(self.embed), ptr(ids_dev), ptr(h), T, H, self.V, ptr(ssA), st)
+            ss_cur = None if ssA is None else ssA[:1]
         qkv = torch.empty((T, self.qkv_dim), dtype=torch.bfloat16, device=dev)
         att = torch.empty((T, self.n_heads * self.hd), dtype=torch.bfloat16, device=dev)
         act = torch.empty((T, self.I), dtype=torch.bfloat16, device=dev)
@@ -267,7 +277,7 @@ class Phi3B200:
             cosT, sinT, tbs, bt, bts, kvs = self._nc_cos, self._nc_sin, self._nc_tbs, None, 0, self._nc_kvs
         for li, lw in enumerate(self.layers):
             pool = cache.pool[li] if cache is not None else None
-            self.linear(h, lw['qkv'], qkv, _lib.EPI_NONE, norm_w=lw['ln1'])
+            self.linear(h, lw['qkv'], qkv, _lib.EPI_NONE, norm_w=lw['ln1'], ss_in=ss_cur)
             call('p3_rope_kvwrite', ptr(qkv), ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads, self.n_kv, self.hd, past,
                  n_beam, ptr(pool), ptr(bt), bts, 1 if (write_cache and cache is not None) else 0, ptr(past_dev), st)
             qp = qkv.data_ptr()
@@ -288,9 +298,10 @@ class Phi3B200:
                      ptr(pool), ptr(bt), bts, n_beam, st)
             if ev is not None:
                 self._ev(ev, 'attn', B * past * 2 * self.n_kv * self.hd * 2)
-            self.linear(att, lw['o'], h, _lib.EPI_RESIDUAL, resid=h)
-            self.linear(h, lw['gu'], act, _lib.EPI_SWIGLU, norm_w=lw['ln2'])
-            self.linear(act, lw['down'], h, _lib.EPI_RESIDUAL, resid=h)
+            self.linear(att, lw['o'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssB)
+            self.linear(h, lw['gu'], act, _lib.EPI_SWIGLU, norm_w=lw['ln2'], ss_in=ssB)
+            self.linear(act, lw['down'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssA)
+            ss_cur = ssA
         if logits_rows == 'last':
             hl = h.view(B, L, H)[:, -1, :]
             R = 1
@@ -298,7 +309,7 @@ class Phi3B200:
             hl, R = h, L
         hl = hl.reshape(B * R, H) if hl.is_contiguous() else hl.contiguous().reshape(B * R, H)
         logits = torch.empty((B * R, self.V), dtype=torch.float32, device=dev)
-        self.linear(hl, self.lm_head, logits, _lib.EPI_F32, norm_w=self.norm)
+        self.linear(hl, self.lm_head, logits, _lib.EPI_F32, norm_w=self.norm, ss_in=ss_cur if (R == L) else None)
         return logits.view(B, R, self.V)
 
     # ------------------------------------------------------------------ reference call protocol (phi:606, 576-592)
@@ -312,7 +323,7 @@ class Phi3B200:
         h = None
         if pixel_values is not None and self.vision is not None:
             h = torch.empty((B * L, self.H), dtype=torch.bfloat16, device=self.dev)
-            call('p3_embed_gather', ptr(self.embed), ptr(ids_dev), ptr(h), B * L, self.H, self.V, _stream())
+            call('p3_embed_gather', ptr(self.embed), ptr(ids_dev), ptr(h), B * L, self.H, self.V, None, _stream())
             h = self._vision_embed(h, L, pixel_values, image_sizes, positions)
         if cache is None:
             L_all = L + max_tokens

@@ -56,7 +56,7 @@ def test_embed_gather_negative_ids(dev):
     tab = bf(torch.randn(100, 64, device=dev))
     ids = torch.tensor([3, -1, 99, 0, -7, 250], dtype=torch.int32, device=dev)
     out = torch.empty(6, 64, device=dev, dtype=torch.bfloat16)
-    L.call('p3_embed_gather', tab.data_ptr(), ids.data_ptr(), out.data_ptr(), 6, 64, 100, st())
+    L.call('p3_embed_gather', tab.data_ptr(), ids.data_ptr(), out.data_ptr(), 6, 64, 100, None, st())
     exp = tab[torch.tensor([3, 0, 99, 0, 0, 0], device=dev)]
     assert torch.equal(out, exp)
 
@@ -172,21 +172,21 @@ def test_gemm_skinny(dev, M, mode):
         from phi3_b200.model import interleave_gate_up
         out = torch.zeros(M, N // 2, device=dev, dtype=torch.bfloat16)
         L.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr(), 1e-5, interleave_gate_up(w).data_ptr(), out.data_ptr(),
-               N // 2, None, M, N, K, 4, st())
+               N // 2, None, M, N, K, 4, None, 0, None, st())
         g, u = bf(acc[:, :N // 2]).float(), bf(acc[:, N // 2:]).float()
         ref = bf(bf(torch.nn.functional.silu(g)).float() * u)
     elif mode == 'f32':
         out = torch.zeros(M, N, device=dev)
-        L.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr(), 1e-5, w.data_ptr(), out.data_ptr(), N, None, M, N, K, 5, st())
+        L.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr(), 1e-5, w.data_ptr(), out.data_ptr(), N, None, M, N, K, 5, None, 0, None, st())
         ref = acc
     elif mode == 'resid':
         out = bf(torch.randn(M, N, device=dev))
         ref = bf(out.float() + bf(acc).float())
-        L.call('p3_gemm_skinny', x.data_ptr(), K, None, 1e-5, w.data_ptr(), out.data_ptr(), N, out.data_ptr(), M, N, K, 3, st())
+        L.call('p3_gemm_skinny', x.data_ptr(), K, None, 1e-5, w.data_ptr(), out.data_ptr(), N, out.data_ptr(), M, N, K, 3, None, 0, None, st())
     else:
         out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
         L.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr() if mode == 'norm' else None, 1e-5, w.data_ptr(),
-               out.data_ptr(), N, None, M, N, K, 0, st())
+               out.data_ptr(), N, None, M, N, K, 0, None, 0, None, st())
         ref = bf(acc)
     _check(out, ref, tol=1e-2)
 
@@ -342,3 +342,41 @@ def test_kv_quant_roundtrip_matches_oracle(dev):
                 n = min(64, S - p * 64)
                 got = pool[bt[b, p], kv, :, :n].cpu()
                 assert torch.equal(got, deq[b, :, p * 64:p * 64 + n]), (kv, b, p)
+
+
+def test_skinny_ss_partials_feed_fused_rmsnorm(dev):
+    """RESIDUAL epilogue emits per-CTA sum-of-squares partials; a following norm-fused skinny GEMM fed
+    with them must equal the one that recomputes the statistic from X."""
+    L = _mods()
+    torch.manual_seed(8)
+    M, H = 7, 3072
+    act = bf(torch.randn(M, H, device=dev))
+    wo = bf(torch.randn(H, H, device=dev) * H ** -0.5)
+    h = bf(torch.randn(M, H, device=dev))
+    ss = torch.zeros((H // 16, 16), device=dev)
+    L.call('p3_gemm_skinny', act.data_ptr(), H, None, 1e-5, wo.data_ptr(), h.data_ptr(), H, h.data_ptr(), M, H, H, 3,
+           None, 0, ss.data_ptr(), st())
+    torch.cuda.synchronize()
+    ref_ss = h.float().pow(2).sum(-1)
+    got_ss = ss.sum(0)[:M]
+    assert (got_ss - ref_ss).abs().max() <= 1e-3 * ref_ss.max()
+    assert (ss[:, M:] == 0).all()
+    nw = bf(1 + 0.1 * torch.randn(H, device=dev))
+    w2 = bf(torch.randn(1024, H, device=dev) * H ** -0.5)
+    o1 = torch.zeros(M, 1024, device=dev, dtype=torch.bfloat16)
+    o2 = torch.zeros_like(o1)
+    L.call('p3_gemm_skinny', h.data_ptr(), H, nw.data_ptr(), 1e-5, w2.data_ptr(), o1.data_ptr(), 1024, None, M, 1024, H, 0,
+           ss.data_ptr(), H // 16, None, st())
+    L.call('p3_gemm_skinny', h.data_ptr(), H, nw.data_ptr(), 1e-5, w2.data_ptr(), o2.data_ptr(), 1024, None, M, 1024, H, 0,
+           None, 0, None, st())
+    torch.cuda.synchronize()
+    assert (o1.float() - o2.float()).abs().max() <= 2 ** -7 * o2.float().abs().max()
+    assert (o1 != o2).float().mean() < 0.02
+    # embed_gather's ss_out
+    tab = bf(torch.randn(50, H, device=dev))
+    ids = torch.tensor([3, 7, 49], dtype=torch.int32, device=dev)
+    out = torch.empty(3, H, device=dev, dtype=torch.bfloat16)
+    sse = torch.zeros(16, device=dev)
+    L.call('p3_embed_gather', tab.data_ptr(), ids.data_ptr(), out.data_ptr(), 3, H, 50, sse.data_ptr(), st())
+    torch.cuda.synchronize()
+    assert (sse[:3] - tab[ids.long()].float().pow(2).sum(-1)).abs().max() < 1e-2
