@@ -77,6 +77,14 @@ int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, float eps, co
                    const void* resid, int M, int N, int K, int epi, const float* ss_in, int n_ss_in, float* ss_out,
                    cudaStream_t st);
 
+/* Decode-time qkv_proj + _rotate_half/SuRoPE + KVCache write in ONE launch (phi:442-453): each CTA owns
+ * 16 rotary pairs (column c and c + hd/2 of one head) so the rotation fuses into the epilogue. */
+int p3_gemm_skinny_qkv_rope(const void* X, int64_t ldx, const void* norm_w, float eps, const void* Wqkv, void* qkv,
+                            const float* ss_in, int n_ss_in, const float* cosT, const float* sinT, int64_t tab_bstride,
+                            int B, int L, int n_heads, int n_kv, int hd, int K, int past, const int32_t* past_dev,
+                            int row_div, void* pool, const int32_t* block_table, int bt_stride, int write_cache,
+                            cudaStream_t st);
+
 /* nn.Linear for prefill / ViT / projector (phi:140-143,155-156,391,437-438,465-466,604) and the
  * patch-embed conv as GEMM (phi:186-192): out[M,N] = X[M,K] . W[N,K]^T on tcgen05 tensor cores
  * (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue). bias bf16 [N] or NULL. row_map int32 [M] or
@@ -98,7 +106,8 @@ int p3_attention_prefill(const void* q, const void* k, const void* v, int64_t ld
 
 /* Decode-time attention for L<=16 new tokens per row over a paged KV cache (split-KV):
  * phi:454-457 with KVCache reads phi:523-527 (n_beam shared prefix: row_div) / phi:548.
- * workspace: fp32, p3_attention_decode_workspace() bytes. */
+ * workspace: p3_attention_decode_workspace() bytes, MUST be zero-filled once before first use (it holds the
+ * split-arrival counters, which the kernel resets itself); needed when n_splits > 1. */
 int64_t p3_attention_decode_workspace(int B, int L, int n_heads, int hd, int n_splits);
 int p3_attention_decode(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* out,
                         int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale, int past,

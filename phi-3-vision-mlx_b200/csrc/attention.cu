@@ -37,6 +37,7 @@ struct AttnParams {
     // decode only
     int n_splits, tiles_per_split;
     float* ws_o; float* ws_ml;
+    int* counters;              // [B*n_heads] split-arrival counters (zero on entry, reset by the merging CTA)
     // quantised-cache decode: positions [0, n_quant) (multiple of 64) live in the q4 pools
     int n_quant;
     const uint8_t* qcodes;      // [page][2][n_kv][64][D/2]
@@ -512,6 +513,33 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
             if (d == 0) { p.ws_ml[base * 2] = mm; p.ws_ml[base * 2 + 1] = ll; }
         }
     }
+    if (p.n_splits > 1 && p.counters) {
+        // the last split of this (row, head) to arrive merges all partials (fixed order -> deterministic)
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(&p.counters[b * p.n_heads + h], 1) == p.n_splits - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            for (int idx = tid; idx < p.L * D; idx += 128) {
+                int r = idx / D, d = idx % D;
+                size_t base0 = (((size_t)b * p.n_heads + h) * p.n_splits) * 16 + r;
+                float mm = -INFINITY;
+                for (int sp = 0; sp < p.n_splits; sp++) mm = fmaxf(mm, __ldcg(&p.ws_ml[(base0 + (size_t)sp * 16) * 2]));
+                float mu = (mm == -INFINITY) ? 0.f : mm;
+                float acc = 0.f, ll = 0.f;
+                for (int sp = 0; sp < p.n_splits; sp++) {
+                    size_t bs = base0 + (size_t)sp * 16;
+                    float f = ex2_approx(__ldcg(&p.ws_ml[bs * 2]) - mu);
+                    acc += f * __ldcg(&p.ws_o[bs * D + d]);
+                    ll += f * __ldcg(&p.ws_ml[bs * 2 + 1]);
+                }
+                p.out[((size_t)b * p.L + r) * p.ldo + h * D + d] = __float2bfloat16_rn(ll > 0.f ? acc / ll : 0.f);
+            }
+            if (tid == 0) p.counters[b * p.n_heads + h] = 0;
+        }
+    }
 }
 
 template <int D>
@@ -554,7 +582,7 @@ static int fill_params(AttnParams& p, const void* q, const void* k, const void* 
     p.scale_log2 = scale * 1.4426950408889634f;
     p.causal = causal; p.past = past; p.past_host = past; p.past_dev = nullptr; p.kv_start = kv_start;
     p.pool = (const bf16*)pool; p.block_table = block_table; p.bt_stride = bt_stride; p.row_div = row_div;
-    p.n_splits = 1; p.tiles_per_split = 0; p.ws_o = nullptr; p.ws_ml = nullptr;
+    p.n_splits = 1; p.tiles_per_split = 0; p.ws_o = nullptr; p.ws_ml = nullptr; p.counters = nullptr;
     p.n_quant = 0; p.qcodes = nullptr; p.qmeta = nullptr;
     return 0;
 }
@@ -584,7 +612,7 @@ extern "C" int p3_attention_prefill(const void* q, const void* k, const void* v,
 
 extern "C" int64_t p3_attention_decode_workspace(int B, int L, int n_heads, int hd, int n_splits) {
     (void)L;
-    return (int64_t)B * n_heads * n_splits * 16 * (hd + 2) * 4;
+    return (int64_t)B * n_heads * n_splits * 16 * (hd + 2) * 4 + (int64_t)B * n_heads * 4;   // partials + arrival counters
 }
 
 template <int D, bool Q4>
@@ -598,11 +626,7 @@ static int launch_decode(AttnParams& p, cudaStream_t st) {
         set = true;
     }
     p3_launch_pdl(attn_decode_kernel<D, Q4>, grid, dim3(128), (size_t)smem, st, p);
-    P3_CHECK_LAUNCH("attention_decode");
-    if (p.n_splits > 1) {
-        p3_launch_pdl(attn_merge_kernel<D>, dim3(p.n_heads, p.B), dim3(128), 0, st, p);
-        P3_CHECK_LAUNCH("attention_merge");
-    }
+    P3_CHECK_LAUNCH("attention_decode");       // split partials are merged in-kernel by the last CTA to arrive
     return 0;
 }
 
@@ -616,6 +640,7 @@ static int decode_common(AttnParams& p, int L, int past, int n_splits, void* wor
     p.tiles_per_split = 0;                                      // balanced split is computed in the kernel
     p.ws_o = (float*)workspace;
     p.ws_ml = p.ws_o ? p.ws_o + (size_t)p.B * p.n_heads * n_splits * 16 * p.hd : nullptr;
+    p.counters = p.ws_o ? reinterpret_cast<int*>(p.ws_ml + (size_t)p.B * p.n_heads * n_splits * 16 * 2) : nullptr;
     if (p.hd == 96) return q4 ? launch_decode<96, true>(p, st) : launch_decode<96, false>(p, st);
     return q4 ? launch_decode<64, true>(p, st) : launch_decode<64, false>(p, st);
 }

@@ -30,7 +30,13 @@ struct SkParams {
     int M, N, K, epi;
     const float* ss_in; int n_ss_in;     // per-token sum-of-squares partials [n_ss_in][16] written by the producer of X
     float* ss_out;                       // RESIDUAL epilogue: partial[blockIdx.x][16] of the rows this CTA produced
+    // P3_EPI_ROPE_QKV: SuRoPE + paged-KV write fused into the qkv projection (phi.py:442-453)
+    const float *cosT, *sinT; int64_t tab_bstride;
+    int L, n_heads, n_kv, hd, past, row_div, write_cache;
+    const int32_t* past_dev;
+    bf16* pool; const int32_t* block_table; int bt_stride;
 };
+#define P3_EPI_ROPE_QKV 7
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 
@@ -57,7 +63,31 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
     // W row pointers for this lane (rows g and g+8 of each 16-row tile)
     const bf16* wrow[MT][2];
     int out_col0;
-    if (p.epi == P3_EPI_SWIGLU) {
+    int rope_head = -1, rope_grp = 0;                                              // ROPE_QKV: which head / 16-col group
+    if (p.epi == P3_EPI_ROPE_QKV) {
+        // CTAs [0, (n_heads+n_kv)*hd/32): head h, group j -> tile 0 = cols h*hd + 16j.., tile 1 = the rotary
+        // partners at +hd/2 (so each (x1,x2) pair meets in one CTA); remaining CTAs: 32 V rows each
+        const int gpr = p.hd / 32, n_rope = (p.n_heads + p.n_kv) * gpr;
+        int r0;
+        if ((int)blockIdx.x < n_rope) {
+            rope_head = blockIdx.x / gpr; rope_grp = blockIdx.x % gpr;
+            r0 = rope_head * p.hd + rope_grp * 16;
+            out_col0 = r0;
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                wrow[mt][0] = p.W + (size_t)(r0 + mt * (p.hd / 2) + g) * K + t * 8;
+                wrow[mt][1] = p.W + (size_t)(r0 + mt * (p.hd / 2) + g + 8) * K + t * 8;
+            }
+        } else {
+            r0 = (p.n_heads + p.n_kv) * p.hd + ((int)blockIdx.x - n_rope) * 32;
+            out_col0 = r0;
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                wrow[mt][0] = p.W + (size_t)(r0 + mt * 16 + g) * K + t * 8;
+                wrow[mt][1] = p.W + (size_t)(r0 + mt * 16 + g + 8) * K + t * 8;
+            }
+        }
+    } else if (p.epi == P3_EPI_SWIGLU) {
         // interleaved gate/up layout: [128 gate rows | 128 up rows] per 256-row block
         int o0 = blockIdx.x * 16;
         int gate0 = (o0 / 128) * 256 + (o0 % 128);
@@ -238,7 +268,49 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
         }
     __syncthreads();
 
-    if (p.epi == P3_EPI_SWIGLU) {
+    if (p.epi == P3_EPI_ROPE_QKV) {
+        const int past = p.past_dev ? *p.past_dev : p.past;
+        const int half = p.hd / 2, qkv_dim = (p.n_heads + 2 * p.n_kv) * p.hd;
+        bf16* outp = reinterpret_cast<bf16*>(p.out);
+        for (int o = tid; o < 8 * NT * 16; o += SK_THREADS) {
+            int r = o & 15, tok = o >> 4;
+            if (tok >= p.M) continue;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int w = 0; w < SK_WARPS; w++) { a0 += s_red[w][0][tok][r]; a1 += s_red[w][MT - 1][tok][r]; }
+            const int b = tok / p.L, pos = past + tok % p.L;
+            bf16* row = outp + (size_t)tok * p.ldo;
+            bf16 *kd = nullptr, *vd = nullptr;
+            if (p.write_cache) {
+                int page = p.block_table[(size_t)(b / p.row_div) * p.bt_stride + pos / P3_PAGE];
+                kd = p.pool + (size_t)page * kv_page_elems(p.n_kv, p.hd) + (size_t)(pos % P3_PAGE) * p.hd;
+                vd = kd + (size_t)p.n_kv * P3_PAGE * p.hd;
+            }
+            if (rope_head >= 0) {                                                  // q or k head: rotate (phi.py:418-423)
+                const float x1 = bf16_round(a0), x2 = bf16_round(a1);              // qkv_proj output is bf16 in the reference flow
+                const int d = rope_grp * 16 + r;
+                const size_t ti = (size_t)(b / p.row_div) * p.tab_bstride + (size_t)pos * half + d;
+                const float cs = p.cosT[ti], sn = p.sinT[ti];
+                const bf16 o1 = __float2bfloat16_rn(x1 * cs - x2 * sn), o2 = __float2bfloat16_rn(x2 * cs + x1 * sn);
+                row[rope_head * p.hd + d] = o1;
+                row[rope_head * p.hd + half + d] = o2;
+                if (kd && rope_head >= p.n_heads) {
+                    bf16* k = kd + (size_t)(rope_head - p.n_heads) * P3_PAGE * p.hd;
+                    k[d] = o1; k[half + d] = o2;
+                }
+            } else {                                                               // v rows: copy to qkv buffer + cache
+                const int c0 = out_col0 - (p.n_heads + p.n_kv) * p.hd;             // column inside the V block
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    const bf16 v = __float2bfloat16_rn(mt == 0 ? a0 : a1);
+                    const int c = c0 + mt * 16 + r;
+                    row[(p.n_heads + p.n_kv) * p.hd + c] = v;
+                    if (vd) vd[(size_t)(c / p.hd) * P3_PAGE * p.hd + c % p.hd] = v;
+                }
+            }
+        }
+        (void)qkv_dim;
+    } else if (p.epi == P3_EPI_SWIGLU) {
         for (int o = tid; o < 8 * NT * 16; o += SK_THREADS) {
             int r = o & 15, tok = o >> 4;
             if (tok >= p.M) continue;
@@ -303,8 +375,10 @@ extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, fl
     P3_CHECK_ARG(epi != P3_EPI_RESIDUAL || resid, "gemm_skinny: residual epilogue needs resid");
     P3_CHECK_ARG(ldx % 8 == 0, "gemm_skinny: ldx must be a multiple of 8");
     P3_CHECK_ARG(!ss_out || (epi == P3_EPI_RESIDUAL && N < 148 * 32 * 2), "gemm_skinny: ss_out needs the 16-row residual configuration");
-    SkParams p{(const bf16*)X, ldx, (const bf16*)norm_w, eps, (const bf16*)W, out, ldo, (const bf16*)resid, M, N, K, epi,
-               ss_in, n_ss_in, ss_out};
+    SkParams p{};
+    p.X = (const bf16*)X; p.ldx = ldx; p.norm_w = (const bf16*)norm_w; p.eps = eps; p.W = (const bf16*)W; p.out = out;
+    p.ldo = ldo; p.resid = (const bf16*)resid; p.M = M; p.N = N; p.K = K; p.epi = epi;
+    p.ss_in = ss_in; p.n_ss_in = n_ss_in; p.ss_out = ss_out;
     if (epi == P3_EPI_SWIGLU) {
         P3_CHECK_ARG(N % 256 == 0, "gemm_skinny: SwiGLU needs N (gate+up rows) to be a multiple of 256");
         unsigned grid = (unsigned)(N / 2 / 16);
@@ -316,4 +390,26 @@ extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, fl
     }
     unsigned grid = (unsigned)((N + 15) / 16);
     return M <= 8 ? launch_skinny<1, 1>(p, grid, st) : launch_skinny<2, 1>(p, grid, st);
+}
+
+// qkv_proj + SuRoPE + paged KV write in one launch (decode, B*L <= 16 tokens): phi.py:442-453.
+extern "C" int p3_gemm_skinny_qkv_rope(const void* X, int64_t ldx, const void* norm_w, float eps, const void* Wqkv,
+                                       void* qkv, const float* ss_in, int n_ss_in, const float* cosT, const float* sinT,
+                                       int64_t tab_bstride, int B, int L, int n_heads, int n_kv, int hd, int K, int past,
+                                       const int32_t* past_dev, int row_div, void* pool, const int32_t* block_table,
+                                       int bt_stride, int write_cache, cudaStream_t st) {
+    const int M = B * L;
+    P3_CHECK_ARG(M >= 1 && M <= 16, "gemm_skinny_qkv_rope: B*L must be in [1,16] (got %d)", M);
+    P3_CHECK_ARG(K % 64 == 0 && ldx % 8 == 0, "gemm_skinny_qkv_rope: K %% 64 and ldx %% 8 required");
+    P3_CHECK_ARG(hd % 32 == 0 && (n_kv * hd) % 32 == 0, "gemm_skinny_qkv_rope: head_dim must be a multiple of 32");
+    P3_CHECK_ARG(!write_cache || (pool && block_table), "gemm_skinny_qkv_rope: cache write needs pool and block table");
+    SkParams p{};
+    p.X = (const bf16*)X; p.ldx = ldx; p.norm_w = (const bf16*)norm_w; p.eps = eps; p.W = (const bf16*)Wqkv; p.out = qkv;
+    p.ldo = (int64_t)(n_heads + 2 * n_kv) * hd; p.M = M; p.N = (n_heads + 2 * n_kv) * hd; p.K = K; p.epi = P3_EPI_ROPE_QKV;
+    p.ss_in = ss_in; p.n_ss_in = n_ss_in;
+    p.cosT = cosT; p.sinT = sinT; p.tab_bstride = tab_bstride; p.L = L; p.n_heads = n_heads; p.n_kv = n_kv; p.hd = hd;
+    p.past = past; p.past_dev = past_dev; p.row_div = row_div; p.write_cache = write_cache;
+    p.pool = (bf16*)pool; p.block_table = block_table; p.bt_stride = bt_stride;
+    unsigned grid = (unsigned)((n_heads + n_kv) * (hd / 32) + n_kv * hd / 32);
+    return M <= 8 ? launch_skinny<1, 2>(p, grid, st) : launch_skinny<2, 2>(p, grid, st);
 }

@@ -267,8 +267,8 @@ class Phi3B200:
             if n_splits is None:
                 n_splits = pick_splits(B * self.n_heads, max(1, (past + PAGE - 1) // PAGE))
             if n_splits > 1:
-                ws = torch.empty(_lib.lib().p3_attention_decode_workspace(B, L, self.n_heads, self.hd, n_splits) // 4,
-                                 dtype=torch.float32, device=dev)
+                ws = torch.zeros(_lib.lib().p3_attention_decode_workspace(B, L, self.n_heads, self.hd, n_splits) // 4,
+                                 dtype=torch.float32, device=dev)        # zero: holds the split-arrival counters
         qoff, koff, voff = 0, self.n_heads * self.hd * 2, (self.n_heads + self.n_kv) * self.hd * 2
         if cache is not None:
             cosT, sinT, tbs = cache.cos, cache.sin, cache.tab_bstride
@@ -277,9 +277,17 @@ class Phi3B200:
             cosT, sinT, tbs, bt, bts, kvs = self._nc_cos, self._nc_sin, self._nc_tbs, None, 0, self._nc_kvs
         for li, lw in enumerate(self.layers):
             pool = cache.pool[li] if cache is not None else None
-            self.linear(h, lw['qkv'], qkv, _lib.EPI_NONE, norm_w=lw['ln1'], ss_in=ss_cur)
-            call('p3_rope_kvwrite', ptr(qkv), ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads, self.n_kv, self.hd, past,
-                 n_beam, ptr(pool), ptr(bt), bts, 1 if (write_cache and cache is not None) else 0, ptr(past_dev), st)
+            wc = 1 if (write_cache and cache is not None) else 0
+            if T <= 16:                                   # decode: qkv_proj + rope + KV write in one launch
+                ev = self._ev()
+                call('p3_gemm_skinny_qkv_rope', ptr(h), h.stride(0), ptr(lw['ln1']), self.eps, ptr(lw['qkv']), ptr(qkv),
+                     ptr(ss_cur), 0 if ss_cur is None else ss_cur.shape[0], ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads,
+                     self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, st)
+                self._ev(ev, 'skinny', self.qkv_dim * H * 2)
+            else:
+                self.linear(h, lw['qkv'], qkv, _lib.EPI_NONE, norm_w=lw['ln1'], ss_in=ss_cur)
+                call('p3_rope_kvwrite', ptr(qkv), ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads, self.n_kv, self.hd, past,
+                     n_beam, ptr(pool), ptr(bt), bts, wc, ptr(past_dev), st)
             qp = qkv.data_ptr()
             ev = self._ev() if use_decode_attn else None
             if use_decode_attn:

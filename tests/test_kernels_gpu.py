@@ -259,7 +259,7 @@ def test_attention_decode(dev, cfg):
                                                  torch.zeros(nseq, 1, dtype=torch.int32, device=dev))
     out = torch.zeros(B * Lq, H * D, device=dev, dtype=torch.bfloat16)
     nb = L.lib().p3_attention_decode_workspace(B, Lq, H, D, n_splits)
-    ws = torch.empty(nb // 4, device=dev)
+    ws = torch.zeros(nb // 4, device=dev)
     p = qkv.data_ptr()
     L.call('p3_attention_decode', p, p + H * D * 2, p + 2 * H * D * 2, 3 * H * D, 3 * H * D, 3 * H * D, out.data_ptr(),
            H * D, B, Lq, H, H, D, D ** -0.5, past, kv_start.data_ptr(), pool.data_ptr(), bt.data_ptr(), bt.stride(0),
@@ -380,3 +380,35 @@ def test_skinny_ss_partials_feed_fused_rmsnorm(dev):
     L.call('p3_embed_gather', tab.data_ptr(), ids.data_ptr(), out.data_ptr(), 3, H, 50, sse.data_ptr(), st())
     torch.cuda.synchronize()
     assert (sse[:3] - tab[ids.long()].float().pow(2).sum(-1)).abs().max() < 1e-2
+
+
+@pytest.mark.parametrize('M', [(2, 1), (8, 1), (2, 5), (12, 1)])
+def test_fused_qkv_rope_matches_unfused(dev, M):
+    """p3_gemm_skinny_qkv_rope == p3_gemm_skinny (norm fused) followed by p3_rope_kvwrite."""
+    L = _mods()
+    B, Lq = M
+    T, H, nh, D, past, S = B * Lq, 3072, 32, 96, 70, 160
+    torch.manual_seed(9)
+    x = bf(torch.randn(T, H, device=dev))
+    nw = bf(1 + 0.1 * torch.randn(H, device=dev))
+    w = bf(torch.randn(3 * nh * D, H, device=dev) * H ** -0.5)
+    ang = torch.rand(B, S, D // 2, device=dev) * 6
+    cos, sin = (torch.cos(ang) * 1.19).contiguous(), (torch.sin(ang) * 1.19).contiguous()
+    pps = (S + 63) // 64
+    bt = torch.arange(B * pps, dtype=torch.int32, device=dev).reshape(B, pps)
+    pool1 = torch.zeros(B * pps, 2, nh, 64, D, device=dev, dtype=torch.bfloat16)
+    pool2 = torch.zeros_like(pool1)
+    q1 = torch.zeros(T, 3 * nh * D, device=dev, dtype=torch.bfloat16)
+    q2 = torch.zeros_like(q1)
+    L.call('p3_gemm_skinny', x.data_ptr(), H, nw.data_ptr(), 1e-5, w.data_ptr(), q1.data_ptr(), 3 * nh * D, None, T, 3 * nh * D, H, 0,
+           None, 0, None, st())
+    L.call('p3_rope_kvwrite', q1.data_ptr(), cos.data_ptr(), sin.data_ptr(), S * (D // 2), B, Lq, nh, nh, D, past, 1,
+           pool1.data_ptr(), bt.data_ptr(), pps, 1, None, st())
+    L.call('p3_gemm_skinny_qkv_rope', x.data_ptr(), H, nw.data_ptr(), 1e-5, w.data_ptr(), q2.data_ptr(), None, 0, cos.data_ptr(),
+           sin.data_ptr(), S * (D // 2), B, Lq, nh, nh, D, H, past, None, 1, pool2.data_ptr(), bt.data_ptr(), pps, 1, st())
+    torch.cuda.synchronize()
+    tol = 2 ** -7 * q1.float().abs().max()
+    assert (q1.float() - q2.float()).abs().max() <= tol
+    assert (q1 != q2).float().mean() < 0.01
+    assert (pool1.float() - pool2.float()).abs().max() <= tol
+    assert (pool2 != 0).any()
