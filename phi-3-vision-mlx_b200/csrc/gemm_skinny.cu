@@ -40,19 +40,19 @@ struct SkParams {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 
-template <int NT, int MT>
+template <int NT, int MT, int DEPTH_>
 struct SkCfg {
     static constexpr int W_SLOTS = 4 * MT, X_SLOTS = 2 * NT;
     static constexpr int STAGE = (W_SLOTS + X_SLOTS) * 512 + 128;            // + 128 B of norm gains
-    static constexpr int DEPTH = (MT == 1) ? (NT == 1 ? 4 : 3) : 2;   // keeps 2 CTAs/SM (<= ~110 KB each)
+    static constexpr int DEPTH = DEPTH_;
     static constexpr int RING = SK_WARPS * DEPTH * STAGE;
     static constexpr int RED = SK_WARPS * MT * 8 * NT * 17 * 4;
     static constexpr int SMEM = RING > RED ? RING : RED;
 };
 
-template <int NT, int MT>
-__global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) {
-    using C = SkCfg<NT, MT>;
+template <int NT, int MT, int DEPTH>
+__global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112 * 1024) ? 2 : 1) gemm_skinny_kernel(SkParams p) {
+    using C = SkCfg<NT, MT, DEPTH>;
     extern __shared__ __align__(128) uint8_t sk_smem[];
     __shared__ float s_rs[16];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -184,6 +184,12 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
         __syncthreads();
     }
 
+    // RESIDUAL epilogue (MT == 1): this thread's output element is known up front -> fetch the residual now
+    float resid_pref = 0.f;
+    if (p.epi == P3_EPI_RESIDUAL && MT == 1 && tid < 8 * NT * 16) {
+        int r = tid & 15, tok = tid >> 4, n = out_col0 + r;
+        if (tok < p.M && n < p.N) resid_pref = __bfloat162float(p.resid[(size_t)tok * p.ldo + n]);
+    }
     float acc[MT][NT][4];
 #pragma unroll
     for (int mt = 0; mt < MT; mt++)
@@ -334,7 +340,7 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
                 if (p.epi == P3_EPI_F32) {
                     reinterpret_cast<float*>(p.out)[off] = s;
                 } else if (p.epi == P3_EPI_RESIDUAL) {
-                    float rv = __bfloat162float(p.resid[off]);
+                    float rv = (MT == 1) ? resid_pref : __bfloat162float(p.resid[off]);
                     bf16 hv = __float2bfloat16_rn(rv + bf16_round(s));
                     reinterpret_cast<bf16*>(p.out)[off] = hv;
                     sq = __bfloat162float(hv) * __bfloat162float(hv);
@@ -351,18 +357,38 @@ __global__ void __launch_bounds__(SK_THREADS, 2) gemm_skinny_kernel(SkParams p) 
     }
 }
 
-template <int NT, int MT>
-static int launch_skinny(const SkParams& p, unsigned grid, cudaStream_t st) {
-    using C = SkCfg<NT, MT>;
+template <int NT, int MT, int DEPTH>
+static int launch_skinny_d(const SkParams& p, unsigned grid, cudaStream_t st) {
+    using C = SkCfg<NT, MT, DEPTH>;
     static bool set = false;
     if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel<NT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel<NT, MT, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         P3_CHECK_ARG(e == cudaSuccess, "gemm_skinny: smem attribute: %s", cudaGetErrorString(e));
         set = true;
     }
-    p3_launch_pdl(gemm_skinny_kernel<NT, MT>, dim3(grid), dim3(SK_THREADS), (size_t)C::SMEM, st, p);
+    p3_launch_pdl(gemm_skinny_kernel<NT, MT, DEPTH>, dim3(grid), dim3(SK_THREADS), (size_t)C::SMEM, st, p);
     P3_CHECK_LAUNCH("gemm_skinny");
     return 0;
+}
+
+// ring depth: default keeps 2 CTAs/SM; P3_SK_DEPTH overrides (tuning only)
+static int sk_depth_override() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("P3_SK_DEPTH"); v = e ? atoi(e) : 0; }
+    return v;
+}
+template <int NT, int MT>
+static int launch_skinny(const SkParams& p, unsigned grid, cudaStream_t st) {
+    int d = sk_depth_override();
+    if (d == 0) d = (MT == 1) ? (NT == 1 ? 4 : 3) : 2;
+    switch (d) {
+        case 2: return launch_skinny_d<NT, MT, 2>(p, grid, st);
+        case 3: return launch_skinny_d<NT, MT, 3>(p, grid, st);
+        case 4: return launch_skinny_d<NT, MT, 4>(p, grid, st);
+        case 6: return launch_skinny_d<NT, MT, 6>(p, grid, st);
+        case 8: return launch_skinny_d<NT, MT, (MT == 1 ? 8 : 4)>(p, grid, st);
+        default: return launch_skinny_d<NT, MT, 2>(p, grid, st);
+    }
 }
 
 extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, void* out,

@@ -26,17 +26,23 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def pick_splits(n_bh, tiles, slots=2 * 148, min_tiles=3, max_splits=32):
-    """Split-KV factor for decode attention: fill whole waves of the 2-CTA/SM grid (296 slots) while
-    keeping >= min_tiles 64-token pages per split. Returns the split count with the best wave efficiency."""
-    best, best_eff = 1, 0.0
+def pick_splits(n_bh, tiles, slots=2 * 148, max_splits=32):
+    """Split-KV factor for decode attention from a cost model fitted to tools/microbench.py on B200:
+        T(s) = 2 us + 2.5 us * waves + bytes / min(5.95 TB/s, concurrent_CTAs * 34 GB/s)
+    (waves = ceil(n_bh*s / 296 resident CTAs); one CTA alone sustains ~34 GB/s from its 72 KB in
+    flight). Long streams per CTA beat full waves: 256 CTAs x 34 pages reach 91 % of the measured
+    HBM peak, 2048 CTAs x 4 pages only 62 %."""
+    best, best_t = 1, float('inf')
+    total_mb = n_bh * tiles * 24.576e-3
     for s in range(1, max_splits + 1):
-        if s > 1 and tiles // s < min_tiles:
+        if s > 1 and tiles / s < 2:
             break
-        waves = n_bh * s / slots
-        eff = waves / max(1.0, float(-(-n_bh * s // slots)))
-        if eff > best_eff + 0.02:
-            best, best_eff = s, eff
+        ctas = n_bh * s
+        waves = -(-ctas // slots)
+        bw = min(5950.0, min(ctas, slots) * 34.0)                 # GB/s
+        t = 2.0 + 2.5 * waves + total_mb / bw * 1e3               # us
+        if t < best_t * 0.98:
+            best, best_t = s, t
     return best
 
 
