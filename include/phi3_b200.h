@@ -107,12 +107,15 @@ int p3_attention_prefill(const void* q, const void* k, const void* v, int64_t ld
 /* Decode-time attention for L<=16 new tokens per row over a paged KV cache (split-KV):
  * phi:454-457 with KVCache reads phi:523-527 (n_beam shared prefix: row_div) / phi:548.
  * workspace: p3_attention_decode_workspace() bytes, MUST be zero-filled once before first use (it holds the
- * split-arrival counters, which the kernel resets itself); needed when n_splits > 1. */
+ * split-arrival counters, which the kernel resets itself); needed when n_splits > 1.
+ * l2_prefetch (may be NULL): l2_prefetch_bytes of the NEXT kernel's weights (o_proj) that the CTAs pull into
+ * L2 (prefetch.global.L2::evict_last) while the KV pages stream. */
 int64_t p3_attention_decode_workspace(int B, int L, int n_heads, int hd, int n_splits);
 int p3_attention_decode(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* out,
                         int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale, int past,
                         const int32_t* kv_start, const void* pool, const int32_t* block_table, int bt_stride,
-                        int row_div, int n_splits, void* workspace, const int32_t* past_dev, cudaStream_t st);
+                        int row_div, int n_splits, void* workspace, const int32_t* past_dev, const void* l2_prefetch,
+                        int64_t l2_prefetch_bytes, cudaStream_t st);
 
 /* 4-bit g32 KV-cache quantisation (mx.quantize/dequantize, phi:532,536-537). Quantises the
  * first n_tokens positions of the bf16 pool pages of each cache row in place into a q4 pool
@@ -123,7 +126,8 @@ int p3_attention_decode_q4(const void* q, const void* k, const void* v, int64_t 
                            void* out, int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale, int past,
                            int n_quant, const int32_t* kv_start, const void* pool, const void* qcodes,
                            const void* qmeta, const int32_t* block_table, int bt_stride, int row_div, int n_splits,
-                           void* workspace, const int32_t* past_dev, cudaStream_t st);
+                           void* workspace, const int32_t* past_dev, const void* l2_prefetch, int64_t l2_prefetch_bytes,
+                           cudaStream_t st);
 
 /* Vision front end. */
 /* PIL BILINEAR resize (phi:299), white pad to x336 (phi:300-306), (x/255-mean)/std (phi:309):

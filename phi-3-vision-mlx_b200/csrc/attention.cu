@@ -37,6 +37,7 @@ struct AttnParams {
     // decode only
     int n_splits, tiles_per_split;
     float* ws_o; float* ws_ml;
+    const uint8_t* l2_prefetch; int64_t l2_prefetch_bytes;   // next kernel's weights (o_proj) pulled into L2 while KV streams
     int* counters;              // [B*n_heads] split-arrival counters (zero on entry, reset by the merging CTA)
     // quantised-cache decode: positions [0, n_quant) (multiple of 64) live in the q4 pools
     int n_quant;
@@ -364,9 +365,21 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
     const int vr = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;   // V row for PV
     const int pr_k = (lane >> 4) * 8 + (lane & 7), pr_v = (lane & 7) + ((lane >> 3) & 1) * 8;  // present tile rows
 
+    // The o_proj weights (18.9 MB at Phi-3.5 sizes) are too small to stream efficiently on their own and
+    // cannot be prefetched by their own kernel while this one holds the SMs' shared memory, so each
+    // CTA pulls its slice of them into L2 three quarters of the way through its KV stream.
+    const int pf_iter = (n_iter * 3) / 4;
     for (int it = 0; it < n_iter; it++) {
         cp_async_wait<DEC_STAGES - 2>();
         __syncthreads();
+        if (it == pf_iter && p.l2_prefetch) {
+            const int64_t n_cta = (int64_t)gridDim.x * gridDim.y * gridDim.z;
+            const int64_t cta = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            const int64_t lines = (p.l2_prefetch_bytes + 127) / 128;
+            const int64_t per = (lines + n_cta - 1) / n_cta;
+            for (int64_t i = cta * per + tid; i < min((cta + 1) * per, lines); i += 128)
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p.l2_prefetch + i * 128));
+        }
         {   // refill the stage that was consumed in the previous iteration
             const int nx = it + DEC_STAGES - 1;
             if (nx < n_cached) {
@@ -583,6 +596,7 @@ static int fill_params(AttnParams& p, const void* q, const void* k, const void* 
     p.causal = causal; p.past = past; p.past_host = past; p.past_dev = nullptr; p.kv_start = kv_start;
     p.pool = (const bf16*)pool; p.block_table = block_table; p.bt_stride = bt_stride; p.row_div = row_div;
     p.n_splits = 1; p.tiles_per_split = 0; p.ws_o = nullptr; p.ws_ml = nullptr; p.counters = nullptr;
+    p.l2_prefetch = nullptr; p.l2_prefetch_bytes = 0;
     p.n_quant = 0; p.qcodes = nullptr; p.qmeta = nullptr;
     return 0;
 }
@@ -649,11 +663,12 @@ extern "C" int p3_attention_decode(const void* q, const void* k, const void* v, 
                                    void* out, int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale,
                                    int past, const int32_t* kv_start, const void* pool, const int32_t* block_table,
                                    int bt_stride, int row_div, int n_splits, void* workspace, const int32_t* past_dev,
-                                   cudaStream_t st) {
+                                   const void* l2_prefetch, int64_t l2_prefetch_bytes, cudaStream_t st) {
     AttnParams p;
     if (fill_params(p, q, k, v, ldq, ldk, ldv, out, ldo, B, L, n_heads, n_kv, hd, scale, 1, past, kv_start, pool,
                     block_table, bt_stride, row_div)) return -1;
     p.past_dev = past_dev;
+    p.l2_prefetch = (const uint8_t*)l2_prefetch; p.l2_prefetch_bytes = l2_prefetch_bytes;
     return decode_common(p, L, past, n_splits, workspace, false, st);
 }
 
@@ -661,7 +676,8 @@ extern "C" int p3_attention_decode_q4(const void* q, const void* k, const void* 
                                       void* out, int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale,
                                       int past, int n_quant, const int32_t* kv_start, const void* pool, const void* qcodes,
                                       const void* qmeta, const int32_t* block_table, int bt_stride, int row_div,
-                                      int n_splits, void* workspace, const int32_t* past_dev, cudaStream_t st) {
+                                      int n_splits, void* workspace, const int32_t* past_dev, const void* l2_prefetch,
+                                      int64_t l2_prefetch_bytes, cudaStream_t st) {
     AttnParams p;
     if (fill_params(p, q, k, v, ldq, ldk, ldv, out, ldo, B, L, n_heads, n_kv, hd, scale, 1, past, kv_start, pool,
                     block_table, bt_stride, row_div)) return -1;
@@ -669,5 +685,6 @@ extern "C" int p3_attention_decode_q4(const void* q, const void* k, const void* 
     P3_CHECK_ARG(n_quant == 0 || (qcodes && qmeta), "attention_decode_q4: q4 pools missing");
     p.n_quant = n_quant; p.qcodes = (const uint8_t*)qcodes; p.qmeta = (const bf16*)qmeta;
     p.past_dev = past_dev;
+    p.l2_prefetch = (const uint8_t*)l2_prefetch; p.l2_prefetch_bytes = l2_prefetch_bytes;
     return decode_common(p, L, past, n_splits, workspace, true, st);
 }

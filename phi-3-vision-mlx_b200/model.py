@@ -54,27 +54,66 @@ def interleave_gate_up(w):
     return torch.stack([g, u], dim=1).reshape(2 * I, -1).contiguous()
 
 
-class KVCacheB200(list):
-    """Opaque cache handle returned to the decode drivers (the reference returns a list of
-    per-layer KVCache objects, phi:581; drivers only pass it back). `self[0].offset` works."""
+class _KVSlab:
+    """Device buffers behind one KV cache shape (B, L, max_tokens): page pool, block table, rope
+    tables, decode-loop state and the captured decode-step CUDA graph. Slabs are recycled through
+    `Phi3B200._slabs` when the cache object that borrowed them is dropped, so repeated generate()
+    calls of the same shape neither re-allocate (7 GB at 8 x 2304 tokens) nor re-capture."""
 
-    def __init__(self, cfg, B, L, max_tokens, dev, quantized):
-        super().__init__([self])
+    def __init__(self, cfg, B, L, max_tokens, dev):
         nl, nkv = cfg.num_hidden_layers, cfg.num_key_value_heads
         hd = cfg.hidden_size // cfg.num_attention_heads
-        self.B, self.S_max, self.max_tokens = B, L + max_tokens, max_tokens
-        self.offset = 0
-        self.quantized, self.n_quant = quantized, 0
-        self.pages_per_seq = (self.S_max + PAGE - 1) // PAGE
+        self.pages_per_seq = (L + max_tokens + PAGE - 1) // PAGE
         n_pages = B * self.pages_per_seq
-        # zero-initialised: masked slots must hold finite values (0 * NaN would poison P.V)
+        # zero-initialised: masked slots must hold finite values (0 * NaN would poison P.V); recycled
+        # slabs only ever contain finite bf16 values written by the kernels
         self.pool = torch.zeros((nl, n_pages, 2, nkv, PAGE, hd), dtype=torch.bfloat16, device=dev)
         self.block_table = torch.arange(n_pages, dtype=torch.int32, device=dev).reshape(B, self.pages_per_seq)
         self.kv_start = torch.zeros(B, dtype=torch.int32, device=dev)
         self.cos = self.sin = None
-        self.tab_bstride = 0
         self.qcodes = self.qmeta = None
-        self.past_dev = None                 # device copy of offset (CUDA-graph decode)
+        self.session = None                  # DecodeSession state + graph, keyed by max_steps
+
+
+class KVCacheB200(list):
+    """Opaque cache handle returned to the decode drivers (the reference returns a list of
+    per-layer KVCache objects, phi:581; drivers only pass it back). `self[0].offset` works."""
+
+    def __init__(self, model, B, L, max_tokens, quantized):
+        super().__init__([self])
+        self.B, self.S_max, self.max_tokens = B, L + max_tokens, max_tokens
+        self.offset = 0
+        self.quantized, self.n_quant = quantized, 0
+        self._key = (B, L, max_tokens, bool(quantized))
+        self._slabs = model._slabs
+        free = self._slabs.get(self._key)
+        self.slab = free.pop() if free else _KVSlab(model.cfg, B, L, max_tokens, model.dev)
+        sl = self.slab
+        self.pages_per_seq, self.pool, self.block_table, self.kv_start = sl.pages_per_seq, sl.pool, sl.block_table, sl.kv_start
+        self.cos = self.sin = None
+        self.tab_bstride = 0
+        self.qcodes, self.qmeta = sl.qcodes, sl.qmeta
+
+    def set_tables(self, cos, sin, tbs, kvs):
+        """Copy per-call tables into the slab's static buffers (addresses stay fixed for the graph)."""
+        sl = self.slab
+        if sl.cos is None or sl.cos.shape != cos.shape:
+            sl.cos, sl.sin, sl.session = cos.clone(), sin.clone(), None
+        else:
+            sl.cos.copy_(cos); sl.sin.copy_(sin)
+        sl.kv_start.copy_(kvs)
+        self.cos, self.sin, self.tab_bstride = sl.cos, sl.sin, tbs
+
+    def __del__(self):
+        try:
+            if self._key not in self._slabs and len(self._slabs) >= 6:      # bound the recycled memory
+                self._slabs.pop(next(iter(self._slabs)))
+            lst = self._slabs.setdefault(self._key, [])
+            if len(lst) < 2 and self.slab is not None:
+                self.slab.qcodes, self.slab.qmeta = self.qcodes, self.qmeta
+                lst.append(self.slab)
+        except Exception:
+            pass
 
 
 class Phi3B200:
@@ -109,6 +148,7 @@ class Phi3B200:
         self.vision = None
         if any(k.startswith('model.vision_embed_tokens') for k in w):
             self._load_vision(w, d)
+        self._slabs = {}              # recycled KV slabs, keyed by (B, L, max_tokens, quantized)
         self.force_long_rope = None   # parallel.py: LongRoPE switch decided from the global batch (H7)
         self.profile = None      # bench.py: list of (kind, ev0, ev1, algorithmic_bytes) when instrumenting
 
@@ -296,16 +336,18 @@ class Phi3B200:
                      n_beam, ptr(pool), ptr(bt), bts, wc, ptr(past_dev), st)
             qp = qkv.data_ptr()
             ev = self._ev() if use_decode_attn else None
+            pf_bytes = lw['o'].numel() * 2 if T <= 16 else 0      # o_proj weights ride into L2 behind the KV stream
             if use_decode_attn:
                 if cache.quantized and cache.n_quant > 0:
                     call('p3_attention_decode_q4', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim,
                          self.qkv_dim, ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale,
                          past, cache.n_quant, ptr(kvs), ptr(pool), ptr(cache.qcodes[li]), ptr(cache.qmeta[li]), ptr(bt),
-                         bts, n_beam, n_splits, ptr(ws), ptr(past_dev), st)
+                         bts, n_beam, n_splits, ptr(ws), ptr(past_dev), ptr(lw['o']), pf_bytes, st)
                 else:
                     call('p3_attention_decode', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim,
                          self.qkv_dim, ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale,
-                         past, ptr(kvs), ptr(pool), ptr(bt), bts, n_beam, n_splits, ptr(ws), ptr(past_dev), st)
+                         past, ptr(kvs), ptr(pool), ptr(bt), bts, n_beam, n_splits, ptr(ws), ptr(past_dev), ptr(lw['o']),
+                         pf_bytes, st)
             else:
                 call('p3_attention_prefill', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim, self.qkv_dim,
                      ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale, 1, past, ptr(kvs),
@@ -350,8 +392,8 @@ class Phi3B200:
                 self._nc_cos, self._nc_sin, self._nc_tbs, self._nc_kvs = cos, sin, tbs, kvs
                 logits = self._forward_tokens(ids_dev, B, L, None, 1, False, 0, logits_rows, h=h)
                 return logits, None
-            cache = KVCacheB200(self.cfg, B, L, max_tokens, self.dev, self.use_quantized_cache)
-            cache.cos, cache.sin, cache.tab_bstride, cache.kv_start = cos, sin, tbs, kvs
+            cache = KVCacheB200(self, B, L, max_tokens, self.use_quantized_cache)
+            cache.set_tables(cos, sin, tbs, kvs)
         if n_beam > 1 and cache.quantized and not getattr(self.cfg, 'allow_beam_with_quantized_cache', False):
             raise NotImplementedError('Beam Search is not yet compatible with Quantized Cache')   # phi:524-525
         past = cache.offset
@@ -371,9 +413,10 @@ class Phi3B200:
     def _quantize_prompt(self, cache, n_tokens):
         """mx.quantize of the prompt K,V (phi:531-533): later steps read the 4-bit image."""
         nl, n_pages = cache.pool.shape[0], cache.pool.shape[1]
-        cache.qcodes = torch.zeros((nl, n_pages, 2, self.n_kv, PAGE, self.hd // 2), dtype=torch.uint8, device=self.dev)
-        cache.qmeta = torch.zeros((nl, n_pages, 2, self.n_kv, PAGE, self.hd // 32, 2), dtype=torch.bfloat16,
-                                  device=self.dev)
+        if cache.qcodes is None:
+            cache.qcodes = torch.zeros((nl, n_pages, 2, self.n_kv, PAGE, self.hd // 2), dtype=torch.uint8, device=self.dev)
+            cache.qmeta = torch.zeros((nl, n_pages, 2, self.n_kv, PAGE, self.hd // 32, 2), dtype=torch.bfloat16,
+                                      device=self.dev)
         for li in range(nl):
             call('p3_kv_quantize_q4g32', ptr(cache.pool[li]), ptr(cache.qcodes[li]), ptr(cache.qmeta[li]),
                  ptr(cache.block_table), cache.block_table.stride(0), cache.B, n_tokens, self.n_kv, self.hd, _stream())
@@ -398,23 +441,31 @@ class DecodeSession:
     """One CUDA graph = one greedy decode step (embed -> 32 layers -> lm_head -> argmax -> bookkeeping).
     `past`, the step counter, the current token and the token history live on the device, so
     replaying the graph advances generation with zero host synchronisation (the reference syncs
-    at mx.eval and `eos_id in token` every token, pv:393,397,113)."""
+    at mx.eval and `eos_id in token` every token, pv:393,397,113). The state buffers and the graph
+    live in the cache's slab and are reused by later sessions of the same shape."""
 
     def __init__(self, model, first_token, cache, max_steps, use_graph=True):
         self.m, self.cache, self.max_steps = model, cache, max_steps
         B = cache.B
         dev = model.dev
         self.B = B
-        self.hist = torch.zeros((B, max_steps + 1), dtype=torch.int32, device=dev)
         first_token = first_token.to(dev, torch.int32).reshape(B).contiguous()
-        self.hist[:, 0] = first_token
-        self.tok = first_token.clone()
-        self.step_dev = torch.ones(1, dtype=torch.int32, device=dev)
-        self.past_dev = torch.full((1,), cache.offset, dtype=torch.int32, device=dev)
-        self.eos = (first_token == 32007).to(torch.int32)
         self.steps_run = 0
         self.graph = None
         self.launches_per_step = 0
+        st = cache.slab.session if use_graph else None
+        if st is not None and st['max_steps'] == max_steps and st['offset0'] == cache.offset:
+            # recycled slab: same buffers, same graph -> just reset the device-side state
+            self.hist, self.tok, self.step_dev, self.past_dev, self.eos = st['hist'], st['tok'], st['step'], st['past'], st['eos']
+            self.n_splits, self.graph, self.launches_per_step = st['n_splits'], st['graph'], st['lps']
+            self._reset(first_token)
+            return
+        self.hist = torch.zeros((B, max_steps + 1), dtype=torch.int32, device=dev)
+        self.tok = first_token.clone()
+        self.step_dev = torch.ones(1, dtype=torch.int32, device=dev)
+        self.past_dev = torch.full((1,), cache.offset, dtype=torch.int32, device=dev)
+        self.eos = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._reset(first_token)
         if max_steps <= 0:
             return
         if cache.offset + max_steps > cache.S_max:
@@ -429,14 +480,22 @@ class DecodeSession:
                 self._one_step()                              # warm-up: smem attributes, allocator pools
             cur.wait_stream(s)
             torch.cuda.synchronize()
-            # the warm-up step really executed; roll the device state back before capture
-            self.step_dev.fill_(1); self.past_dev.fill_(cache.offset); self.tok.copy_(first_token)
-            self.eos.copy_((first_token == 32007).to(torch.int32))
+            self._reset(first_token)                          # the warm-up step really executed: roll back
             self.graph = torch.cuda.CUDAGraph()
             n0 = _lib.launches
             with torch.cuda.graph(self.graph):
                 self._one_step()
             self.launches_per_step = _lib.launches - n0
+            cache.slab.session = dict(max_steps=max_steps, offset0=cache.offset, hist=self.hist, tok=self.tok,
+                                      step=self.step_dev, past=self.past_dev, eos=self.eos, n_splits=self.n_splits,
+                                      graph=self.graph, lps=self.launches_per_step)
+
+    def _reset(self, first_token):
+        self.hist[:, 0] = first_token
+        self.tok.copy_(first_token)
+        self.step_dev.fill_(1)
+        self.past_dev.fill_(self.cache.offset)
+        self.eos.copy_((first_token == 32007).to(torch.int32))
 
     def _one_step(self):
         m = self.m
@@ -465,4 +524,4 @@ class DecodeSession:
 
     def finish(self):
         self.cache.offset = self.cache.offset + self.steps_run
-        return self.hist[:, :self.steps_run + 1]
+        return self.hist[:, :self.steps_run + 1].clone()      # the slab (and its hist buffer) is recycled

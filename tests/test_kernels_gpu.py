@@ -263,7 +263,7 @@ def test_attention_decode(dev, cfg):
     p = qkv.data_ptr()
     L.call('p3_attention_decode', p, p + H * D * 2, p + 2 * H * D * 2, 3 * H * D, 3 * H * D, 3 * H * D, out.data_ptr(),
            H * D, B, Lq, H, H, D, D ** -0.5, past, kv_start.data_ptr(), pool.data_ptr(), bt.data_ptr(), bt.stride(0),
-           n_beam, n_splits, ws.data_ptr(), None, st())
+           n_beam, n_splits, ws.data_ptr(), None, None, 0, st())
     x = qkv.view(B, Lq, 3, H, D).permute(2, 0, 3, 1, 4)
     kr, vr = kc.repeat_interleave(n_beam, 0), vc.repeat_interleave(n_beam, 0)
     q, k, v = x[0], torch.cat([kr, x[1]], 2), torch.cat([vr, x[2]], 2)

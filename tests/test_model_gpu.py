@@ -196,3 +196,29 @@ def test_full_size_config1(dev):
         lg, cg = m(tok[:, None], cache=cg)
         assert rms(lg, lo) < 2.5e-2
         tok = lo[:, -1].argmax(-1)
+
+
+def test_slab_recycling_and_graph_reuse(dev):
+    """Same-shape calls reuse the KV slab + captured decode graph; results must not depend on it,
+    and a cache the caller still holds must stay intact."""
+    cfg, w, m, o = _setup()
+    outs = []
+    for seed in (21, 22, 21):
+        ids = _ids(2, 70, seed=seed)
+        lg, c = m(ids, max_tokens=12, logits_rows='last')
+        first = lg[:, -1].argmax(-1)
+        hist = m.greedy_decode(first, c, 11)
+        outs.append(hist.cpu())
+        del c                                   # returns the slab to the pool
+    assert torch.equal(outs[0], outs[2]) and not torch.equal(outs[0], outs[1])
+    assert len(m._slabs[(2, 70, 12, False)]) == 1 and m._slabs[(2, 70, 12, False)][0].session is not None
+    # held cache is not clobbered by a second cache of the same shape
+    ids_a, ids_b = _ids(2, 70, seed=31), _ids(2, 70, seed=32)
+    la, ca = m(ids_a, max_tokens=12)
+    lb, cb = m(ids_b, max_tokens=12)
+    assert ca.pool.data_ptr() != cb.pool.data_ptr()
+    ta = la[:, -1].argmax(-1)
+    la2, _ = m(ta[:, None], cache=ca)
+    lo, co = o(ids_a, max_tokens=12)
+    lo2, _ = o(lo[:, -1].argmax(-1)[:, None], cache=co)
+    assert rel(la2, lo2) < TOL

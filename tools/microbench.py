@@ -66,7 +66,7 @@ def bench_attn():
             def fn(i):
                 _lib.call('p3_attention_decode', p, p + H * D * 2, p + 2 * H * D * 2, 3 * H * D, 3 * H * D, 3 * H * D,
                           out.data_ptr(), H * D, B, 1, H, H, D, D ** -0.5, S, kv0.data_ptr(), pools[i % copies].data_ptr(),
-                          bt.data_ptr(), pps, 1, ns, ws.data_ptr(), None, st())
+                          bt.data_ptr(), pps, 1, ns, ws.data_ptr(), None, None, 0, st())
             us = timeit(fn)
             gbs = B * S * 2 * H * D * 2 / us / 1e3
             print(f'attn_decode B={B:2d} S={S:5d} splits={ns:2d} ({B * H * ns:5d} CTAs)  {us:7.2f} us  {gbs:7.0f} GB/s  {100 * gbs / PEAK:5.1f}%')
