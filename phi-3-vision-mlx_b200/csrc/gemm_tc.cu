@@ -7,7 +7,8 @@
 //   warp 1   : MMA issuer    — one elected lane issues tcgen05.mma.cta_group::1.kind::f16
 //                              (UMMA 128 x BN x 16), accumulators in TMEM (2 x BN columns, double buffered)
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue      — tcgen05.ld 32x32b, fused bias / GELU / residual / SwiGLU / fp32 / row scatter
+//   warps 4-11: epilogue     — tcgen05.ld 32x32b (two warps per TMEM lane quarter, half the columns each),
+//                              fused bias / GELU / residual / SwiGLU / fp32 / row scatter
 // Both operands are K-major (activations [M,K] and nn.Linear weights [N,K]), so no transposes.
 #include "common.cuh"
 #include "../../include/phi3_b200.h"
@@ -26,7 +27,7 @@ struct GemmEpi {
 __device__ __forceinline__ float epi_act(int kind, float x) {
     // CLIP fc1 and the projector run in fp32 in the reference (fp32 activations x bf16 weights
     // promote to fp32), so the activation is applied to the unrounded accumulator.
-    if (kind == P3_EPI_QGELU) return x / (1.f + __expf(-1.702f * x));
+    if (kind == P3_EPI_QGELU) return __fdividef(x, 1.f + __expf(-1.702f * x));
     if (kind == P3_EPI_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
     return x;
 }
@@ -106,8 +107,16 @@ __device__ __forceinline__ void epi_store32(const GemmEpi& ep, int64_t orow, int
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(acc[i]);
     if (ep.bias) {
+        if (n0 + 32 <= N) {
+            uint4 bv[4];
 #pragma unroll
-        for (int i = 0; i < 32; i++) if (n0 + i < N) v[i] += __bfloat162float(ep.bias[n0 + i]);
+            for (int i = 0; i < 4; i++) bv[i] = __ldg(reinterpret_cast<const uint4*>(ep.bias + n0) + i);
+            const uint32_t* bu = reinterpret_cast<const uint32_t*>(bv);
+#pragma unroll
+            for (int i = 0; i < 16; i++) { float2 f = unpack_bf16(bu[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
+        } else {
+            for (int i = 0; i < 32; i++) if (n0 + i < N) v[i] += __bfloat162float(ep.bias[n0 + i]);
+        }
     }
     if (ep.kind == P3_EPI_F32 || ep.kind == P3_EPI_RESIDUAL_F32) {
         float* o = reinterpret_cast<float*>(ep.out) + orow * ep.ldo + n0;
@@ -166,7 +175,7 @@ __device__ __forceinline__ void epi_store32(const GemmEpi& ep, int64_t orow, int
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpi ep,
                int M, int N, int K) {
     using C = TcCfg<BN>;
@@ -191,7 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -242,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp >= 4) {
-        const int q = warp - 4;
+        const int q = warp & 3, half = (warp - 4) >> 2;       // TMEM lane quarter, column half
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int m_idx = (tile % m_tiles) * C::BM, n_idx = (tile / m_tiles) * BN;
@@ -254,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             if (ep.kind == P3_EPI_SWIGLU) {
                 // interleaved weights: columns [0,BN/2) gate, [BN/2,BN) matching up
-                for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+                for (int c0 = half * (BN / 4); c0 < (half + 1) * (BN / 4); c0 += 32) {
                     uint32_t g[32], u[32];
                     tc_ld32(taddr + c0, g);
                     tc_ld32(taddr + BN / 2 + c0, u);
@@ -280,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             } else {
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                     uint32_t v[32];
                     tc_ld32(taddr + c0, v);
                     if (row_ok && n_idx + c0 < N) epi_store32(ep, orow, n_idx + c0, N, v);
@@ -443,7 +452,7 @@ static int launch_tc(const void* X, int64_t ldx, const void* W, int64_t ldw, con
     }
     int64_t tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
     unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
-    gemm_tc_kernel<BN><<<grid, 256, C::SMEM, st>>>(ta, tb, ep, (int)M, N, K);
+    gemm_tc_kernel<BN><<<grid, 384, C::SMEM, st>>>(ta, tb, ep, (int)M, N, K);
     P3_CHECK_LAUNCH("gemm_tc");
     return 0;
 }
