@@ -63,6 +63,12 @@ int p3_row_stats(const float* logits, int64_t R, int64_t ld, int V, int32_t* arg
                  float* lse_out, int n_top, int32_t* topk_ids, float* topk_lp, int n_gather,
                  const int32_t* gather_ids, float* gather_lp, cudaStream_t st);
 
+/* Nucleus (top-p) sampling — extension: the reference decodes greedily only (pv:386,392).
+ * tau = largest probability v with sum_{p_i>=v} p_i >= top_p (exact bisection, no sort); token drawn by
+ * inverse CDF in index order over {p_i >= tau} with the caller's uniform u[R] in [0,1). tau_out may be NULL. */
+int p3_top_p_sample(const float* logits, int64_t R, int64_t ld, int V, float top_p, float temperature, const float* u,
+                    int32_t* out, float* tau_out, cudaStream_t st);
+
 /* Greedy-loop bookkeeping on the device (pv:390-398 without the two host syncs per token):
  * history[b][*step] = tok[b]; eos_seen[b] |= (tok[b]==32007); ++*step; ++*past (past may be NULL). */
 int p3_decode_advance(const int32_t* tok, int32_t* history, int64_t ld, int B, int32_t* step, int32_t* past,

@@ -355,3 +355,93 @@ extern "C" int p3_decode_advance(const int32_t* tok, int32_t* history, int64_t l
     P3_CHECK_LAUNCH("decode_advance");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// top_p_sample: nucleus sampling (north_star "top-p kernel"; the reference is greedy only, pv:386,392 —
+// this is an extension, SURVEY.md H13, validated against a torch restatement of the same rule).
+// Per row: p = softmax(logits / temperature); tau = the largest probability value v such that
+// sum_{p_i >= v} p_i >= top_p (exact: bisection over the float bit pattern, no sort); the token is
+// drawn by inverse CDF in INDEX order over the nucleus {i : p_i >= tau} with the supplied uniform u.
+// ------------------------------------------------------------------------------------------
+#define TP_THREADS 256
+__device__ __forceinline__ float block_sum_tp(float v, float* sh) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < TP_THREADS / 32; w++) t += sh[w];
+    return t;
+}
+
+__global__ void top_p_sample_kernel(const float* __restrict__ logits, int64_t ld, int V, float top_p, float inv_temp,
+                                    const float* __restrict__ u, int32_t* __restrict__ out, float* __restrict__ tau_out) {
+    __shared__ float sh[TP_THREADS / 32];
+    __shared__ float s_chunk[TP_THREADS];
+    __shared__ int s_pick;
+    pdl_trigger();
+    pdl_wait();
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const float* row = logits + (size_t)r * ld;
+    float mx = -INFINITY;
+    for (int i = tid; i < V; i += TP_THREADS) mx = fmaxf(mx, row[i] * inv_temp);
+    mx = warp_max(mx);
+    __syncthreads();
+    if ((tid & 31) == 0) sh[tid >> 5] = mx;
+    __syncthreads();
+    mx = sh[0];
+#pragma unroll
+    for (int w = 1; w < TP_THREADS / 32; w++) mx = fmaxf(mx, sh[w]);
+    float z = 0.f;
+    for (int i = tid; i < V; i += TP_THREADS) z += __expf(row[i] * inv_temp - mx);
+    z = block_sum_tp(z, sh);
+    const float inv_z = 1.f / z;
+    // bisection over bit patterns of positive floats in (0, 1]
+    uint32_t lo = 0u, hi = __float_as_uint(1.0f);           // f(lo) >= top_p always; find the largest v with f(v) >= top_p
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo + 1) / 2;
+        float thr = __uint_as_float(mid), m = 0.f;
+        for (int i = tid; i < V; i += TP_THREADS) { float p = __expf(row[i] * inv_temp - mx) * inv_z; if (p >= thr) m += p; }
+        m = block_sum_tp(m, sh);
+        if (m >= top_p) lo = mid; else hi = mid - 1;
+    }
+    const float tau = __uint_as_float(lo);
+    // inverse CDF in index order over the nucleus: contiguous chunk per thread
+    const int per = (V + TP_THREADS - 1) / TP_THREADS, i0 = tid * per, i1 = min(V, i0 + per);
+    float cs = 0.f;
+    for (int i = i0; i < i1; i++) { float p = __expf(row[i] * inv_temp - mx) * inv_z; if (p >= tau) cs += p; }
+    s_chunk[tid] = cs;
+    if (tid == 0) s_pick = -1;
+    __syncthreads();
+    if (tid == 0) {
+        float mass = 0.f;
+        for (int t = 0; t < TP_THREADS; t++) mass += s_chunk[t];
+        float target = u[r] * mass, acc = 0.f;
+        int t = 0;
+        for (; t < TP_THREADS - 1; t++) { if (acc + s_chunk[t] > target) break; acc += s_chunk[t]; }
+        s_pick = t;
+        s_chunk[0] = target - acc;                           // residual target inside the chosen chunk (slot 0 reused)
+    }
+    __syncthreads();
+    if (tid == s_pick) {
+        float target = s_chunk[0], acc = 0.f;
+        int last = -1, pick = -1;
+        for (int i = i0; i < i1; i++) {
+            float p = __expf(row[i] * inv_temp - mx) * inv_z;
+            if (p >= tau) { last = i; acc += p; if (pick < 0 && acc > target) pick = i; }
+        }
+        out[r] = pick >= 0 ? pick : last;
+        if (tau_out) tau_out[r] = tau;
+    }
+}
+
+extern "C" int p3_top_p_sample(const float* logits, int64_t R, int64_t ld, int V, float top_p, float temperature,
+                               const float* u, int32_t* out, float* tau_out, cudaStream_t st) {
+    P3_CHECK_ARG(top_p > 0.f && top_p <= 1.f && temperature > 0.f, "top_p_sample: need 0 < top_p <= 1 and temperature > 0");
+    if (R == 0) return 0;
+    p3_launch_pdl(top_p_sample_kernel, dim3((unsigned)R), dim3(TP_THREADS), 0, st, logits, ld, V, top_p, 1.f / temperature, u,
+                  out, tau_out);
+    P3_CHECK_LAUNCH("top_p_sample");
+    return 0;
+}

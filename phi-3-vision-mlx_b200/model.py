@@ -75,12 +75,20 @@ class _KVSlab:
         self.session = None                  # DecodeSession state + graph, keyed by max_steps
 
 
-class KVCacheB200(list):
+class KVCacheB200:
     """Opaque cache handle returned to the decode drivers (the reference returns a list of
-    per-layer KVCache objects, phi:581; drivers only pass it back). `self[0].offset` works."""
+    per-layer KVCache objects, phi:581; drivers only pass it back). Indexing returns the handle
+    itself so `cache[0].offset` works (no self-referencing list: the slab must be released by
+    reference counting the moment the caller drops the cache)."""
+
+    def __getitem__(self, i):
+        return self
+
+    def __len__(self):
+        return self.n_layers
 
     def __init__(self, model, B, L, max_tokens, quantized):
-        super().__init__([self])
+        self.n_layers = model.cfg.num_hidden_layers
         self.B, self.S_max, self.max_tokens = B, L + max_tokens, max_tokens
         self.offset = 0
         self.quantized, self.n_quant = quantized, 0
@@ -150,6 +158,7 @@ class Phi3B200:
             self._load_vision(w, d)
         self._slabs = {}              # recycled KV slabs, keyed by (B, L, max_tokens, quantized)
         self.force_long_rope = None   # parallel.py: LongRoPE switch decided from the global batch (H7)
+        self.prefill_chunk = 8192     # long prompts are prefilled in chunks against the paged cache (config 4: 128K)
         self.profile = None      # bench.py: list of (kind, ev0, ev1, algorithmic_bytes) when instrumenting
 
     # ------------------------------------------------------------------ vision weights
@@ -358,6 +367,8 @@ class Phi3B200:
             self.linear(h, lw['gu'], act, _lib.EPI_SWIGLU, norm_w=lw['ln2'], ss_in=ssB)
             self.linear(act, lw['down'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssA)
             ss_cur = ssA
+        if logits_rows == 'none':
+            return None
         if logits_rows == 'last':
             hl = h.view(B, L, H)[:, -1, :]
             R = 1
@@ -401,7 +412,20 @@ class Phi3B200:
             raise ValueError(f'KV cache overflow: {past}+{L} > {cache.S_max}')
         write = n_beam == 1
         first_fill = write and past == 0
-        logits = self._forward_tokens(ids_dev, B, L, cache, n_beam, write, past, logits_rows, h=h)
+        if write and logits_rows == 'last' and L > self.prefill_chunk:
+            # chunked prefill: keys [0, past+c0) come from the paged pool, the chunk's own keys from its
+            # qkv buffer; activations stay O(chunk) so a 128K prompt fits (the reference materialises
+            # L x L scores and an L x L mask and cannot run it)
+            ids2 = ids_dev.view(B, L)
+            h2 = None if h is None else h.view(B, L, self.H)
+            logits = None
+            for c0 in range(0, L, self.prefill_chunk):
+                c1 = min(L, c0 + self.prefill_chunk)
+                logits = self._forward_tokens(ids2[:, c0:c1].contiguous().reshape(-1), B, c1 - c0, cache, 1, True, past + c0,
+                                              'last' if c1 == L else 'none',
+                                              h=None if h2 is None else h2[:, c0:c1].contiguous().reshape(-1, self.H))
+        else:
+            logits = self._forward_tokens(ids_dev, B, L, cache, n_beam, write, past, logits_rows, h=h)
         if write:
             cache.offset = past + L                                               # phi:544-547
         if first_fill and cache.quantized:

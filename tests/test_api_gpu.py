@@ -144,3 +144,33 @@ def test_vision_generate_end_to_end(dev):
     hist = api._generate(model, proc, prompt, imgs, max_tokens=6, verbose=False, stream=False, mute=True, return_tokens=True)
     assert torch.equal(hist.cpu().long()[:, :2], ref[:, :2])
     assert (hist.cpu().long() == ref).float().mean() >= 0.8
+
+
+def test_constrain_beam_with_quantized_cache_extension(dev):
+    """BASELINE config 5 semantics (quantize_cache + use_beam), defined by extension: identical
+    to the bf16-cache algorithm with the prompt KV replaced by its 4-bit g32 image. n_beam 3 and 4."""
+    import phi3_b200  # noqa
+    from phi3_b200 import configs, weights, api
+    from phi3_b200.processor import ByteTokenizer
+    from oracle.phi3_oracle import Phi3Oracle
+    from oracle import drivers
+    cfg = configs.tiny(use_quantized_cache=True)
+    w = weights.random_weights(cfg, seed=3)
+    model, proc = api.load(blind_model=True, cfg=cfg, weights=w, tokenizer=ByteTokenizer(), quantize_cache=True,
+                           allow_beam_with_quantized_cache=True)
+    ora = Phi3Oracle(model.cfg, w, prec='b200')
+    prompts = [api._preprocess(p) for p in api._apply_chat_template(
+        ['A question that is long enough to fill more than one sixty-four token page of the cache, yes indeed it is',
+         'Another long question, also spanning more than a single page of the key value cache for sure, really'], None, False)[0]]
+    text = ' The answer is'
+    ids_c = list(proc.tokenizer.encode(text, add_special_tokens=False)[1:])
+    for nb in (3, 4):
+        inp = proc(prompts)
+        S = inp['input_ids'].shape[1]
+        assert S > 64
+        synth, _ = drivers.constrain_ids(ora, inp, ids_c, 4, use_beam=True, n_beam=nb)
+        ref_ids = torch.cat([inp['input_ids'], synth], 1).tolist()
+        ref_ids = [(r[:r.index(32007, S)] if 32007 in r[S:] else r) for r in ref_ids]
+        ref_ids = [[t for t in r if t not in (0, 1)] for r in ref_ids]
+        got = api._constrain(model, proc, prompts, [(4, text)], mute=True, verbose=False, use_beam=True, n_beam=nb, return_ids=True)
+        assert got[0] == ref_ids

@@ -412,3 +412,31 @@ def test_fused_qkv_rope_matches_unfused(dev, M):
     assert (q1 != q2).float().mean() < 0.01
     assert (pool1.float() - pool2.float()).abs().max() <= tol
     assert (pool2 != 0).any()
+
+
+@pytest.mark.parametrize('top_p,temp', [(0.9, 1.0), (0.5, 0.7), (1.0, 1.0), (0.05, 1.3)])
+def test_top_p_sample_matches_torch_restatement(dev, top_p, temp):
+    L = _mods()
+    torch.manual_seed(10)
+    R, V = 6, 32064
+    lg = (torch.randn(R, V, device=dev) * 4).contiguous()
+    u = torch.rand(R, device=dev)
+    out = torch.zeros(R, dtype=torch.int32, device=dev)
+    tau = torch.zeros(R, device=dev)
+    L.call('p3_top_p_sample', lg.data_ptr(), R, V, V, top_p, temp, u.data_ptr(), out.data_ptr(), tau.data_ptr(), st())
+    torch.cuda.synchronize()
+    p = torch.softmax(lg.double() / temp, -1)
+    sp, si = p.sort(-1, descending=True)
+    cum = sp.cumsum(-1)
+    keep_sorted = (cum - sp) < top_p                      # smallest prefix whose mass reaches top_p
+    tau_ref = torch.where(keep_sorted, sp, torch.ones_like(sp)).min(-1).values
+    for r in range(R):
+        assert abs(tau[r].item() - tau_ref[r].item()) <= 2e-6 * max(tau_ref[r].item(), 1e-30) + 1e-12
+        nucleus = p[r] >= tau_ref[r] * (1 - 1e-6)
+        assert nucleus[out[r].item()]
+        cdf = (p[r] * nucleus).cumsum(-1)
+        want = int(torch.searchsorted(cdf, u[r].double() * cdf[-1], right=True).item())
+        got = out[r].item()
+        if got != want:                                   # fp32 vs fp64 cdf: only a neighbour inside the nucleus is acceptable
+            idx = torch.nonzero(nucleus).flatten().tolist()
+            assert abs(idx.index(got) - idx.index(min(want, idx[-1]))) <= 1

@@ -222,3 +222,42 @@ def test_slab_recycling_and_graph_reuse(dev):
     lo, co = o(ids_a, max_tokens=12)
     lo2, _ = o(lo[:, -1].argmax(-1)[:, None], cache=co)
     assert rel(la2, lo2) < TOL
+
+
+def test_chunked_prefill_matches_oracle(dev):
+    """Chunked prefill against the paged pool (the path BASELINE config 4 needs) incl. left padding."""
+    cfg, w, m, o = _setup()
+    m.prefill_chunk = 128
+    ids = _ids(2, 300, seed=41)
+    ids[1, :37] = 0
+    pids = torch.stack([torch.arange(300), torch.cat([torch.ones(37, dtype=torch.long), torch.arange(263)])])
+    mask = torch.ones(2, 300, dtype=torch.long)
+    mask[1, :37] = 0
+    lo, co = o(ids, pids=pids, mask=mask, max_tokens=6)
+    lg, cg = m(ids, pids=pids, mask=mask, max_tokens=6, logits_rows='last')
+    assert cg.offset == 300 and rel(lg[:, -1], lo[:, -1]) < TOL
+    tok = lo[:, -1].argmax(-1)
+    for _ in range(3):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        assert rel(lg, lo) < TOL
+        tok = lo[:, -1].argmax(-1)
+
+
+def test_long_rope_factors_past_4096(dev):
+    """L_all > 4096 switches SuRoPE to the long factors (phi.py:492, H7); chunked prefill + decode."""
+    cfg, w, m, o = _setup()
+    m.prefill_chunk = 2048
+    ids = _ids(1, 4200, seed=43)
+    lo, co = o(ids, max_tokens=4)
+    lg, cg = m(ids, max_tokens=4, logits_rows='last')
+    assert rel(lg[:, -1], lo[:, -1]) < TOL
+    tok = lo[:, -1].argmax(-1)
+    lo, co = o(tok[:, None], cache=co)
+    lg, cg = m(tok[:, None], cache=cg)
+    assert rel(lg, lo) < TOL
+    # the switch really matters: forcing short factors must change the result
+    m.force_long_rope = False
+    lg_short, _ = m(ids, max_tokens=4, logits_rows='last')
+    m.force_long_rope = None
+    assert rel(lg_short[:, -1], lo[:, -1] * 0 + lg[:, -1].cpu()) > 1e-3
