@@ -65,9 +65,10 @@ int p3_row_stats(const float* logits, int64_t R, int64_t ld, int V, int32_t* arg
 
 /* Nucleus (top-p) sampling — extension: the reference decodes greedily only (pv:386,392).
  * tau = largest probability v with sum_{p_i>=v} p_i >= top_p (exact bisection, no sort); token drawn by
- * inverse CDF in index order over {p_i >= tau} with the caller's uniform u[R] in [0,1). tau_out may be NULL. */
+ * inverse CDF in index order over {p_i >= tau} with the caller's uniform u[R] in [0,1). tau_out may be NULL.
+ * step_dev (device int32, may be NULL): u is a table and row *step_dev * u_stride is used (graph replay). */
 int p3_top_p_sample(const float* logits, int64_t R, int64_t ld, int V, float top_p, float temperature, const float* u,
-                    int32_t* out, float* tau_out, cudaStream_t st);
+                    int32_t* out, float* tau_out, const int32_t* step_dev, int64_t u_stride, cudaStream_t st);
 
 /* Greedy-loop bookkeeping on the device (pv:390-398 without the two host syncs per token):
  * history[b][*step] = tok[b]; eos_seen[b] |= (tok[b]==32007); ++*step; ++*past (past may be NULL). */

@@ -28,7 +28,7 @@ _SIGS = {
     'p3_attention_decode_q4': [_p, _p, _p, _l, _l, _l, _p, _l, _i, _i, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p, _i,
                                _i, _i, _p, _p, _p, _l, _p],
     'p3_kv_quantize_q4g32': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
-    'p3_top_p_sample': [_p, _l, _l, _i, _f, _f, _p, _p, _p, _p],
+    'p3_top_p_sample': [_p, _l, _l, _i, _f, _f, _p, _p, _p, _p, _l, _p],
     'p3_decode_advance': [_p, _p, _l, _i, _p, _p, _p, _p],
     'p3_hd_resize_h': [_p, _l, _l, _i, _i, _p, _i, _p, _p, _i, _p],
     'p3_hd_resize_v_pad': [_p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p],

@@ -204,7 +204,7 @@ class LogitStopper:
 
 
 def _generate(model, processor, prompt, images=None, max_tokens=512, verbose=True, return_tps=False, early_stop=False,
-              stream=True, mute=False, return_tokens=False, eos_check_every=16):
+              stream=True, mute=False, return_tokens=False, eos_check_every=16, top_p=None, temperature=1.0, seed=0):
     """pv:376-409. The loop body is one CUDA-graph replay per token; EOS for all rows
     (TokenStopper, pv:106-117) is polled every `eos_check_every` steps instead of twice per token —
     rows are truncated at their first EOS afterwards exactly as the reference does (pv:73)."""
@@ -219,14 +219,23 @@ def _generate(model, processor, prompt, images=None, max_tokens=512, verbose=Tru
     per_token_sync = (streamer.stream and B == 1) or bool(logit_stopper.early_stop)
     tic = Tic()
     logits, cache = model(**dict_input, max_tokens=max_tokens, logits_rows='last')
-    st = _row_stats(model, logits[:, -1, :])
-    token = st['argmax']
+    sampler = None
+    if top_p is not None:
+        # extension (the reference is greedy only): nucleus sampling with a seeded uniform table [steps, B]
+        g = torch.Generator(device=model.dev).manual_seed(int(seed))
+        u = torch.rand((max_tokens + 1, B), generator=g, device=model.dev)
+        token = torch.empty(B, dtype=torch.int32, device=model.dev)
+        call('p3_top_p_sample', ptr(logits[:, -1, :]), B, logits.stride(0), model.V, float(top_p), float(temperature),
+             ptr(u), ptr(token), None, None, 0, _stream())
+        sampler = (top_p, temperature, u)
+    else:
+        token = _row_stats(model, logits[:, -1, :])['argmax']
     if per_token_sync:
         if streamer.stream:
             streamer.stream_token(int(token[0].item()))
     torch.cuda.synchronize()
     prompt_time = tic()
-    ses = model.decode_session(token, cache, max_tokens - 1, use_graph=not bool(logit_stopper.early_stop))
+    ses = model.decode_session(token, cache, max_tokens - 1, use_graph=not bool(logit_stopper.early_stop), sampler=sampler)
     for i in range(max_tokens - 1):
         if logit_stopper.early_stop:
             # un-graphed step so the EOS log-prob of this step can be read (pv:395)

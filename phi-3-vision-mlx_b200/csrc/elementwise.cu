@@ -376,7 +376,8 @@ __device__ __forceinline__ float block_sum_tp(float v, float* sh) {
 }
 
 __global__ void top_p_sample_kernel(const float* __restrict__ logits, int64_t ld, int V, float top_p, float inv_temp,
-                                    const float* __restrict__ u, int32_t* __restrict__ out, float* __restrict__ tau_out) {
+                                    const float* __restrict__ u, int32_t* __restrict__ out, float* __restrict__ tau_out,
+                                    const int32_t* __restrict__ step_dev, int64_t u_stride) {
     __shared__ float sh[TP_THREADS / 32];
     __shared__ float s_chunk[TP_THREADS];
     __shared__ int s_pick;
@@ -384,6 +385,7 @@ __global__ void top_p_sample_kernel(const float* __restrict__ logits, int64_t ld
     pdl_wait();
     const int r = blockIdx.x, tid = threadIdx.x;
     const float* row = logits + (size_t)r * ld;
+    if (step_dev) u += (size_t)(*step_dev) * u_stride;       // decode graph: row of the uniform table for this step
     float mx = -INFINITY;
     for (int i = tid; i < V; i += TP_THREADS) mx = fmaxf(mx, row[i] * inv_temp);
     mx = warp_max(mx);
@@ -399,6 +401,7 @@ __global__ void top_p_sample_kernel(const float* __restrict__ logits, int64_t ld
     const float inv_z = 1.f / z;
     // bisection over bit patterns of positive floats in (0, 1]
     uint32_t lo = 0u, hi = __float_as_uint(1.0f);           // f(lo) >= top_p always; find the largest v with f(v) >= top_p
+    if (top_p >= 1.f) hi = 0u;                               // whole vocabulary: fp32 mass can round below 1
     while (lo < hi) {
         uint32_t mid = lo + (hi - lo + 1) / 2;
         float thr = __uint_as_float(mid), m = 0.f;
@@ -437,11 +440,12 @@ __global__ void top_p_sample_kernel(const float* __restrict__ logits, int64_t ld
 }
 
 extern "C" int p3_top_p_sample(const float* logits, int64_t R, int64_t ld, int V, float top_p, float temperature,
-                               const float* u, int32_t* out, float* tau_out, cudaStream_t st) {
+                               const float* u, int32_t* out, float* tau_out, const int32_t* step_dev, int64_t u_stride,
+                               cudaStream_t st) {
     P3_CHECK_ARG(top_p > 0.f && top_p <= 1.f && temperature > 0.f, "top_p_sample: need 0 < top_p <= 1 and temperature > 0");
     if (R == 0) return 0;
     p3_launch_pdl(top_p_sample_kernel, dim3((unsigned)R), dim3(TP_THREADS), 0, st, logits, ld, V, top_p, 1.f / temperature, u,
-                  out, tau_out);
+                  out, tau_out, step_dev, u_stride);
     P3_CHECK_LAUNCH("top_p_sample");
     return 0;
 }

@@ -447,8 +447,8 @@ class Phi3B200:
         cache.n_quant = (n_tokens // PAGE) * PAGE
 
     # ------------------------------------------------------------------ device-resident greedy loop (pv:390-398)
-    def decode_session(self, first_token, cache, max_steps, use_graph=True):
-        return DecodeSession(self, first_token, cache, max_steps, use_graph)
+    def decode_session(self, first_token, cache, max_steps, use_graph=True, sampler=None):
+        return DecodeSession(self, first_token, cache, max_steps, use_graph, sampler)
 
     def greedy_decode(self, first_token, cache, n_steps, use_graph=True, eos_check_every=0):
         """n_steps decode steps from `first_token` [B] with no per-token host sync.
@@ -468,8 +468,12 @@ class DecodeSession:
     at mx.eval and `eos_id in token` every token, pv:393,397,113). The state buffers and the graph
     live in the cache's slab and are reused by later sessions of the same shape."""
 
-    def __init__(self, model, first_token, cache, max_steps, use_graph=True):
+    def __init__(self, model, first_token, cache, max_steps, use_graph=True, sampler=None):
         self.m, self.cache, self.max_steps = model, cache, max_steps
+        # sampler = None (greedy argmax, the reference's only mode) or (top_p, temperature, u_table [steps+1, B])
+        self.sampler = sampler
+        if sampler is not None:
+            cache.slab.session = None          # a sampling graph is not interchangeable with the greedy one
         B = cache.B
         dev = model.dev
         self.B = B
@@ -510,9 +514,10 @@ class DecodeSession:
             with torch.cuda.graph(self.graph):
                 self._one_step()
             self.launches_per_step = _lib.launches - n0
-            cache.slab.session = dict(max_steps=max_steps, offset0=cache.offset, hist=self.hist, tok=self.tok,
-                                      step=self.step_dev, past=self.past_dev, eos=self.eos, n_splits=self.n_splits,
-                                      graph=self.graph, lps=self.launches_per_step)
+            if sampler is None:
+                cache.slab.session = dict(max_steps=max_steps, offset0=cache.offset, hist=self.hist, tok=self.tok,
+                                          step=self.step_dev, past=self.past_dev, eos=self.eos, n_splits=self.n_splits,
+                                          graph=self.graph, lps=self.launches_per_step)
 
     def _reset(self, first_token):
         self.hist[:, 0] = first_token
@@ -525,8 +530,13 @@ class DecodeSession:
         m = self.m
         logits = m._forward_tokens(self.tok, self.B, 1, self.cache, 1, True, self.cache.offset + self.steps_run, 'last',
                                    past_dev=self.past_dev, n_splits=self.n_splits)
-        call('p3_row_stats', ptr(logits), self.B, m.V, m.V, ptr(self.tok), None, None, 0, None, None, 0, None, None,
-             _stream())
+        if self.sampler is None:
+            call('p3_row_stats', ptr(logits), self.B, m.V, m.V, ptr(self.tok), None, None, 0, None, None, 0, None, None,
+                 _stream())
+        else:
+            top_p, temp, u = self.sampler
+            call('p3_top_p_sample', ptr(logits), self.B, m.V, m.V, float(top_p), float(temp), ptr(u), ptr(self.tok), None,
+                 ptr(self.step_dev), u.stride(0), _stream())
         call('p3_decode_advance', ptr(self.tok), ptr(self.hist), self.hist.stride(0), self.B, ptr(self.step_dev),
              ptr(self.past_dev), ptr(self.eos), _stream())
 

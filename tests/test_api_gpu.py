@@ -174,3 +174,16 @@ def test_constrain_beam_with_quantized_cache_extension(dev):
         ref_ids = [[t for t in r if t not in (0, 1)] for r in ref_ids]
         got = api._constrain(model, proc, prompts, [(4, text)], mute=True, verbose=False, use_beam=True, n_beam=nb, return_ids=True)
         assert got[0] == ref_ids
+
+
+def test_generate_top_p_extension(dev):
+    api, model, proc, ora = _setup()
+    kw = dict(max_tokens=10, verbose=False, stream=False, mute=True, return_tokens=True)
+    p = api._apply_chat_template(['hello there', 'general kenobi'], None, False)[0]
+    a = api._generate(model, proc, p, top_p=0.9, temperature=1.5, seed=1, **kw).cpu()
+    b = api._generate(model, proc, p, top_p=0.9, temperature=1.5, seed=1, **kw).cpu()
+    c = api._generate(model, proc, p, top_p=0.9, temperature=1.5, seed=2, **kw).cpu()
+    g = api._generate(model, proc, p, **kw).cpu()
+    tiny_p = api._generate(model, proc, p, top_p=1e-6, seed=5, **kw).cpu()
+    assert torch.equal(a, b) and not torch.equal(a, c)          # seeded, reproducible
+    assert torch.equal(tiny_p, g)                               # top_p -> 0 degenerates to greedy

@@ -423,7 +423,7 @@ def test_top_p_sample_matches_torch_restatement(dev, top_p, temp):
     u = torch.rand(R, device=dev)
     out = torch.zeros(R, dtype=torch.int32, device=dev)
     tau = torch.zeros(R, device=dev)
-    L.call('p3_top_p_sample', lg.data_ptr(), R, V, V, top_p, temp, u.data_ptr(), out.data_ptr(), tau.data_ptr(), st())
+    L.call('p3_top_p_sample', lg.data_ptr(), R, V, V, top_p, temp, u.data_ptr(), out.data_ptr(), tau.data_ptr(), None, 0, st())
     torch.cuda.synchronize()
     p = torch.softmax(lg.double() / temp, -1)
     sp, si = p.sort(-1, descending=True)
@@ -431,7 +431,11 @@ def test_top_p_sample_matches_torch_restatement(dev, top_p, temp):
     keep_sorted = (cum - sp) < top_p                      # smallest prefix whose mass reaches top_p
     tau_ref = torch.where(keep_sorted, sp, torch.ones_like(sp)).min(-1).values
     for r in range(R):
-        assert abs(tau[r].item() - tau_ref[r].item()) <= 2e-6 * max(tau_ref[r].item(), 1e-30) + 1e-12
+        if top_p < 1.0:
+            assert abs(tau[r].item() - tau_ref[r].item()) <= 2e-6 * max(tau_ref[r].item(), 1e-30) + 1e-12
+        else:
+            assert tau[r].item() == 0.0
+            tau_ref[r] = 0.0
         nucleus = p[r] >= tau_ref[r] * (1 - 1e-6)
         assert nucleus[out[r].item()]
         cdf = (p[r] * nucleus).cumsum(-1)
