@@ -9,9 +9,10 @@
 // rows and splits K over its 8 warps; partial sums are reduced through shared memory.
 //
 // Pipeline: every warp runs a private DEPTH-stage cp.async (LDGSTS) ring in shared memory that
-// carries, per 64-wide k chunk, its W slices, its X slices and the RMSNorm gains. Each lane reads
-// back exactly the bytes it copied, so the ring needs no barrier (cp.async.wait_group only) and
-// no registers: bytes in flight are bounded by shared memory (2 CTAs/SM x 8 warps x DEPTH stages).
+// carries, per 64-wide k chunk, its W slices and the RMSNorm gains. Each lane reads back exactly the
+// bytes it copied, so the ring needs no barrier (cp.async.wait_group only) and no registers: weight
+// bytes in flight are bounded by shared memory (2 CTAs/SM x 8 warps x DEPTH stages = 192 KB/SM).
+// The (L2-resident) activations are fetched into registers one chunk ahead.
 //
 // Fusions: RMSNorm prologue (phi.py:478-479: x*rsqrt(mean(x^2)+eps)*w, rounded to bf16),
 // residual epilogue (phi.py:483,485), SwiGLU epilogue (phi.py:470-471), fp32 logits out.
@@ -42,8 +43,8 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x))
 
 template <int NT, int MT, int DEPTH_>
 struct SkCfg {
-    static constexpr int W_SLOTS = 4 * MT, X_SLOTS = 2 * NT;
-    static constexpr int STAGE = (W_SLOTS + X_SLOTS) * 512 + 128;            // + 128 B of norm gains
+    static constexpr int W_SLOTS = 4 * MT, X_SLOTS = 0;                      // X travels in registers (L2-resident, 1 chunk ahead)
+    static constexpr int STAGE = W_SLOTS * 512 + 128;                        // + 128 B of norm gains
     static constexpr int DEPTH = DEPTH_;
     static constexpr int RING = SK_WARPS * DEPTH * STAGE;
     static constexpr int RED = SK_WARPS * MT * 8 * NT * 17 * 4;
@@ -131,13 +132,17 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
         if (p.norm_w && lane < 8)
             cp_async16(ring + stage * C::STAGE + (C::W_SLOTS + C::X_SLOTS) * 512 + lane * 16, p.norm_w + k0 + lane * 8);
     };
-    auto issue_x = [&](int ci, int stage) {                                      // activations: produced by the previous kernel
-        const uint32_t sb = ring + stage * C::STAGE + lane * 16;
+    uint4 xnext[NT][2];
+    auto load_x = [&](int ci) {                                                  // activations: produced by the previous kernel
         const int k0 = ci * 64;
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
-            cp_async16(sb + (C::W_SLOTS + nt * 2 + 0) * 512, xrow[nt] + k0, xbytes[nt]);
-            cp_async16(sb + (C::W_SLOTS + nt * 2 + 1) * 512, xrow[nt] + k0 + 32, xbytes[nt]);
+            if (xbytes[nt]) {
+                xnext[nt][0] = *reinterpret_cast<const uint4*>(xrow[nt] + k0);
+                xnext[nt][1] = *reinterpret_cast<const uint4*>(xrow[nt] + k0 + 32);
+            } else {
+                xnext[nt][0] = make_uint4(0, 0, 0, 0); xnext[nt][1] = make_uint4(0, 0, 0, 0);
+            }
         }
     };
 
@@ -150,13 +155,8 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
         cp_async_commit();
     }
     pdl_wait();
-    int ci_issue = warp;
-#pragma unroll
-    for (int s = 0; s < C::DEPTH; s++) {
-        if (ci_issue < n_chunks) issue_x(ci_issue, s);
-        cp_async_commit();
-        ci_issue += SK_WARPS;
-    }
+    int ci_issue = warp + C::DEPTH * SK_WARPS;
+    if (warp < n_chunks) load_x(warp);
 
     // ---- RMSNorm prologue: rs[m] = rsqrt(mean(x^2) + eps), from the producer's partial sums when
     // available (fixed summation order: deterministic), else recomputed from X (L2 resident)
@@ -215,10 +215,8 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
                 for (int kh = 0; kh < 2; kh++)
                     wcur[mt][hh][kh] = *reinterpret_cast<const uint4*>(sb + ((mt * 2 + hh) * 2 + kh) * 512 + lane * 16);
 #pragma unroll
-        for (int nt = 0; nt < NT; nt++)
-#pragma unroll
-            for (int kh = 0; kh < 2; kh++)
-                xf[nt][kh] = *reinterpret_cast<const uint4*>(sb + (C::W_SLOTS + nt * 2 + kh) * 512 + lane * 16);
+        for (int nt = 0; nt < NT; nt++) { xf[nt][0] = xnext[nt][0]; xf[nt][1] = xnext[nt][1]; }
+        if (ci + SK_WARPS < n_chunks) load_x(ci + SK_WARPS);                      // next chunk's X, one iteration ahead
         if (p.norm_w) {
             uint4 nw[2];
             nw[0] = *reinterpret_cast<const uint4*>(sb + (C::W_SLOTS + C::X_SLOTS) * 512 + t * 16);
@@ -238,7 +236,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
         }
         // the stage is in registers now: refill it with the chunk DEPTH iterations ahead
         __syncwarp();
-        if (ci_issue < n_chunks) { issue_w(ci_issue, stage); issue_x(ci_issue, stage); }
+        if (ci_issue < n_chunks) issue_w(ci_issue, stage);
         cp_async_commit();
         ci_issue += SK_WARPS;
         if (++stage == C::DEPTH) stage = 0;
@@ -380,7 +378,7 @@ static int sk_depth_override() {
 template <int NT, int MT>
 static int launch_skinny(const SkParams& p, unsigned grid, cudaStream_t st) {
     int d = sk_depth_override();
-    if (d == 0) d = (MT == 1) ? (NT == 1 ? 4 : 3) : 2;
+    if (d == 0) d = (MT == 1) ? 4 : 2;                       // measured best (tools/microbench.py): deeper rings do not pay, residency does
     switch (d) {
         case 2: return launch_skinny_d<NT, MT, 2>(p, grid, st);
         case 3: return launch_skinny_d<NT, MT, 3>(p, grid, st);
