@@ -154,31 +154,83 @@ __device__ __forceinline__ void softmax_update(float (*s)[4], float* m, float* l
 }
 
 // ------------------------------------------------------------------------------------------
-// prefill / ViT
+// prefill / ViT: 128 query rows per CTA (8 warps x 16 rows), 64-key tiles, 3-stage cp.async ring.
+// Per-thread copy slots are hoisted out of the tile loop for the two common cases (tile entirely in
+// the paged pool / entirely in the fresh qkv buffer); masking runs only on boundary tiles; a warp
+// skips tiles that lie entirely above its causal diagonal; exp2 is one FFMA + one MUFU.
 // ------------------------------------------------------------------------------------------
+#define PF_STAGES 3
+#define PF_THREADS 256
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int D>
-__global__ void __launch_bounds__(128) attn_prefill_kernel(AttnParams p) {
-    constexpr int CPR = D / 8, TILE = 64 * D * 2;
+__global__ void __launch_bounds__(PF_THREADS, 2) attn_prefill_kernel(AttnParams p) {
+    constexpr int CPR = D / 8, TILE = 64 * D * 2, NSLOT = 64 * CPR / PF_THREADS;
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t sq = smem_u32(smem), skv = sq + TILE;       // skv: [2 stages][K,V]
+    const uint32_t sq = smem_u32(smem), skv = sq + 2 * TILE;   // Q: 128 rows; skv: [PF_STAGES][K,V]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int i0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+    const int i0 = (gridDim.x - 1 - blockIdx.x) * 128, h = blockIdx.y, b = blockIdx.z;   // heavy (late) row blocks first
     const int kvh = h / (p.n_heads / p.n_kv);
     const int s_total = p.past + p.L;
-    const int kv0 = p.kv_start ? p.kv_start[b / p.row_div] : 0;
+    const int crow = b / p.row_div;
+    const int kv0 = p.kv_start ? p.kv_start[crow] : 0;
 
-    // Q tile
-    for (int idx = tid; idx < 64 * CPR; idx += 128) {
+    for (int idx = tid; idx < 128 * CPR; idx += PF_THREADS) {
         int r = idx / CPR, c = idx % CPR;
         int i = i0 + r;
         const bf16* src = p.q + ((size_t)b * p.L + (i < p.L ? i : 0)) * p.ldq + h * D + c * 8;
         cp_async16(sq + tile_off<D>(r, c), src, i < p.L ? 16 : 0);
     }
-    int n_begin = kv0 / 64;
+    const int n_begin = kv0 / 64;
     int n_end = (s_total + 63) / 64;
-    if (p.causal) n_end = min(n_end, (p.past + min(i0 + 63, p.L - 1)) / 64 + 1);
-    if (n_begin < n_end) load_kv_tile<D, 128>(p, b, kvh, n_begin, s_total, skv, skv + TILE);
-    cp_async_commit();
+    if (p.causal) n_end = min(n_end, (p.past + min(i0 + 127, p.L - 1)) / 64 + 1);
+    const int n_tiles = max(n_end - n_begin, 0);
+
+    // hoisted copy slots
+    uint32_t soff[NSLOT];
+    int goff[NSLOT];                                            // element offset inside the fresh k/v rows
+#pragma unroll
+    for (int i = 0; i < NSLOT; i++) {
+        int idx = tid + PF_THREADS * i, r = idx / CPR, c = idx % CPR;
+        soff[i] = tile_off<D>(r, c);
+        goff[i] = r * (int)p.ldk + c * 8;
+    }
+    const size_t head_elems = (size_t)P3_PAGE * D, page_elems = 2 * (size_t)p.n_kv * head_elems;
+    const int32_t* bt = p.block_table ? p.block_table + (size_t)crow * p.bt_stride : nullptr;
+
+    auto issue = [&](int n, int stage) {
+        const uint32_t sk = skv + stage * 2 * TILE, sv = sk + TILE;
+        const int j0 = n * 64;
+        if (j0 + 64 <= p.past) {                                // whole tile from the paged pool
+            const bf16* kp = p.pool + (size_t)bt[n] * page_elems + (size_t)kvh * head_elems + tid * 8;
+            const bf16* vp = kp + (size_t)p.n_kv * head_elems;
+#pragma unroll
+            for (int i = 0; i < NSLOT; i++) {
+                cp_async16(sk + soff[i], kp + i * (PF_THREADS * 8));
+                cp_async16(sv + soff[i], vp + i * (PF_THREADS * 8));
+            }
+        } else if (j0 >= p.past && j0 + 64 <= s_total && p.ldk == p.ldv) {   // whole tile from the fresh qkv rows
+            const size_t tok0 = (size_t)b * p.L + (j0 - p.past);
+            const bf16* kp = p.k + tok0 * p.ldk + kvh * D;
+            const bf16* vp = p.v + tok0 * p.ldv + kvh * D;
+#pragma unroll
+            for (int i = 0; i < NSLOT; i++) {
+                cp_async16(sk + soff[i], kp + goff[i]);
+                cp_async16(sv + soff[i], vp + goff[i]);
+            }
+        } else {
+            load_kv_tile<D, PF_THREADS>(p, b, kvh, n, s_total, sk, sv);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < PF_STAGES - 1; i++) {
+        if (i < n_tiles) issue(n_begin + i, i);
+        cp_async_commit();                                      // group 0 also carries the Q tile
+    }
 
     uint32_t qf[D / 16][4];
     float o[D / 8][4];
@@ -188,45 +240,62 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(AttnParams p) {
         for (int j = 0; j < 4; j++) o[dt][j] = 0.f;
     float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
     const int qi0 = p.past + i0 + warp * 16 + g, qi1 = qi0 + 8;   // absolute query positions of rows g, g+8
+    const int q_hi = p.past + i0 + warp * 16 + 15;               // last query row of this warp
 
-    for (int n = n_begin; n < n_end; n++) {
-        const int buf = (n - n_begin) & 1;
-        if (n + 1 < n_end) {
-            load_kv_tile<D, 128>(p, b, kvh, n + 1, s_total, skv + (buf ^ 1) * 2 * TILE, skv + (buf ^ 1) * 2 * TILE + TILE);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+    for (int itn = 0; itn < n_tiles; itn++) {
+        const int n = n_begin + itn;
+        cp_async_wait<PF_STAGES - 2>();
         __syncthreads();
-        if (n == n_begin) {
+        if (itn + PF_STAGES - 1 < n_tiles) issue(n + PF_STAGES - 1, (itn + PF_STAGES - 1) % PF_STAGES);
+        cp_async_commit();
+        if (itn == 0) {
 #pragma unroll
             for (int ks = 0; ks < D / 16; ks++) {
                 int r = warp * 16 + (lane & 15), c = ks * 2 + (lane >> 4);
                 ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], sq + tile_off<D>(r, c));
             }
         }
-        const uint32_t sk = skv + buf * 2 * TILE, sv = sk + TILE;
+        const int j0 = n * 64;
+        if (p.causal && j0 > q_hi) continue;                    // tile entirely above this warp's diagonal
+        const uint32_t sk = skv + (itn % PF_STAGES) * 2 * TILE, sv = sk + TILE;
         float s[8][4];
         qk_mma<D, 8>(qf, sk, 0, s, lane);
-        const int j0 = n * 64;
-        const bool need_mask = (j0 < kv0) || (j0 + 63 >= s_total) || (p.causal && j0 + 63 > p.past + i0);
+        const bool need_mask = (j0 < kv0) || (j0 + 63 >= s_total) || (p.causal && j0 + 63 > p.past + i0 + warp * 16);
+        if (need_mask) {
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++)
+            for (int nt = 0; nt < 8; nt++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                float v = s[nt][e] * p.scale_log2;
-                if (need_mask) {
+                for (int e = 0; e < 4; e++) {
                     int j = j0 + nt * 8 + 2 * t + (e & 1);
                     int qi = (e & 2) ? qi1 : qi0;
                     bool ok = (j >= kv0) && (j < s_total) && (!p.causal || j <= qi);
-                    if (!ok) v = -INFINITY;
+                    if (!ok) s[nt][e] = -INFINITY;
                 }
-                s[nt][e] = v;
-            }
-        softmax_update<D, 8>(s, m, l, o);
+        }
+        // online softmax in the exp2 domain on raw scores (scale folded into the FFMA)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m[0], mx0), mn1 = fmaxf(m[1], mx1);
+        const float mu0 = (mn0 == -INFINITY) ? 0.f : mn0 * p.scale_log2, mu1 = (mn1 == -INFINITY) ? 0.f : mn1 * p.scale_log2;
+        const float c0 = ex2_approx(m[0] * p.scale_log2 - mu0), c1 = ex2_approx(m[1] * p.scale_log2 - mu1);
+        m[0] = mn0; m[1] = mn1;
+        float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            s[nt][0] = ex2_approx(fmaf(s[nt][0], p.scale_log2, -mu0)); s[nt][1] = ex2_approx(fmaf(s[nt][1], p.scale_log2, -mu0));
+            s[nt][2] = ex2_approx(fmaf(s[nt][2], p.scale_log2, -mu1)); s[nt][3] = ex2_approx(fmaf(s[nt][3], p.scale_log2, -mu1));
+            ls0 += s[nt][0] + s[nt][1]; ls1 += s[nt][2] + s[nt][3];
+        }
+        l[0] = fmaf(l[0], c0, ls0); l[1] = fmaf(l[1], c1, ls1);
+#pragma unroll
+        for (int dt = 0; dt < D / 8; dt++) { o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1; }
         pv_mma<D, 8>(s, sv, 0, o, lane);
-        __syncthreads();
     }
     cp_async_wait<0>();
 #pragma unroll
@@ -255,11 +324,6 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(AttnParams p) {
 // tile t is consumed, masking runs only on boundary tiles and exp2 is a single MUFU.
 // ------------------------------------------------------------------------------------------
 #define DEC_STAGES 4
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 template <int D, bool Q4>
 __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
@@ -609,16 +673,16 @@ extern "C" int p3_attention_prefill(const void* q, const void* k, const void* v,
     if (fill_params(p, q, k, v, ldq, ldk, ldv, out, ldo, B, L, n_heads, n_kv, hd, scale, causal, past, kv_start, pool,
                     block_table, bt_stride, row_div)) return -1;
     if (B == 0 || L == 0) return 0;
-    dim3 grid((L + 63) / 64, n_heads, B);
-    int smem = 5 * 64 * hd * 2;
+    dim3 grid((L + 127) / 128, n_heads, B);
+    int smem = (2 + 2 * PF_STAGES) * 64 * hd * 2;
     if (hd == 96) {
         static bool set = false;
         if (!set) { cudaFuncSetAttribute(attn_prefill_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
-        attn_prefill_kernel<96><<<grid, 128, smem, st>>>(p);
+        attn_prefill_kernel<96><<<grid, PF_THREADS, smem, st>>>(p);
     } else {
         static bool set = false;
         if (!set) { cudaFuncSetAttribute(attn_prefill_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
-        attn_prefill_kernel<64><<<grid, 128, smem, st>>>(p);
+        attn_prefill_kernel<64><<<grid, PF_THREADS, smem, st>>>(p);
     }
     P3_CHECK_LAUNCH("attention_prefill");
     return 0;
