@@ -14,6 +14,7 @@
 #include "../../include/phi3_b200.h"
 #include <cuda.h>
 #include <mutex>
+#include <cstdlib>
 
 struct GemmEpi {
     const bf16* bias;
@@ -309,6 +310,182 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// 2-CTA variant: a CTA pair (cluster 2x1, same TPC) computes a 256 x 256 tile with
+// tcgen05.mma.cta_group::2 (UMMA 256 x 256 x 16). Each CTA TMA-loads its own 128 rows of A and only
+// HALF of the W tile (128 rows); the tensor cores read the other half from the peer's shared
+// memory, so L2->SM operand traffic per FLOP drops by a third (96 -> 64 B/cycle/SM at full rate) and
+// the 6-stage ring holds 2x the K depth. The leader CTA (rank 0) issues every MMA; its commits are
+// multicast to both CTAs' barriers; both CTAs' epilogue warps release the accumulator stage on the
+// leader's barrier through the cluster shared window.
+// ------------------------------------------------------------------------------------------
+#define P3_PEER_MASK 0xFEFFFFFFu        // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cta0, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cta0), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_mc(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+struct Tc2Cfg {
+    static constexpr int BM = 128, BN = 256, BK = 64, STAGES = 6;
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2;      // per CTA: own A rows + half of W rows
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpi ep,
+                int M, int N, int K) {
+    using C = Tc2Cfg;
+    constexpr int BN = C::BN;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
+    const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const bool leader = rank == 0;
+    const int m_pairs = (M + 2 * C::BM - 1) / (2 * C::BM), n_tiles = (N + BN - 1) / BN;
+    const int total = m_pairs * n_tiles, kb = (K + C::BK - 1) / C::BK;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 512); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = cluster_id; tile < total; tile += n_clusters) {
+                const int m_idx = (tile % m_pairs) * (2 * C::BM) + (int)rank * C::BM;
+                const int n_idx = (tile / m_pairs) * BN + (int)rank * (BN / 2);
+                for (int k = 0; k < kb; k++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);   // both CTAs' bytes land on CTA 0's barrier
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                    const uint32_t fb0 = full_bar(stage) & P3_PEER_MASK;
+                    tma_load_2d_2sm(sa, &tmA, fb0, k * C::BK, m_idx);
+                    tma_load_2d_2sm(sa + C::A_BYTES, &tmB, fb0, k * C::BK, n_idx);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = cluster_id; tile < total; tile += n_clusters) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int k = 0; k < kb; k++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + C::A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < C::BK / 16; kk++)
+                        tc_mma_bf16_2sm(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, C::IDESC, (k | kk) ? 1u : 0u);
+                    tc_commit_2sm_mc(empty_bar(stage));                                 // frees the slot in both CTAs
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_2sm_mc(tfull_bar(acc));                                       // accumulators ready in both CTAs
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < total; tile += n_clusters) {
+            const int m_idx = (tile % m_pairs) * (2 * C::BM) + (int)rank * C::BM, n_idx = (tile / m_pairs) * BN;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row = m_idx + q * 32 + lane;
+            const bool row_ok = row < M;
+            const int64_t orow = row_ok ? (ep.row_map ? (int64_t)ep.row_map[row] : (int64_t)row) : 0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            if (ep.kind == P3_EPI_SWIGLU) {
+                for (int c0 = half * (BN / 4); c0 < (half + 1) * (BN / 4); c0 += 32) {
+                    uint32_t g[32], u[32];
+                    tc_ld32(taddr + c0, g);
+                    tc_ld32(taddr + BN / 2 + c0, u);
+                    const int on0 = n_idx / 2 + c0;
+                    if (row_ok && on0 < N / 2) {
+                        uint4 ov[4];
+                        uint32_t* ou = reinterpret_cast<uint32_t*>(ov);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            float g0 = bf16_round(__uint_as_float(g[2 * i])), g1 = bf16_round(__uint_as_float(g[2 * i + 1]));
+                            float u0 = bf16_round(__uint_as_float(u[2 * i])), u1 = bf16_round(__uint_as_float(u[2 * i + 1]));
+                            float a0 = bf16_round(g0 / (1.f + __expf(-g0))), a1 = bf16_round(g1 / (1.f + __expf(-g1)));
+                            ou[i] = pack_bf16(a0 * u0, a1 * u1);
+                        }
+                        bf16* o = reinterpret_cast<bf16*>(ep.out) + orow * ep.ldo + on0;
+                        if (on0 + 32 <= N / 2 && (ep.ldo & 7) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(o)[i] = ov[i];
+                        } else {
+                            const bf16* ob = reinterpret_cast<const bf16*>(ov);
+                            for (int i = 0; i < 32; i++) if (on0 + i < N / 2) o[i] = ob[i];
+                        }
+                    }
+                }
+            } else {
+                for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + c0, v);
+                    if (row_ok && n_idx + c0 < N) epi_store32(ep, orow, n_idx + c0, N, v);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(tempty_bar(acc) & P3_PEER_MASK);                        // the leader's MMA warp owns this barrier
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // mma.sync cross-check GEMM (tests / bring-up only; not the product path)
 // ------------------------------------------------------------------------------------------
 #define FB_BM 64
@@ -457,6 +634,31 @@ static int launch_tc(const void* X, int64_t ldx, const void* W, int64_t ldw, con
     return 0;
 }
 
+static int gemm_2cta_mode() {                  // P3_GEMM_2CTA=0 forces the single-CTA kernel (A/B testing)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("P3_GEMM_2CTA"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
+static int launch_tc2(const void* X, int64_t ldx, const void* W, int64_t ldw, const GemmEpi& ep, int64_t M, int N, int K,
+                      cudaStream_t st) {
+    using C = Tc2Cfg;
+    CUtensorMap ta, tb;
+    if (make_tmap(&ta, X, M, K, ldx, C::BM)) return -1;
+    if (make_tmap(&tb, W, N, K, ldw, C::BN / 2)) return -1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        P3_CHECK_ARG(e == cudaSuccess, "gemm: cannot set %d B dynamic smem: %s", C::SMEM, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    int64_t tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
+    int64_t clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+    gemm_tc2_kernel<<<(unsigned)(2 * clusters), 384, C::SMEM, st>>>(ta, tb, ep, (int)M, N, K);
+    P3_CHECK_LAUNCH("gemm_tc2");
+    return 0;
+}
+
 extern "C" int p3_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
                        const void* resid, const int32_t* row_map, int64_t M, int N, int K, int epi, int impl,
                        cudaStream_t st) {
@@ -476,6 +678,8 @@ extern "C" int p3_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, c
         return 0;
     }
     int64_t m_tiles = (M + 127) / 128;
+    if (impl == 0 && gemm_2cta_mode() && M > 128 && ((m_tiles + 1) / 2) * ((N + 255) / 256) >= num_sms() / 4)
+        return launch_tc2(X, ldx, W, ldw, ep, M, N, K, st);
     bool small = m_tiles * ((N + 255) / 256) < 2 * num_sms();
     if (epi == P3_EPI_SWIGLU || !small) return launch_tc<256>(X, ldx, W, ldw, ep, M, N, K, st);
     return launch_tc<128>(X, ldx, W, ldw, ep, M, N, K, st);
