@@ -89,6 +89,22 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// Tile rasterisation: n-fastest inside bands of `nb` n-tiles so the band's W tiles (nb * BN * K * 2 B, sized
+// to ~48 MB) stay L2-resident while A streams through once per band. (m-fastest order re-read A once
+// per n-tile: ncu showed 2.1 GB of DRAM reads for a 157 MB problem.)
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int nb, int& mt, int& nt) {
+    const int band_tiles = nb * m_tiles;
+    const int band = tile / band_tiles, rem = tile - band * band_tiles;
+    const int nb_this = min(nb, n_tiles - band * nb);
+    mt = rem / nb_this;
+    nt = band * nb + rem - mt * nb_this;
+}
+__host__ __device__ __forceinline__ int band_width(int K, int BN, int n_tiles) {
+    long long per = (long long)BN * K * 2;
+    int nb = (int)((48ll << 20) / (per > 0 ? per : 1));
+    return nb < 1 ? 1 : (nb > n_tiles ? n_tiles : nb);
+}
+
 template <int BN>
 struct TcCfg {
     static constexpr int BM = 128, BK = 64;
@@ -194,6 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (M + C::BM - 1) / C::BM, n_tiles = (N + BN - 1) / BN;
     const int total = m_tiles * n_tiles, kb = (K + C::BK - 1) / C::BK;
+    const int nb = band_width(K, BN, n_tiles);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -217,7 +234,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int m_idx = (tile % m_tiles) * C::BM, n_idx = (tile / m_tiles) * BN;
+                int mt_, nt_;
+                tile_coords(tile, m_tiles, n_tiles, nb, mt_, nt_);
+                const int m_idx = mt_ * C::BM, n_idx = nt_ * BN;
                 for (int k = 0; k < kb; k++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
@@ -255,7 +274,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3, half = (warp - 4) >> 2;       // TMEM lane quarter, column half
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const int m_idx = (tile % m_tiles) * C::BM, n_idx = (tile / m_tiles) * BN;
+            int mt_, nt_;
+            tile_coords(tile, m_tiles, n_tiles, nb, mt_, nt_);
+            const int m_idx = mt_ * C::BM, n_idx = nt_ * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const int row = m_idx + q * 32 + lane;
@@ -369,6 +390,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int m_pairs = (M + 2 * C::BM - 1) / (2 * C::BM), n_tiles = (N + BN - 1) / BN;
     const int total = m_pairs * n_tiles, kb = (K + C::BK - 1) / C::BK;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int nb = band_width(K, BN, n_tiles);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -392,8 +414,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = cluster_id; tile < total; tile += n_clusters) {
-                const int m_idx = (tile % m_pairs) * (2 * C::BM) + (int)rank * C::BM;
-                const int n_idx = (tile / m_pairs) * BN + (int)rank * (BN / 2);
+                int mt_, nt_;
+                tile_coords(tile, m_pairs, n_tiles, nb, mt_, nt_);
+                const int m_idx = mt_ * (2 * C::BM) + (int)rank * C::BM;
+                const int n_idx = nt_ * BN + (int)rank * (BN / 2);
                 for (int k = 0; k < kb; k++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);   // both CTAs' bytes land on CTA 0's barrier
@@ -432,7 +456,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int q = warp & 3, half = (warp - 4) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = cluster_id; tile < total; tile += n_clusters) {
-            const int m_idx = (tile % m_pairs) * (2 * C::BM) + (int)rank * C::BM, n_idx = (tile / m_pairs) * BN;
+            int mt_, nt_;
+            tile_coords(tile, m_pairs, n_tiles, nb, mt_, nt_);
+            const int m_idx = mt_ * (2 * C::BM) + (int)rank * C::BM, n_idx = nt_ * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const int row = m_idx + q * 32 + lane;

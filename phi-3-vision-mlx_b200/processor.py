@@ -191,6 +191,7 @@ class Phi3VImageProcessor:
         self.device = torch.device(device)
         self.lut = torch.from_numpy(((np.arange(256)[:, None] / 255.0 - IMAGE_MEAN) / IMAGE_STD)).contiguous()
         self._lut_dev = None
+        self._tables = {}            # device-resident coefficient / tap tables, keyed by geometry
 
     def _one(self, img):
         dev = self.device
@@ -205,19 +206,30 @@ class Phi3VImageProcessor:
         g = hd_geometry(w0, h0, self.num_crops)
         # logical (possibly transposed) source view: element strides
         sy, sx = (3, w0 * 3) if g['trans'] else (w0 * 3, 3)
-        bh, kh, ksh = pil_bilinear_coeffs(g['in_w'], g['new_w'])
-        bv, kv, ksv = pil_bilinear_coeffs(g['in_h'], g['new_h'])
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        bh_d, kh_d, bv_d, kv_d = t(bh), t(kh), t(bv), t(kv)
+
+        def coeffs(n_in, n_out):
+            key = ('pil', n_in, n_out)
+            if key not in self._tables:
+                b_, k_, ks_ = pil_bilinear_coeffs(n_in, n_out)
+                self._tables[key] = (t(b_), t(k_), ks_)
+            return self._tables[key]
+
+        def taps(n):
+            key = ('i336', n)
+            if key not in self._tables:
+                i_, w_ = interp336_tables(n)
+                self._tables[key] = (t(i_), t(w_))
+            return self._tables[key]
+        bh_d, kh_d, ksh = coeffs(g['in_w'], g['new_w'])
+        bv_d, kv_d, ksv = coeffs(g['in_h'], g['new_h'])
         tmp = torch.empty((g['in_h'], g['new_w'], 3), dtype=torch.uint8, device=dev)
         call('p3_hd_resize_h', ptr(arr), sy, sx, g['in_w'], g['in_h'], ptr(tmp), g['new_w'], ptr(bh_d), ptr(kh_d), ksh, st)
         H, W = g['H'], g['W']
         out = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
         call('p3_hd_resize_v_pad', ptr(tmp), g['new_w'], g['in_h'], g['new_h'], ptr(bv_d), ptr(kv_d), ksv, g['top'],
              g['padded_h'], 1 if g['trans'] else 0, ptr(out), st)
-        hi, hw = interp336_tables(H)
-        wi, ww = interp336_tables(W)
-        hi_d, hw_d, wi_d, ww_d = t(hi), t(hw), t(wi), t(ww)
+        (hi_d, hw_d), (wi_d, ww_d) = taps(H), taps(W)
         if self._lut_dev is None:
             self._lut_dev = self.lut.to(dev)
         n = (H // 336) * (W // 336) + 1
