@@ -79,10 +79,12 @@ int p3_decode_advance(const int32_t* tok, int32_t* history, int64_t ld, int B, i
  * (norm_w != NULL: X is the raw hidden state). epi in {NONE, RESIDUAL, SWIGLU, F32}.
  * ss_in (fp32 [n_ss_in][16], may be NULL): per-token partial sums of squares of X written by the
  * kernel that produced X (p3_embed_gather / a RESIDUAL p3_gemm_skinny via ss_out, which writes
- * [ceil(N/16)][16]); without it the RMSNorm statistic is recomputed from X. */
+ * [ceil(N/16)][16]); without it the RMSNorm statistic is recomputed from X.
+ * l2_prefetch (may be NULL): the NEXT kernel's weights; every CTA pulls a slice into L2 before it waits on its
+ * predecessor, so HBM keeps streaming across the kernel boundary (own weights are loaded L2::evict_first). */
 int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, void* out, int64_t ldo,
                    const void* resid, int M, int N, int K, int epi, const float* ss_in, int n_ss_in, float* ss_out,
-                   cudaStream_t st);
+                   const void* l2_prefetch, int64_t l2_prefetch_bytes, cudaStream_t st);
 
 /* Decode-time qkv_proj + _rotate_half/SuRoPE + KVCache write in ONE launch (phi:442-453): each CTA owns
  * 16 rotary pairs (column c and c + hd/2 of one head) so the rotation fuses into the epilogue. */
@@ -90,7 +92,7 @@ int p3_gemm_skinny_qkv_rope(const void* X, int64_t ldx, const void* norm_w, floa
                             const float* ss_in, int n_ss_in, const float* cosT, const float* sinT, int64_t tab_bstride,
                             int B, int L, int n_heads, int n_kv, int hd, int K, int past, const int32_t* past_dev,
                             int row_div, void* pool, const int32_t* block_table, int bt_stride, int write_cache,
-                            cudaStream_t st);
+                            const void* l2_prefetch, int64_t l2_prefetch_bytes, cudaStream_t st);
 
 /* nn.Linear for prefill / ViT / projector (phi:140-143,155-156,391,437-438,465-466,604) and the
  * patch-embed conv as GEMM (phi:186-192): out[M,N] = X[M,K] . W[N,K]^T on tcgen05 tensor cores

@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
     const bf16* pool_k = p.pool + (size_t)kvh * head_elems + tid * 8;          // + page * page_elems
     const size_t v_delta = (size_t)p.n_kv * head_elems;
 
+    const uint64_t pol = l2_evict_first_policy();
     auto issue_cached = [&](int it, int page) {
         const uint32_t sk = skv + (it % DEC_STAGES) * 2 * TILE;
         if (Q4 && (n_lo + it) * 64 < p.n_quant) {
@@ -390,8 +391,13 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
         const bf16* kp = pool_k + (size_t)page * page_elems;
 #pragma unroll
         for (int i = 0; i < NSLOT; i++) {
-            cp_async16(sk + soff[i], kp + i * 1024);
-            cp_async16(sk + TILE + soff[i], kp + v_delta + i * 1024);
+            if (D == 96) {          // KV pages are read once per step: L2 evict-first
+                cp_async16_stream(sk + soff[i], kp + i * 1024, pol);
+                cp_async16_stream(sk + TILE + soff[i], kp + v_delta + i * 1024, pol);
+            } else {                // (ptxas 12.9 emits an unencodable LDGSTS descriptor pair for the D=64 instance)
+                cp_async16(sk + soff[i], kp + i * 1024);
+                cp_async16(sk + TILE + soff[i], kp + v_delta + i * 1024);
+            }
         }
     };
     auto issue_present = [&](int it) {
@@ -439,10 +445,7 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
         if (it == pf_iter && p.l2_prefetch) {
             const int64_t n_cta = (int64_t)gridDim.x * gridDim.y * gridDim.z;
             const int64_t cta = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-            const int64_t lines = (p.l2_prefetch_bytes + 127) / 128;
-            const int64_t per = (lines + n_cta - 1) / n_cta;
-            for (int64_t i = cta * per + tid; i < min((cta + 1) * per, lines); i += 128)
-                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p.l2_prefetch + i * 128));
+            l2_prefetch_slice(p.l2_prefetch, p.l2_prefetch_bytes, cta, n_cta, tid, 128);
         }
         {   // refill the stage that was consumed in the previous iteration
             const int nx = it + DEC_STAGES - 1;

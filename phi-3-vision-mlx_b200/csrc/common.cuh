@@ -52,6 +52,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes = 16) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// streaming variant: L2 evict-first (weights / KV pages are read once per step and must not displace
+// the lines other kernels prefetched for their successors)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async16_stream(uint32_t dst, const void* src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+// each CTA of a grid pulls its slice of [ptr, ptr+bytes) into L2 (the next kernel's weights)
+__device__ __forceinline__ void l2_prefetch_slice(const uint8_t* ptr, int64_t bytes, int64_t cta, int64_t n_cta, int tid, int nthreads) {
+    const int64_t lines = (bytes + 127) / 128, per = (lines + n_cta - 1) / n_cta;
+    const int64_t end = (cta + 1) * per < lines ? (cta + 1) * per : lines;
+    for (int64_t i = cta * per + tid; i < end; i += nthreads)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + i * 128));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }

@@ -36,6 +36,7 @@ struct SkParams {
     int L, n_heads, n_kv, hd, past, row_div, write_cache;
     const int32_t* past_dev;
     bf16* pool; const int32_t* block_table; int bt_stride;
+    const uint8_t* l2_pf; int64_t l2_pf_bytes;   // next kernel's weights, pulled into L2 while this one streams
 };
 #define P3_EPI_ROPE_QKV 7
 
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
 
     // stage layout (per warp): W slots [mt][row-half][k-half], X slots [nt][k-half], each 32 lanes x 16 B;
     // then 128 B of norm gains (64 elements, read back with broadcast)
+    const uint64_t pol = l2_evict_first_policy();
     auto issue_w = [&](int ci, int stage) {                                      // weights + norm gains: immutable
         const uint32_t sb = ring + stage * C::STAGE + lane * 16;
         const int k0 = ci * 64;
@@ -126,8 +128,8 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
         for (int mt = 0; mt < MT; mt++)
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
-                cp_async16(sb + ((mt * 2 + hh) * 2 + 0) * 512, wrow[mt][hh] + k0);
-                cp_async16(sb + ((mt * 2 + hh) * 2 + 1) * 512, wrow[mt][hh] + k0 + 32);
+                cp_async16_stream(sb + ((mt * 2 + hh) * 2 + 0) * 512, wrow[mt][hh] + k0, pol);
+                cp_async16_stream(sb + ((mt * 2 + hh) * 2 + 1) * 512, wrow[mt][hh] + k0 + 32, pol);
             }
         if (p.norm_w && lane < 8)
             cp_async16(ring + stage * C::STAGE + (C::W_SLOTS + C::X_SLOTS) * 512 + lane * 16, p.norm_w + k0 + lane * 8);
@@ -154,6 +156,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
         if (warp + s * SK_WARPS < n_chunks) issue_w(warp + s * SK_WARPS, s);
         cp_async_commit();
     }
+    if (p.l2_pf) l2_prefetch_slice(p.l2_pf, p.l2_pf_bytes, blockIdx.x, gridDim.x, tid, SK_THREADS);
     pdl_wait();
     int ci_issue = warp + C::DEPTH * SK_WARPS;
     if (warp < n_chunks) load_x(warp);
@@ -391,7 +394,8 @@ static int launch_skinny(const SkParams& p, unsigned grid, cudaStream_t st) {
 
 extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, void* out,
                               int64_t ldo, const void* resid, int M, int N, int K, int epi, const float* ss_in,
-                              int n_ss_in, float* ss_out, cudaStream_t st) {
+                              int n_ss_in, float* ss_out, const void* l2_prefetch, int64_t l2_prefetch_bytes,
+                              cudaStream_t st) {
     P3_CHECK_ARG(M >= 1 && M <= 16, "gemm_skinny: M must be in [1,16] (got %d)", M);
     P3_CHECK_ARG(K % 64 == 0, "gemm_skinny: K must be a multiple of 64 (got %d)", K);
     P3_CHECK_ARG(epi == P3_EPI_NONE || epi == P3_EPI_RESIDUAL || epi == P3_EPI_SWIGLU || epi == P3_EPI_F32,
@@ -403,6 +407,7 @@ extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, fl
     p.X = (const bf16*)X; p.ldx = ldx; p.norm_w = (const bf16*)norm_w; p.eps = eps; p.W = (const bf16*)W; p.out = out;
     p.ldo = ldo; p.resid = (const bf16*)resid; p.M = M; p.N = N; p.K = K; p.epi = epi;
     p.ss_in = ss_in; p.n_ss_in = n_ss_in; p.ss_out = ss_out;
+    p.l2_pf = (const uint8_t*)l2_prefetch; p.l2_pf_bytes = l2_prefetch_bytes;
     if (epi == P3_EPI_SWIGLU) {
         P3_CHECK_ARG(N % 256 == 0, "gemm_skinny: SwiGLU needs N (gate+up rows) to be a multiple of 256");
         unsigned grid = (unsigned)(N / 2 / 16);
@@ -421,7 +426,8 @@ extern "C" int p3_gemm_skinny_qkv_rope(const void* X, int64_t ldx, const void* n
                                        void* qkv, const float* ss_in, int n_ss_in, const float* cosT, const float* sinT,
                                        int64_t tab_bstride, int B, int L, int n_heads, int n_kv, int hd, int K, int past,
                                        const int32_t* past_dev, int row_div, void* pool, const int32_t* block_table,
-                                       int bt_stride, int write_cache, cudaStream_t st) {
+                                       int bt_stride, int write_cache, const void* l2_prefetch, int64_t l2_prefetch_bytes,
+                                       cudaStream_t st) {
     const int M = B * L;
     P3_CHECK_ARG(M >= 1 && M <= 16, "gemm_skinny_qkv_rope: B*L must be in [1,16] (got %d)", M);
     P3_CHECK_ARG(K % 64 == 0 && ldx % 8 == 0, "gemm_skinny_qkv_rope: K %% 64 and ldx %% 8 required");
@@ -434,6 +440,7 @@ extern "C" int p3_gemm_skinny_qkv_rope(const void* X, int64_t ldx, const void* n
     p.cosT = cosT; p.sinT = sinT; p.tab_bstride = tab_bstride; p.L = L; p.n_heads = n_heads; p.n_kv = n_kv; p.hd = hd;
     p.past = past; p.past_dev = past_dev; p.row_div = row_div; p.write_cache = write_cache;
     p.pool = (bf16*)pool; p.block_table = block_table; p.bt_stride = bt_stride;
+    p.l2_pf = (const uint8_t*)l2_prefetch; p.l2_pf_bytes = l2_prefetch_bytes;
     unsigned grid = (unsigned)((n_heads + n_kv) * (hd / 32) + n_kv * hd / 32);
     return M <= 8 ? launch_skinny<1, 2>(p, grid, st) : launch_skinny<2, 2>(p, grid, st);
 }

@@ -159,6 +159,9 @@ class Phi3B200:
         self._slabs = {}              # recycled KV slabs, keyed by (B, L, max_tokens, quantized)
         self.force_long_rope = None   # parallel.py: LongRoPE switch decided from the global batch (H7)
         self.prefill_chunk = 8192     # long prompts are prefilled in chunks against the paged cache (config 4: 128K)
+        import os as _os
+        self.pf_chain = _os.environ.get('P3_PF_CHAIN', '1') != '0'
+        self._skip = set(filter(None, _os.environ.get('P3_SKIP', '').split(',')))   # timing ablation only (tools/ablate.py)
         self.profile = None      # bench.py: list of (kind, ev0, ev1, algorithmic_bytes) when instrumenting
 
     # ------------------------------------------------------------------ vision weights
@@ -196,12 +199,15 @@ class Phi3B200:
              ptr(row_map), M, N, K, epi, self.gemm_impl, _stream())
         return out
 
-    def skinny(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None, ss_in=None, ss_out=None):
+    L2_PF_CAP = int(__import__('os').environ.get('P3_PF_CAP_MB', '16')) << 20   # bytes of the next kernel's weights parked in L2
+
+    def skinny(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None, ss_in=None, ss_out=None, nxt=None):
         M, K = x.shape
         ev = self._ev()
         n_ss = 0 if ss_in is None else ss_in.shape[0]
+        pf = 0 if nxt is None else min(nxt.numel() * 2, self.L2_PF_CAP)
         call('p3_gemm_skinny', ptr(x), x.stride(0), ptr(norm_w), self.eps, ptr(w), ptr(out), out.stride(0),
-             ptr(resid), M, w.shape[0], K, epi, ptr(ss_in), n_ss, ptr(ss_out), _stream())
+             ptr(resid), M, w.shape[0], K, epi, ptr(ss_in), n_ss, ptr(ss_out), ptr(nxt), pf, _stream())
         self._ev(ev, 'skinny', w.shape[0] * K * 2)
         return out
 
@@ -214,10 +220,11 @@ class Phi3B200:
             self.profile.append((kind, start, e, nbytes))
         return e
 
-    def linear(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None, ss_in=None, ss_out=None):
-        """Route by token count: <=16 rows is a weight stream (skinny), else tensor-core GEMM."""
+    def linear(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None, ss_in=None, ss_out=None, nxt=None):
+        """Route by token count: <=16 rows is a weight stream (skinny), else tensor-core GEMM.
+        `nxt`: weights of the kernel that follows (decode only): pulled into L2 across the kernel boundary."""
         if x.shape[0] <= 16:
-            return self.skinny(x, w, out, epi, norm_w, resid, ss_in, ss_out)
+            return self.skinny(x, w, out, epi, norm_w, resid, ss_in, ss_out, nxt)
         if norm_w is not None:
             xn = torch.empty_like(x)
             call('p3_rmsnorm', ptr(x), ptr(norm_w), ptr(xn), x.shape[0], x.shape[1], self.eps, _stream())
@@ -333,11 +340,13 @@ class Phi3B200:
         for li, lw in enumerate(self.layers):
             pool = cache.pool[li] if cache is not None else None
             wc = 1 if (write_cache and cache is not None) else 0
-            if T <= 16:                                   # decode: qkv_proj + rope + KV write in one launch
+            if 'qkv' in self._skip and T <= 16:
+                pass
+            elif T <= 16:                                   # decode: qkv_proj + rope + KV write in one launch
                 ev = self._ev()
                 call('p3_gemm_skinny_qkv_rope', ptr(h), h.stride(0), ptr(lw['ln1']), self.eps, ptr(lw['qkv']), ptr(qkv),
                      ptr(ss_cur), 0 if ss_cur is None else ss_cur.shape[0], ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads,
-                     self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, st)
+                     self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, None, 0, st)
                 self._ev(ev, 'skinny', self.qkv_dim * H * 2)
             else:
                 self.linear(h, lw['qkv'], qkv, _lib.EPI_NONE, norm_w=lw['ln1'], ss_in=ss_cur)
@@ -346,7 +355,9 @@ class Phi3B200:
             qp = qkv.data_ptr()
             ev = self._ev() if use_decode_attn else None
             pf_bytes = lw['o'].numel() * 2 if T <= 16 else 0      # o_proj weights ride into L2 behind the KV stream
-            if use_decode_attn:
+            if use_decode_attn and 'attn' in self._skip:
+                pass
+            elif use_decode_attn:
                 if cache.quantized and cache.n_quant > 0:
                     call('p3_attention_decode_q4', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim,
                          self.qkv_dim, ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale,
@@ -363,9 +374,14 @@ class Phi3B200:
                      ptr(pool), ptr(bt), bts, n_beam, st)
             if ev is not None:
                 self._ev(ev, 'attn', B * past * 2 * self.n_kv * self.hd * 2)
-            self.linear(att, lw['o'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssB)
-            self.linear(h, lw['gu'], act, _lib.EPI_SWIGLU, norm_w=lw['ln2'], ss_in=ssB)
-            self.linear(act, lw['down'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssA)
+            # decode: every kernel parks (part of) its successor's weights in L2 so HBM never idles at a boundary
+            nxt_qkv = self.layers[li + 1]['qkv'] if li + 1 < len(self.layers) else self.lm_head
+            if not ('o' in self._skip and T <= 16):
+                self.linear(att, lw['o'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssB, nxt=lw['gu'] if self.pf_chain else None)
+            if not ('gu' in self._skip and T <= 16):
+                self.linear(h, lw['gu'], act, _lib.EPI_SWIGLU, norm_w=lw['ln2'], ss_in=ssB, nxt=lw['down'] if self.pf_chain else None)
+            if not ('down' in self._skip and T <= 16):
+                self.linear(act, lw['down'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssA, nxt=nxt_qkv if self.pf_chain else None)
             ss_cur = ssA
         if logits_rows == 'none':
             return None

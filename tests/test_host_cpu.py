@@ -50,7 +50,7 @@ def test_bad_arguments_fail_loudly_without_gpu():
     import phi3_b200  # noqa
     from phi3_b200 import _lib
     with pytest.raises(RuntimeError, match='M must be in'):
-        _lib.call('p3_gemm_skinny', None, 8, None, 1e-5, None, None, 8, None, 17, 64, 64, 0, None, 0, None, None)
+        _lib.call('p3_gemm_skinny', None, 8, None, 1e-5, None, None, 8, None, 17, 64, 64, 0, None, 0, None, None, 0, None)
     with pytest.raises(RuntimeError, match='head_dim must be 96 or 64'):
         _lib.call('p3_attention_prefill', None, None, None, 8, 8, 8, None, 8, 1, 1, 1, 1, 80, 1.0, 1, 0, None, None, None, 0, 1, None)
     with pytest.raises(RuntimeError, match='n_top'):

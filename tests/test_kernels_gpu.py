@@ -172,21 +172,21 @@ def test_gemm_skinny(dev, M, mode):
         from phi3_b200.model import interleave_gate_up
         out = torch.zeros(M, N // 2, device=dev, dtype=torch.bfloat16)
         L.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr(), 1e-5, interleave_gate_up(w).data_ptr(), out.data_ptr(),
-               N // 2, None, M, N, K, 4, None, 0, None, st())
+               N // 2, None, M, N, K, 4, None, 0, None, None, 0, st())
         g, u = bf(acc[:, :N // 2]).float(), bf(acc[:, N // 2:]).float()
         ref = bf(bf(torch.nn.functional.silu(g)).float() * u)
     elif mode == 'f32':
         out = torch.zeros(M, N, device=dev)
-        L.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr(), 1e-5, w.data_ptr(), out.data_ptr(), N, None, M, N, K, 5, None, 0, None, st())
+        L.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr(), 1e-5, w.data_ptr(), out.data_ptr(), N, None, M, N, K, 5, None, 0, None, None, 0, st())
         ref = acc
     elif mode == 'resid':
         out = bf(torch.randn(M, N, device=dev))
         ref = bf(out.float() + bf(acc).float())
-        L.call('p3_gemm_skinny', x.data_ptr(), K, None, 1e-5, w.data_ptr(), out.data_ptr(), N, out.data_ptr(), M, N, K, 3, None, 0, None, st())
+        L.call('p3_gemm_skinny', x.data_ptr(), K, None, 1e-5, w.data_ptr(), out.data_ptr(), N, out.data_ptr(), M, N, K, 3, None, 0, None, None, 0, st())
     else:
         out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
         L.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr() if mode == 'norm' else None, 1e-5, w.data_ptr(),
-               out.data_ptr(), N, None, M, N, K, 0, None, 0, None, st())
+               out.data_ptr(), N, None, M, N, K, 0, None, 0, None, None, 0, st())
         ref = bf(acc)
     _check(out, ref, tol=1e-2)
 
@@ -355,7 +355,7 @@ def test_skinny_ss_partials_feed_fused_rmsnorm(dev):
     h = bf(torch.randn(M, H, device=dev))
     ss = torch.zeros((H // 16, 16), device=dev)
     L.call('p3_gemm_skinny', act.data_ptr(), H, None, 1e-5, wo.data_ptr(), h.data_ptr(), H, h.data_ptr(), M, H, H, 3,
-           None, 0, ss.data_ptr(), st())
+           None, 0, ss.data_ptr(), None, 0, st())
     torch.cuda.synchronize()
     ref_ss = h.float().pow(2).sum(-1)
     got_ss = ss.sum(0)[:M]
@@ -366,9 +366,9 @@ def test_skinny_ss_partials_feed_fused_rmsnorm(dev):
     o1 = torch.zeros(M, 1024, device=dev, dtype=torch.bfloat16)
     o2 = torch.zeros_like(o1)
     L.call('p3_gemm_skinny', h.data_ptr(), H, nw.data_ptr(), 1e-5, w2.data_ptr(), o1.data_ptr(), 1024, None, M, 1024, H, 0,
-           ss.data_ptr(), H // 16, None, st())
+           ss.data_ptr(), H // 16, None, None, 0, st())
     L.call('p3_gemm_skinny', h.data_ptr(), H, nw.data_ptr(), 1e-5, w2.data_ptr(), o2.data_ptr(), 1024, None, M, 1024, H, 0,
-           None, 0, None, st())
+           None, 0, None, None, 0, st())
     torch.cuda.synchronize()
     assert (o1.float() - o2.float()).abs().max() <= 2 ** -7 * o2.float().abs().max()
     assert (o1 != o2).float().mean() < 0.02
@@ -401,11 +401,11 @@ def test_fused_qkv_rope_matches_unfused(dev, M):
     q1 = torch.zeros(T, 3 * nh * D, device=dev, dtype=torch.bfloat16)
     q2 = torch.zeros_like(q1)
     L.call('p3_gemm_skinny', x.data_ptr(), H, nw.data_ptr(), 1e-5, w.data_ptr(), q1.data_ptr(), 3 * nh * D, None, T, 3 * nh * D, H, 0,
-           None, 0, None, st())
+           None, 0, None, None, 0, st())
     L.call('p3_rope_kvwrite', q1.data_ptr(), cos.data_ptr(), sin.data_ptr(), S * (D // 2), B, Lq, nh, nh, D, past, 1,
            pool1.data_ptr(), bt.data_ptr(), pps, 1, None, st())
     L.call('p3_gemm_skinny_qkv_rope', x.data_ptr(), H, nw.data_ptr(), 1e-5, w.data_ptr(), q2.data_ptr(), None, 0, cos.data_ptr(),
-           sin.data_ptr(), S * (D // 2), B, Lq, nh, nh, D, H, past, None, 1, pool2.data_ptr(), bt.data_ptr(), pps, 1, st())
+           sin.data_ptr(), S * (D // 2), B, Lq, nh, nh, D, H, past, None, 1, pool2.data_ptr(), bt.data_ptr(), pps, 1, None, 0, st())
     torch.cuda.synchronize()
     tol = 2 ** -7 * q1.float().abs().max()
     assert (q1.float() - q2.float()).abs().max() <= tol

@@ -43,7 +43,7 @@ def bench_skinny():
 
         def fn(i):
             _lib.call('p3_gemm_skinny', x.data_ptr(), K, nw.data_ptr() if norm else None, 1e-5, W[i % copies].data_ptr(),
-                      out.data_ptr(), No, out.data_ptr() if epi == 3 else None, M, N, K, epi, None, 0, None, st())
+                      out.data_ptr(), No, out.data_ptr() if epi == 3 else None, M, N, K, epi, None, 0, None, None, 0, st())
         us = timeit(fn)
         gbs = N * K * 2 / us / 1e3
         print(f'skinny {name:22s} N={N:6d} K={K:5d}  {us:7.2f} us  {gbs:7.0f} GB/s  {100 * gbs / PEAK:5.1f}% of measured HBM peak')
