@@ -134,6 +134,10 @@ class Phi3B200:
         self.gemm_impl = gemm_impl
         self.H = cfg.hidden_size
         self.n_heads, self.n_kv = cfg.num_attention_heads, cfg.num_key_value_heads
+        if self.n_kv != self.n_heads:
+            # the reference graph has no repeat_kv (phi.py:454 multiplies q[B,H,..] with k[B,Hkv,..] directly), so
+            # grouped-query checkpoints are outside its behaviour; the kernels take n_kv but the host graph does not
+            raise NotImplementedError('num_key_value_heads != num_attention_heads is not supported by the reference graph')
         self.hd = self.H // self.n_heads
         self.qkv_dim = (self.n_heads + 2 * self.n_kv) * self.hd
         self.I = cfg.intermediate_size

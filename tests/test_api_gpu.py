@@ -187,3 +187,22 @@ def test_generate_top_p_extension(dev):
     tiny_p = api._generate(model, proc, p, top_p=1e-6, seed=5, **kw).cpu()
     assert torch.equal(a, b) and not torch.equal(a, c)          # seeded, reproducible
     assert torch.equal(tiny_p, g)                               # top_p -> 0 degenerates to greedy
+
+
+def test_api_edge_cases(dev):
+    api, model, proc, ora = _setup()
+    # single-token prompt, max_tokens = 1 (no decode loop), B = 1 str in -> str out
+    out = api.generate('x', preload=(model, proc), max_tokens=1, verbose=False, stream=False, apply_chat_template=False)
+    assert isinstance(out, str)
+    # constrain with max_new = 0 appends exactly the constraint
+    out = api.constrain('Question?', constraints=[(0, ' The')], preload=(model, proc), verbose=False)
+    assert out.endswith(' The') or ' The' in out
+    # 16 prompts (largest skinny batch) and ragged lengths
+    prompts = ['p' * (i + 1) for i in range(16)]
+    outs = api.generate(prompts, preload=(model, proc), max_tokens=4, verbose=False, stream=False)
+    assert len(outs) == 16
+    # 17 prompts (decode falls back to the tensor-core GEMM path, no graph)
+    outs = api.generate(prompts + ['q'], preload=(model, proc), max_tokens=3, verbose=False, stream=False)
+    assert len(outs) == 17
+    ch = api.choose(prompts[:3], choices='AB', preload=(model, proc), verbose=False)
+    assert all(c in 'AB' for c in ch)

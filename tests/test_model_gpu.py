@@ -261,3 +261,70 @@ def test_long_rope_factors_past_4096(dev):
     lg_short, _ = m(ids, max_tokens=4, logits_rows='last')
     m.force_long_rope = None
     assert rel(lg_short[:, -1], lo[:, -1] * 0 + lg[:, -1].cpu()) > 1e-3
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (1, 16), (1, 17), (16, 1), (2, 8), (3, 63), (2, 64), (2, 65), (5, 129)])
+def test_token_count_and_page_boundaries(dev, shape):
+    """skinny (<=16 tokens) vs tensor-core GEMM routing, L = 1, page-boundary prompt lengths, decode across a
+    page boundary, B up to 16."""
+    cfg, w, m, o = _setup()
+    B, L = shape
+    ids = _ids(B, L, seed=50 + B * 131 + L)
+    lo, co = o(ids, max_tokens=4)
+    lg, cg = m(ids, max_tokens=4)
+    assert rel(lg, lo) < TOL
+    tok = lo[:, -1].argmax(-1)
+    for _ in range(3):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        assert rel(lg, lo) < TOL
+        tok = lo[:, -1].argmax(-1)
+
+
+def test_heavy_left_padding_skips_whole_pages(dev):
+    """kv_start beyond one 64-token page: the decode kernel starts at a later tile; pad rows stay finite."""
+    cfg, w, m, o = _setup()
+    L = 200
+    ids = _ids(2, L, seed=61)
+    pad = 150
+    ids[1, :pad] = 0
+    pids = torch.stack([torch.arange(L), torch.cat([torch.ones(pad, dtype=torch.long), torch.arange(L - pad)])])
+    mask = torch.ones(2, L, dtype=torch.long)
+    mask[1, :pad] = 0
+    lo, co = o(ids, pids=pids, mask=mask, max_tokens=5)
+    lg, cg = m(ids, pids=pids, mask=mask, max_tokens=5)
+    assert torch.isfinite(lg).all()
+    valid = mask.bool()
+    assert ((lg.cpu() - lo).abs()[valid].max() / lo[valid].abs().max()).item() < TOL
+    tok = lo[:, -1].argmax(-1)
+    for _ in range(4):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        assert rel(lg, lo) < TOL
+        tok = lo[:, -1].argmax(-1)
+
+
+def test_two_images_one_prompt(dev):
+    """two images of different crop grids spliced into one row (positions / idx advance, phi.py:412-415)"""
+    cfg, w, m, o = _setup(vision=True)
+    g = torch.Generator().manual_seed(7)
+    pv = torch.zeros(2, 5, 3, 336, 336)
+    pv[0] = torch.randn(5, 3, 336, 336, generator=g)                  # 2x2 grid
+    pv[1, :3] = torch.randn(3, 3, 336, 336, generator=g)              # 1x2 grid (+2 zero-pad crops)
+    sizes = torch.tensor([[672, 672], [336, 672]])
+    n1 = (4 + 1) * 144 + 1 + 3 * 12
+    n2 = (2 + 1) * 144 + 1 + 2 * 12
+    ids = torch.cat([torch.tensor([1, 9]), torch.full((n1,), -1), torch.tensor([1, 7]), torch.full((n2,), -2), torch.tensor([1, 5, 6])])[None]
+    pos = torch.nonzero(ids < 0)
+    lo, _ = o(ids, pixel_values=pv, image_sizes=sizes, positions=pos, max_tokens=2)
+    lg, _ = m(ids, pixel_values=pv, image_sizes=sizes, positions=pos, max_tokens=2)
+    assert rel(lg, lo) < TOL
+
+
+def test_gqa_is_rejected_like_the_reference_graph(dev):
+    import phi3_b200  # noqa
+    from phi3_b200 import configs
+    from phi3_b200.model import Phi3B200
+    cfg = configs.tiny(num_key_value_heads=2)
+    with pytest.raises(NotImplementedError):
+        Phi3B200(cfg, {})
