@@ -193,6 +193,8 @@ def test_api_edge_cases(dev):
     api, model, proc, ora = _setup()
     # single-token prompt, max_tokens = 1 (no decode loop), B = 1 str in -> str out
     out = api.generate('x', preload=(model, proc), max_tokens=1, verbose=False, stream=False, apply_chat_template=False)
+    assert isinstance(out, list) and len(out) == 1      # reference: non-streamed output is always batch_decode's list (pv:72-77)
+    out = api.generate('x', preload=(model, proc), max_tokens=2, verbose=False, stream=True, apply_chat_template=False)
     assert isinstance(out, str)
     # constrain with max_new = 0 appends exactly the constraint
     out = api.constrain('Question?', constraints=[(0, ' The')], preload=(model, proc), verbose=False)

@@ -72,6 +72,33 @@ def bench_attn():
             print(f'attn_decode B={B:2d} S={S:5d} splits={ns:2d} ({B * H * ns:5d} CTAs)  {us:7.2f} us  {gbs:7.0f} GB/s  {100 * gbs / PEAK:5.1f}%')
 
 
+def bench_attn_q4():
+    H, D = 32, 96
+    for B, S in [(8, 2176), (16, 448)]:
+        pps = (S + 64) // 64 + 1
+        n_quant = (S // 64) * 64
+        pool = torch.randn(B * pps, 2, H, 64, D, device=dev).to(torch.bfloat16)
+        qc = torch.zeros(B * pps, 2, H, 64, D // 2, dtype=torch.uint8, device=dev)
+        qm = torch.zeros(B * pps, 2, H, 64, D // 32, 2, dtype=torch.bfloat16, device=dev)
+        bt = torch.arange(B * pps, dtype=torch.int32, device=dev).reshape(B, pps)
+        _lib.call('p3_kv_quantize_q4g32', pool.data_ptr(), qc.data_ptr(), qm.data_ptr(), bt.data_ptr(), pps, B, S, H, D, st())
+        qkv = torch.randn(B, 3 * H * D, device=dev).to(torch.bfloat16)
+        out = torch.zeros(B, H * D, device=dev, dtype=torch.bfloat16)
+        kv0 = torch.zeros(B, dtype=torch.int32, device=dev)
+        for ns in sorted({1, 2, 4}):
+            ws = torch.zeros(_lib.lib().p3_attention_decode_workspace(B, 1, H, D, ns) // 4, device=dev)
+            p = qkv.data_ptr()
+
+            def fn(i):
+                _lib.call('p3_attention_decode_q4', p, p + H * D * 2, p + 2 * H * D * 2, 3 * H * D, 3 * H * D, 3 * H * D,
+                          out.data_ptr(), H * D, B, 1, H, H, D, D ** -0.5, S, n_quant, kv0.data_ptr(), pool.data_ptr(),
+                          qc.data_ptr(), qm.data_ptr(), bt.data_ptr(), pps, 1, ns, ws.data_ptr(), None, None, 0, st())
+            us = timeit(fn)
+            q4_bytes = B * n_quant * 2 * H * (D // 2 + (D // 32) * 4) + B * (S - n_quant) * 2 * H * D * 2
+            print(f'attn_decode_q4 B={B:2d} S={S:5d} splits={ns:2d}  {us:7.2f} us  {q4_bytes / us / 1e3:7.0f} GB/s of q4 bytes '
+                  f'({100 * q4_bytes / us / 1e3 / PEAK:5.1f}%)  = {B * S * 2 * H * D * 2 / us / 1e3:7.0f} GB/s bf16-equivalent')
+
+
 def bench_gemm():
     for M, N, K, epi in [(16384, 9216, 3072, 0), (16384, 3072, 3072, 3), (16384, 16384, 3072, 4), (16384, 3072, 8192, 3),
                          (23080, 3072, 1024, 0), (23080, 4096, 1024, 1), (23080, 1024, 4096, 6), (2885, 3072, 1024, 0),
@@ -98,3 +125,5 @@ if __name__ == '__main__':
         bench_attn()
     if 'gemm' in which:
         bench_gemm()
+    if 'q4' in which:
+        bench_attn_q4()
