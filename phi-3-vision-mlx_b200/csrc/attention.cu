@@ -11,39 +11,8 @@
 // Keys [0,past) are read from the paged pool, keys [past,past+L) from the freshly roped
 // qkv buffer ("dual source"), which is what makes the read-only beam step of phi.py:523-527 a
 // plain call with row_div = n_beam.
-#include "common.cuh"
+#include "attn_common.cuh"
 #include "../../include/phi3_b200.h"
-
-template <int D> struct Swz;
-template <> struct Swz<96> { static __device__ __forceinline__ int f(int c, int r) { return c ^ ((r >> 1) & 3); } };
-template <> struct Swz<64> { static __device__ __forceinline__ int f(int c, int r) { return c ^ (r & 7); } };
-
-// byte offset of 16B chunk c of row r inside a [rows][D] bf16 tile
-template <int D>
-__device__ __forceinline__ uint32_t tile_off(int r, int c) { return (uint32_t)(r * (D * 2) + Swz<D>::f(c, r) * 16); }
-
-struct AttnParams {
-    const bf16 *q, *k, *v;
-    int64_t ldq, ldk, ldv;
-    bf16* out; int64_t ldo;
-    int B, L, n_heads, n_kv, hd;
-    float scale_log2;
-    int causal, past;
-    int past_host; const int32_t* past_dev;   // decode: past read from device memory when past_dev != NULL (CUDA-graph replay)
-    const int32_t* kv_start;
-    const bf16* pool;
-    const int32_t* block_table; int bt_stride;
-    int row_div;
-    // decode only
-    int n_splits, tiles_per_split;
-    float* ws_o; float* ws_ml;
-    const uint8_t* l2_prefetch; int64_t l2_prefetch_bytes;   // next kernel's weights (o_proj) pulled into L2 while KV streams
-    int* counters;              // [B*n_heads] split-arrival counters (zero on entry, reset by the merging CTA)
-    // quantised-cache decode: positions [0, n_quant) (multiple of 64) live in the q4 pools
-    int n_quant;
-    const uint8_t* qcodes;      // [page][2][n_kv][64][D/2]
-    const bf16* qmeta;          // [page][2][n_kv][64][D/32][2] (scale, bias)
-};
 
 // Load a 64-key K tile and V tile (absolute key positions [64n, 64n+64)) into shared memory.
 template <int D, int THREADS>
@@ -161,11 +130,6 @@ __device__ __forceinline__ void softmax_update(float (*s)[4], float* m, float* l
 // ------------------------------------------------------------------------------------------
 #define PF_STAGES 3
 #define PF_THREADS 256
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 template <int D>
 __global__ void __launch_bounds__(PF_THREADS, 2) attn_prefill_kernel(AttnParams p) {
@@ -663,7 +627,7 @@ static int fill_params(AttnParams& p, const void* q, const void* k, const void* 
     p.causal = causal; p.past = past; p.past_host = past; p.past_dev = nullptr; p.kv_start = kv_start;
     p.pool = (const bf16*)pool; p.block_table = block_table; p.bt_stride = bt_stride; p.row_div = row_div;
     p.n_splits = 1; p.tiles_per_split = 0; p.ws_o = nullptr; p.ws_ml = nullptr; p.counters = nullptr;
-    p.l2_prefetch = nullptr; p.l2_prefetch_bytes = 0;
+    p.l2_prefetch = nullptr; p.l2_prefetch_bytes = 0; p.zero = 0;
     p.n_quant = 0; p.qcodes = nullptr; p.qmeta = nullptr;
     return 0;
 }
@@ -696,6 +660,8 @@ extern "C" int64_t p3_attention_decode_workspace(int B, int L, int n_heads, int 
     return (int64_t)B * n_heads * n_splits * 16 * (hd + 2) * 4 + (int64_t)B * n_heads * 4;   // partials + arrival counters
 }
 
+int launch_decode_q4_d96(AttnParams& p, cudaStream_t st);      // attention_q4.cu
+
 template <int D, bool Q4>
 static int launch_decode(AttnParams& p, cudaStream_t st) {
     dim3 grid(p.n_splits, p.n_heads, p.B);
@@ -722,7 +688,7 @@ static int decode_common(AttnParams& p, int L, int past, int n_splits, void* wor
     p.ws_o = (float*)workspace;
     p.ws_ml = p.ws_o ? p.ws_o + (size_t)p.B * p.n_heads * n_splits * 16 * p.hd : nullptr;
     p.counters = p.ws_o ? reinterpret_cast<int*>(p.ws_ml + (size_t)p.B * p.n_heads * n_splits * 16 * 2) : nullptr;
-    if (p.hd == 96) return q4 ? launch_decode<96, true>(p, st) : launch_decode<96, false>(p, st);
+    if (p.hd == 96) return q4 ? launch_decode_q4_d96(p, st) : launch_decode<96, false>(p, st);   // q4: register-dequant kernel
     return q4 ? launch_decode<64, true>(p, st) : launch_decode<64, false>(p, st);
 }
 

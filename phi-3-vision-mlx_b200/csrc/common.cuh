@@ -60,6 +60,10 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     return pol;
 }
 __device__ __forceinline__ void cp_async16_stream(uint32_t dst, const void* src, uint64_t pol) {
+    // NOTE: with a [R + UR + imm] shared address (a warp-uniform stage base) ptxas 12.9 places the 64-bit
+    // policy descriptor in an odd uniform register (desc[UR1]) and the hardware rejects the LDGSTS as an
+    // illegal instruction. Callers keep the stage base in a vector register (stage index + zero*tid);
+    // the build greps the SASS for odd descriptors (Makefile `check-sass`).
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "l"(pol) : "memory");
 }
 // each CTA of a grid pulls its slice of [ptr, ptr+bytes) into L2 (the next kernel's weights)

@@ -235,6 +235,13 @@ class Phi3B200:
             x = xn
         return self.gemm(x, w, out, epi, resid=resid)
 
+    def _splits(self, cache, B, tiles):
+        n_bh = B * self.n_heads
+        if cache is not None and cache.quantized:
+            # the 4-bit kernel is ALU-bound (register dequant), 3 CTAs/SM resident: fill the 444 slots
+            return max(1, min((3 * 148 + n_bh // 2) // n_bh, max(1, tiles // 4)))
+        return pick_splits(n_bh, tiles)
+
     # ------------------------------------------------------------------ rope table (phi:487-507)
     def _rope_table(self, L_all, pids):
         cfg = self.cfg
@@ -331,7 +338,7 @@ class Phi3B200:
         ws = None
         if use_decode_attn:
             if n_splits is None:
-                n_splits = pick_splits(B * self.n_heads, max(1, (past + PAGE - 1) // PAGE))
+                n_splits = self._splits(cache, B, max(1, (past + PAGE - 1) // PAGE))
             if n_splits > 1:
                 ws = torch.zeros(_lib.lib().p3_attention_decode_workspace(B, L, self.n_heads, self.hd, n_splits) // 4,
                                  dtype=torch.float32, device=dev)        # zero: holds the split-arrival counters
@@ -519,7 +526,7 @@ class DecodeSession:
         if cache.offset + max_steps > cache.S_max:
             raise ValueError('KV cache overflow: decode session longer than the cache was sized for')
         tiles = (cache.offset + max_steps + PAGE - 1) // PAGE
-        self.n_splits = pick_splits(B * model.n_heads, tiles)
+        self.n_splits = model._splits(cache, B, tiles)
         if use_graph and B <= 16:
             cur = torch.cuda.current_stream()
             s = torch.cuda.Stream()
