@@ -208,3 +208,39 @@ def test_api_edge_cases(dev):
     assert len(outs) == 17
     ch = api.choose(prompts[:3], choices='AB', preload=(model, proc), verbose=False)
     assert all(c in 'AB' for c in ch)
+
+
+def test_early_stop_and_streaming_paths(dev, capsys):
+    """LogitStopper (pv:79-104) runs un-graphed B=1 steps; Streamer prints incrementally (pv:52-65)."""
+    api, model, proc, ora = _setup()
+    out = api.generate('Tell me something', preload=(model, proc), max_tokens=12, verbose=True, stream=True, early_stop=3)
+    assert isinstance(out, str)
+    printed = capsys.readouterr().out
+    assert '*** Prompt ***' in printed and 'tokens-per-sec' in printed
+    ref = api.generate('Tell me something', preload=(model, proc), max_tokens=12, verbose=False, stream=True)
+    assert out == ref[:len(out)] or ref == out[:len(ref)]          # early stop only truncates the greedy continuation
+
+
+def test_load_from_safetensors_dir(dev, tmp_path):
+    """N2 (real-weight loading path): HF-layout safetensors incl. the [O,I,kh,kw] patch-embedding transpose (pv:371-374)."""
+    import phi3_b200  # noqa
+    from safetensors.torch import save_file
+    from phi3_b200 import configs, weights, api
+    from phi3_b200.processor import ByteTokenizer
+    cfg = configs.tiny(vision=True)
+    clip = configs.tiny_clip(3)
+    w = weights.random_weights(cfg, seed=5, clip_cfg=clip)
+    hf = dict(w)
+    key = 'model.vision_embed_tokens.img_processor.vision_model.embeddings.patch_embedding.weight'
+    hf[key] = w[key].permute(0, 3, 1, 2).contiguous()               # HF stores [O,I,kh,kw]
+    half = len(hf) // 2
+    items = list(hf.items())
+    save_file({k: v.contiguous() for k, v in items[:half]}, str(tmp_path / 'model-00001-of-00002.safetensors'))
+    save_file({k: v.contiguous() for k, v in items[half:]}, str(tmp_path / 'model-00002-of-00002.safetensors'))
+    m1, p1 = api.load(cfg=cfg, weights=str(tmp_path), tokenizer=ByteTokenizer(), clip_cfg=clip, num_crops=4)
+    m2, p2 = api.load(cfg=cfg, weights=w, tokenizer=ByteTokenizer(), clip_cfg=clip, num_crops=4)
+    img = np.random.RandomState(1).randint(0, 256, (300, 400, 3), dtype=np.uint8)
+    prompt, imgs = api._apply_chat_template('hi', [img], False)
+    a = m1(**p1(prompt, imgs), max_tokens=2)[0]
+    b = m2(**p2(prompt, imgs), max_tokens=2)[0]
+    assert torch.equal(a, b)
