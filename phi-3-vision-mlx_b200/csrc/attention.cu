@@ -3,11 +3,11 @@
 //    Replaces the explicit scores/softmax/PV of phi.py:454-457 and the dense Mask4D of
 //    phi.py:550-563 (predicate: causal + per-row left-pad start) and
 //    mx.fast.scaled_dot_product_attention of phi.py:148 (causal = 0).
-//  * attn_decode_kernel  : memory-bound split-KV attention for <=16 new tokens per row over the
+//  * attn_decode_kernel  : (bf16; the 4-bit variant lives in attention_q4.cu) memory-bound split-KV attention for <=16 new tokens per row over the
 //    paged bf16 KV pool (phi.py:454-457 + KVCache reads phi.py:523-527,548). 16-byte coalesced
 //    cp.async loads of whole 12 KB page slices into a 4-stage shared-memory ring, warp-shuffle
 //    softmax reductions, tensor-core (mma.sync) dot products so L<=16 queries cost one pass.
-//  * attn_merge_kernel   : combines split partials.
+//    (split partials are merged in-kernel by the last CTA of each (row, head) to arrive)
 // Keys [0,past) are read from the paged pool, keys [past,past+L) from the freshly roped
 // qkv buffer ("dual source"), which is what makes the read-only beam step of phi.py:523-527 a
 // plain call with row_div = n_beam.
@@ -289,14 +289,12 @@ __global__ void __launch_bounds__(PF_THREADS, 2) attn_prefill_kernel(AttnParams 
 // ------------------------------------------------------------------------------------------
 #define DEC_STAGES 4
 
-template <int D, bool Q4>
+template <int D>
 __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
     constexpr int CPR = D / 8, TILE = 64 * D * 2, NSLOT = 64 * CPR / 128;
-    constexpr int QC = 64 * D / 2, QM = 64 * (D / 32) * 4;      // bytes of codes / meta per (page, kv, head)
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sq = smem_u32(smem);                         // 16 x D query tile
     const uint32_t skv = sq + 16 * D * 2;                       // [DEC_STAGES][K,V]
-    const uint32_t sdq = skv + DEC_STAGES * 2 * TILE;           // Q4: dequantised bf16 K,V tile
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int kvh = h / (p.n_heads / p.n_kv);
@@ -336,22 +334,6 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
     const uint64_t pol = l2_evict_first_policy();
     auto issue_cached = [&](int it, int page) {
         const uint32_t sk = skv + (it % DEC_STAGES) * 2 * TILE;
-        if (Q4 && (n_lo + it) * 64 < p.n_quant) {
-            // stage layout: [K codes | V codes | K meta | V meta]
-            const uint8_t* kc = p.qcodes + ((size_t)page * 2 * p.n_kv + kvh) * QC;
-            const uint8_t* vc = kc + (size_t)p.n_kv * QC;
-            const uint8_t* km = reinterpret_cast<const uint8_t*>(p.qmeta) + ((size_t)page * 2 * p.n_kv + kvh) * QM;
-            const uint8_t* vm = km + (size_t)p.n_kv * QM;
-            for (int idx = tid; idx < QC / 16; idx += 128) {
-                cp_async16(sk + idx * 16, kc + idx * 16);
-                cp_async16(sk + QC + idx * 16, vc + idx * 16);
-            }
-            for (int idx = tid; idx < QM / 16; idx += 128) {
-                cp_async16(sk + 2 * QC + idx * 16, km + idx * 16);
-                cp_async16(sk + 2 * QC + QM + idx * 16, vm + idx * 16);
-            }
-            return;
-        }
         const bf16* kp = pool_k + (size_t)page * page_elems;
 #pragma unroll
         for (int i = 0; i < NSLOT; i++) {
@@ -429,30 +411,8 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
                 ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], sq + tile_off<D>(r, c));
             }
         }
-        uint32_t sk = skv + (it % DEC_STAGES) * 2 * TILE, sv = sk + TILE;
+        const uint32_t sk = skv + (it % DEC_STAGES) * 2 * TILE, sv = sk + TILE;
         const bool present = it >= n_cached;
-        if (Q4 && !present && (n_lo + it) * 64 < p.n_quant) {
-            // dequantise codes -> bf16 swizzled tiles: deq = bf16(q*scale + bias) (mx.dequantize, phi.py:536-537)
-            const uint8_t* st = smem + (sk - smem_u32(smem));
-            for (int idx = tid; idx < 2 * 64 * CPR; idx += 128) {
-                int kv = idx / (64 * CPR), rem = idx % (64 * CPR);
-                int r = rem / CPR, c = rem % CPR;
-                uint32_t codes = *reinterpret_cast<const uint32_t*>(st + kv * QC + r * (D / 2) + c * 4);
-                uint32_t meta = *reinterpret_cast<const uint32_t*>(st + 2 * QC + kv * QM + (r * (D / 32) + c / 4) * 4);
-                float2 sb = unpack_bf16(meta);
-                uint4 ov;
-                uint32_t* ou = reinterpret_cast<uint32_t*>(&ov);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    float lo = __fadd_rn(__fmul_rn((float)((codes >> (8 * j)) & 15), sb.x), sb.y);
-                    float hi = __fadd_rn(__fmul_rn((float)((codes >> (8 * j + 4)) & 15), sb.x), sb.y);
-                    ou[j] = pack_bf16(lo, hi);
-                }
-                *reinterpret_cast<uint4*>(smem + (sdq - smem_u32(smem)) + kv * TILE + tile_off<D>(r, c)) = ov;
-            }
-            __syncthreads();
-            sk = sdq; sv = sdq + TILE;
-        }
         if (present && warp != 0) continue;                     // 16 new keys: one warp
         // ---- S = Q K^T for this warp's 16 keys
         float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -586,28 +546,6 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
     }
 }
 
-template <int D>
-__global__ void attn_merge_kernel(AttnParams p) {
-    pdl_trigger();
-    pdl_wait();
-    const int h = blockIdx.x, b = blockIdx.y;
-    for (int idx = threadIdx.x; idx < p.L * D; idx += blockDim.x) {
-        int r = idx / D, d = idx % D;
-        size_t base0 = (((size_t)b * p.n_heads + h) * p.n_splits) * 16 + r;
-        float mm = -INFINITY;
-        for (int s = 0; s < p.n_splits; s++) mm = fmaxf(mm, p.ws_ml[(base0 + (size_t)s * 16) * 2]);
-        float mu = (mm == -INFINITY) ? 0.f : mm;
-        float acc = 0.f, ll = 0.f;
-        for (int s = 0; s < p.n_splits; s++) {
-            size_t bs = base0 + (size_t)s * 16;
-            float f = exp2f(p.ws_ml[bs * 2] - mu);
-            acc += f * p.ws_o[bs * D + d];
-            ll += f * p.ws_ml[bs * 2 + 1];
-        }
-        p.out[((size_t)b * p.L + r) * p.ldo + h * D + d] = __float2bfloat16_rn(ll > 0.f ? acc / ll : 0.f);
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // host entry points
 // ------------------------------------------------------------------------------------------
@@ -662,17 +600,17 @@ extern "C" int64_t p3_attention_decode_workspace(int B, int L, int n_heads, int 
 
 int launch_decode_q4_d96(AttnParams& p, cudaStream_t st);      // attention_q4.cu
 
-template <int D, bool Q4>
+template <int D>
 static int launch_decode(AttnParams& p, cudaStream_t st) {
     dim3 grid(p.n_splits, p.n_heads, p.B);
-    int smem = 16 * D * 2 + DEC_STAGES * 2 * 64 * D * 2 + (Q4 ? 2 * 64 * D * 2 : 0);
+    int smem = 16 * D * 2 + DEC_STAGES * 2 * 64 * D * 2;
     static bool set = false;
     if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<D, Q4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         P3_CHECK_ARG(e == cudaSuccess, "attention_decode: smem attribute: %s", cudaGetErrorString(e));
         set = true;
     }
-    p3_launch_pdl(attn_decode_kernel<D, Q4>, grid, dim3(128), (size_t)smem, st, p);
+    p3_launch_pdl(attn_decode_kernel<D>, grid, dim3(128), (size_t)smem, st, p);
     P3_CHECK_LAUNCH("attention_decode");       // split partials are merged in-kernel by the last CTA to arrive
     return 0;
 }
@@ -688,8 +626,9 @@ static int decode_common(AttnParams& p, int L, int past, int n_splits, void* wor
     p.ws_o = (float*)workspace;
     p.ws_ml = p.ws_o ? p.ws_o + (size_t)p.B * p.n_heads * n_splits * 16 * p.hd : nullptr;
     p.counters = p.ws_o ? reinterpret_cast<int*>(p.ws_ml + (size_t)p.B * p.n_heads * n_splits * 16 * 2) : nullptr;
-    if (p.hd == 96) return q4 ? launch_decode_q4_d96(p, st) : launch_decode<96, false>(p, st);   // q4: register-dequant kernel
-    return q4 ? launch_decode<64, true>(p, st) : launch_decode<64, false>(p, st);
+    P3_CHECK_ARG(!q4 || p.hd == 96, "attention_decode_q4: only head_dim 96 is supported");
+    if (p.hd == 96) return q4 ? launch_decode_q4_d96(p, st) : launch_decode<96>(p, st);   // q4: register-dequant kernel (attention_q4.cu)
+    return launch_decode<64>(p, st);
 }
 
 extern "C" int p3_attention_decode(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
