@@ -570,6 +570,9 @@ static int fill_params(AttnParams& p, const void* q, const void* k, const void* 
     return 0;
 }
 
+bool attn_prefill_tc_eligible(const AttnParams& p);             // attention_tc.cu
+int launch_prefill_tc(const AttnParams& p, cudaStream_t st);
+
 extern "C" int p3_attention_prefill(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                                     void* out, int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale,
                                     int causal, int past, const int32_t* kv_start, const void* pool,
@@ -578,6 +581,7 @@ extern "C" int p3_attention_prefill(const void* q, const void* k, const void* v,
     if (fill_params(p, q, k, v, ldq, ldk, ldv, out, ldo, B, L, n_heads, n_kv, hd, scale, causal, past, kv_start, pool,
                     block_table, bt_stride, row_div)) return -1;
     if (B == 0 || L == 0) return 0;
+    if (attn_prefill_tc_eligible(p)) return launch_prefill_tc(p, st);   // tcgen05 flash attention (attention_tc.cu)
     dim3 grid((L + 127) / 128, n_heads, B);
     int smem = (2 + 2 * PF_STAGES) * 64 * hd * 2;
     if (hd == 96) {
