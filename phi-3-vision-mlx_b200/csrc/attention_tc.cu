@@ -3,35 +3,47 @@
 // causal + left-pad predicate of phi.py:550-563, keys [0,past) from the paged pool and keys
 // [past,past+L) from the fresh qkv rows (phi.py:454-457; ViT: phi.py:148 with causal = 0).
 //
-// One CTA = 128 query rows of one (sequence, head); key tiles of 128.
-//   warps 0-7 : softmax — two threads per query row (TMEM lane = row; warps w and w+4 take 64 keys each and
-//               exchange the tile maximum through shared memory): tcgen05.ld of the S row into registers, running max with
-//               lazy rescaling (O and l are only rescaled when the max grows by more than 2^8), exp2 via one
-//               FFMA + one MUFU, P rounded to bf16 and written to shared memory in the K-major
-//               128B-swizzled UMMA layout (double buffered); final O / l and the store.
-//   warp 8    : TMA producer — Q once, then K and V tiles through two independent mbarrier rings
-//               (K is released as soon as S = QK^T retires, V after O += PV). Pool pages are 64-key boxes.
-//   warp 9    : TMEM allocation + MMA issuer — S(j+1) = Q K(j+1)^T is issued before O += P(j) V(j) so the
-//               tensor pipe computes the next scores while the softmax warps work on the current ones.
-// TMEM: S double buffered (2 x 128 columns), O (D columns). Operands: Q, K as K-major SW128 tiles (one or
-// two 64-dim boxes; head_dim 96 uses half of the second box), V consumed in place as an MN-major B operand
-// (its [key][dim] layout is already N-contiguous), P as a K-major A operand.
+// One CTA = 256 query rows (two 128-row tiles a, b) of one (sequence, head); key tiles of 128, shared by both
+// query tiles (halves the L2 -> SM traffic per flop; the two softmax warpgroups ping-pong on the MUFU pipe).
+//   warps 0-3 / 4-7 : softmax of query tile a / b — thread r owns query row r (TMEM lane r). TMEM reads are the
+//               scarce resource (~64 B/clk/SM: a 128x128 fp32 S tile costs as much as its 16K exponentials), so S
+//               is swept once per tile (32-column chunks, next chunk in flight while the current one is processed):
+//               P = exp2(S*scale - m*scale) (one FFMA + one MUFU) against the running reference maximum m of the
+//               previous tiles, rounded to bf16 and written to shared memory in the K-major 128B-swizzled UMMA
+//               layout, while the tile's own maximum is collected in the same sweep. O and l are rescaled lazily
+//               (reference grew by more than 2^8: before the next tile; more than 2^64: the tile is redone).
+//   warp 8    : TMA producer — Q tiles once, then K and V tiles through two independent mbarrier rings.
+//               Pool pages are 64-key boxes; the fresh rows come straight from the qkv buffer.
+//   warp 9    : TMEM allocation + MMA issuer — per key tile and query tile: S = Q K^T (as soon as the softmax
+//               warpgroup has released S), then O += P V of the previous key tile.
+// TMEM: S_a, S_b (128 columns each), O_a, O_b (D columns each). Operands: Q, K as K-major tiles — a 64-dim
+// SWIZZLE_128B box plus, for head_dim 96, a 32-dim SWIZZLE_64B box; V consumed in place as an MN-major B
+// operand (its [key][dim] layout is already N-contiguous; N = 64 + N = 32 UMMAs); P as a K-major A operand.
 #include "attn_common.cuh"
 #include "tc_common.cuh"
 #include "../../include/phi3_b200.h"
 #include <cstdlib>
+#include <cstdio>
+#include <type_traits>
 
 template <int D>
 struct FaCfg {
-    static constexpr int NB = (D + 63) / 64;            // 64-dim boxes per tile row
-    static constexpr int BOX = 128 * 128;               // bytes: 128 rows x 64 bf16, 128B swizzle
-    static constexpr int Q_BYTES = NB * BOX, KV_BYTES = NB * BOX, P_BYTES = 2 * BOX;   // P is double buffered
-    static constexpr int STAGES = (D == 96) ? 2 : 3;
-    static constexpr int XCH_BYTES = (D == 96) ? 0 : 2048;   // D = 96 keeps the exchange slots in unused Q columns
-    static constexpr int SMEM = Q_BYTES + 2 * STAGES * KV_BYTES + 2 * P_BYTES + 1024 + 256 + XCH_BYTES;
-    static constexpr int TMEM_COLS = 512, S_COL = 0, O_COL = 256;
-    static constexpr uint32_t IDESC_QK = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-    static constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((128u >> 4) << 24);
+    static constexpr bool TWO = (D == 96);              // second, 32-dim box
+    static constexpr int B0 = 128 * 128;                // bytes: 128 rows x 64 bf16, 128B swizzle
+    static constexpr int B1 = TWO ? 128 * 64 : 0;       // bytes: 128 rows x 32 bf16, 64B swizzle
+    static constexpr int TILE = B0 + B1;                // one Q / K / V tile
+    static constexpr int P_BYTES = 2 * B0;              // 128 rows x 128 keys bf16
+    static constexpr int STAGES = TWO ? 2 : 3;
+    static constexpr int SMEM = 2 * TILE + 2 * STAGES * TILE + 2 * P_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = 512, S_COL = 0, O_COL = 256;   // S_x at 128 x, O_x at 256 + 128 x
+    static constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+    static constexpr uint32_t IDESC_QK = IDESC_BASE | ((128u >> 3) << 17);
+    static constexpr uint32_t IDESC_PV0 = IDESC_BASE | (1u << 16) | ((64u >> 3) << 17);   // B (V) MN-major
+    static constexpr uint32_t IDESC_PV1 = IDESC_BASE | (1u << 16) | ((32u >> 3) << 17);
+};
+
+struct FaMaps {                                         // [0]: 64-column SW128 box, [1]: 32-column SW64 box (head_dim 96)
+    CUtensorMap q[2], k[2], v[2], pool[2];
 };
 
 #define FA_THREADS 320
@@ -41,52 +53,58 @@ struct FaCfg {
 
 template <int D>
 __global__ void __launch_bounds__(FA_THREADS, 1)
-attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmPool, AttnParams p) {
+attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long long* dbg) {
     using C = FaCfg<D>;
     constexpr int ST = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sQ = base, sK0 = sQ + C::Q_BYTES, sV0 = sK0 + ST * C::KV_BYTES, sP = sV0 + ST * C::KV_BYTES;
+    const uint32_t sQ = base, sK0 = sQ + 2 * C::TILE, sV0 = sK0 + ST * C::TILE, sP = sV0 + ST * C::TILE;
     const uint32_t bars = sP + 2 * C::P_BYTES;
     const uint32_t q_full = bars;
     auto k_full = [&](int s) { return bars + 8u * (1 + s); };
     auto k_empty = [&](int s) { return bars + 8u * (1 + ST + s); };
     auto v_full = [&](int s) { return bars + 8u * (1 + 2 * ST + s); };
     auto v_empty = [&](int s) { return bars + 8u * (1 + 3 * ST + s); };
-    auto s_full = [&](int s) { return bars + 8u * (1 + 4 * ST + s); };
-    auto s_free = [&](int s) { return bars + 8u * (3 + 4 * ST + s); };
-    auto p_full = [&](int j) { return bars + 8u * (10 + 4 * ST + (j & 1)); };   // P(j) written (alternating, like o_done)
-    // O += P(j) V(j) retired; two barriers alternating with the tile parity so that a waiter that lags by up to
-    // two tiles never sees an aliased phase parity
-    auto o_done = [&](int j) { return bars + 8u * (6 + 4 * ST + (j & 1)); };
-    const uint32_t tmem_slot = bars + 8u * (8 + 4 * ST);
+    auto s_full = [&](int x) { return bars + 8u * (1 + 4 * ST + x); };    // S_x(j) complete in TMEM
+    auto sm_done = [&](int x) { return bars + 8u * (3 + 4 * ST + x); };   // softmax_x(j) done: S_x free, P_x(j) in smem
+    auto o_done = [&](int x) { return bars + 8u * (5 + 4 * ST + x); };    // O_x += P_x(j) V(j) retired
+    const uint32_t tmem_slot = bars + 8u * (7 + 4 * ST);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i0 = (gridDim.x - 1 - blockIdx.x) * 128, h = blockIdx.y, b = blockIdx.z;   // heavy (late) row blocks first
+    const int i0 = (gridDim.x - 1 - blockIdx.x) * 256, h = blockIdx.y, b = blockIdx.z;   // heavy (late) row blocks first
     const int kvh = h / (p.n_heads / p.n_kv);
     const int past = p.past, s_total = past + p.L;
     const int crow = b / p.row_div;
     const int kv0 = p.kv_start ? p.kv_start[crow] : 0;
     const int n_begin = kv0 / 128;
-    int n_end = (s_total + 127) / 128;
-    if (p.causal) n_end = min(n_end, (past + min(i0 + 127, p.L - 1)) / 128 + 1);
-    const int n_tiles = max(n_end - n_begin, 0);
+    const bool act_b = i0 + 128 < p.L;
+    int n_x[2];
+#pragma unroll
+    for (int x = 0; x < 2; x++) {
+        int n_end = (s_total + 127) / 128;
+        if (p.causal) n_end = min(n_end, (past + min(i0 + 128 * x + 127, p.L - 1)) / 128 + 1);
+        n_x[x] = max(n_end - n_begin, 0);
+    }
+    if (!act_b) n_x[1] = 0;
+    const int n_max = max(n_x[0], n_x[1]);
+    const bool dbg_on = dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define FA_T(slot, it, k) do { if (dbg_on && (it) < 64) dbg[((slot) * 64 + (it)) * 8 + (k)] = clock64(); } while (0)
 
     if (warp == FA_W_TMA && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmPool)) : "memory");
+#pragma unroll
+        for (int i = 0; i < (C::TWO ? 2 : 1); i++) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.q[i])) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.k[i])) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.v[i])) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.pool[i])) : "memory");
+        }
     }
     if (warp == FA_W_MMA) {
         if (lane == 0) {
             mbar_init(q_full, 1);
             for (int s = 0; s < ST; s++) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
-            for (int s = 0; s < 2; s++) { mbar_init(s_full(s), 1); mbar_init(s_free(s), 8); }
-            mbar_init(p_full(0), 8); mbar_init(p_full(1), 8);    // one elected arrival per softmax warp
-            mbar_init(o_done(0), 1); mbar_init(o_done(1), 1);
+            for (int x = 0; x < 2; x++) { mbar_init(s_full(x), 1); mbar_init(sm_done(x), 4); mbar_init(o_done(x), 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -100,200 +118,226 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
     if (warp == FA_W_TMA) {
         // ---------------- TMA producer ----------------
-        if (lane == 0 && n_tiles > 0) {
-            mbar_expect_tx(q_full, C::Q_BYTES);
-#pragma unroll
-            for (int bx = 0; bx < C::NB; bx++) tma_load_2d(sQ + bx * C::BOX, &tmQ, q_full, h * D + 64 * bx, b * p.L + i0);
+        if (lane == 0 && n_max > 0) {
+            mbar_expect_tx(q_full, C::TILE * (act_b ? 2 : 1));
+            for (int x = 0; x < (act_b ? 2 : 1); x++) {
+                tma_load_2d(sQ + x * C::TILE, &tm.q[0], q_full, h * D, b * p.L + i0 + 128 * x);
+                if (C::TWO) tma_load_2d(sQ + x * C::TILE + C::B0, &tm.q[1], q_full, h * D + 64, b * p.L + i0 + 128 * x);
+            }
             const int32_t* bt = p.block_table ? p.block_table + (size_t)crow * p.bt_stride : nullptr;
             auto load_tile = [&](int n, int kv, uint32_t dst, uint32_t bar) {
-                mbar_expect_tx(bar, C::KV_BYTES);
+                mbar_expect_tx(bar, C::TILE);
                 if (n * 128 < past) {                            // two 64-key pages of the pool
 #pragma unroll
                     for (int pg = 0; pg < 2; pg++) {
                         const int row = ((bt[2 * n + pg] * 2 + kv) * p.n_kv + kvh) * P3_PAGE;
-#pragma unroll
-                        for (int bx = 0; bx < C::NB; bx++)
-                            tma_load_2d(dst + bx * C::BOX + pg * (64 * 128), &tmPool, bar, 64 * bx, row);
+                        tma_load_2d(dst + pg * (64 * 128), &tm.pool[0], bar, 0, row);
+                        if (C::TWO) tma_load_2d(dst + C::B0 + pg * (64 * 64), &tm.pool[1], bar, 64, row);
                     }
                 } else {                                         // 128 fresh rows of the qkv buffer
                     const int tok = b * p.L + (n * 128 - past);
-#pragma unroll
-                    for (int bx = 0; bx < C::NB; bx++)
-                        tma_load_2d(dst + bx * C::BOX, kv ? &tmV : &tmK, bar, kvh * D + 64 * bx, tok);
+                    tma_load_2d(dst, kv ? &tm.v[0] : &tm.k[0], bar, kvh * D, tok);
+                    if (C::TWO) tma_load_2d(dst + C::B0, kv ? &tm.v[1] : &tm.k[1], bar, kvh * D + 64, tok);
                 }
             };
-            for (int it = 0; it < n_tiles; it++) {
+            for (int it = 0; it < n_max; it++) {
                 const int st = it % ST;
                 const uint32_t ph = (uint32_t)(it / ST) & 1u;
                 mbar_wait(k_empty(st), ph ^ 1u);
-                load_tile(n_begin + it, 0, sK0 + st * C::KV_BYTES, k_full(st));
+                load_tile(n_begin + it, 0, sK0 + st * C::TILE, k_full(st));
                 mbar_wait(v_empty(st), ph ^ 1u);
-                load_tile(n_begin + it, 1, sV0 + st * C::KV_BYTES, v_full(st));
+                load_tile(n_begin + it, 1, sV0 + st * C::TILE, v_full(st));
             }
         }
     } else if (warp == FA_W_MMA) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0 && n_tiles > 0) {
+        if (lane == 0 && n_max > 0) {
             mbar_wait(q_full, 0);
-            for (int it = 0; it <= n_tiles; it++) {
-                if (it < n_tiles) {                              // S(it) = Q K(it)^T
-                    const int st = it % ST, sb = it & 1;
-                    mbar_wait(k_full(st), (uint32_t)(it / ST) & 1u);
-                    mbar_wait(s_free(sb), ((uint32_t)(it >> 1) & 1u) ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + C::S_COL + sb * 128;
+            for (int it = 0; it <= n_max; it++) {                // iteration n_max only drains the last PVs
+                const int st = it % ST, stp = (it + ST - 1) % ST;  // stage of key tile it / it-1
+                if (it < n_max) mbar_wait(k_full(st), (uint32_t)(it / ST) & 1u);
+                bool v_ready = false;
 #pragma unroll
-                    for (int kk = 0; kk < D / 16; kk++) {
-                        const uint64_t ad = umma_desc_sw128(sQ + (kk >> 2) * C::BOX) + 2 * (kk & 3);
-                        const uint64_t bd = umma_desc_sw128(sK0 + st * C::KV_BYTES + (kk >> 2) * C::BOX) + 2 * (kk & 3);
-                        tc_mma_bf16(d_tmem, ad, bd, C::IDESC_QK, kk ? 1u : 0u);
-                    }
-                    tc_commit(k_empty(st));
-                    tc_commit(s_full(sb));
-                }
-                if (it > 0) {                                    // O += P(j) V(j)
-                    const int j = it - 1, st = j % ST;
-                    mbar_wait(v_full(st), (uint32_t)(j / ST) & 1u);
-                    mbar_wait(p_full(j), (uint32_t)(j >> 1) & 1u);
+                for (int x = 0; x < 2; x++) {
+                    const bool do_s = it < n_x[x], do_pv = it > 0 && it - 1 < n_x[x];
+                    if (!do_s && !do_pv) continue;
+                    if (it > 0) mbar_wait(sm_done(x), (uint32_t)(it - 1) & 1u);   // softmax_x(it-1) finished (exactly one wait per tile)
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + C::O_COL;
+                    FA_T(2 + x, it, 0);
+                    if (do_s) {                                  // S_x(it) = Q_x K(it)^T
+                        const uint32_t d_tmem = tmem_base + C::S_COL + x * 128;
+                        const uint32_t qa = sQ + x * C::TILE, kb = sK0 + st * C::TILE;
 #pragma unroll
-                    for (int kk = 0; kk < 8; kk++) {             // 16 keys per UMMA
-                        const uint64_t ad = umma_desc_sw128(sP + (j & 1) * C::P_BYTES + (kk >> 2) * C::BOX) + 2 * (kk & 3);
-                        const uint64_t bd = umma_desc_mn_sw128(sV0 + st * C::KV_BYTES + kk * (16 * 128), C::BOX, 1024);
-                        tc_mma_bf16(d_tmem, ad, bd, C::IDESC_PV, (j | kk) ? 1u : 0u);
+                        for (int kk = 0; kk < 4; kk++)
+                            tc_mma_bf16(d_tmem, umma_desc_sw128(qa) + 2 * kk, umma_desc_sw128(kb) + 2 * kk, C::IDESC_QK, kk ? 1u : 0u);
+                        if (C::TWO) {
+#pragma unroll
+                            for (int kk = 0; kk < 2; kk++)
+                                tc_mma_bf16(d_tmem, umma_desc_sw64(qa + C::B0) + 2 * kk, umma_desc_sw64(kb + C::B0) + 2 * kk, C::IDESC_QK, 1u);
+                        }
+                        tc_commit(s_full(x));
+                        // K(it) is released once its last S has been issued (x = 1, or x = 0 when tile b has no S this round)
+                        if (x == 1 || !(it < n_x[1])) tc_commit(k_empty(st));
                     }
-                    tc_commit(v_empty(st));
-                    tc_commit(o_done(j));
+                    if (do_pv) {                                 // O_x += P_x(it-1) V(it-1)
+                        if (!v_ready) { mbar_wait(v_full(stp), (uint32_t)((it - 1) / ST) & 1u); tc_fence_after(); v_ready = true; }
+                        const uint32_t d_tmem = tmem_base + C::O_COL + x * 128;
+                        const uint32_t pa = sP + x * C::P_BYTES, vb = sV0 + stp * C::TILE;
+                        const uint32_t acc0 = it > 1 ? 1u : 0u;
+#pragma unroll
+                        for (int kk = 0; kk < 8; kk++) {         // 16 keys per UMMA
+                            const uint64_t ad = umma_desc_sw128(pa + (kk >> 2) * C::B0) + 2 * (kk & 3);
+                            tc_mma_bf16(d_tmem, ad, umma_desc_mn_sw128(vb + kk * (16 * 128), 0, 1024), C::IDESC_PV0, acc0 | (kk ? 1u : 0u));
+                            if (C::TWO)
+                                tc_mma_bf16(d_tmem + 64, ad, umma_desc_mn_sw64(vb + C::B0 + kk * (16 * 64)), C::IDESC_PV1, acc0 | (kk ? 1u : 0u));
+                        }
+                        tc_commit(o_done(x));
+                    }
+                    FA_T(2 + x, it, 1);
                 }
+                if (it > 0) tc_commit(v_empty(stp));
             }
         }
     } else {
-        // ---------------- softmax: two threads per query row (warps w and w+4 split the 128 keys) ----------------
-        const int wq = warp & 3, half = warp >> 2;
+        // ---------------- softmax warpgroup x: thread = query row ----------------
+        const int x = warp >> 2, wq = warp & 3;
         const int row = wq * 32 + lane;
-        const int qi = past + i0 + row;
+        const int nt = n_x[x];
+        const int qi = past + i0 + 128 * x + row;
         const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
+        const uint32_t t_s = t_lane + C::S_COL + x * 128, t_o = t_lane + C::O_COL + x * 128;
         const float sl = p.scale_log2;
         float m = -INFINITY, l = 0.f;
         const int rx = row & 7;
-        const uint32_t p_row = sP + half * C::BOX + row * 128;   // this thread's 64 keys are one 64-column box of P
-        // 16 B exchange slot per row: float [parity][half]. D = 96: logical chunk 4 of Q box 1 (dims 96..103 of the
-        // padded tile, written once by the Q load and never read by an MMA); D = 64: a separate region.
-        const uint32_t xch = (D == 96) ? (sQ + C::BOX + row * 128 + ((4 ^ rx) << 4)) : (bars + 256 + row * 16);
-        auto exchange = [&](int par, float mine) -> float {      // returns the partner thread's value
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + par * 8 + half * 4), "f"(mine) : "memory");
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
-            float other;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch + par * 8 + (half ^ 1) * 4) : "memory");
-            return other;
-        };
-        for (int it = 0; it < n_tiles; it++) {
-            const int sb = it & 1, j0 = (n_begin + it) * 128 + half * 64;
-            mbar_wait(s_full(sb), (uint32_t)(it >> 1) & 1u);
+        const uint32_t p_row = sP + x * C::P_BYTES + row * 128;
+        float pend = 1.f;                                        // rescale of O_x and l decided after the previous tile
+        bool has_pend = false;
+        for (int it = 0; it < nt; it++) {
+            const int j0 = (n_begin + it) * 128;
+            mbar_wait(s_full(x), (uint32_t)it & 1u);
+            if (wq == 0 && lane == 0) FA_T(x, it, 0);
+            if (it > 0) mbar_wait(o_done(x), (uint32_t)(it - 1) & 1u);   // PV_x(it-1) retired: P_x is free, O_x is stable
             tc_fence_after();
-            const uint32_t t_s = t_lane + C::S_COL + sb * 128 + half * 64;
-            // this thread's half of the S row (64 fp32) lives in registers: one TMEM round trip per tile
-            uint32_t s[64];
-            tc_ld32_nowait(t_s, s);
-            tc_ld32_nowait(t_s + 32, s + 32);
-            tc_wait_ld();
-            tc_reg_fence32(s);
-            tc_reg_fence32(s + 32);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_free(sb));              // S(it+2) may overwrite the buffer now
-            const bool need_mask = (j0 < kv0) || (j0 + 63 >= s_total) || (p.causal && j0 + 63 > past + i0 + wq * 32);
-            if (need_mask) {
-#pragma unroll
-                for (int i = 0; i < 64; i++) {
-                    const int j = j0 + i;
-                    const bool ok = (j >= kv0) && (j < s_total) && (!p.causal || j <= qi);
-                    if (!ok) s[i] = 0xff800000u;
-                }
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 64; i += 4) {
-                mx0 = fmaxf(mx0, __uint_as_float(s[i])); mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-                mx2 = fmaxf(mx2, __uint_as_float(s[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
-            }
-            float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-            mx = fmaxf(mx, exchange(it & 1, mx));                // both threads of a row now hold the same tile maximum
-            const bool grow = mx * sl > m * sl + FA_RESCALE_LOG2;  // false when both are -inf
-            const bool resc = grow && it > 0 && m != -INFINITY;
-            float corr = 1.f;
-            if (grow) {
-                corr = (m == -INFINITY) ? 0.f : ex2_approx((m - mx) * sl);
-                m = mx;
-                l *= corr;
-            }
-            if (it > 1) mbar_wait(o_done(it - 2), (uint32_t)((it - 2) >> 1) & 1u);   // PV(it-2) retired: P buffer (it & 1) is free again
-            if (__any_sync(0xffffffffu, resc)) {                 // rare: the running max grew by more than 2^8
-                mbar_wait(o_done(it - 1), (uint32_t)((it - 1) >> 1) & 1u);   // O is complete up to tile it-1 and PV(it) waits for our P
-                tc_fence_after();
-                const float cf = resc ? corr : 1.f;
+            if (wq == 0 && lane == 0) FA_T(x, it, 1);
+            auto scale_o = [&](float cf) {                       // warp-collective: every lane runs the TMEM round trip
 #pragma unroll 1
-                for (int c = half; c < D / 32; c += 2) {         // the two threads of a row split the O columns
+                for (int c = 0; c < D / 32; c++) {
                     uint32_t v[32];
-                    tc_ld32(t_lane + C::O_COL + 32 * c, v);
+                    tc_ld32(t_o + 32 * c, v);
 #pragma unroll
                     for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * cf);
-                    tc_st32(t_lane + C::O_COL + 32 * c, v);
+                    tc_st32(t_o + 32 * c, v);
                 }
-                tc_fence_before();
+            };
+            if (__any_sync(0xffffffffu, has_pend)) scale_o(has_pend ? pend : 1.f);
+            if (has_pend) { l *= pend; has_pend = false; }
+            const bool need_mask = (j0 < kv0) || (j0 + 127 >= s_total) || (p.causal && j0 + 127 > past + i0 + 128 * x + wq * 32);
+            // One sweep over the S row in TMEM, 32 columns at a time with the next chunk in flight: row maximum
+            // and / or P = exp2(S * scale - mu) -> bf16 -> shared memory (K-major SW128 A operand).
+            auto sweep = [&](auto do_max, auto do_exp, float mu, float& mx_out, float& ls_out) {
+                constexpr bool DM = decltype(do_max)::value, DE = decltype(do_exp)::value;
+                uint32_t buf[2][32];
+                tc_ld32_nowait(t_s, buf[0]);
+                tc_wait_ld();
+                tc_reg_fence32(buf[0]);
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY, ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t* v = buf[c & 1];
+                    if (c < 3) tc_ld32_nowait(t_s + 32 * (c + 1), buf[(c + 1) & 1]);
+                    if (need_mask) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            const int j = j0 + 32 * c + i;
+                            const bool ok = (j >= kv0) && (j < s_total) && (!p.causal || j <= qi);
+                            if (!ok) v[i] = 0xff800000u;
+                        }
+                    }
+                    if (DM) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            mx0 = fmaxf(mx0, __uint_as_float(v[i])); mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+                            mx2 = fmaxf(mx2, __uint_as_float(v[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+                        }
+                    }
+                    if (DE) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), sl, -mu));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), sl, -mu));
+                            ls0 += p0; ls1 += p1;
+                            pk[i] = pack_bf16(p0, p1);
+                        }
+                        const uint32_t dst = p_row + (c >> 1) * C::B0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int cc = (c & 1) * 4 + q;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((cc ^ rx) << 4)), "r"(pk[4 * q]),
+                                         "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                        }
+                    }
+                    if (c < 3) { tc_wait_ld(); tc_reg_fence32(buf[(c + 1) & 1]); }
+                }
+                if (DM) mx_out = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if (DE) ls_out = ls0 + ls1;
+            };
+            // Streaming softmax: P is computed against the reference maximum m carried over from the previous
+            // tiles while this tile's own maximum is found in the same sweep (TMEM is read once per tile). If the
+            // tile's maximum turns out to exceed the reference by more than 2^64 (or there was no reference yet),
+            // the tile is redone against its own maximum; smaller growth (> 2^8) only schedules a rescale of O
+            // and l for the next tile. O / l is invariant under the reference, so the result is exact either way.
+            float mx = -INFINITY, ls = 0.f;
+            bool redo = true;
+            if (it > 0) {
+                sweep(std::true_type{}, std::true_type{}, (m == -INFINITY) ? 0.f : m * sl, mx, ls);
+                redo = (m == -INFINITY) ? (mx != -INFINITY) : ((mx - m) * sl > 64.f);
+            } else {
+                sweep(std::true_type{}, std::false_type{}, 0.f, mx, ls);
             }
-            // P = exp2(S * scale - m * scale) -> bf16 -> shared memory (K-major SW128 A operand)
-            const float mu = (m == -INFINITY) ? 0.f : m * sl;
-            float ls0 = 0.f, ls1 = 0.f;
-            const uint32_t dst = p_row + (it & 1) * C::P_BYTES;
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[32 * c + 2 * i]), sl, -mu));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[32 * c + 2 * i + 1]), sl, -mu));
-                    ls0 += p0; ls1 += p1;
-                    pk[i] = pack_bf16(p0, p1);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int cc = c * 4 + q;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((cc ^ rx) << 4)), "r"(pk[4 * q]),
-                                 "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
-                }
+            if (__any_sync(0xffffffffu, redo)) {
+                float corr = 1.f;
+                if (redo) { corr = (m == -INFINITY) ? 0.f : ex2_approx((m - mx) * sl); m = mx; }
+                if (it > 0) scale_o(corr);                       // PV_x(it-1) has retired and PV_x(it) waits for this P
+                l *= corr;
+                sweep(std::false_type{}, std::true_type{}, (m == -INFINITY) ? 0.f : m * sl, mx, ls);
             }
-            l += ls0 + ls1;
+            l += ls;
+            if (wq == 0 && lane == 0) FA_T(x, it, 2);
+            const float grow = (mx - m) * sl;                    // NaN (no keys yet) compares false
+            if (grow > FA_RESCALE_LOG2) { pend = ex2_approx(-grow); has_pend = true; m = mx; }
+            tc_fence_before();                                   // S_x reads (and any O_x rescale) are complete
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_full(it));
+            if (lane == 0) mbar_arrive(sm_done(x));
+            if (wq == 0 && lane == 0) FA_T(x, it, 3);
         }
-        // epilogue: O / l
-        if (n_tiles > 0) {
-            mbar_wait(o_done(n_tiles - 1), (uint32_t)((n_tiles - 1) >> 1) & 1u);
-            tc_fence_after();
-            l += exchange(n_tiles & 1, l);
-        }
-        const float inv = l > 0.f ? 1.f / l : 0.f;
-        const int i = i0 + row;
-        bf16* orow = p.out + ((size_t)b * p.L + (i < p.L ? i : 0)) * p.ldo + h * D;
-#pragma unroll 1
-        for (int c = half; c < D / 32; c += 2) {
-            uint32_t v[32];
-            if (n_tiles > 0) {
-                tc_ld32(t_lane + C::O_COL + 32 * c, v);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 32; k++) v[k] = 0u;
+        // ---- epilogue: O / l
+        if (x == 0 || act_b) {
+            if (nt > 0) {
+                mbar_wait(o_done(x), (uint32_t)(nt - 1) & 1u);
+                tc_fence_after();
             }
-            if (i < p.L) {
-                uint4 ov[4];
-                uint32_t* ou = reinterpret_cast<uint32_t*>(ov);
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+            const int i = i0 + 128 * x + row;
+            bf16* orow = p.out + ((size_t)b * p.L + (i < p.L ? i : 0)) * p.ldo + h * D;
+#pragma unroll 1
+            for (int c = 0; c < D / 32; c++) {
+                uint32_t v[32];
+                if (nt > 0) {
+                    tc_ld32(t_o + 32 * c, v);
+                } else {
 #pragma unroll
-                for (int k = 0; k < 16; k++) ou[k] = pack_bf16(__uint_as_float(v[2 * k]) * inv, __uint_as_float(v[2 * k + 1]) * inv);
+                    for (int k = 0; k < 32; k++) v[k] = 0u;
+                }
+                if (i < p.L) {
+                    uint4 ov[4];
+                    uint32_t* ou = reinterpret_cast<uint32_t*>(ov);
 #pragma unroll
-                for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(orow + 32 * c)[k] = ov[k];
+                    for (int k = 0; k < 16; k++) ou[k] = pack_bf16(__uint_as_float(v[2 * k]) * inv, __uint_as_float(v[2 * k + 1]) * inv);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(orow + 32 * c)[k] = ov[k];
+                }
             }
         }
     }
@@ -326,15 +370,21 @@ bool attn_prefill_tc_eligible(const AttnParams& p) {
 template <int D>
 static int launch_tc_d(const AttnParams& p, cudaStream_t st) {
     using C = FaCfg<D>;
-    CUtensorMap tq, tk, tv, tp;
+    FaMaps tm;
     const int64_t rows = (int64_t)p.B * p.L;
-    CUresult r = tc_encode_2d(&tq, p.q, rows, (int64_t)p.n_heads * D, p.ldq, 128);
-    if (r == CUDA_SUCCESS) r = tc_encode_2d(&tk, p.k, rows, (int64_t)p.n_kv * D, p.ldk, 128);
-    if (r == CUDA_SUCCESS) r = tc_encode_2d(&tv, p.v, rows, (int64_t)p.n_kv * D, p.ldv, 128);
-    if (r == CUDA_SUCCESS) {
-        if (p.past > 0) r = tc_encode_2d(&tp, p.pool, (int64_t)1 << 31, D, D, P3_PAGE);   // rows: upper bound, pages are addressed via the block table
-        else tp = tk;
+    CUresult r = CUDA_SUCCESS;
+    for (int i = 0; i < (C::TWO ? 2 : 1) && r == CUDA_SUCCESS; i++) {
+        const int bc = i ? 32 : 64;
+        r = tc_encode_2d(&tm.q[i], p.q, rows, (int64_t)p.n_heads * D, p.ldq, 128, bc);
+        if (r == CUDA_SUCCESS) r = tc_encode_2d(&tm.k[i], p.k, rows, (int64_t)p.n_kv * D, p.ldk, 128, bc);
+        if (r == CUDA_SUCCESS) r = tc_encode_2d(&tm.v[i], p.v, rows, (int64_t)p.n_kv * D, p.ldv, 128, bc);
+        if (r == CUDA_SUCCESS) {
+            // pool rows: an upper bound — pages are addressed through the block table
+            if (p.past > 0) r = tc_encode_2d(&tm.pool[i], p.pool, (int64_t)1 << 31, D, D, P3_PAGE, bc);
+            else tm.pool[i] = tm.k[i];
+        }
     }
+    if (!C::TWO) { tm.q[1] = tm.q[0]; tm.k[1] = tm.k[0]; tm.v[1] = tm.v[0]; tm.pool[1] = tm.pool[0]; }
     P3_CHECK_ARG(r == CUDA_SUCCESS, "attention_prefill: cuTensorMapEncodeTiled failed (%d)", (int)r);
     static bool set = false;
     if (!set) {
@@ -342,9 +392,26 @@ static int launch_tc_d(const AttnParams& p, cudaStream_t st) {
         P3_CHECK_ARG(e == cudaSuccess, "attention_prefill: cannot set %d B dynamic smem: %s", C::SMEM, cudaGetErrorString(e));
         set = true;
     }
-    dim3 grid((p.L + 127) / 128, p.n_heads, p.B);
-    attn_prefill_tc_kernel<D><<<grid, FA_THREADS, C::SMEM, st>>>(tq, tk, tv, tp, p);
+    dim3 grid((p.L + 255) / 256, p.n_heads, p.B);
+    long long* dbg = nullptr;
+    const bool want_dbg = getenv("P3_FA_DBG") != nullptr;
+    if (want_dbg) { cudaMalloc(&dbg, 4 * 64 * 8 * 8); cudaMemset(dbg, 0, 4 * 64 * 8 * 8); }
+    attn_prefill_tc_kernel<D><<<grid, FA_THREADS, C::SMEM, st>>>(tm, p, dbg);
     P3_CHECK_LAUNCH("attention_prefill_tc");
+    if (want_dbg) {
+        static long long h[4 * 64 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(dbg);
+        long long t0 = h[0];
+        for (int it = 0; it < 64 && h[(0 * 64 + it) * 8]; it++) {
+            printf("it %2d | smA: sfull %7lld odone %7lld swept %7lld arrived %7lld | smB: %7lld %7lld %7lld %7lld | mmaA: woke %7lld issued %7lld | mmaB: %7lld %7lld\n", it,
+                   h[(0 * 64 + it) * 8 + 0] - t0, h[(0 * 64 + it) * 8 + 1] - t0, h[(0 * 64 + it) * 8 + 2] - t0, h[(0 * 64 + it) * 8 + 3] - t0,
+                   h[(1 * 64 + it) * 8 + 0] - t0, h[(1 * 64 + it) * 8 + 1] - t0, h[(1 * 64 + it) * 8 + 2] - t0, h[(1 * 64 + it) * 8 + 3] - t0,
+                   h[(2 * 64 + it) * 8 + 0] - t0, h[(2 * 64 + it) * 8 + 1] - t0, h[(3 * 64 + it) * 8 + 0] - t0, h[(3 * 64 + it) * 8 + 1] - t0);
+        }
+        fflush(stdout);
+    }
     return 0;
 }
 

@@ -94,6 +94,25 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// K-major, 64B-swizzled tile (64 B rows = 32 bf16, 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+// MN-major, 64B-swizzled: 32 contiguous MN elements per 64 B row, 8 K-rows per 512 B atom (SBO); one MN block
+__device__ __forceinline__ uint64_t umma_desc_mn_sw64(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+
 // MN-major, 128B-swizzled UMMA descriptor (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units):
 // 64 contiguous MN elements per 128 B row, 8 K-rows per 1024 B swizzle atom; LBO = byte distance between
 // 64-element MN blocks, SBO = byte distance between 8-row K groups.
@@ -126,16 +145,17 @@ static EncodeTiledFn get_encode() {
 }
 
 
-// 2D bf16 tensor [rows][cols] with row pitch ld (elements), box = 64 columns (128 B, SWIZZLE_128B) x box_rows;
-// out-of-bounds elements read as zero.
-static inline CUresult tc_encode_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2D bf16 tensor [rows][cols] with row pitch ld (elements), box = box_cols columns x box_rows rows; box_cols = 64
+// uses SWIZZLE_128B (128 B rows), box_cols = 32 SWIZZLE_64B (64 B rows); out-of-bounds elements read as zero.
+static inline CUresult tc_encode_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                                    int box_cols = 64) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return CUDA_ERROR_NOT_SUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+               CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }

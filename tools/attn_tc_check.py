@@ -50,11 +50,15 @@ def run(B, H, D, Lq, past, causal, kvs, tc, qkv, kc, vc):
 
 
 def check(cfg):
-    B, H, D, Lq, past, causal, kv = cfg
+    B, H, D, Lq, past, causal, kv = cfg[:7]
     torch.manual_seed(3)
     qkv = bf(torch.randn(B * Lq, 3 * H * D, device=dev))
     kc, vc = bf(torch.randn(B, H, past, D, device=dev)), bf(torch.randn(B, H, past, D, device=dev))
     kvs = torch.tensor(kv[:B], dtype=torch.int32, device=dev)
+    if len(cfg) > 7:                                    # growing score magnitude: exercises the lazy-rescale and redo paths
+        kview = qkv.view(B, Lq, 3, H, D)[:, :, 1]
+        ramp = torch.tensor([cfg[7] ** (i // 128) for i in range(Lq)], device=dev, dtype=torch.float32)
+        kview.mul_(ramp[None, :, None, None].to(torch.bfloat16))
     x = qkv.view(B, Lq, 3, H, D).permute(2, 0, 3, 1, 4)
     q, k, v = x[0], torch.cat([kc, x[1]], 2), torch.cat([vc, x[2]], 2)
     r = ref(q, k, v, D ** -0.5, causal, past, kvs.long()).transpose(1, 2).reshape(B, Lq, H, D)
@@ -102,7 +106,8 @@ if __name__ == '__main__':
     cfgs = [(1, 1, 64, 128, 0, False, [0, 0, 0]), (1, 1, 96, 128, 0, False, [0, 0, 0]), (1, 1, 96, 128, 0, True, [0, 0, 0]),
             (1, 2, 96, 256, 0, True, [0, 0, 0]), (2, 4, 96, 200, 0, True, [0, 17, 70]), (1, 16, 64, 577, 0, False, [0, 0, 0]),
             (2, 3, 96, 300, 256, True, [0, 200, 0]), (1, 2, 96, 640, 128, True, [5, 0, 0]), (3, 2, 64, 577, 0, False, [0, 0, 0]),
-            (1, 4, 96, 2048, 0, True, [0, 0, 0]), (2, 2, 96, 1100, 0, True, [0, 300, 0])]
+            (1, 4, 96, 2048, 0, True, [0, 0, 0]), (2, 2, 96, 1100, 0, True, [0, 300, 0]),
+            (1, 2, 96, 1024, 0, True, [0, 0, 0], 3.0), (1, 2, 96, 768, 0, False, [0, 0, 0], 40.0), (2, 2, 64, 700, 0, False, [0, 0, 0], 6.0)]
     bad = 0
     for c in cfgs:
         print('cfg (B,H,D,L,past,causal,kv_start)=', c, flush=True)
