@@ -9,16 +9,18 @@
 //               scarce resource (~64 B/clk/SM: a 128x128 fp32 S tile costs as much as its 16K exponentials), so S
 //               is swept once per tile (32-column chunks, next chunk in flight while the current one is processed):
 //               P = exp2(S*scale - m*scale) (one FFMA + one MUFU) against the running reference maximum m of the
-//               previous tiles, rounded to bf16 and written to shared memory in the K-major 128B-swizzled UMMA
-//               layout, while the tile's own maximum is collected in the same sweep. O and l are rescaled lazily
+//               previous tiles, rounded to bf16 and stored back to TMEM over the consumed S columns (P is the A operand
+//               of the PV UMMA straight from tensor memory: no shared-memory round trip), while the tile's own
+//               maximum is collected in the same sweep. O and l are rescaled lazily
 //               (reference grew by more than 2^8: before the next tile; more than 2^64: the tile is redone).
 //   warp 8    : TMA producer — Q tiles once, then K and V tiles through two independent mbarrier rings.
 //               Pool pages are 64-key boxes; the fresh rows come straight from the qkv buffer.
-//   warp 9    : TMEM allocation + MMA issuer — per key tile and query tile: S = Q K^T (as soon as the softmax
-//               warpgroup has released S), then O += P V of the previous key tile.
+//   warp 9    : TMEM allocation + MMA issuer — per key tile and query tile, once the softmax warpgroup has stored P:
+//               O += P V of the previous key tile (A from TMEM), then S = Q K^T of the next one (overwrites P; UMMAs
+//               execute in issue order).
 // TMEM: S_a, S_b (128 columns each), O_a, O_b (D columns each). Operands: Q, K as K-major tiles — a 64-dim
 // SWIZZLE_128B box plus, for head_dim 96, a 32-dim SWIZZLE_64B box; V consumed in place as an MN-major B
-// operand (its [key][dim] layout is already N-contiguous; N = 64 + N = 32 UMMAs); P as a K-major A operand.
+// operand (its [key][dim] layout is already N-contiguous; N = 64 + N = 32 UMMAs); P as the TMEM A operand.
 #include "attn_common.cuh"
 #include "tc_common.cuh"
 #include "../../include/phi3_b200.h"
@@ -32,10 +34,10 @@ struct FaCfg {
     static constexpr int B0 = 128 * 128;                // bytes: 128 rows x 64 bf16, 128B swizzle
     static constexpr int B1 = TWO ? 128 * 64 : 0;       // bytes: 128 rows x 32 bf16, 64B swizzle
     static constexpr int TILE = B0 + B1;                // one Q / K / V tile
-    static constexpr int P_BYTES = 2 * B0;              // 128 rows x 128 keys bf16
-    static constexpr int STAGES = TWO ? 2 : 3;
-    static constexpr int SMEM = 2 * TILE + 2 * STAGES * TILE + 2 * P_BYTES + 1024 + 256;
-    static constexpr int TMEM_COLS = 512, S_COL = 0, O_COL = 256;   // S_x at 128 x, O_x at 256 + 128 x
+    static constexpr int STAGES = 3;
+    static constexpr int SMEM = 2 * TILE + 2 * STAGES * TILE + 1024 + 256;
+    // S_x at 128 x (P_x, bf16 pairs, overwrites its first 64 columns once the S row has been consumed), O_x at 256 + 128 x
+    static constexpr int TMEM_COLS = 512, S_COL = 0, O_COL = 256;
     static constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
     static constexpr uint32_t IDESC_QK = IDESC_BASE | ((128u >> 3) << 17);
     static constexpr uint32_t IDESC_PV0 = IDESC_BASE | (1u << 16) | ((64u >> 3) << 17);   // B (V) MN-major
@@ -50,6 +52,7 @@ struct FaMaps {                                         // [0]: 64-column SW128 
 #define FA_W_TMA 8
 #define FA_W_MMA 9
 #define FA_RESCALE_LOG2 8.0f
+#define FA_PAIR_GROUP 8
 
 template <int D>
 __global__ void __launch_bounds__(FA_THREADS, 1)
@@ -58,21 +61,27 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
     constexpr int ST = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sQ = base, sK0 = sQ + 2 * C::TILE, sV0 = sK0 + ST * C::TILE, sP = sV0 + ST * C::TILE;
-    const uint32_t bars = sP + 2 * C::P_BYTES;
+    const uint32_t sQ = base, sK0 = sQ + 2 * C::TILE, sV0 = sK0 + ST * C::TILE;
+    const uint32_t bars = sV0 + ST * C::TILE;
     const uint32_t q_full = bars;
     auto k_full = [&](int s) { return bars + 8u * (1 + s); };
     auto k_empty = [&](int s) { return bars + 8u * (1 + ST + s); };
     auto v_full = [&](int s) { return bars + 8u * (1 + 2 * ST + s); };
     auto v_empty = [&](int s) { return bars + 8u * (1 + 3 * ST + s); };
-    auto s_full = [&](int x) { return bars + 8u * (1 + 4 * ST + x); };    // S_x(j) complete in TMEM
-    auto sm_done = [&](int x) { return bars + 8u * (3 + 4 * ST + x); };   // softmax_x(j) done: S_x free, P_x(j) in smem
-    auto o_done = [&](int x) { return bars + 8u * (5 + 4 * ST + x); };    // O_x += P_x(j) V(j) retired
+    auto s_full = [&](int x) { return bars + 8u * (1 + 4 * ST + x); };    // O_x += P_x(j-1) V(j-1) retired and S_x(j) complete
+    auto sm_done = [&](int x) { return bars + 8u * (3 + 4 * ST + x); };   // softmax_x(j) done: P_x(j) stored over S_x
     const uint32_t tmem_slot = bars + 8u * (7 + 4 * ST);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i0 = (gridDim.x - 1 - blockIdx.x) * 256, h = blockIdx.y, b = blockIdx.z;   // heavy (late) row blocks first
+    // CTA order: groups of FA_PAIR_GROUP query-row blocks, heaviest (latest rows) first across ALL (sequence, head)
+    // pairs — a per-head heavy-first order leaves the last head's 64-tile CTA for the tail — while the blocks of
+    // one group and head stay adjacent so that their K/V reads share L2.
+    const int n_pairs = (p.L + 255) / 256, hb = p.n_heads * p.B;
+    const int grp = blockIdx.x / (FA_PAIR_GROUP * hb), rem = blockIdx.x - grp * (FA_PAIR_GROUP * hb);
+    const int gs = min(FA_PAIR_GROUP, n_pairs - grp * FA_PAIR_GROUP);
+    const int bh = rem / gs, pr = grp * FA_PAIR_GROUP + (rem - bh * gs);
+    const int i0 = (n_pairs - 1 - pr) * 256, h = bh % p.n_heads, b = bh / p.n_heads;
     const int kvh = h / (p.n_heads / p.n_kv);
     const int past = p.past, s_total = past + p.L;
     const int crow = b / p.row_div;
@@ -88,9 +97,14 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
     }
     if (!act_b) n_x[1] = 0;
     const int n_max = max(n_x[0], n_x[1]);
-    const bool dbg_on = dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-#define FA_T(slot, it, k) do { if (dbg_on && (it) < 64) dbg[((slot) * 64 + (it)) * 8 + (k)] = clock64(); } while (0)
+#ifdef P3_FA_TIMING   // clock64 stamps of CTA 0's pipeline (slot: 0/1 softmax a/b, 2/3 MMA issue for a/b); printed by the launcher
+    const bool dbg_on = dbg && blockIdx.x == 0;
+#define FA_T(slot, it, k) do { if (dbg_on && (it) < 64 && (threadIdx.x & 31) == 0) dbg[((slot) * 64 + (it)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define FA_T(slot, it, k) do { } while (0)
+#endif
 
+    FA_T(3, 0, 5);
     if (warp == FA_W_TMA && lane == 0) {
 #pragma unroll
         for (int i = 0; i < (C::TWO ? 2 : 1); i++) {
@@ -104,7 +118,7 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
         if (lane == 0) {
             mbar_init(q_full, 1);
             for (int s = 0; s < ST; s++) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
-            for (int x = 0; x < 2; x++) { mbar_init(s_full(x), 1); mbar_init(sm_done(x), 4); mbar_init(o_done(x), 1); }
+            for (int x = 0; x < 2; x++) { mbar_init(s_full(x), 1); mbar_init(sm_done(x), 4); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -115,6 +129,7 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    FA_T(3, 0, 6);
 
     if (warp == FA_W_TMA) {
         // ---------------- TMA producer ----------------
@@ -151,11 +166,13 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
         }
     } else if (warp == FA_W_MMA) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0 && n_max > 0) {
+        if (n_max > 0) {                                         // whole warp converged; UMMAs / commits by one elected lane
             mbar_wait(q_full, 0);
             for (int it = 0; it <= n_max; it++) {                // iteration n_max only drains the last PVs
                 const int st = it % ST, stp = (it + ST - 1) % ST;  // stage of key tile it / it-1
+                FA_T(2, it, 5);
                 if (it < n_max) mbar_wait(k_full(st), (uint32_t)(it / ST) & 1u);
+                FA_T(2, it, 6);
                 bool v_ready = false;
 #pragma unroll
                 for (int x = 0; x < 2; x++) {
@@ -164,7 +181,22 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                     if (it > 0) mbar_wait(sm_done(x), (uint32_t)(it - 1) & 1u);   // softmax_x(it-1) finished (exactly one wait per tile)
                     tc_fence_after();
                     FA_T(2 + x, it, 0);
-                    if (do_s) {                                  // S_x(it) = Q_x K(it)^T
+                    if (elect_one()) {
+                    if (do_pv) {                                 // O_x += P_x(it-1) V(it-1), P read from TMEM
+                        if (!v_ready) { mbar_wait(v_full(stp), (uint32_t)((it - 1) / ST) & 1u); tc_fence_after(); v_ready = true; }
+                        FA_T(2 + x, it, 2);
+                        const uint32_t d_tmem = tmem_base + C::O_COL + x * 128, a_tmem = tmem_base + C::S_COL + x * 128;
+                        const uint32_t vb = sV0 + stp * C::TILE;
+                        const uint32_t acc0 = it > 1 ? 1u : 0u;
+#pragma unroll
+                        for (int kk = 0; kk < 8; kk++) {         // 16 keys = 8 TMEM columns per UMMA
+                            tc_mma_bf16_ts(d_tmem, a_tmem + 8 * kk, umma_desc_mn_sw128(vb + kk * (16 * 128), 0, 1024), C::IDESC_PV0, acc0 | (kk ? 1u : 0u));
+                            if (C::TWO)
+                                tc_mma_bf16_ts(d_tmem + 64, a_tmem + 8 * kk, umma_desc_mn_sw64(vb + C::B0 + kk * (16 * 64)), C::IDESC_PV1, acc0 | (kk ? 1u : 0u));
+                        }
+                    }
+                    FA_T(2 + x, it, 3);
+                    if (do_s) {                                  // S_x(it) = Q_x K(it)^T (executes after the PV above: overwrites P_x)
                         const uint32_t d_tmem = tmem_base + C::S_COL + x * 128;
                         const uint32_t qa = sQ + x * C::TILE, kb = sK0 + st * C::TILE;
 #pragma unroll
@@ -175,27 +207,17 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                             for (int kk = 0; kk < 2; kk++)
                                 tc_mma_bf16(d_tmem, umma_desc_sw64(qa + C::B0) + 2 * kk, umma_desc_sw64(kb + C::B0) + 2 * kk, C::IDESC_QK, 1u);
                         }
-                        tc_commit(s_full(x));
                         // K(it) is released once its last S has been issued (x = 1, or x = 0 when tile b has no S this round)
                         if (x == 1 || !(it < n_x[1])) tc_commit(k_empty(st));
                     }
-                    if (do_pv) {                                 // O_x += P_x(it-1) V(it-1)
-                        if (!v_ready) { mbar_wait(v_full(stp), (uint32_t)((it - 1) / ST) & 1u); tc_fence_after(); v_ready = true; }
-                        const uint32_t d_tmem = tmem_base + C::O_COL + x * 128;
-                        const uint32_t pa = sP + x * C::P_BYTES, vb = sV0 + stp * C::TILE;
-                        const uint32_t acc0 = it > 1 ? 1u : 0u;
-#pragma unroll
-                        for (int kk = 0; kk < 8; kk++) {         // 16 keys per UMMA
-                            const uint64_t ad = umma_desc_sw128(pa + (kk >> 2) * C::B0) + 2 * (kk & 3);
-                            tc_mma_bf16(d_tmem, ad, umma_desc_mn_sw128(vb + kk * (16 * 128), 0, 1024), C::IDESC_PV0, acc0 | (kk ? 1u : 0u));
-                            if (C::TWO)
-                                tc_mma_bf16(d_tmem + 64, ad, umma_desc_mn_sw64(vb + C::B0 + kk * (16 * 64)), C::IDESC_PV1, acc0 | (kk ? 1u : 0u));
-                        }
-                        tc_commit(o_done(x));
+                    FA_T(2 + x, it, 4);
+                    tc_commit(s_full(x));                        // phase it: PV_x(it-1) retired (+ S_x(it) ready)
                     }
+                    __syncwarp();
                     FA_T(2 + x, it, 1);
                 }
-                if (it > 0) tc_commit(v_empty(stp));
+                if (it > 0 && elect_one()) tc_commit(v_empty(stp));
+                __syncwarp();
             }
         }
     } else {
@@ -208,17 +230,13 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
         const uint32_t t_s = t_lane + C::S_COL + x * 128, t_o = t_lane + C::O_COL + x * 128;
         const float sl = p.scale_log2;
         float m = -INFINITY, l = 0.f;
-        const int rx = row & 7;
-        const uint32_t p_row = sP + x * C::P_BYTES + row * 128;
         float pend = 1.f;                                        // rescale of O_x and l decided after the previous tile
         bool has_pend = false;
         for (int it = 0; it < nt; it++) {
             const int j0 = (n_begin + it) * 128;
-            mbar_wait(s_full(x), (uint32_t)it & 1u);
-            if (wq == 0 && lane == 0) FA_T(x, it, 0);
-            if (it > 0) mbar_wait(o_done(x), (uint32_t)(it - 1) & 1u);   // PV_x(it-1) retired: P_x is free, O_x is stable
+            mbar_wait(s_full(x), (uint32_t)it & 1u);             // S_x(it) ready; O_x += P_x(it-1) V(it-1) has retired
             tc_fence_after();
-            if (wq == 0 && lane == 0) FA_T(x, it, 1);
+            if (wq == 0) FA_T(x, it, 0);
             auto scale_o = [&](float cf) {                       // warp-collective: every lane runs the TMEM round trip
 #pragma unroll 1
                 for (int c = 0; c < D / 32; c++) {
@@ -232,8 +250,9 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
             if (__any_sync(0xffffffffu, has_pend)) scale_o(has_pend ? pend : 1.f);
             if (has_pend) { l *= pend; has_pend = false; }
             const bool need_mask = (j0 < kv0) || (j0 + 127 >= s_total) || (p.causal && j0 + 127 > past + i0 + 128 * x + wq * 32);
+            uint32_t pk[64];                                     // the P row, bf16 pairs
             // One sweep over the S row in TMEM, 32 columns at a time with the next chunk in flight: row maximum
-            // and / or P = exp2(S * scale - mu) -> bf16 -> shared memory (K-major SW128 A operand).
+            // and / or P = exp2(S * scale - mu) rounded to bf16.
             auto sweep = [&](auto do_max, auto do_exp, float mu, float& mx_out, float& ls_out) {
                 constexpr bool DM = decltype(do_max)::value, DE = decltype(do_exp)::value;
                 uint32_t buf[2][32];
@@ -261,20 +280,12 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                         }
                     }
                     if (DE) {
-                        uint32_t pk[16];
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
                             const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), sl, -mu));
                             const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), sl, -mu));
                             ls0 += p0; ls1 += p1;
-                            pk[i] = pack_bf16(p0, p1);
-                        }
-                        const uint32_t dst = p_row + (c >> 1) * C::B0;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int cc = (c & 1) * 4 + q;
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((cc ^ rx) << 4)), "r"(pk[4 * q]),
-                                         "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                            pk[16 * c + i] = pack_bf16(p0, p1);
                         }
                     }
                     if (c < 3) { tc_wait_ld(); tc_reg_fence32(buf[(c + 1) & 1]); }
@@ -303,19 +314,22 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                 sweep(std::false_type{}, std::true_type{}, (m == -INFINITY) ? 0.f : m * sl, mx, ls);
             }
             l += ls;
-            if (wq == 0 && lane == 0) FA_T(x, it, 2);
+            if (wq == 0) FA_T(x, it, 2);
             const float grow = (mx - m) * sl;                    // NaN (no keys yet) compares false
             if (grow > FA_RESCALE_LOG2) { pend = ex2_approx(-grow); has_pend = true; m = mx; }
-            tc_fence_before();                                   // S_x reads (and any O_x rescale) are complete
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // P_x(it) over the first 64 columns of S_x (the S row is fully consumed; S_x(it+1) is issued after PV_x(it))
+            tc_st32_nowait(t_s, pk);
+            tc_st32_nowait(t_s + 32, pk + 32);
+            tc_wait_st();
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(sm_done(x));
-            if (wq == 0 && lane == 0) FA_T(x, it, 3);
+            if (wq == 0) FA_T(x, it, 3);
         }
         // ---- epilogue: O / l
         if (x == 0 || act_b) {
             if (nt > 0) {
-                mbar_wait(o_done(x), (uint32_t)(nt - 1) & 1u);
+                mbar_wait(s_full(x), (uint32_t)nt & 1u);         // phase nt: the last PV_x has retired
                 tc_fence_after();
             }
             const float inv = l > 0.f ? 1.f / l : 0.f;
@@ -341,8 +355,10 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
             }
         }
     }
+    if (warp < 4) FA_T(3, 1 + warp, 5);
     tc_fence_before();
     __syncthreads();
+    FA_T(3, 0, 7);
     if (warp == FA_W_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
@@ -392,26 +408,31 @@ static int launch_tc_d(const AttnParams& p, cudaStream_t st) {
         P3_CHECK_ARG(e == cudaSuccess, "attention_prefill: cannot set %d B dynamic smem: %s", C::SMEM, cudaGetErrorString(e));
         set = true;
     }
-    dim3 grid((p.L + 255) / 256, p.n_heads, p.B);
+    dim3 grid(((p.L + 255) / 256) * p.n_heads * p.B);
     long long* dbg = nullptr;
+#ifdef P3_FA_TIMING
     const bool want_dbg = getenv("P3_FA_DBG") != nullptr;
     if (want_dbg) { cudaMalloc(&dbg, 4 * 64 * 8 * 8); cudaMemset(dbg, 0, 4 * 64 * 8 * 8); }
+#endif
     attn_prefill_tc_kernel<D><<<grid, FA_THREADS, C::SMEM, st>>>(tm, p, dbg);
     P3_CHECK_LAUNCH("attention_prefill_tc");
+#ifdef P3_FA_TIMING
     if (want_dbg) {
         static long long h[4 * 64 * 8];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
         cudaFree(dbg);
         long long t0 = h[0];
+        auto H = [&](int s, int it, int k) { return h[(s * 64 + it) * 8 + k] - t0; };
         for (int it = 0; it < 64 && h[(0 * 64 + it) * 8]; it++) {
-            printf("it %2d | smA: sfull %7lld odone %7lld swept %7lld arrived %7lld | smB: %7lld %7lld %7lld %7lld | mmaA: woke %7lld issued %7lld | mmaB: %7lld %7lld\n", it,
-                   h[(0 * 64 + it) * 8 + 0] - t0, h[(0 * 64 + it) * 8 + 1] - t0, h[(0 * 64 + it) * 8 + 2] - t0, h[(0 * 64 + it) * 8 + 3] - t0,
-                   h[(1 * 64 + it) * 8 + 0] - t0, h[(1 * 64 + it) * 8 + 1] - t0, h[(1 * 64 + it) * 8 + 2] - t0, h[(1 * 64 + it) * 8 + 3] - t0,
-                   h[(2 * 64 + it) * 8 + 0] - t0, h[(2 * 64 + it) * 8 + 1] - t0, h[(3 * 64 + it) * 8 + 0] - t0, h[(3 * 64 + it) * 8 + 1] - t0);
+            printf("it %2d | smA: sfull %7lld swept %7lld arrived %7lld | smB: %7lld %7lld %7lld | mma top %7lld kfull %7lld | A: woke %7lld vfull %7lld pv %7lld s %7lld commit %7lld | B: %7lld %7lld %7lld %7lld %7lld\n", it,
+                   H(0, it, 0), H(0, it, 2), H(0, it, 3), H(1, it, 0), H(1, it, 2), H(1, it, 3), H(2, it, 5), H(2, it, 6),
+                   H(2, it, 0), H(2, it, 2), H(2, it, 3), H(2, it, 4), H(2, it, 1), H(3, it, 0), H(3, it, 2), H(3, it, 3), H(3, it, 4), H(3, it, 1));
         }
+        printf("entry %lld setup %lld | softmax A warps done %lld %lld %lld %lld | end %lld\n", H(3, 0, 5), H(3, 0, 6), H(3, 1, 5), H(3, 2, 5), H(3, 3, 5), H(3, 4, 5), H(3, 0, 7));
         fflush(stdout);
     }
+#endif
     return 0;
 }
 

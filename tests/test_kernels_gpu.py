@@ -244,6 +244,59 @@ def test_attention_prefill(dev, cfg):
     _check(out, ref, tol=2e-2)
 
 
+def _prefill_call(L, qkv, kc, vc, kv_start, B, H, D, Lq, past, causal, dev):
+    out = torch.full((B * Lq, H * D), float('nan'), device=dev, dtype=torch.bfloat16)
+    pool, bt = _paged(kc, vc, dev) if past else (None, None)
+    p = qkv.data_ptr()
+    L.call('p3_attention_prefill', p, p + H * D * 2, p + 2 * H * D * 2, 3 * H * D, 3 * H * D, 3 * H * D, out.data_ptr(),
+           H * D, B, Lq, H, H, D, D ** -0.5, int(causal), past, kv_start.data_ptr(),
+           None if pool is None else pool.data_ptr(), None if bt is None else bt.data_ptr(), 0 if bt is None else bt.stride(0), 1, st())
+    torch.cuda.synchronize()
+    return out
+
+
+# (B, H, D, L, past, causal, kv_start, key-magnitude ramp per 128-key tile)
+_TC_CFGS = [(1, 1, 64, 128, 0, False, [0], 1.0), (1, 2, 96, 256, 0, True, [0], 1.0), (2, 3, 96, 300, 256, True, [0, 200], 1.0),
+            (1, 2, 96, 640, 128, True, [5], 1.0), (3, 2, 64, 577, 0, False, [0, 0, 0], 1.0), (1, 4, 96, 2048, 0, True, [0], 1.0),
+            (2, 2, 96, 1100, 0, True, [0, 300], 1.0), (1, 2, 96, 1024, 0, True, [0], 3.0), (1, 2, 96, 768, 0, False, [0], 40.0),
+            (2, 2, 64, 700, 0, False, [0, 0], 6.0), (1, 2, 96, 1000, 384, True, [130], 1.0)]
+
+
+@pytest.mark.parametrize('cfg', _TC_CFGS)
+def test_attention_prefill_tcgen05(dev, cfg):
+    """tcgen05 flash attention (attention_tc.cu) vs the fp32 restatement and vs the mma.sync kernel on the same inputs:
+    paged past (past % 128 == 0), left padding, ragged last tiles, ViT shape, and score ramps that drive the
+    lazy-rescale (> 2^8) and redo (> 2^64) paths of the streaming softmax."""
+    import os
+    L = _mods()
+    B, H, D, Lq, past, causal, kv, ramp = cfg
+    torch.manual_seed(5)
+    qkv = bf(torch.randn(B * Lq, 3 * H * D, device=dev))
+    if ramp != 1.0:
+        r = torch.tensor([ramp ** (i // 128) for i in range(Lq)], device=dev)
+        qkv.view(B, Lq, 3, H, D)[:, :, 1].mul_(r[None, :, None, None].to(torch.bfloat16))
+    kc, vc = bf(torch.randn(B, H, past, D, device=dev)), bf(torch.randn(B, H, past, D, device=dev))
+    kv_start = torch.tensor(kv, dtype=torch.int32, device=dev)
+    x = qkv.view(B, Lq, 3, H, D).permute(2, 0, 3, 1, 4)
+    q, k, v = x[0], torch.cat([kc, x[1]], 2), torch.cat([vc, x[2]], 2)
+    ref = _attn_ref(q, k, v, D ** -0.5, causal, past, kv_start.long()).transpose(1, 2).reshape(B * Lq, H * D)
+    old = os.environ.get('P3_ATTN_TC')
+    try:
+        os.environ['P3_ATTN_TC'] = '1'
+        out_tc = _prefill_call(L, qkv, kc, vc, kv_start, B, H, D, Lq, past, causal, dev)
+        os.environ['P3_ATTN_TC'] = '0'
+        out_mma = _prefill_call(L, qkv, kc, vc, kv_start, B, H, D, Lq, past, causal, dev)
+    finally:
+        if old is None:
+            os.environ.pop('P3_ATTN_TC', None)
+        else:
+            os.environ['P3_ATTN_TC'] = old
+    assert not torch.isnan(out_tc.float()).any()
+    _check(out_tc, ref, tol=1e-2)
+    _check(out_mma, ref, tol=1e-2)
+    _check(out_tc, out_mma.float(), tol=1e-2)
+
+
 @pytest.mark.parametrize('cfg', [(2, 4, 96, 1, 300, 1, 1), (2, 4, 96, 1, 300, 3, 1), (3, 2, 96, 5, 1000, 4, 1),
                                  (4, 2, 96, 6, 257, 2, 2), (1, 32, 96, 1, 2100, 5, 1), (2, 2, 96, 16, 64, 1, 1),
                                  (2, 2, 96, 3, 0, 1, 1), (2, 4, 64, 2, 130, 2, 1)])
