@@ -190,27 +190,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        // The whole warp stays converged and one elected lane issues: under `if (lane == 0)` nvcc keeps the UMMA
+        // descriptors in vector registers and wraps every UTCHMMA in an ELECT / R2UR loop (~70 cycles per issue).
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int k = 0; k < kb; k++) {
+                mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int k = 0; k < kb; k++) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + C::A_BYTES);
+                const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + C::A_BYTES);
+                if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < C::BK / 16; kk++)   // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
                         tc_mma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, C::IDESC, (k | kk) ? 1u : 0u);
                     tc_commit(empty_bar(stage));
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (k == kb - 1) tc_commit(tfull_bar(acc));
                 }
-                tc_commit(tfull_bar(acc));
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         const int q = warp & 3, half = (warp - 4) >> 2;       // TMEM lane quarter, column half
@@ -372,7 +375,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
+        if (leader) {                                           // converged warp, elected issuing lane (see gemm_tc_kernel)
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = cluster_id; tile < total; tile += n_clusters) {
@@ -384,13 +387,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                     const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + C::A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < C::BK / 16; kk++)
-                        tc_mma_bf16_2sm(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, C::IDESC, (k | kk) ? 1u : 0u);
-                    tc_commit_2sm_mc(empty_bar(stage));                                 // frees the slot in both CTAs
+                        for (int kk = 0; kk < C::BK / 16; kk++)
+                            tc_mma_bf16_2sm(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, C::IDESC, (k | kk) ? 1u : 0u);
+                        tc_commit_2sm_mc(empty_bar(stage));                             // frees the slot in both CTAs
+                        if (k == kb - 1) tc_commit_2sm_mc(tfull_bar(acc));              // accumulators ready in both CTAs
+                    }
+                    __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit_2sm_mc(tfull_bar(acc));                                       // accumulators ready in both CTAs
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
