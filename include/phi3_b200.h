@@ -107,7 +107,10 @@ int p3_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* 
  * phi:550-563) and mx.fast.scaled_dot_product_attention phi:148 (causal=0).
  * q/k/v point into the (roped) qkv buffer; row strides in elements; head h at +h*hd.
  * Keys [0,past) come from the paged pool (cache row b/row_div), keys [past,past+L) from k/v.
- * kv_start int32 [B] (left-pad length; NULL = 0). Pad queries produce zeros. */
+ * kv_start int32 [B] (left-pad length; NULL = 0). Pad queries produce zeros.
+ * Runs the tcgen05 flash-attention kernel (S and P in TMEM, TMA operands) when past % 128 == 0, L >= 64 and
+ * the pointers / strides are 16-byte aligned; otherwise (and with P3_ATTN_TC=0 in the environment, used by the
+ * tests as a cross-check) the mma.sync kernel with the same contract. */
 int p3_attention_prefill(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* out,
                          int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale, int causal, int past,
                          const int32_t* kv_start, const void* pool, const int32_t* block_table, int bt_stride,
