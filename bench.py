@@ -92,6 +92,7 @@ def run_cuda(args):
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # stdout carries exactly one line: the JSON result
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import phi3_b200  # noqa
     from phi3_b200 import configs, weights, _lib
