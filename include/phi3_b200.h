@@ -94,6 +94,20 @@ int p3_gemm_skinny_qkv_rope(const void* X, int64_t ldx, const void* norm_w, floa
                             int row_div, void* pool, const int32_t* block_table, int bt_stride, int write_cache,
                             const void* l2_prefetch, int64_t l2_prefetch_bytes, cudaStream_t st);
 
+/* quantize_model=True (pv:264,291-305: nn.quantize(model, group_size=64, bits=4) -> QuantizedLinear): the two decode-time
+ * entries above over the 4-bit image of W. Wq uint8 [N][K/2] and Wmeta bf16 [N][K/64][2] = (scale, bias) in the lane order
+ * written by phi3_b200/quant.py::pack_w4g64; y = sum_k x_k (scale_g q_k + bias_g) accumulated in fp32 (codes and a
+ * matrix of ones go through the tensor cores per 64-wide group, the affine map is applied to the group sums). K % 128 == 0.
+ * Prefill / ViT GEMMs of a quantised model run p3_gemm on the bf16 dequantised image. */
+int p3_gemm_skinny_w4(const void* X, int64_t ldx, const void* norm_w, float eps, const void* Wq, const void* Wmeta, void* out,
+                      int64_t ldo, const void* resid, int M, int N, int K, int epi, const float* ss_in, int n_ss_in,
+                      float* ss_out, const void* l2_prefetch, int64_t l2_prefetch_bytes, cudaStream_t st);
+int p3_gemm_skinny_qkv_rope_w4(const void* X, int64_t ldx, const void* norm_w, float eps, const void* Wq, const void* Wmeta,
+                               void* qkv, const float* ss_in, int n_ss_in, const float* cosT, const float* sinT,
+                               int64_t tab_bstride, int B, int L, int n_heads, int n_kv, int hd, int K, int past,
+                               const int32_t* past_dev, int row_div, void* pool, const int32_t* block_table, int bt_stride,
+                               int write_cache, const void* l2_prefetch, int64_t l2_prefetch_bytes, cudaStream_t st);
+
 /* nn.Linear for prefill / ViT / projector (phi:140-143,155-156,391,437-438,465-466,604) and the
  * patch-embed conv as GEMM (phi:186-192): out[M,N] = X[M,K] . W[N,K]^T on tcgen05 tensor cores
  * (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue). bias bf16 [N] or NULL. row_map int32 [M] or

@@ -22,6 +22,8 @@ _SIGS = {
     'p3_row_stats': [_p, _l, _l, _i, _p, _p, _p, _i, _p, _p, _i, _p, _p, _p],
     'p3_gemm_skinny': [_p, _l, _p, _f, _p, _p, _l, _p, _i, _i, _i, _i, _p, _i, _p, _p, _l, _p],
     'p3_gemm_skinny_qkv_rope': [_p, _l, _p, _f, _p, _p, _p, _i, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _i, _p, _l, _p],
+    'p3_gemm_skinny_w4': [_p, _l, _p, _f, _p, _p, _p, _l, _p, _i, _i, _i, _i, _p, _i, _p, _p, _l, _p],
+    'p3_gemm_skinny_qkv_rope_w4': [_p, _l, _p, _f, _p, _p, _p, _p, _i, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _i, _p, _l, _p],
     'p3_gemm': [_p, _l, _p, _l, _p, _p, _l, _p, _p, _l, _i, _i, _i, _i, _p],
     'p3_attention_prefill': [_p, _p, _p, _l, _l, _l, _p, _l, _i, _i, _i, _i, _i, _f, _i, _i, _p, _p, _p, _i, _i, _p],
     'p3_attention_decode': [_p, _p, _p, _l, _l, _l, _p, _l, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _l, _p],

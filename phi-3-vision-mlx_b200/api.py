@@ -8,7 +8,9 @@ kernel of libphi3b200.so.
 Differences a caller can see (all opt-in or forced by the offline environment):
   * `load()` accepts tokenizer=, weights= (dict or safetensors dir), cfg=, random_init=,
     num_crops=, device= through **kwargs — there are no checkpoint / tokenizer files offline;
-  * quantize_model / use_adapter raise NotImplementedError (SURVEY.md §8f rows N3/N4);
+  * quantize_model=True quantises the given (bf16) weights at load time — 4-bit, group 64, every Linear / Embedding, as
+    `nn.quantize(model, 64, 4)` does for the reference's pre-quantised checkpoint (pv:264,291-305) — instead of reading a
+    `quantized_model.safetensors`; use_adapter raises NotImplementedError (SURVEY.md §8f row N4);
   * constrain(..., n_beam=3) exposes the beam width the reference hard-codes (pv:505);
   * images may be PIL images or uint8 HWC arrays (no URL fetching offline).
 """
@@ -53,8 +55,6 @@ def _read_safetensors(path):
 
 def load(blind_model=False, quantize_model=False, quantize_cache=False, use_adapter=False, **kwargs):
     """pv:1279-1322. Returns (model, processor)."""
-    if quantize_model:
-        raise NotImplementedError('quantize_model (4-bit weights) is outside the B200 hot-path scope (SURVEY §8f N3)')
     if use_adapter:
         raise NotImplementedError('use_adapter (LoRA) is outside the B200 hot-path scope (SURVEY §8f N4)')
     device = kwargs.pop('device', 'cuda')
@@ -84,7 +84,7 @@ def load(blind_model=False, quantize_model=False, quantize_cache=False, use_adap
             tokenizer = ByteTokenizer()
     for k, v in kwargs.items():                                            # remaining kwargs override cfg (pv:359-363)
         setattr(cfg, k, v)
-    model = Phi3B200(cfg, weights, device=device, clip_cfg=clip_cfg)
+    model = Phi3B200(cfg, weights, device=device, clip_cfg=clip_cfg, quantize_model=quantize_model)
     processor = Phi3FProcessor(tokenizer) if blind_model else Phi3VProcessor(tokenizer, num_crops=num_crops, device=device)
     return model, processor
 

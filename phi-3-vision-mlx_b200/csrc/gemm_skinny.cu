@@ -26,6 +26,7 @@ struct SkParams {
     const bf16* X; int64_t ldx;
     const bf16* norm_w; float eps;
     const bf16* W;
+    const uint8_t* Wq; const bf16* Wmeta; // W4 variant: packed 4-bit codes [N][K/2] and (scale, bias) bf16 [N][K/64][2] (quant.py layout)
     void* out; int64_t ldo;
     const bf16* resid;
     int M, N, K, epi;
@@ -42,28 +43,37 @@ struct SkParams {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 
-template <int NT, int MT, int DEPTH_>
+template <int NT, int MT, int DEPTH_, bool W4 = false>
 struct SkCfg {
     static constexpr int W_SLOTS = 4 * MT, X_SLOTS = 0;                      // X travels in registers (L2-resident, 1 chunk ahead)
-    static constexpr int STAGE = W_SLOTS * 512 + 128;                        // + 128 B of norm gains
+    static constexpr int CHUNK = W4 ? 128 : 64;                              // k elements per ring stage
+    // bf16: W slices + 128 B of norm gains. W4: per (row tile, row half) 512 B of codes + 256 B of (scale, bias), + 256 B of gains
+    static constexpr int STAGE = W4 ? (MT * 2 * 768 + 256) : (W_SLOTS * 512 + 128);
+    static constexpr int META_OFF = MT * 2 * 512, GAIN_OFF = W4 ? MT * 2 * 768 : W_SLOTS * 512;
     static constexpr int DEPTH = DEPTH_;
     static constexpr int RING = SK_WARPS * DEPTH * STAGE;
     static constexpr int RED = SK_WARPS * MT * 8 * NT * 17 * 4;
     static constexpr int SMEM = RING > RED ? RING : RED;
 };
 
-template <int NT, int MT, int DEPTH>
-__global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112 * 1024) ? 2 : 1) gemm_skinny_kernel(SkParams p) {
-    using C = SkCfg<NT, MT, DEPTH>;
+// extracts the adjacent weight pair j of a packed word as bf16x2 (128 + q): nibbles j and j + 4 (quant.py::pack_w4g64)
+__device__ __forceinline__ uint32_t w4_pair(uint32_t w, int j) { return ((w >> (4 * j)) & 0x000F000Fu) | 0x43004300u; }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int NT, int MT, int DEPTH, bool W4>
+__global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <= 112 * 1024) ? 2 : 1) gemm_skinny_kernel(SkParams p) {
+    using C = SkCfg<NT, MT, DEPTH, W4>;
     extern __shared__ __align__(128) uint8_t sk_smem[];
     __shared__ float s_rs[16];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int K = p.K, n_chunks = K / 64;
+    const int K = p.K, n_chunks = K / C::CHUNK;
     const uint32_t ring = smem_u32(sk_smem) + warp * (C::DEPTH * C::STAGE);
 
-    // W row pointers for this lane (rows g and g+8 of each 16-row tile)
-    const bf16* wrow[MT][2];
+    // W rows of this lane (rows g and g+8 of each 16-row tile)
+    int wr[MT][2];
     int out_col0;
     int rope_head = -1, rope_grp = 0;                                              // ROPE_QKV: which head / 16-col group
     if (p.epi == P3_EPI_ROPE_QKV) {
@@ -77,16 +87,16 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
             out_col0 = r0;
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
-                wrow[mt][0] = p.W + (size_t)(r0 + mt * (p.hd / 2) + g) * K + t * 8;
-                wrow[mt][1] = p.W + (size_t)(r0 + mt * (p.hd / 2) + g + 8) * K + t * 8;
+                wr[mt][0] = r0 + mt * (p.hd / 2) + g;
+                wr[mt][1] = r0 + mt * (p.hd / 2) + g + 8;
             }
         } else {
             r0 = (p.n_heads + p.n_kv) * p.hd + ((int)blockIdx.x - n_rope) * 32;
             out_col0 = r0;
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
-                wrow[mt][0] = p.W + (size_t)(r0 + mt * 16 + g) * K + t * 8;
-                wrow[mt][1] = p.W + (size_t)(r0 + mt * 16 + g + 8) * K + t * 8;
+                wr[mt][0] = r0 + mt * 16 + g;
+                wr[mt][1] = r0 + mt * 16 + g + 8;
             }
         }
     } else if (p.epi == P3_EPI_SWIGLU) {
@@ -96,32 +106,53 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
         out_col0 = o0;
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) {
-            wrow[mt][0] = p.W + (size_t)(gate0 + mt * 128 + g) * K + t * 8;
-            wrow[mt][1] = p.W + (size_t)(gate0 + mt * 128 + g + 8) * K + t * 8;
+            wr[mt][0] = gate0 + mt * 128 + g;
+            wr[mt][1] = gate0 + mt * 128 + g + 8;
         }
     } else {
         int n0 = blockIdx.x * 16 * MT;
         out_col0 = n0;
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) {
-            int r0 = min(n0 + mt * 16 + g, p.N - 1), r1 = min(n0 + mt * 16 + g + 8, p.N - 1);
-            wrow[mt][0] = p.W + (size_t)r0 * K + t * 8;
-            wrow[mt][1] = p.W + (size_t)r1 * K + t * 8;
+            wr[mt][0] = min(n0 + mt * 16 + g, p.N - 1);
+            wr[mt][1] = min(n0 + mt * 16 + g + 8, p.N - 1);
         }
     }
+    const bf16* wrow[MT][2];                                                     // bf16 stream: 16 B (8 weights) per lane and load
+    const uint8_t* qrow[MT][2]; const bf16* mrow[MT][2];                         // W4 stream: 16 B (32 weights) + 8 B (2 groups' scale, bias)
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            wrow[mt][hh] = W4 ? nullptr : p.W + (size_t)wr[mt][hh] * K + t * 8;
+            qrow[mt][hh] = W4 ? p.Wq + (size_t)wr[mt][hh] * (K / 2) + t * 16 : nullptr;
+            mrow[mt][hh] = W4 ? p.Wmeta + (size_t)wr[mt][hh] * (K / 64) * 2 : nullptr;
+        }
     const bf16* xrow[NT];
     int xbytes[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) {
         int m = nt * 8 + g;
         xbytes[nt] = m < p.M ? 16 : 0;                                          // rows >= M are zero-filled
-        xrow[nt] = p.X + (size_t)(m < p.M ? m : 0) * p.ldx + t * 8;
+        xrow[nt] = p.X + (size_t)(m < p.M ? m : 0) * p.ldx + t * (W4 ? 16 : 8);
     }
 
     // stage layout (per warp): W slots [mt][row-half][k-half], X slots [nt][k-half], each 32 lanes x 16 B;
     // then 128 B of norm gains (64 elements, read back with broadcast)
     const uint64_t pol = l2_evict_first_policy();
     auto issue_w = [&](int ci, int stage) {                                      // weights + norm gains: immutable
+        if constexpr (W4) {
+            const uint32_t sb = ring + stage * C::STAGE;
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    cp_async16_stream(sb + (mt * 2 + hh) * 512 + lane * 16, qrow[mt][hh] + ci * 64, pol);
+                    cp_async8(sb + C::META_OFF + (mt * 2 + hh) * 256 + lane * 8, mrow[mt][hh] + ci * 4);
+                }
+            if (p.norm_w && lane < 16) cp_async16(sb + C::GAIN_OFF + lane * 16, p.norm_w + ci * 128 + lane * 8);
+            return;
+        }
         const uint32_t sb = ring + stage * C::STAGE + lane * 16;
         const int k0 = ci * 64;
 #pragma unroll
@@ -134,8 +165,17 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
         if (p.norm_w && lane < 8)
             cp_async16(ring + stage * C::STAGE + (C::W_SLOTS + C::X_SLOTS) * 512 + lane * 16, p.norm_w + k0 + lane * 8);
     };
-    uint4 xnext[NT][2];
+    uint4 xnext[NT][W4 ? 4 : 2];
     auto load_x = [&](int ci) {                                                  // activations: produced by the previous kernel
+        if constexpr (W4) {                                                      // lane t: k = 128 ci + 64 grp + 16 t + (0..15)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    xnext[nt][q] = xbytes[nt] ? *reinterpret_cast<const uint4*>(xrow[nt] + ci * 128 + (q >> 1) * 64 + (q & 1) * 8)
+                                              : make_uint4(0, 0, 0, 0);
+            return;
+        }
         const int k0 = ci * 64;
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
@@ -209,6 +249,93 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
         cp_async_wait<C::DEPTH - 1>();                                           // oldest group (this chunk) has landed
         __syncwarp();                                                            // norm gains were copied by lanes 0-7
         const uint8_t* sb = sk_smem + (size_t)warp * (C::DEPTH * C::STAGE) + stage * C::STAGE;
+        if constexpr (W4) {
+            uint4 qc[MT][2]; uint2 qm[MT][2]; uint4 xq[NT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    qc[mt][hh] = *reinterpret_cast<const uint4*>(sb + (mt * 2 + hh) * 512 + lane * 16);
+                    qm[mt][hh] = *reinterpret_cast<const uint2*>(sb + C::META_OFF + (mt * 2 + hh) * 256 + lane * 8);
+                }
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) xq[nt][q] = xnext[nt][q];
+            if (ci + SK_WARPS < n_chunks) load_x(ci + SK_WARPS);
+            if (p.norm_w) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint4 nw = *reinterpret_cast<const uint4*>(sb + C::GAIN_OFF + ((q >> 1) * 64 + t * 16 + (q & 1) * 8) * 2);
+                    const uint32_t* uw = reinterpret_cast<const uint32_t*>(&nw);
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) {
+                        uint32_t* ux = reinterpret_cast<uint32_t*>(&xq[nt][q]);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            float2 f = unpack_bf16(ux[j]), w = unpack_bf16(uw[j]);
+                            ux[j] = pack_bf16(f.x * rs[nt] * w.x, f.y * rs[nt] * w.y);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (ci_issue < n_chunks) issue_w(ci_issue, stage);
+            cp_async_commit();
+            ci_issue += SK_WARPS;
+            if (++stage == C::DEPTH) stage = 0;
+            // per 64-wide group: MMA on the raw codes (as bf16 128+q) and on a matrix of ones (-> sum of x), then
+            // y += scale * sum((128+q) x) + (bias - 128 scale) * sum(x)   ==  sum((scale q + bias) x)  in fp32
+            const uint32_t ones[4] = {0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u};
+#pragma unroll
+            for (int gi = 0; gi < 2; gi++) {
+                float accg[MT][NT][4], accx[NT][4];
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) accx[nt][j] = 0.f;
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) accg[mt][nt][j] = 0.f;
+                }
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    const int i = s >> 1, j0 = 2 * (s & 1);
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) {
+                        const uint32_t* ux = reinterpret_cast<const uint32_t*>(&xq[nt][gi * 2 + i]);
+                        mma_bf16_16816(accx[nt], ones, ux[j0], ux[j0 + 1]);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        const uint32_t* c0 = reinterpret_cast<const uint32_t*>(&qc[mt][0]);
+                        const uint32_t* c1 = reinterpret_cast<const uint32_t*>(&qc[mt][1]);
+                        const uint32_t w0 = c0[gi * 2 + i], w1 = c1[gi * 2 + i];
+                        uint32_t a[4] = {w4_pair(w0, j0), w4_pair(w1, j0), w4_pair(w0, j0 + 1), w4_pair(w1, j0 + 1)};
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) {
+                            const uint32_t* ux = reinterpret_cast<const uint32_t*>(&xq[nt][gi * 2 + i]);
+                            mma_bf16_16816(accg[mt][nt], a, ux[j0], ux[j0 + 1]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const float2 m0 = unpack_bf16(gi ? qm[mt][0].y : qm[mt][0].x);   // (scale, bias) of row g
+                    const float2 m1 = unpack_bf16(gi ? qm[mt][1].y : qm[mt][1].x);   // row g + 8
+                    const float c0 = m0.y - 128.f * m0.x, c1 = m1.y - 128.f * m1.x;
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) {
+                        acc[mt][nt][0] += m0.x * accg[mt][nt][0] + c0 * accx[nt][0];
+                        acc[mt][nt][1] += m0.x * accg[mt][nt][1] + c0 * accx[nt][1];
+                        acc[mt][nt][2] += m1.x * accg[mt][nt][2] + c1 * accx[nt][2];
+                        acc[mt][nt][3] += m1.x * accg[mt][nt][3] + c1 * accx[nt][3];
+                    }
+                }
+            }
+            continue;
+        }
         uint4 wcur[MT][2][2], xf[NT][2];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++)
@@ -358,16 +485,16 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH>::SMEM <= 112
     }
 }
 
-template <int NT, int MT, int DEPTH>
+template <int NT, int MT, int DEPTH, bool W4 = false>
 static int launch_skinny_d(const SkParams& p, unsigned grid, cudaStream_t st) {
-    using C = SkCfg<NT, MT, DEPTH>;
+    using C = SkCfg<NT, MT, DEPTH, W4>;
     static bool set = false;
     if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel<NT, MT, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel<NT, MT, DEPTH, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         P3_CHECK_ARG(e == cudaSuccess, "gemm_skinny: smem attribute: %s", cudaGetErrorString(e));
         set = true;
     }
-    p3_launch_pdl(gemm_skinny_kernel<NT, MT, DEPTH>, dim3(grid), dim3(SK_THREADS), (size_t)C::SMEM, st, p);
+    p3_launch_pdl(gemm_skinny_kernel<NT, MT, DEPTH, W4>, dim3(grid), dim3(SK_THREADS), (size_t)C::SMEM, st, p);
     P3_CHECK_LAUNCH("gemm_skinny");
     return 0;
 }
@@ -380,6 +507,7 @@ static int sk_depth_override() {
 }
 template <int NT, int MT>
 static int launch_skinny(const SkParams& p, unsigned grid, cudaStream_t st) {
+    if (p.Wq) return launch_skinny_d<NT, MT, 4, true>(p, grid, st);          // 4-bit stream: 4 stages x 128 k per warp
     int d = sk_depth_override();
     if (d == 0) d = (MT == 1) ? 4 : 2;                       // measured best (tools/microbench.py): deeper rings do not pay, residency does
     switch (d) {
@@ -392,12 +520,13 @@ static int launch_skinny(const SkParams& p, unsigned grid, cudaStream_t st) {
     }
 }
 
-extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, void* out,
-                              int64_t ldo, const void* resid, int M, int N, int K, int epi, const float* ss_in,
-                              int n_ss_in, float* ss_out, const void* l2_prefetch, int64_t l2_prefetch_bytes,
-                              cudaStream_t st) {
+static int skinny_impl(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, const void* Wq,
+                       const void* Wmeta, void* out, int64_t ldo, const void* resid, int M, int N, int K, int epi,
+                       const float* ss_in, int n_ss_in, float* ss_out, const void* l2_prefetch, int64_t l2_prefetch_bytes,
+                       cudaStream_t st) {
     P3_CHECK_ARG(M >= 1 && M <= 16, "gemm_skinny: M must be in [1,16] (got %d)", M);
     P3_CHECK_ARG(K % 64 == 0, "gemm_skinny: K must be a multiple of 64 (got %d)", K);
+    P3_CHECK_ARG(!Wq || (K % 128 == 0 && Wmeta), "gemm_skinny_w4: K must be a multiple of 128 and meta must be given");
     P3_CHECK_ARG(epi == P3_EPI_NONE || epi == P3_EPI_RESIDUAL || epi == P3_EPI_SWIGLU || epi == P3_EPI_F32,
                  "gemm_skinny: unsupported epilogue %d", epi);
     P3_CHECK_ARG(epi != P3_EPI_RESIDUAL || resid, "gemm_skinny: residual epilogue needs resid");
@@ -405,6 +534,7 @@ extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, fl
     P3_CHECK_ARG(!ss_out || (epi == P3_EPI_RESIDUAL && N < 148 * 32 * 2), "gemm_skinny: ss_out needs the 16-row residual configuration");
     SkParams p{};
     p.X = (const bf16*)X; p.ldx = ldx; p.norm_w = (const bf16*)norm_w; p.eps = eps; p.W = (const bf16*)W; p.out = out;
+    p.Wq = (const uint8_t*)Wq; p.Wmeta = (const bf16*)Wmeta;
     p.ldo = ldo; p.resid = (const bf16*)resid; p.M = M; p.N = N; p.K = K; p.epi = epi;
     p.ss_in = ss_in; p.n_ss_in = n_ss_in; p.ss_out = ss_out;
     p.l2_pf = (const uint8_t*)l2_prefetch; p.l2_pf_bytes = l2_prefetch_bytes;
@@ -421,20 +551,40 @@ extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, fl
     return M <= 8 ? launch_skinny<1, 1>(p, grid, st) : launch_skinny<2, 1>(p, grid, st);
 }
 
+extern "C" int p3_gemm_skinny(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, void* out,
+                              int64_t ldo, const void* resid, int M, int N, int K, int epi, const float* ss_in,
+                              int n_ss_in, float* ss_out, const void* l2_prefetch, int64_t l2_prefetch_bytes,
+                              cudaStream_t st) {
+    return skinny_impl(X, ldx, norm_w, eps, W, nullptr, nullptr, out, ldo, resid, M, N, K, epi, ss_in, n_ss_in, ss_out,
+                       l2_prefetch, l2_prefetch_bytes, st);
+}
+
+// quantize_model=True (pv:264,291-305): the same op over the 4-bit g64 image of W (quant.py::pack_w4g64 layout)
+extern "C" int p3_gemm_skinny_w4(const void* X, int64_t ldx, const void* norm_w, float eps, const void* Wq, const void* Wmeta,
+                                 void* out, int64_t ldo, const void* resid, int M, int N, int K, int epi, const float* ss_in,
+                                 int n_ss_in, float* ss_out, const void* l2_prefetch, int64_t l2_prefetch_bytes,
+                                 cudaStream_t st) {
+    P3_CHECK_ARG(Wq && Wmeta, "gemm_skinny_w4: codes and meta are required");
+    return skinny_impl(X, ldx, norm_w, eps, nullptr, Wq, Wmeta, out, ldo, resid, M, N, K, epi, ss_in, n_ss_in, ss_out,
+                       l2_prefetch, l2_prefetch_bytes, st);
+}
+
 // qkv_proj + SuRoPE + paged KV write in one launch (decode, B*L <= 16 tokens): phi.py:442-453.
-extern "C" int p3_gemm_skinny_qkv_rope(const void* X, int64_t ldx, const void* norm_w, float eps, const void* Wqkv,
-                                       void* qkv, const float* ss_in, int n_ss_in, const float* cosT, const float* sinT,
-                                       int64_t tab_bstride, int B, int L, int n_heads, int n_kv, int hd, int K, int past,
-                                       const int32_t* past_dev, int row_div, void* pool, const int32_t* block_table,
-                                       int bt_stride, int write_cache, const void* l2_prefetch, int64_t l2_prefetch_bytes,
-                                       cudaStream_t st) {
+static int skinny_qkv_rope_impl(const void* X, int64_t ldx, const void* norm_w, float eps, const void* Wqkv, const void* Wq,
+                                const void* Wmeta, void* qkv, const float* ss_in, int n_ss_in, const float* cosT, const float* sinT,
+                                int64_t tab_bstride, int B, int L, int n_heads, int n_kv, int hd, int K, int past,
+                                const int32_t* past_dev, int row_div, void* pool, const int32_t* block_table,
+                                int bt_stride, int write_cache, const void* l2_prefetch, int64_t l2_prefetch_bytes,
+                                cudaStream_t st) {
     const int M = B * L;
+    P3_CHECK_ARG(!Wq || (K % 128 == 0 && Wmeta), "gemm_skinny_qkv_rope_w4: K must be a multiple of 128 and meta must be given");
     P3_CHECK_ARG(M >= 1 && M <= 16, "gemm_skinny_qkv_rope: B*L must be in [1,16] (got %d)", M);
     P3_CHECK_ARG(K % 64 == 0 && ldx % 8 == 0, "gemm_skinny_qkv_rope: K %% 64 and ldx %% 8 required");
     P3_CHECK_ARG(hd % 32 == 0 && (n_kv * hd) % 32 == 0, "gemm_skinny_qkv_rope: head_dim must be a multiple of 32");
     P3_CHECK_ARG(!write_cache || (pool && block_table), "gemm_skinny_qkv_rope: cache write needs pool and block table");
     SkParams p{};
     p.X = (const bf16*)X; p.ldx = ldx; p.norm_w = (const bf16*)norm_w; p.eps = eps; p.W = (const bf16*)Wqkv; p.out = qkv;
+    p.Wq = (const uint8_t*)Wq; p.Wmeta = (const bf16*)Wmeta;
     p.ldo = (int64_t)(n_heads + 2 * n_kv) * hd; p.M = M; p.N = (n_heads + 2 * n_kv) * hd; p.K = K; p.epi = P3_EPI_ROPE_QKV;
     p.ss_in = ss_in; p.n_ss_in = n_ss_in;
     p.cosT = cosT; p.sinT = sinT; p.tab_bstride = tab_bstride; p.L = L; p.n_heads = n_heads; p.n_kv = n_kv; p.hd = hd;
@@ -443,4 +593,27 @@ extern "C" int p3_gemm_skinny_qkv_rope(const void* X, int64_t ldx, const void* n
     p.l2_pf = (const uint8_t*)l2_prefetch; p.l2_pf_bytes = l2_prefetch_bytes;
     unsigned grid = (unsigned)((n_heads + n_kv) * (hd / 32) + n_kv * hd / 32);
     return M <= 8 ? launch_skinny<1, 2>(p, grid, st) : launch_skinny<2, 2>(p, grid, st);
+}
+
+extern "C" int p3_gemm_skinny_qkv_rope(const void* X, int64_t ldx, const void* norm_w, float eps, const void* Wqkv,
+                                       void* qkv, const float* ss_in, int n_ss_in, const float* cosT, const float* sinT,
+                                       int64_t tab_bstride, int B, int L, int n_heads, int n_kv, int hd, int K, int past,
+                                       const int32_t* past_dev, int row_div, void* pool, const int32_t* block_table,
+                                       int bt_stride, int write_cache, const void* l2_prefetch, int64_t l2_prefetch_bytes,
+                                       cudaStream_t st) {
+    return skinny_qkv_rope_impl(X, ldx, norm_w, eps, Wqkv, nullptr, nullptr, qkv, ss_in, n_ss_in, cosT, sinT, tab_bstride, B, L,
+                                n_heads, n_kv, hd, K, past, past_dev, row_div, pool, block_table, bt_stride, write_cache,
+                                l2_prefetch, l2_prefetch_bytes, st);
+}
+
+extern "C" int p3_gemm_skinny_qkv_rope_w4(const void* X, int64_t ldx, const void* norm_w, float eps, const void* Wq,
+                                          const void* Wmeta, void* qkv, const float* ss_in, int n_ss_in, const float* cosT,
+                                          const float* sinT, int64_t tab_bstride, int B, int L, int n_heads, int n_kv, int hd,
+                                          int K, int past, const int32_t* past_dev, int row_div, void* pool,
+                                          const int32_t* block_table, int bt_stride, int write_cache, const void* l2_prefetch,
+                                          int64_t l2_prefetch_bytes, cudaStream_t st) {
+    P3_CHECK_ARG(Wq && Wmeta, "gemm_skinny_qkv_rope_w4: codes and meta are required");
+    return skinny_qkv_rope_impl(X, ldx, norm_w, eps, nullptr, Wq, Wmeta, qkv, ss_in, n_ss_in, cosT, sinT, tab_bstride, B, L,
+                                n_heads, n_kv, hd, K, past, past_dev, row_div, pool, block_table, bt_stride, write_cache,
+                                l2_prefetch, l2_prefetch_bytes, st);
 }

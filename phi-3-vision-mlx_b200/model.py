@@ -19,6 +19,7 @@ import math
 import torch
 from . import _lib
 from ._lib import call, ptr, PAGE
+from .quant import W4, fake_quant
 from .configs import CLIP_VIT_L14_336
 
 
@@ -125,7 +126,7 @@ class KVCacheB200:
 
 
 class Phi3B200:
-    def __init__(self, cfg, weights, device='cuda', clip_cfg=None, gemm_impl=0):
+    def __init__(self, cfg, weights, device='cuda', clip_cfg=None, gemm_impl=0, quantize_model=False):
         if not torch.cuda.is_available():
             raise RuntimeError('Phi3B200 needs a CUDA device (sm_100a); there is no CPU fallback')
         _lib.lib()
@@ -147,16 +148,31 @@ class Phi3B200:
         self.use_quantized_cache = bool(getattr(cfg, 'use_quantized_cache', False))
         d = lambda t: t.to(self.dev, torch.bfloat16).contiguous()
         w = weights
-        self.embed = d(w['model.embed_tokens.weight'])
+        # quantize_model (pv:264,291-305: nn.quantize(model, 64, 4) over every Linear / Embedding): the matrices are
+        # replaced by their 4-bit images. `lin` keeps bf16(dequantised) for the tensor-core GEMMs and registers the
+        # packed 4-bit stream of the decode-time skinny GEMM under the tensor's address; `emb` is dequantise-only.
+        self.quantize_model = bool(quantize_model)
+        self._w4 = {}
+
+        def lin(t, row_perm=None):
+            t = d(t)
+            if not self.quantize_model:
+                return t if row_perm is None else row_perm(t)
+            q = W4(t, pack=True, row_perm=row_perm)
+            self._w4[q.deq.data_ptr()] = (q.codes, q.meta)
+            return q.deq
+        emb = (lambda t: fake_quant(d(t))) if self.quantize_model else d
+        self._lin_prefill, self._emb = ((lambda t: fake_quant(d(t))) if self.quantize_model else d), emb
+        self.embed = emb(w['model.embed_tokens.weight'])
         self.layers = []
         for i in range(cfg.num_hidden_layers):
             p = f'model.layers.{i}.'
             self.layers.append(dict(
-                ln1=d(w[p + 'input_layernorm.weight']), qkv=d(w[p + 'self_attn.qkv_proj.weight']),
-                o=d(w[p + 'self_attn.o_proj.weight']), ln2=d(w[p + 'post_attention_layernorm.weight']),
-                gu=interleave_gate_up(d(w[p + 'mlp.gate_up_proj.weight'])), down=d(w[p + 'mlp.down_proj.weight'])))
+                ln1=d(w[p + 'input_layernorm.weight']), qkv=lin(w[p + 'self_attn.qkv_proj.weight']),
+                o=lin(w[p + 'self_attn.o_proj.weight']), ln2=d(w[p + 'post_attention_layernorm.weight']),
+                gu=lin(w[p + 'mlp.gate_up_proj.weight'], interleave_gate_up), down=lin(w[p + 'mlp.down_proj.weight'])))
         self.norm = d(w['model.norm.weight'])
-        self.lm_head = d(w['lm_head.weight'])
+        self.lm_head = lin(w['lm_head.weight'])
         self.vision = None
         if any(k.startswith('model.vision_embed_tokens') for k in w):
             self._load_vision(w, d)
@@ -176,23 +192,24 @@ class Phi3B200:
         kp = 640                                         # 588 padded to a multiple of the 64-wide K block
         pw = torch.zeros((D, kp), dtype=torch.bfloat16, device=self.dev)
         pw[:, :588] = d(w[P + 'embeddings.patch_embedding.weight']).reshape(D, -1)     # [O,kh,kw,I] (pv:374)
+        ql, qe = self._lin_prefill, self._emb           # quantize_model: Linear / Embedding weights -> 4-bit images (conv stays)
         v = dict(kpad=kp, patch_w=pw, cls=d(w[P + 'embeddings.class_embedding']),
-                 pos=d(w[P + 'embeddings.position_embedding.weight']),
+                 pos=qe(w[P + 'embeddings.position_embedding.weight']),
                  pre_w=d(w[P + 'pre_layrnorm.weight']), pre_b=d(w[P + 'pre_layrnorm.bias']), layers=[])
         for j in range(cc.num_hidden_layers - 1):        # the reference runs layers[:-1] (phi:219)
             L = P + f'encoder.layers.{j}.'
             v['layers'].append(dict(
                 ln1w=d(w[L + 'layer_norm1.weight']), ln1b=d(w[L + 'layer_norm1.bias']),
-                qkv_w=torch.cat([d(w[L + f'self_attn.{n}_proj.weight']) for n in 'qkv'], 0).contiguous(),
+                qkv_w=torch.cat([ql(w[L + f'self_attn.{n}_proj.weight']) for n in 'qkv'], 0).contiguous(),
                 qkv_b=torch.cat([d(w[L + f'self_attn.{n}_proj.bias']) for n in 'qkv'], 0).contiguous(),
-                out_w=d(w[L + 'self_attn.out_proj.weight']), out_b=d(w[L + 'self_attn.out_proj.bias']),
+                out_w=ql(w[L + 'self_attn.out_proj.weight']), out_b=d(w[L + 'self_attn.out_proj.bias']),
                 ln2w=d(w[L + 'layer_norm2.weight']), ln2b=d(w[L + 'layer_norm2.bias']),
-                fc1_w=d(w[L + 'mlp.fc1.weight']), fc1_b=d(w[L + 'mlp.fc1.bias']),
-                fc2_w=d(w[L + 'mlp.fc2.weight']), fc2_b=d(w[L + 'mlp.fc2.bias'])))
+                fc1_w=ql(w[L + 'mlp.fc1.weight']), fc1_b=d(w[L + 'mlp.fc1.bias']),
+                fc2_w=ql(w[L + 'mlp.fc2.weight']), fc2_b=d(w[L + 'mlp.fc2.bias'])))
         Vp = 'model.vision_embed_tokens.'
         v.update(glb_GN=d(w[Vp + 'glb_GN']).reshape(-1), sub_GN=d(w[Vp + 'sub_GN']).reshape(-1),
-                 p0_w=d(w[Vp + 'img_projection.0.weight']), p0_b=d(w[Vp + 'img_projection.0.bias']),
-                 p2_w=d(w[Vp + 'img_projection.2.weight']), p2_b=d(w[Vp + 'img_projection.2.bias']))
+                 p0_w=ql(w[Vp + 'img_projection.0.weight']), p0_b=d(w[Vp + 'img_projection.0.bias']),
+                 p2_w=ql(w[Vp + 'img_projection.2.weight']), p2_b=d(w[Vp + 'img_projection.2.bias']))
         self.vision = v
 
     # ------------------------------------------------------------------ thin kernel wrappers
@@ -209,11 +226,26 @@ class Phi3B200:
         M, K = x.shape
         ev = self._ev()
         n_ss = 0 if ss_in is None else ss_in.shape[0]
-        pf = 0 if nxt is None else min(nxt.numel() * 2, self.L2_PF_CAP)
+        nxt, pf = self._prefetch_target(nxt)
+        q = self._w4.get(w.data_ptr())
+        if q is not None:                                   # quantize_model: stream the 4-bit codes instead of bf16
+            call('p3_gemm_skinny_w4', ptr(x), x.stride(0), ptr(norm_w), self.eps, ptr(q[0]), ptr(q[1]), ptr(out), out.stride(0),
+                 ptr(resid), M, w.shape[0], K, epi, ptr(ss_in), n_ss, ptr(ss_out), ptr(nxt), pf, _stream())
+            self._ev(ev, 'skinny', q[0].numel() + q[1].numel() * 2)
+            return out
         call('p3_gemm_skinny', ptr(x), x.stride(0), ptr(norm_w), self.eps, ptr(w), ptr(out), out.stride(0),
              ptr(resid), M, w.shape[0], K, epi, ptr(ss_in), n_ss, ptr(ss_out), ptr(nxt), pf, _stream())
         self._ev(ev, 'skinny', w.shape[0] * K * 2)
         return out
+
+    def _prefetch_target(self, nxt):
+        """(tensor, bytes) of the next kernel's weight stream to park in L2: the 4-bit codes when the matrix is quantised"""
+        if nxt is None:
+            return None, 0
+        q = self._w4.get(nxt.data_ptr())
+        if q is not None:
+            return q[0], min(q[0].numel(), self.L2_PF_CAP)
+        return nxt, min(nxt.numel() * 2, self.L2_PF_CAP)
 
     def _ev(self, start=None, kind=None, nbytes=0):
         if self.profile is None:
@@ -355,17 +387,26 @@ class Phi3B200:
                 pass
             elif T <= 16:                                   # decode: qkv_proj + rope + KV write in one launch
                 ev = self._ev()
-                call('p3_gemm_skinny_qkv_rope', ptr(h), h.stride(0), ptr(lw['ln1']), self.eps, ptr(lw['qkv']), ptr(qkv),
-                     ptr(ss_cur), 0 if ss_cur is None else ss_cur.shape[0], ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads,
-                     self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, None, 0, st)
-                self._ev(ev, 'skinny', self.qkv_dim * H * 2)
+                q4 = self._w4.get(lw['qkv'].data_ptr())
+                if q4 is not None:
+                    call('p3_gemm_skinny_qkv_rope_w4', ptr(h), h.stride(0), ptr(lw['ln1']), self.eps, ptr(q4[0]), ptr(q4[1]),
+                         ptr(qkv), ptr(ss_cur), 0 if ss_cur is None else ss_cur.shape[0], ptr(cosT), ptr(sinT), tbs, B, L,
+                         self.n_heads, self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, None, 0, st)
+                    self._ev(ev, 'skinny', q4[0].numel() + q4[1].numel() * 2)
+                else:
+                    call('p3_gemm_skinny_qkv_rope', ptr(h), h.stride(0), ptr(lw['ln1']), self.eps, ptr(lw['qkv']), ptr(qkv),
+                         ptr(ss_cur), 0 if ss_cur is None else ss_cur.shape[0], ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads,
+                         self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, None, 0, st)
+                    self._ev(ev, 'skinny', self.qkv_dim * H * 2)
             else:
                 self.linear(h, lw['qkv'], qkv, _lib.EPI_NONE, norm_w=lw['ln1'], ss_in=ss_cur)
                 call('p3_rope_kvwrite', ptr(qkv), ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads, self.n_kv, self.hd, past,
                      n_beam, ptr(pool), ptr(bt), bts, wc, ptr(past_dev), st)
             qp = qkv.data_ptr()
             ev = self._ev() if use_decode_attn else None
-            pf_bytes = lw['o'].numel() * 2 if T <= 16 else 0      # o_proj weights ride into L2 behind the KV stream
+            o_pf, pf_bytes = self._prefetch_target(lw['o']) if T <= 16 else (None, 0)   # o_proj weights ride into L2 behind the KV stream
+            if T <= 16:
+                pf_bytes = o_pf.numel() * o_pf.element_size()
             if use_decode_attn and 'attn' in self._skip:
                 pass
             elif use_decode_attn:
@@ -373,11 +414,11 @@ class Phi3B200:
                     call('p3_attention_decode_q4', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim,
                          self.qkv_dim, ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale,
                          past, cache.n_quant, ptr(kvs), ptr(pool), ptr(cache.qcodes[li]), ptr(cache.qmeta[li]), ptr(bt),
-                         bts, n_beam, n_splits, ptr(ws), ptr(past_dev), ptr(lw['o']), pf_bytes, st)
+                         bts, n_beam, n_splits, ptr(ws), ptr(past_dev), ptr(o_pf), pf_bytes, st)
                 else:
                     call('p3_attention_decode', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim,
                          self.qkv_dim, ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale,
-                         past, ptr(kvs), ptr(pool), ptr(bt), bts, n_beam, n_splits, ptr(ws), ptr(past_dev), ptr(lw['o']),
+                         past, ptr(kvs), ptr(pool), ptr(bt), bts, n_beam, n_splits, ptr(ws), ptr(past_dev), ptr(o_pf),
                          pf_bytes, st)
             else:
                 call('p3_attention_prefill', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim, self.qkv_dim,

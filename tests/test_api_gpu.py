@@ -244,3 +244,28 @@ def test_load_from_safetensors_dir(dev, tmp_path):
     a = m1(**p1(prompt, imgs), max_tokens=2)[0]
     b = m2(**p2(prompt, imgs), max_tokens=2)[0]
     assert torch.equal(a, b)
+
+
+def test_quantize_model_flag_generates_like_the_quantised_oracle(dev):
+    """load(quantize_model=True) (pv:1279, 264): weights are quantised at load; generate() rolls out the same tokens as
+    the oracle running on its own restatement of nn.quantize(model, 64, 4)."""
+    import phi3_b200  # noqa
+    from phi3_b200 import configs, weights, api
+    from phi3_b200.processor import ByteTokenizer
+    from oracle.phi3_oracle import Phi3Oracle, quantize_model_weights
+    from oracle import drivers
+    cfg = configs.tiny(vision=False)
+    w = weights.random_weights(cfg, seed=3)
+    model, proc = api.load(blind_model=True, quantize_model=True, cfg=cfg, weights=w, tokenizer=ByteTokenizer())
+    assert model.quantize_model
+    ora = Phi3Oracle(model.cfg, quantize_model_weights(w), prec='b200')
+    prompts = ['The quick brown fox', 'Hello', 'A somewhat longer prompt about nothing']
+    templ, _ = api._apply_chat_template(prompts, None, False)
+    ref = drivers.generate_ids(ora, proc(templ), 12)
+    got = api._generate(model, proc, templ, max_tokens=12, verbose=False, stream=False, mute=True, return_tokens=True).cpu().long()
+    assert got.shape == ref.shape and torch.equal(got[:, :2], ref[:, :2])
+    assert (got == ref).float().mean() >= 0.85
+    txt = api.generate(prompts, preload=(model, proc), max_tokens=6, verbose=False, stream=False)
+    assert isinstance(txt, list) and len(txt) == 3
+    with pytest.raises(NotImplementedError):
+        api.load(blind_model=True, use_adapter=True, cfg=cfg, weights=w, tokenizer=ByteTokenizer())

@@ -152,3 +152,37 @@ def test_dp_map_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert 'DPMAP_OK' in outs[0]
+
+
+def test_weight_quantiser_matches_oracle_and_pack_roundtrip():
+    """quantize_model: product quantiser (phi3_b200/quant.py) == oracle restatement; the packed 4-bit stream unpacks
+    (with the kernel's nibble arithmetic, emulated here) to the same codes."""
+    import torch
+    import phi3_b200  # noqa
+    from phi3_b200 import quant
+    from oracle.phi3_oracle import quantize_q4g32, quantize_model_weights
+    torch.manual_seed(0)
+    w = (torch.randn(48, 256) * 0.02).to(torch.bfloat16)
+    w[3, :64] = 0                                               # an all-zero group
+    c, s, b = quant.quantize_w4g64(w)
+    q, sc, bi = quantize_q4g32(w, prec='b200', group=64, dtype=torch.float64)
+    assert (c.reshape(48, 4, 64) == q).all() and (s.float() == sc.squeeze(-1)).all() and (b.float() == bi.squeeze(-1)).all()
+    deq = quant.dequantize_w4g64(c, s, b).float()
+    ref = quantize_model_weights({'x.weight': w, 'n.weight': w[0]})
+    assert (deq - ref['x.weight']).abs().max() <= 2 ** -8 * ref['x.weight'].abs().max()
+    assert ref['n.weight'] is w[0] or (ref['n.weight'] == w[0]).all()         # 1-D (norm) weights are not quantised
+    assert (ref['x.weight'] - w.float()).abs().max() <= 0.08 * w.float().abs().max()   # 4-bit: half a step of (max-min)/15
+    packed, meta = quant.pack_w4g64(c, s, b)
+    N, K = c.shape
+    words = (packed.view(N, K // 128, 4, 4, 4).to(torch.int64) * (256 ** torch.arange(4))).sum(-1)
+    rec = torch.zeros(N, K, dtype=torch.int64)
+    for ch in range(K // 128):
+        for t in range(4):
+            for gi in range(2):
+                for i in range(2):
+                    wv = words[:, ch, t, gi * 2 + i]
+                    for j in range(4):
+                        k = 128 * ch + 64 * gi + 16 * t + 8 * i + 2 * j
+                        rec[:, k], rec[:, k + 1] = (wv >> (4 * j)) & 0xF, (wv >> (4 * j + 16)) & 0xF
+    assert (rec == c.to(torch.int64)).all()
+    assert (meta[..., 0] == s).all() and (meta[..., 1] == b).all()

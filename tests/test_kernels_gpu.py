@@ -467,6 +467,87 @@ def test_fused_qkv_rope_matches_unfused(dev, M):
     assert (pool2 != 0).any()
 
 
+@pytest.mark.parametrize('M', [1, 5, 8, 13, 16])
+@pytest.mark.parametrize('mode', ['plain', 'norm', 'resid', 'swiglu', 'f32'])
+def test_gemm_skinny_w4(dev, M, mode):
+    """quantize_model decode GEMM (4-bit g64 codes, affine map applied to per-group tensor-core sums) vs
+    x @ dequantise(quantise(W)).T computed by torch in fp32."""
+    L = _mods()
+    from phi3_b200 import quant
+    from phi3_b200.model import interleave_gate_up
+    torch.manual_seed(12)
+    K = 3072 if mode != 'resid' else 8192
+    N = {'plain': 9216, 'norm': 9216, 'resid': 3072, 'swiglu': 4096, 'f32': 32064}[mode]
+    x = bf(torch.randn(M, K, device=dev))
+    w = bf(torch.randn(N, K, device=dev) * K ** -0.5)
+    nw = bf(1 + 0.1 * torch.randn(K, device=dev))
+    q = quant.W4(w, row_perm=interleave_gate_up if mode == 'swiglu' else None)
+    codes, scale, bias = quant.quantize_w4g64(w)
+    wq = (codes.reshape(N, K // 64, 64).float() * scale.float()[..., None] + bias.float()[..., None]).reshape(N, K)   # unrounded image
+    xin = x
+    if mode in ('norm', 'swiglu', 'f32'):
+        xf = x.float()
+        xin = bf(xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * nw.float())
+    acc = xin.float() @ wq.T
+    c, m = q.codes.data_ptr(), q.meta.data_ptr()
+    if mode == 'swiglu':
+        out = torch.zeros(M, N // 2, device=dev, dtype=torch.bfloat16)
+        L.call('p3_gemm_skinny_w4', x.data_ptr(), K, nw.data_ptr(), 1e-5, c, m, out.data_ptr(), N // 2, None, M, N, K, 4, None, 0,
+               None, None, 0, st())
+        g, u = bf(acc[:, :N // 2]).float(), bf(acc[:, N // 2:]).float()
+        ref = bf(bf(torch.nn.functional.silu(g)).float() * u)
+    elif mode == 'f32':
+        out = torch.zeros(M, N, device=dev)
+        L.call('p3_gemm_skinny_w4', x.data_ptr(), K, nw.data_ptr(), 1e-5, c, m, out.data_ptr(), N, None, M, N, K, 5, None, 0, None, None, 0, st())
+        ref = acc
+    elif mode == 'resid':
+        out = bf(torch.randn(M, N, device=dev))
+        ref = bf(out.float() + bf(acc).float())
+        L.call('p3_gemm_skinny_w4', x.data_ptr(), K, None, 1e-5, c, m, out.data_ptr(), N, out.data_ptr(), M, N, K, 3, None, 0, None, None, 0, st())
+    else:
+        out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        L.call('p3_gemm_skinny_w4', x.data_ptr(), K, nw.data_ptr() if mode == 'norm' else None, 1e-5, c, m,
+               out.data_ptr(), N, None, M, N, K, 0, None, 0, None, None, 0, st())
+        ref = bf(acc)
+    _check(out, ref, tol=1e-2)
+    # and it is the same op as the bf16 kernel over the dequantised image (what the prefill GEMMs use)
+    if mode == 'plain':
+        out2 = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        L.call('p3_gemm_skinny', x.data_ptr(), K, None, 1e-5, q.deq.data_ptr(), out2.data_ptr(), N, None, M, N, K, 0, None, 0,
+               None, None, 0, st())
+        _check(out, out2.float(), tol=1e-2)
+
+
+@pytest.mark.parametrize('M', [(1, 1), (8, 1), (2, 5)])
+def test_fused_qkv_rope_w4_matches_bf16_kernel_on_dequantised_weights(dev, M):
+    L = _mods()
+    from phi3_b200 import quant
+    B, Lq = M
+    T, H, nh, D, past, S = B * Lq, 3072, 32, 96, 70, 160
+    torch.manual_seed(19)
+    x = bf(torch.randn(T, H, device=dev))
+    nw = bf(1 + 0.1 * torch.randn(H, device=dev))
+    q = quant.W4(bf(torch.randn(3 * nh * D, H, device=dev) * H ** -0.5))
+    ang = torch.rand(B, S, D // 2, device=dev) * 6
+    cos, sin = (torch.cos(ang) * 1.19).contiguous(), (torch.sin(ang) * 1.19).contiguous()
+    pps = (S + 63) // 64
+    bt = torch.arange(B * pps, dtype=torch.int32, device=dev).reshape(B, pps)
+    pool1 = torch.zeros(B * pps, 2, nh, 64, D, device=dev, dtype=torch.bfloat16)
+    pool2 = torch.zeros_like(pool1)
+    q1 = torch.zeros(T, 3 * nh * D, device=dev, dtype=torch.bfloat16)
+    q2 = torch.zeros_like(q1)
+    L.call('p3_gemm_skinny_qkv_rope', x.data_ptr(), H, nw.data_ptr(), 1e-5, q.deq.data_ptr(), q1.data_ptr(), None, 0, cos.data_ptr(),
+           sin.data_ptr(), S * (D // 2), B, Lq, nh, nh, D, H, past, None, 1, pool1.data_ptr(), bt.data_ptr(), pps, 1, None, 0, st())
+    L.call('p3_gemm_skinny_qkv_rope_w4', x.data_ptr(), H, nw.data_ptr(), 1e-5, q.codes.data_ptr(), q.meta.data_ptr(), q2.data_ptr(),
+           None, 0, cos.data_ptr(), sin.data_ptr(), S * (D // 2), B, Lq, nh, nh, D, H, past, None, 1, pool2.data_ptr(),
+           bt.data_ptr(), pps, 1, None, 0, st())
+    torch.cuda.synchronize()
+    tol = 2 ** -6 * q1.float().abs().max()
+    assert (q1.float() - q2.float()).abs().max() <= tol
+    assert (pool1.float() - pool2.float()).abs().max() <= tol
+    assert (pool2 != 0).any()
+
+
 @pytest.mark.parametrize('top_p,temp', [(0.9, 1.0), (0.5, 0.7), (1.0, 1.0), (0.05, 1.3)])
 def test_top_p_sample_matches_torch_restatement(dev, top_p, temp):
     L = _mods()

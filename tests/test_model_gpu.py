@@ -328,3 +328,69 @@ def test_gqa_is_rejected_like_the_reference_graph(dev):
     cfg = configs.tiny(num_key_value_heads=2)
     with pytest.raises(NotImplementedError):
         Phi3B200(cfg, {})
+
+
+def _setup_q(vision=False, layers=2, seed=0):
+    """quantize_model=True on both sides: CUDA model quantises at load (quant.py), the oracle runs the fp32 model over
+    its own restatement of nn.quantize(model, 64, 4) (oracle.quantize_model_weights)."""
+    import phi3_b200  # noqa
+    from phi3_b200 import configs, weights
+    from phi3_b200.model import Phi3B200
+    from oracle.phi3_oracle import Phi3Oracle, quantize_model_weights
+    cfg = configs.tiny(vision=vision, layers=layers)
+    clip = configs.tiny_clip(3) if vision else None
+    w = weights.random_weights(cfg, seed=seed, clip_cfg=clip)
+    return cfg, w, Phi3B200(cfg, w, clip_cfg=clip, quantize_model=True), \
+        Phi3Oracle(cfg, quantize_model_weights(w), prec='b200', clip_cfg=clip)
+
+
+def test_quantize_model_prefill_and_decode(dev):
+    """pv:264,291-305: 4-bit g64 weights. Prefill runs the tensor-core GEMMs on the dequantised image, decode streams
+    the 4-bit codes (p3_gemm_skinny_w4 / p3_gemm_skinny_qkv_rope_w4); both against the oracle's quantised model."""
+    cfg, w, m, o = _setup_q()
+    assert m.quantize_model and len(m._w4) == 4 * cfg.num_hidden_layers + 1
+    ids = _ids(4, 40)
+    lo, co = o(ids, max_tokens=8)
+    lg, cg = m(ids, max_tokens=8)
+    assert rel(lg, lo) < TOL
+    tok = lo[:, -1].argmax(-1)
+    for _ in range(6):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        assert rel(lg, lo) < TOL
+        tok = lo[:, -1].argmax(-1)
+    # the quantised model is a different function from the bf16 one (guards against a silently ignored flag)
+    _, _, m16, _ = _setup()
+    l16, _ = m16(ids, max_tokens=8)
+    lq, _ = m(ids, max_tokens=8)
+    assert rel(lq, l16.float().cpu()) > 5e-2
+
+
+def test_quantize_model_graph_decode_matches_stepwise(dev):
+    cfg, w, m, o = _setup_q()
+    ids = _ids(3, 24, seed=4)
+    lg, cg = m(ids, max_tokens=12)
+    tok = lg[:, -1].argmax(-1)
+    hist = m.greedy_decode(tok, cg, 10, use_graph=True)
+    lo, co = o(ids, max_tokens=12)
+    t = lo[:, -1].argmax(-1)
+    agree, n = 0, 0
+    for i in range(10):
+        lo, co = o(hist[:, i].cpu().long()[:, None], cache=co)              # teacher-forced on the CUDA tokens
+        agree += (lo[:, -1].argmax(-1) == hist[:, i + 1].cpu().long()).sum().item()
+        n += hist.shape[0]
+    assert agree / n >= 0.9
+
+
+def test_quantize_model_vision(dev):
+    """every CLIP / projector Linear and the position embedding are quantised too (nn.quantize walks the whole model)"""
+    cfg, w, m, o = _setup_q(vision=True)
+    g = torch.Generator().manual_seed(2)
+    pv = torch.randn(1, 5, 3, 336, 336, generator=g)
+    sizes = torch.tensor([[672, 672]])
+    n_img = (2 * 2 + 1) * 144 + 1 + (2 + 1) * 12
+    ids = torch.cat([torch.tensor([1, 50, 60]), torch.full((n_img,), -1), torch.tensor([1, 70, 80, 90])])[None]
+    pos = torch.nonzero(ids < 0)
+    lo, _ = o(ids, pixel_values=pv, image_sizes=sizes, positions=pos, max_tokens=2)
+    lg, _ = m(ids, pixel_values=pv, image_sizes=sizes, positions=pos, max_tokens=2)
+    assert rel(lg, lo) < 3e-2
