@@ -182,6 +182,9 @@ class Phi3B200:
         import os as _os
         self.pf_chain = _os.environ.get('P3_PF_CHAIN', '1') != '0'
         self._skip = set(filter(None, _os.environ.get('P3_SKIP', '').split(',')))   # timing ablation only (tools/ablate.py)
+        # decode: RMSNorm as its own tiny PDL kernel instead of fused into every 32-row CTA of the following skinny GEMM.
+        # Neutral for the bf16 weight stream (2.797 vs 2.788 ms/token on the bench), -8 % for the instruction-bound 4-bit one.
+        self.prenorm = _os.environ.get('P3_PRENORM', '1' if self.quantize_model else '0') != '0'
         self.profile = None      # bench.py: list of (kind, ev0, ev1, algorithmic_bytes) when instrumenting
 
     # ------------------------------------------------------------------ vision weights
@@ -224,6 +227,8 @@ class Phi3B200:
 
     def skinny(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None, ss_in=None, ss_out=None, nxt=None):
         M, K = x.shape
+        if norm_w is not None and self.prenorm:
+            x, norm_w, ss_in = self._prenorm(x, norm_w), None, None
         ev = self._ev()
         n_ss = 0 if ss_in is None else ss_in.shape[0]
         nxt, pf = self._prefetch_target(nxt)
@@ -237,6 +242,12 @@ class Phi3B200:
              ptr(resid), M, w.shape[0], K, epi, ptr(ss_in), n_ss, ptr(ss_out), ptr(nxt), pf, _stream())
         self._ev(ev, 'skinny', w.shape[0] * K * 2)
         return out
+
+    def _prenorm(self, x, norm_w):
+        """decode (<= 16 rows): x_hat = bf16(x * rsqrt(mean(x^2) + eps) * w) by a one-CTA-per-row PDL kernel"""
+        xn = torch.empty_like(x)
+        call('p3_rmsnorm', ptr(x), ptr(norm_w), ptr(xn), x.shape[0], x.shape[1], self.eps, _stream())
+        return xn
 
     def _prefetch_target(self, nxt):
         """(tensor, bytes) of the next kernel's weight stream to park in L2: the 4-bit codes when the matrix is quantised"""
@@ -386,16 +397,17 @@ class Phi3B200:
             if 'qkv' in self._skip and T <= 16:
                 pass
             elif T <= 16:                                   # decode: qkv_proj + rope + KV write in one launch
+                hq, nq, sq = (self._prenorm(h, lw['ln1']), None, None) if self.prenorm else (h, lw['ln1'], ss_cur)
                 ev = self._ev()
                 q4 = self._w4.get(lw['qkv'].data_ptr())
                 if q4 is not None:
-                    call('p3_gemm_skinny_qkv_rope_w4', ptr(h), h.stride(0), ptr(lw['ln1']), self.eps, ptr(q4[0]), ptr(q4[1]),
-                         ptr(qkv), ptr(ss_cur), 0 if ss_cur is None else ss_cur.shape[0], ptr(cosT), ptr(sinT), tbs, B, L,
+                    call('p3_gemm_skinny_qkv_rope_w4', ptr(hq), hq.stride(0), ptr(nq), self.eps, ptr(q4[0]), ptr(q4[1]),
+                         ptr(qkv), ptr(sq), 0 if sq is None else sq.shape[0], ptr(cosT), ptr(sinT), tbs, B, L,
                          self.n_heads, self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, None, 0, st)
                     self._ev(ev, 'skinny', q4[0].numel() + q4[1].numel() * 2)
                 else:
-                    call('p3_gemm_skinny_qkv_rope', ptr(h), h.stride(0), ptr(lw['ln1']), self.eps, ptr(lw['qkv']), ptr(qkv),
-                         ptr(ss_cur), 0 if ss_cur is None else ss_cur.shape[0], ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads,
+                    call('p3_gemm_skinny_qkv_rope', ptr(hq), hq.stride(0), ptr(nq), self.eps, ptr(lw['qkv']), ptr(qkv),
+                         ptr(sq), 0 if sq is None else sq.shape[0], ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads,
                          self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, None, 0, st)
                     self._ev(ev, 'skinny', self.qkv_dim * H * 2)
             else:

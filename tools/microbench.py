@@ -49,6 +49,32 @@ def bench_skinny():
         print(f'skinny {name:22s} N={N:6d} K={K:5d}  {us:7.2f} us  {gbs:7.0f} GB/s  {100 * gbs / PEAK:5.1f}% of measured HBM peak')
 
 
+def bench_skinny_w4():
+    """quantize_model decode GEMMs: 4-bit g64 codes (0.5625 B per weight incl. scale/bias) vs the bf16 stream"""
+    from phi3_b200 import quant
+    M, H, I = 8, 3072, 8192
+    shapes = [('qkv+norm', 9216, H, 0, True), ('qkv', 9216, H, 0, False), ('o+resid', H, H, 3, False), ('gate_up+norm+swiglu', 2 * I, H, 4, True),
+              ('down+resid', H, I, 3, False), ('lm_head+norm', 32064, H, 5, True)]
+    for name, N, K, epi, norm in shapes:
+        copies = max(2, int(300e6 // (N * K // 2)) // 4 + 1)
+        Q = [quant.W4(torch.randn(N, K, device=dev).to(torch.bfloat16) * 0.02) for _ in range(copies)]
+        for q in Q:
+            q.deq = None
+        x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        nw = torch.ones(K, device=dev, dtype=torch.bfloat16)
+        No = N // 2 if epi == 4 else N
+        out = torch.zeros(M, No, device=dev, dtype=torch.float32 if epi == 5 else torch.bfloat16)
+
+        def fn(i):
+            q = Q[i % copies]
+            _lib.call('p3_gemm_skinny_w4', x.data_ptr(), K, nw.data_ptr() if norm else None, 1e-5, q.codes.data_ptr(), q.meta.data_ptr(),
+                      out.data_ptr(), No, out.data_ptr() if epi == 3 else None, M, N, K, epi, None, 0, None, None, 0, st())
+        us = timeit(fn)
+        nbytes = N * K // 2 + N * (K // 64) * 4
+        gbs = nbytes / us / 1e3
+        print(f'skinny_w4 {name:22s} N={N:6d} K={K:5d}  {us:7.2f} us  {gbs:7.0f} GB/s  {100 * gbs / PEAK:5.1f}% of measured HBM peak')
+
+
 def bench_attn():
     H, D = 32, 96
     for B, S in [(8, 2176), (8, 512), (1, 2176), (16, 400), (4, 8192)]:
@@ -123,6 +149,8 @@ if __name__ == '__main__':
         bench_skinny()
     if 'attn' in which:
         bench_attn()
+    if 'w4' in which:
+        bench_skinny_w4()
     if 'gemm' in which:
         bench_gemm()
     if 'q4' in which:

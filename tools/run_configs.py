@@ -39,8 +39,32 @@ def gen(model, ids, new, **kw):
 
 
 def main():
-    which = [int(a) for a in sys.argv[1:]] or [1, 2, 4, 5]
+    args = sys.argv[1:]
+    which = [int(a) for a in args if a.isdigit()] or ([] if 'w4' in args else [1, 2, 4, 5])
     g = torch.Generator().manual_seed(0)
+    if 'w4' in args:
+        # quantize_model=True (4-bit g64 weights, pv:264,291-305) on config 1 and on the bench's decode shape
+        cfg = configs.PHI35_MINI
+        qm = Phi3B200(cfg, weights.random_weights(cfg, seed=0, device=dev), device=dev, quantize_model=True)
+        ids = torch.randint(3, 32000, (4, 32), generator=g); ids[:, 0] = 1
+        for _ in range(2):
+            t_all, (t_dec, hist) = sync_time(lambda: gen(qm, ids, 128))
+        print(json.dumps({'config': '1 + quantize_model', 'desc': 'Phi-3.5-mini 4-bit g64 weights, 4 prompts x 32 ctx x 128 new',
+                          'total_ms': round(t_all * 1e3, 2), 'decode_tok_per_s': round(4 * 127 / t_dec, 1),
+                          'decode_ms_per_token': round(t_dec / 127 * 1e3, 3)}), flush=True)
+        ids = torch.randint(3, 32000, (8, 2048), generator=g); ids[:, 0] = 1
+        for _ in range(2):
+            t_all, (t_dec, hist) = sync_time(lambda: gen(qm, ids, 256))
+        print(json.dumps({'config': '3 (text-only shape) + quantize_model', 'desc': '8 x 2048 ctx x 256 new, 4-bit g64 weights, bf16 KV',
+                          'total_ms': round(t_all * 1e3, 2), 'decode_tok_per_s': round(8 * 255 / t_dec, 1),
+                          'decode_ms_per_token': round(t_dec / 255 * 1e3, 3)}), flush=True)
+        ids1 = torch.randint(3, 32000, (1, 32), generator=g); ids1[:, 0] = 1
+        for _ in range(2):
+            t_all, (t_dec, hist) = sync_time(lambda: gen(qm, ids1, 128))
+        print(json.dumps({'config': 'single stream + quantize_model', 'desc': '1 prompt x 32 ctx x 128 new (the reference table\'s case)',
+                          'decode_tok_per_s': round(127 / t_dec, 1), 'decode_ms_per_token': round(t_dec / 127 * 1e3, 3)}), flush=True)
+        del qm
+        torch.cuda.empty_cache()
     if 1 in which or 4 in which or 5 in which:
         cfg = configs.PHI35_MINI
         mini = Phi3B200(cfg, weights.random_weights(cfg, seed=0, device=dev), device=dev)
