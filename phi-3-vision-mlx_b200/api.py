@@ -10,7 +10,12 @@ Differences a caller can see (all opt-in or forced by the offline environment):
     num_crops=, device= through **kwargs — there are no checkpoint / tokenizer files offline;
   * quantize_model=True quantises the given (bf16) weights at load time — 4-bit, group 64, every Linear / Embedding, as
     `nn.quantize(model, 64, 4)` does for the reference's pre-quantised checkpoint (pv:264,291-305) — instead of reading a
-    `quantized_model.safetensors`; use_adapter raises NotImplementedError (SURVEY.md §8f row N4);
+    `quantized_model.safetensors`;
+  * use_adapter=True takes the LoRA adapter from `adapter=` ({'config': adapter_config dict, 'weights': {name: tensor}}) or
+    `adapter_path=` (adapter_config.json + adapters.safetensors, the files train_lora writes, pv:1005-1013) and folds it into
+    the bf16 weights at load: W' = bf16(W + scale*alpha/rank * (A B)^T) — inference with zero extra kernels instead of
+    LoRALinear's two extra matmuls per call (phi:129-133). A LoRA over 4-bit weights cannot be folded: that combination
+    raises NotImplementedError;
   * constrain(..., n_beam=3) exposes the beam width the reference hard-codes (pv:505);
   * images may be PIL images or uint8 HWC arrays (no URL fetching offline).
 """
@@ -27,6 +32,7 @@ from .weights import random_weights
 
 PATH_ORIGINAL_PHI3_VISION = 'models/phi3_v'             # pv:38-41
 PATH_ORIGINAL_PHI3_BLIND = 'models/phi3_mini_128k'
+PATH_ADAPTERS = 'adapters'                              # pv:37
 
 
 class Tic:                                              # phi.py:16-24
@@ -55,8 +61,11 @@ def _read_safetensors(path):
 
 def load(blind_model=False, quantize_model=False, quantize_cache=False, use_adapter=False, **kwargs):
     """pv:1279-1322. Returns (model, processor)."""
-    if use_adapter:
-        raise NotImplementedError('use_adapter (LoRA) is outside the B200 hot-path scope (SURVEY §8f N4)')
+    adapter = kwargs.pop('adapter', None)
+    adapter_path = kwargs.pop('adapter_path', None)
+    if use_adapter and quantize_model:
+        raise NotImplementedError('a LoRA adapter over 4-bit weights cannot be folded into them (pv:264-271 wraps QuantizedLinear); '
+                                  'load the bf16 model with use_adapter=True')
     device = kwargs.pop('device', 'cuda')
     cfg = kwargs.pop('cfg', None) or (PHI35_MINI if blind_model else PHI35_VISION)
     cfg = with_overrides(cfg, use_quantized_cache=quantize_cache)          # pv:1322 -> phi.py:512,572
@@ -84,9 +93,46 @@ def load(blind_model=False, quantize_model=False, quantize_cache=False, use_adap
             tokenizer = ByteTokenizer()
     for k, v in kwargs.items():                                            # remaining kwargs override cfg (pv:359-363)
         setattr(cfg, k, v)
+    if use_adapter:
+        if adapter is None:
+            adapter_path = adapter_path or f'{PATH_ADAPTERS}/{os.path.basename(PATH_ORIGINAL_PHI3_BLIND if blind_model else PATH_ORIGINAL_PHI3_VISION)}'
+            adapter = _read_adapter(adapter_path)                          # pv:266-271, _get_adapter_path pv:462
+        weights = merge_lora(weights, adapter['config'], adapter['weights'], cfg.num_hidden_layers)
     model = Phi3B200(cfg, weights, device=device, clip_cfg=clip_cfg, quantize_model=quantize_model)
     processor = Phi3FProcessor(tokenizer) if blind_model else Phi3VProcessor(tokenizer, num_crops=num_crops, device=device)
     return model, processor
+
+
+def _read_adapter(path):
+    import json
+    if not os.path.isdir(path):
+        raise FileNotFoundError(f'LoRA adapter directory {path} not found (pass adapter= or adapter_path=)')
+    from safetensors.torch import load_file
+    return {'config': json.load(open(os.path.join(path, 'adapter_config.json'))),
+            'weights': load_file(os.path.join(path, 'adapters.safetensors'))}
+
+
+def merge_lora(weights, lora_cfg, lora_weights, n_layers):
+    """_linear_to_lora_layers (pv:234-245) + LoRALinear.__call__ (phi:129-133), folded: for every targeted Linear of the
+    selected decoder layers W <- bf16(W + scale * alpha / rank * (lora_a @ lora_b)^T); lora_a [in, r], lora_b [r, out]."""
+    layers = lora_cfg['lora_layers']
+    if isinstance(layers, int):
+        layers = list(range(n_layers))[-layers:]
+    elif not isinstance(layers, list):
+        raise ValueError('Invalid type for lora_layers. Expected int (number of layers) or list (layer indices or names).')
+    lp = lora_cfg['lora_parameters']
+    scale = float(lp['scale']) * (float(lp['alpha']) / float(lp['rank']))
+    out = dict(weights)
+    for i in layers:
+        for t in lora_cfg['lora_targets']:
+            key = f'model.layers.{i}.{t}'
+            a, b = lora_weights.get(key + '.lora_a'), lora_weights.get(key + '.lora_b')
+            if a is None or b is None:
+                raise KeyError(f'adapter has no {key}.lora_a / .lora_b')
+            w = weights[key + '.weight']
+            delta = (a.to(w.device, torch.float32) @ b.to(w.device, torch.float32)).T      # [out, in]
+            out[key + '.weight'] = (w.to(torch.float32) + scale * delta).to(torch.bfloat16)
+    return out
 
 
 # ------------------------------------------------------------------------------------- helpers

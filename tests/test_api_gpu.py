@@ -268,4 +268,49 @@ def test_quantize_model_flag_generates_like_the_quantised_oracle(dev):
     txt = api.generate(prompts, preload=(model, proc), max_tokens=6, verbose=False, stream=False)
     assert isinstance(txt, list) and len(txt) == 3
     with pytest.raises(NotImplementedError):
-        api.load(blind_model=True, use_adapter=True, cfg=cfg, weights=w, tokenizer=ByteTokenizer())
+        api.load(blind_model=True, use_adapter=True, quantize_model=True, cfg=cfg, weights=w, tokenizer=ByteTokenizer(),
+                 adapter={'config': {}, 'weights': {}})
+
+
+@pytest.mark.parametrize('layers', [1, [0, 2]])
+def test_lora_adapter_folded_at_load_matches_loralinear_oracle(dev, layers, tmp_path):
+    """use_adapter (pv:266-271, phi:84-133): the product folds scale*alpha/r * (A B)^T into the bf16 weights; the oracle
+    evaluates LoRALinear op for op. Also checks the adapter_path route (adapter_config.json + adapters.safetensors)."""
+    import json
+    import phi3_b200  # noqa
+    from phi3_b200 import configs, weights, api
+    from phi3_b200.processor import ByteTokenizer
+    from oracle.phi3_oracle import Phi3Oracle, lora_modules
+    from safetensors.torch import save_file
+    cfg = configs.tiny(vision=False, layers=3)
+    w = weights.random_weights(cfg, seed=3)
+    g = torch.Generator().manual_seed(11)
+    targets, r = ['self_attn.qkv_proj', 'mlp.down_proj'], 4
+    lcfg = {'model_path': 'x', 'adapter_path': 'y', 'lora_layers': layers, 'lora_targets': targets,
+            'lora_parameters': {'rank': r, 'alpha': 8, 'dropout': 0.0, 'scale': 2.0}}
+    idx = list(range(3))[-layers:] if isinstance(layers, int) else layers
+    lw = {}
+    for i in idx:
+        for t in targets:
+            out_d, in_d = w[f'model.layers.{i}.{t}.weight'].shape
+            lw[f'model.layers.{i}.{t}.lora_a'] = (torch.rand(in_d, r, generator=g) * 2 - 1) / in_d ** 0.5
+            lw[f'model.layers.{i}.{t}.lora_b'] = torch.randn(r, out_d, generator=g) * 0.1
+    json.dump(lcfg, open(tmp_path / 'adapter_config.json', 'w'))
+    save_file(lw, str(tmp_path / 'adapters.safetensors'))
+    m1, p1 = api.load(blind_model=True, use_adapter=True, adapter={'config': lcfg, 'weights': lw}, cfg=cfg, weights=w, tokenizer=ByteTokenizer())
+    m2, _ = api.load(blind_model=True, use_adapter=True, adapter_path=str(tmp_path), cfg=cfg, weights=w, tokenizer=ByteTokenizer())
+    m0, _ = api.load(blind_model=True, cfg=cfg, weights=w, tokenizer=ByteTokenizer())
+    ora = Phi3Oracle(m1.cfg, w, prec='b200', lora=lora_modules(lcfg, lw, 3))
+    ids = torch.randint(3, 32000, (3, 24), generator=g); ids[:, 0] = 1
+    lo, co = ora(ids, max_tokens=4)
+    l1, c1 = m1(ids, max_tokens=4)
+    l2, _ = m2(ids, max_tokens=4)
+    l0, _ = m0(ids, max_tokens=4)
+    rel = lambda a, b: ((a.float().cpu() - b.float().cpu()).abs().max() / b.float().abs().max()).item()
+    assert rel(l1, lo) < 2e-2
+    assert torch.equal(l1, l2)
+    assert rel(l0, lo) > 3e-2                               # the adapter changes the function
+    tok = lo[:, -1].argmax(-1)
+    lo, co = ora(tok[:, None], cache=co)
+    l1, c1 = m1(tok[:, None], cache=c1)
+    assert rel(l1, lo) < 2e-2
