@@ -136,7 +136,8 @@ def test_gemm_mma_crosscheck(dev, epi):
 
 
 @pytest.mark.parametrize('shape', [(128, 256, 64), (128, 256, 256), (300, 512, 384), (1000, 1024, 640),
-                                   (257, 32064, 384), (2885, 3072, 1024), (64, 9216, 3072), (4096, 3072, 8192)])
+                                   (257, 32064, 384), (2885, 3072, 1024), (64, 9216, 3072), (4096, 3072, 8192),
+                                   (48, 3072, 3072), (100, 3072, 8192), (17, 1024, 4096)])
 def test_gemm_tcgen05_shapes(dev, shape):
     L = _mods()
     M, N, K = shape
