@@ -130,6 +130,8 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     FA_T(3, 0, 6);
+    pdl_trigger();                                               // setup above overlaps the previous kernel's tail
+    pdl_wait();                                                  // q/k/v, the pool and `out` belong to earlier kernels until here
 
     if (warp == FA_W_TMA) {
         // ---------------- TMA producer ----------------
@@ -414,7 +416,7 @@ static int launch_tc_d(const AttnParams& p, cudaStream_t st) {
     const bool want_dbg = getenv("P3_FA_DBG") != nullptr;
     if (want_dbg) { cudaMalloc(&dbg, 4 * 64 * 8 * 8); cudaMemset(dbg, 0, 4 * 64 * 8 * 8); }
 #endif
-    attn_prefill_tc_kernel<D><<<grid, FA_THREADS, C::SMEM, st>>>(tm, p, dbg);
+    p3_launch_pdl(attn_prefill_tc_kernel<D>, grid, dim3(FA_THREADS), (size_t)C::SMEM, st, tm, p, dbg);
     P3_CHECK_LAUNCH("attention_prefill_tc");
 #ifdef P3_FA_TIMING
     if (want_dbg) {

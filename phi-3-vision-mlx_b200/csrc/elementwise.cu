@@ -51,6 +51,8 @@ __global__ void rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restric
                                int64_t T, int H, float eps) {
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    pdl_trigger();
+    pdl_wait();
     if (row >= T) return;
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * H);
     const uint4* wr = reinterpret_cast<const uint4*>(w);
@@ -150,9 +152,9 @@ extern "C" int p3_rmsnorm(const void* x, const void* w, void* y, int64_t T, int 
     }
     unsigned grid = (unsigned)((T + 3) / 4);
     if (H <= 4096)
-        rmsnorm_kernel<16><<<grid, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, T, H, eps);
+        p3_launch_pdl(rmsnorm_kernel<16>, dim3(grid), dim3(128), (size_t)0, st, (const bf16*)x, (const bf16*)w, (bf16*)y, T, H, eps);
     else
-        rmsnorm_kernel<32><<<grid, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, T, H, eps);
+        p3_launch_pdl(rmsnorm_kernel<32>, dim3(grid), dim3(128), (size_t)0, st, (const bf16*)x, (const bf16*)w, (bf16*)y, T, H, eps);
     P3_CHECK_LAUNCH("rmsnorm");
     return 0;
 }
@@ -167,6 +169,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const bf16* __rest
                                  void* __restrict__ y, int64_t T, int H, float eps) {
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    pdl_trigger();
+    pdl_wait();
     if (row >= T) return;
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * H);
     int nv = H / 4;
@@ -210,8 +214,8 @@ extern "C" int p3_layernorm(const float* x, const void* w, const void* b, void* 
     P3_CHECK_ARG(H % 4 == 0 && H <= 1024, "layernorm: H must be a multiple of 4 and <= 1024");
     if (T == 0) return 0;
     unsigned grid = (unsigned)((T + 3) / 4);
-    if (out_f32) layernorm_kernel<true><<<grid, 128, 0, st>>>(x, (const bf16*)w, (const bf16*)b, y, T, H, eps);
-    else layernorm_kernel<false><<<grid, 128, 0, st>>>(x, (const bf16*)w, (const bf16*)b, y, T, H, eps);
+    if (out_f32) p3_launch_pdl(layernorm_kernel<true>, dim3(grid), dim3(128), (size_t)0, st, x, (const bf16*)w, (const bf16*)b, y, T, H, eps);
+    else p3_launch_pdl(layernorm_kernel<false>, dim3(grid), dim3(128), (size_t)0, st, x, (const bf16*)w, (const bf16*)b, y, T, H, eps);
     P3_CHECK_LAUNCH("layernorm");
     return 0;
 }

@@ -171,6 +171,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // programmatic dependent launch: barrier init / TMEM allocation above overlap the previous kernel's tail; nothing
+    // below (TMA loads of X, residual reads, output writes) may run before that kernel has completed
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -354,6 +358,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // programmatic dependent launch: barrier init / TMEM allocation above overlap the previous kernel's tail; nothing
+    // below (TMA loads of X, residual reads, output writes) may run before that kernel has completed
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -579,7 +587,7 @@ static int launch_tc(const void* X, int64_t ldx, const void* W, int64_t ldw, con
     }
     int64_t tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
     unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
-    gemm_tc_kernel<BN><<<grid, 384, C::SMEM, st>>>(ta, tb, ep, (int)M, N, K);
+    p3_launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(384), (size_t)C::SMEM, st, ta, tb, ep, (int)M, N, K);
     P3_CHECK_LAUNCH("gemm_tc");
     return 0;
 }
@@ -604,7 +612,7 @@ static int launch_tc2(const void* X, int64_t ldx, const void* W, int64_t ldw, co
     }
     int64_t tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
     int64_t clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-    gemm_tc2_kernel<<<(unsigned)(2 * clusters), 384, C::SMEM, st>>>(ta, tb, ep, (int)M, N, K);
+    p3_launch_pdl(gemm_tc2_kernel, dim3((unsigned)(2 * clusters)), dim3(384), (size_t)C::SMEM, st, ta, tb, ep, (int)M, N, K);
     P3_CHECK_LAUNCH("gemm_tc2");
     return 0;
 }
