@@ -92,7 +92,6 @@ def run_cuda(args):
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # stdout carries exactly one line: the JSON result
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import phi3_b200  # noqa
     from phi3_b200 import configs, weights, _lib
@@ -280,7 +279,7 @@ def run_cuda(args):
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_skinny_gemm': gemv,
             'cpu_baseline': cpu, 'wall_s_timed_region': round(wall, 3),
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -337,7 +336,29 @@ def run_reference(args):
             'config': {'workload': 'CPU oracle (restatement of the reference; MLX not installable offline) on the bounded '
                                    'decode sample of the bench workload', 'sample': cb['sample']},
             'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'tok/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    _emit(line)
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly one line, the JSON result: keep a private copy of fd 1 for it and point fd 1 at stderr, so
+    library chatter (e.g. NCCL's version banner, which ignores NCCL_DEBUG_FILE) cannot interleave with the result."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -348,6 +369,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    if not (args.gpus > 1 and int(os.environ.get('WORLD_SIZE', 1)) == 1):      # the self-launching parent just relays its child
+        _claim_stdout()
     if args.impl == 'reference':
         return run_reference(args)
     world = int(os.environ.get('WORLD_SIZE', 1))
