@@ -519,6 +519,25 @@ def test_gemm_skinny_w4(dev, M, mode):
         _check(out, out2.float(), tol=1e-2)
 
 
+@pytest.mark.parametrize('shape', [(3, 1000, 256), (16, 40, 128), (7, 3080, 1024), (9, 384, 384)])
+def test_gemm_skinny_w4_ragged_shapes(dev, shape):
+    """N that is not a multiple of the 16/32-row CTA tile, the smallest K (one 128-wide super-chunk), odd token counts"""
+    L = _mods()
+    from phi3_b200 import quant
+    M, N, K = shape
+    torch.manual_seed(21)
+    x = bf(torch.randn(M, K, device=dev))
+    w = bf(torch.randn(N, K, device=dev) * K ** -0.5)
+    q = quant.W4(w)
+    out = torch.full((M, N), float('nan'), device=dev, dtype=torch.bfloat16)
+    L.call('p3_gemm_skinny_w4', x.data_ptr(), K, None, 1e-5, q.codes.data_ptr(), q.meta.data_ptr(), out.data_ptr(), N, None,
+           M, N, K, 0, None, 0, None, None, 0, st())
+    _check(out, bf(x.float() @ q.deq.float().T), tol=1e-2)
+    with pytest.raises(RuntimeError):                       # K must be a multiple of 128 for the 4-bit stream
+        L.call('p3_gemm_skinny_w4', x.data_ptr(), K, None, 1e-5, q.codes.data_ptr(), q.meta.data_ptr(), out.data_ptr(), N, None,
+               M, N, 192, 0, None, 0, None, None, 0, st())
+
+
 @pytest.mark.parametrize('M', [(1, 1), (8, 1), (2, 5)])
 def test_fused_qkv_rope_w4_matches_bf16_kernel_on_dequantised_weights(dev, M):
     L = _mods()
