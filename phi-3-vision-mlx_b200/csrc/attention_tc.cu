@@ -20,7 +20,8 @@
 //               execute in issue order).
 // TMEM: S_a, S_b (128 columns each), O_a, O_b (D columns each). Operands: Q, K as K-major tiles — a 64-dim
 // SWIZZLE_128B box plus, for head_dim 96, a 32-dim SWIZZLE_64B box; V consumed in place as an MN-major B
-// operand (its [key][dim] layout is already N-contiguous; N = 64 + N = 32 UMMAs); P as the TMEM A operand.
+// operand (its [key][dim] layout is already N-contiguous): two SWIZZLE_128B boxes for head_dim 96 so that one N = 96
+// UMMA covers the head (the upper half of the second box is never read); P as the TMEM A operand.
 #include "attn_common.cuh"
 #include "tc_common.cuh"
 #include "../../include/phi3_b200.h"
@@ -33,19 +34,20 @@ struct FaCfg {
     static constexpr bool TWO = (D == 96);              // second, 32-dim box
     static constexpr int B0 = 128 * 128;                // bytes: 128 rows x 64 bf16, 128B swizzle
     static constexpr int B1 = TWO ? 128 * 64 : 0;       // bytes: 128 rows x 32 bf16, 64B swizzle
-    static constexpr int TILE = B0 + B1;                // one Q / K / V tile
+    static constexpr int TILE = B0 + B1;                // one Q / K tile
+    static constexpr int VTILE = TWO ? 2 * B0 : B0;     // V tile: head_dim 96 takes two SW128 boxes (dims 64..127, upper half unused) so that
+                                                        // O += P V is ONE N = 96 UMMA per 16 keys instead of an N = 64 and an N = 32 one
     static constexpr int STAGES = 3;
-    static constexpr int SMEM = 2 * TILE + 2 * STAGES * TILE + 1024 + 256;
+    static constexpr int SMEM = 2 * TILE + STAGES * (TILE + VTILE) + 1024 + 256;
     // S_x at 128 x (P_x, bf16 pairs, overwrites its first 64 columns once the S row has been consumed), O_x at 256 + 128 x
     static constexpr int TMEM_COLS = 512, S_COL = 0, O_COL = 256;
     static constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
     static constexpr uint32_t IDESC_QK = IDESC_BASE | ((128u >> 3) << 17);
-    static constexpr uint32_t IDESC_PV0 = IDESC_BASE | (1u << 16) | ((64u >> 3) << 17);   // B (V) MN-major
-    static constexpr uint32_t IDESC_PV1 = IDESC_BASE | (1u << 16) | ((32u >> 3) << 17);
+    static constexpr uint32_t IDESC_PV = IDESC_BASE | (1u << 16) | ((uint32_t)(D >> 3) << 17);   // B (V) MN-major, N = D
 };
 
-struct FaMaps {                                         // [0]: 64-column SW128 box, [1]: 32-column SW64 box (head_dim 96)
-    CUtensorMap q[2], k[2], v[2], pool[2];
+struct FaMaps {                                         // [0]: 64-column SW128 box, [1]: 32-column SW64 box (head_dim 96, Q and K)
+    CUtensorMap q[2], k[2], v, pool[2];                 // V (and the pool's V pages) use the [0]-type box twice
 };
 
 #define FA_THREADS 320
@@ -62,7 +64,7 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sQ = base, sK0 = sQ + 2 * C::TILE, sV0 = sK0 + ST * C::TILE;
-    const uint32_t bars = sV0 + ST * C::TILE;
+    const uint32_t bars = sV0 + ST * C::VTILE;
     const uint32_t q_full = bars;
     auto k_full = [&](int s) { return bars + 8u * (1 + s); };
     auto k_empty = [&](int s) { return bars + 8u * (1 + ST + s); };
@@ -110,7 +112,7 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
         for (int i = 0; i < (C::TWO ? 2 : 1); i++) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.q[i])) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.k[i])) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.v[i])) : "memory");
+            if (i == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.v)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.pool[i])) : "memory");
         }
     }
@@ -143,18 +145,26 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
             }
             const int32_t* bt = p.block_table ? p.block_table + (size_t)crow * p.bt_stride : nullptr;
             auto load_tile = [&](int n, int kv, uint32_t dst, uint32_t bar) {
-                mbar_expect_tx(bar, C::TILE);
+                // K: SW128 box (dims 0..63) + SW64 box (dims 64..95). V: two SW128 boxes (dims 0..63, 64..127; the columns past
+                // the head are the next head's or zero-filled, and no UMMA reads them)
+                mbar_expect_tx(bar, kv ? C::VTILE : C::TILE);
                 if (n * 128 < past) {                            // two 64-key pages of the pool
 #pragma unroll
                     for (int pg = 0; pg < 2; pg++) {
                         const int row = ((bt[2 * n + pg] * 2 + kv) * p.n_kv + kvh) * P3_PAGE;
                         tma_load_2d(dst + pg * (64 * 128), &tm.pool[0], bar, 0, row);
-                        if (C::TWO) tma_load_2d(dst + C::B0 + pg * (64 * 64), &tm.pool[1], bar, 64, row);
+                        if (C::TWO) {
+                            if (kv) tma_load_2d(dst + C::B0 + pg * (64 * 128), &tm.pool[0], bar, 64, row);
+                            else tma_load_2d(dst + C::B0 + pg * (64 * 64), &tm.pool[1], bar, 64, row);
+                        }
                     }
                 } else {                                         // 128 fresh rows of the qkv buffer
                     const int tok = b * p.L + (n * 128 - past);
-                    tma_load_2d(dst, kv ? &tm.v[0] : &tm.k[0], bar, kvh * D, tok);
-                    if (C::TWO) tma_load_2d(dst + C::B0, kv ? &tm.v[1] : &tm.k[1], bar, kvh * D + 64, tok);
+                    tma_load_2d(dst, kv ? &tm.v : &tm.k[0], bar, kvh * D, tok);
+                    if (C::TWO) {
+                        if (kv) tma_load_2d(dst + C::B0, &tm.v, bar, kvh * D + 64, tok);
+                        else tma_load_2d(dst + C::B0, &tm.k[1], bar, kvh * D + 64, tok);
+                    }
                 }
             };
             for (int it = 0; it < n_max; it++) {
@@ -163,7 +173,7 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                 mbar_wait(k_empty(st), ph ^ 1u);
                 load_tile(n_begin + it, 0, sK0 + st * C::TILE, k_full(st));
                 mbar_wait(v_empty(st), ph ^ 1u);
-                load_tile(n_begin + it, 1, sV0 + st * C::TILE, v_full(st));
+                load_tile(n_begin + it, 1, sV0 + st * C::VTILE, v_full(st));
             }
         }
     } else if (warp == FA_W_MMA) {
@@ -174,8 +184,8 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                 const int st = it % ST, stp = (it + ST - 1) % ST;  // stage of key tile it / it-1
                 FA_T(2, it, 5);
                 if (it < n_max) mbar_wait(k_full(st), (uint32_t)(it / ST) & 1u);
+                if (it > 0) mbar_wait(v_full(stp), (uint32_t)((it - 1) / ST) & 1u);   // off the softmax -> PV critical path
                 FA_T(2, it, 6);
-                bool v_ready = false;
 #pragma unroll
                 for (int x = 0; x < 2; x++) {
                     const bool do_s = it < n_x[x], do_pv = it > 0 && it - 1 < n_x[x];
@@ -185,17 +195,13 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                     FA_T(2 + x, it, 0);
                     if (elect_one()) {
                     if (do_pv) {                                 // O_x += P_x(it-1) V(it-1), P read from TMEM
-                        if (!v_ready) { mbar_wait(v_full(stp), (uint32_t)((it - 1) / ST) & 1u); tc_fence_after(); v_ready = true; }
                         FA_T(2 + x, it, 2);
                         const uint32_t d_tmem = tmem_base + C::O_COL + x * 128, a_tmem = tmem_base + C::S_COL + x * 128;
-                        const uint32_t vb = sV0 + stp * C::TILE;
+                        const uint32_t vb = sV0 + stp * C::VTILE;
                         const uint32_t acc0 = it > 1 ? 1u : 0u;
 #pragma unroll
-                        for (int kk = 0; kk < 8; kk++) {         // 16 keys = 8 TMEM columns per UMMA
-                            tc_mma_bf16_ts(d_tmem, a_tmem + 8 * kk, umma_desc_mn_sw128(vb + kk * (16 * 128), 0, 1024), C::IDESC_PV0, acc0 | (kk ? 1u : 0u));
-                            if (C::TWO)
-                                tc_mma_bf16_ts(d_tmem + 64, a_tmem + 8 * kk, umma_desc_mn_sw64(vb + C::B0 + kk * (16 * 64)), C::IDESC_PV1, acc0 | (kk ? 1u : 0u));
-                        }
+                        for (int kk = 0; kk < 8; kk++)           // 16 keys = 8 TMEM columns per UMMA; N = D (LBO = the second 64-dim box)
+                            tc_mma_bf16_ts(d_tmem, a_tmem + 8 * kk, umma_desc_mn_sw128(vb + kk * (16 * 128), C::B0, 1024), C::IDESC_PV, acc0 | (kk ? 1u : 0u));
                     }
                     FA_T(2 + x, it, 3);
                     if (do_s) {                                  // S_x(it) = Q_x K(it)^T (executes after the PV above: overwrites P_x)
@@ -395,14 +401,14 @@ static int launch_tc_d(const AttnParams& p, cudaStream_t st) {
         const int bc = i ? 32 : 64;
         r = tc_encode_2d(&tm.q[i], p.q, rows, (int64_t)p.n_heads * D, p.ldq, 128, bc);
         if (r == CUDA_SUCCESS) r = tc_encode_2d(&tm.k[i], p.k, rows, (int64_t)p.n_kv * D, p.ldk, 128, bc);
-        if (r == CUDA_SUCCESS) r = tc_encode_2d(&tm.v[i], p.v, rows, (int64_t)p.n_kv * D, p.ldv, 128, bc);
+        if (r == CUDA_SUCCESS && i == 0) r = tc_encode_2d(&tm.v, p.v, rows, (int64_t)p.n_kv * D, p.ldv, 128, 64);
         if (r == CUDA_SUCCESS) {
             // pool rows: an upper bound — pages are addressed through the block table
             if (p.past > 0) r = tc_encode_2d(&tm.pool[i], p.pool, (int64_t)1 << 31, D, D, P3_PAGE, bc);
             else tm.pool[i] = tm.k[i];
         }
     }
-    if (!C::TWO) { tm.q[1] = tm.q[0]; tm.k[1] = tm.k[0]; tm.v[1] = tm.v[0]; tm.pool[1] = tm.pool[0]; }
+    if (!C::TWO) { tm.q[1] = tm.q[0]; tm.k[1] = tm.k[0]; tm.pool[1] = tm.pool[0]; }
     P3_CHECK_ARG(r == CUDA_SUCCESS, "attention_prefill: cuTensorMapEncodeTiled failed (%d)", (int)r);
     static bool set = false;
     if (!set) {
