@@ -191,11 +191,6 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                     const bool do_s = it < n_x[x], do_pv = it > 0 && it - 1 < n_x[x];
                     if (!do_s && !do_pv) continue;
                     if (it > 0) mbar_wait(sm_done(x), (uint32_t)(it - 1) & 1u);   // softmax_x(it-1) finished (exactly one wait per tile)
-                    // Phase the two softmax warpgroups half a period apart: tile b's first scores are only issued once tile a
-                    // has finished its first key tile. The offset is self-sustaining (each chain is sweep -> PV -> S), and with it
-                    // one warpgroup sweeps with the whole MUFU pipe while the other one's UMMAs run, instead of both sweeping
-                    // at half speed and both waiting on the tensor pipe (measured: period 3600-4100 -> see profiles).
-                    else if (x == 1 && n_x[0] > 0) mbar_wait(sm_done(0), 0u);
                     tc_fence_after();
                     FA_T(2 + x, it, 0);
                     if (elect_one()) {
