@@ -5,9 +5,9 @@
 //
 // One CTA = 256 query rows (two 128-row tiles a, b) of one (sequence, head); key tiles of 128, shared by both
 // query tiles (halves the L2 -> SM traffic per flop; the two softmax warpgroups ping-pong on the MUFU pipe).
-//   warps 0-3 / 4-7 : softmax of query tile a / b — thread r owns query row r (TMEM lane r). TMEM reads are the
-//               scarce resource (~64 B/clk/SM: a 128x128 fp32 S tile costs as much as its 16K exponentials), so S
-//               is swept once per tile (32-column chunks, next chunk in flight while the current one is processed):
+//   warps 0-3 / 4-7 : softmax of query tile a / b — thread r owns query row r (TMEM lane r). The softmax is the critical
+//               chain of the kernel (16 K exponentials per 128x128 tile = 1024 MUFU cycles vs 768 cycles of UMMA at
+//               head_dim 96), so S is swept once per tile (32-column tcgen05.ld chunks, ~64 B/clk per warp):
 //               P = exp2(S*scale - m*scale) (one FFMA + one MUFU) against the running reference maximum m of the
 //               previous tiles, rounded to bf16 and stored back to TMEM over the consumed S columns (P is the A operand
 //               of the PV UMMA straight from tensor memory: no shared-memory round trip), while the tile's own
