@@ -122,7 +122,7 @@ int p3_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* 
  * q/k/v point into the (roped) qkv buffer; row strides in elements; head h at +h*hd.
  * Keys [0,past) come from the paged pool (cache row b/row_div), keys [past,past+L) from k/v.
  * kv_start int32 [B] (left-pad length; NULL = 0). Pad queries produce zeros.
- * Runs the tcgen05 flash-attention kernel (S and P in TMEM, TMA operands) when past % 128 == 0, L >= 64 and
+ * Runs the tcgen05 flash-attention kernel (S and P in TMEM, TMA operands) when past % 64 == 0, L >= 64 and
  * the pointers / strides are 16-byte aligned; otherwise (and with P3_ATTN_TC=0 in the environment, used by the
  * tests as a cross-check) the mma.sync kernel with the same contract. */
 int p3_attention_prefill(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* out,
