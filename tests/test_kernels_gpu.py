@@ -260,13 +260,14 @@ def _prefill_call(L, qkv, kc, vc, kv_start, B, H, D, Lq, past, causal, dev):
 _TC_CFGS = [(1, 1, 64, 128, 0, False, [0], 1.0), (1, 2, 96, 256, 0, True, [0], 1.0), (2, 3, 96, 300, 256, True, [0, 200], 1.0),
             (1, 2, 96, 640, 128, True, [5], 1.0), (3, 2, 64, 577, 0, False, [0, 0, 0], 1.0), (1, 4, 96, 2048, 0, True, [0], 1.0),
             (2, 2, 96, 1100, 0, True, [0, 300], 1.0), (1, 2, 96, 1024, 0, True, [0], 3.0), (1, 2, 96, 768, 0, False, [0], 40.0),
-            (2, 2, 64, 700, 0, False, [0, 0], 6.0), (1, 2, 96, 1000, 384, True, [130], 1.0)]
+            (2, 2, 64, 700, 0, False, [0, 0], 6.0), (1, 2, 96, 1000, 384, True, [130], 1.0),
+            (2, 2, 96, 333, 192, True, [10, 70], 1.0), (1, 3, 96, 64, 64, True, [0], 1.0)]
 
 
 @pytest.mark.parametrize('cfg', _TC_CFGS)
 def test_attention_prefill_tcgen05(dev, cfg):
     """tcgen05 flash attention (attention_tc.cu) vs the fp32 restatement and vs the mma.sync kernel on the same inputs:
-    paged past (past % 128 == 0), left padding, ragged last tiles, ViT shape, and score ramps that drive the
+    paged past (past % 64 == 0), left padding, ragged last tiles, ViT shape, and score ramps that drive the
     lazy-rescale (> 2^8) and redo (> 2^64) paths of the streaming softmax."""
     import os
     L = _mods()
