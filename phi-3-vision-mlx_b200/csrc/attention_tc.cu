@@ -16,9 +16,9 @@
 //               (reference grew by more than 2^8: before the next tile; more than 2^64: the tile is redone).
 //   warp 8    : TMA producer — Q tiles once, then K and V tiles through two independent 4-stage mbarrier rings.
 //               A pool page is one box; the fresh rows come straight from the qkv buffer.
-//   warp 9    : TMEM allocation + MMA issuer (whole warp converged, elect.sync lane issues) — per key tile and query
-//               tile, once the softmax warpgroup has stored P(j): O += P(j) V(j) (A from TMEM), then S(j+2) = Q K(j+2)^T
-//               into the buffer that P(j) occupied (UMMAs execute in issue order).
+//   warps 9, 10 : MMA issuers of query tile a / b (whole warp converged, elect.sync lane issues; warp 9 also owns the TMEM
+//               allocation) — per key tile, once the softmax warpgroup has stored P(j): O += P(j) V(j) (A from TMEM), then
+//               S(j+2) = Q K(j+2)^T into the buffer that P(j) occupied (UMMAs execute in issue order).
 // TMEM: S_a[2], S_b[2] (64 columns each), O_a, O_b (D columns each). Operands: Q, K as K-major tiles — a 64-dim
 // SWIZZLE_128B box plus, for head_dim 96, a 32-dim SWIZZLE_64B box; V consumed in place as an MN-major B
 // operand (its [key][dim] layout is already N-contiguous): two SWIZZLE_128B boxes for head_dim 96 so that one N = 96
@@ -54,9 +54,9 @@ struct FaMaps {                                         // [0]: 64-column SW128 
     CUtensorMap q[2], k[2], v, pool[2];                 // Q boxes have 128 rows, K / V / pool boxes 64; V uses the [0]-type box twice
 };
 
-#define FA_THREADS 320
+#define FA_THREADS 352
 #define FA_W_TMA 8
-#define FA_W_MMA 9
+#define FA_W_MMA 9                                      // warps 9, 10: MMA issuers of query tile a, b
 #define FA_RESCALE_LOG2 8.0f
 #define FA_PAIR_GROUP 8
 
@@ -126,7 +126,7 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
     if (warp == FA_W_MMA) {
         if (lane == 0) {
             mbar_init(q_full, 1);
-            for (int s = 0; s < ST; s++) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+            for (int s = 0; s < ST; s++) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 2); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 2); }   // K/V released by both MMA warps
             for (int x = 0; x < 2; x++) {
                 for (int j = 0; j < 2; j++) {
                     mbar_init(s_full(x, j), 1); mbar_init(o_done(x, j), 1);
@@ -178,12 +178,15 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                 load_tile(n_begin + it, 1, sV0 + st * C::VTILE, v_full(st));
             }
         }
-    } else if (warp == FA_W_MMA) {
-        // ---------------- MMA issuer: whole warp converged; UMMAs / commits by one elected lane ----------------
+    } else if (warp == FA_W_MMA || warp == FA_W_MMA + 1) {
+        // ---------------- MMA issuers: one warp per query tile (whole warp converged; UMMAs / commits by one elected lane).
+        // The two chains sweep -> PV -> S are independent; only the K / V stages are shared, and those are released by a
+        // commit from BOTH warps for every key tile (a warp whose query tile needs fewer key tiles just commits).
+        const int x = warp - FA_W_MMA, nx = n_x[x];
         if (n_max > 0) {
             mbar_wait(q_full, 0);
             // S_x(j) = Q_x K(j)^T into buffer j & 1 (64 fp32 columns)
-            auto issue_s = [&](int x, int j) {
+            auto issue_s = [&](int j) {
                 const int st = j % ST;
                 const uint32_t d_tmem = tmem_base + C::S_COL + x * 128 + (j & 1) * 64;
                 const uint32_t qa = sQ + x * C::QTILE, kb = sK0 + st * C::KTILE;
@@ -197,16 +200,15 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                 }
                 tc_commit(s_full(x, j));
             };
-            // K(j) is released once both query tiles (or the only one that still has key tiles) have issued S(j)
-            auto release_k = [&](int x, int j) { if (x == 1 || !(j < n_x[1])) tc_commit(k_empty(j % ST)); };
-            // prologue: the first two score tiles of both query tiles
+            // prologue: the first two score tiles
             for (int j = 0; j < 2 && j < n_max; j++) {
+                // (a warp that does not use a stage still waits for it before releasing it: its commits can then never run
+                // a ring phase ahead of the other warp's)
                 mbar_wait(k_full(j % ST), (uint32_t)(j / ST) & 1u);
                 tc_fence_after();
                 if (elect_one()) {
-#pragma unroll
-                    for (int x = 0; x < 2; x++)
-                        if (j < n_x[x]) { issue_s(x, j); release_k(x, j); }
+                    if (j < nx) issue_s(j);
+                    tc_commit(k_empty(j % ST));
                 }
                 __syncwarp();
             }
@@ -214,13 +216,11 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                 const int stv = j % ST;
                 mbar_wait(v_full(stv), (uint32_t)(j / ST) & 1u);
                 if (j + 2 < n_max) mbar_wait(k_full((j + 2) % ST), (uint32_t)((j + 2) / ST) & 1u);
-#pragma unroll
-                for (int x = 0; x < 2; x++) {
-                    if (j >= n_x[x]) continue;
-                    mbar_wait(sm_done(x, j), (uint32_t)(j >> 1) & 1u);   // P_x(j) is in TMEM (exactly one wait per tile, in order)
-                    tc_fence_after();
-                    FA_T(2 + x, j, 0);
-                    if (elect_one()) {
+                if (j < nx) mbar_wait(sm_done(x, j), (uint32_t)(j >> 1) & 1u);   // P_x(j) is in TMEM (exactly one wait per tile, in order)
+                tc_fence_after();
+                FA_T(2 + x, j, 0);
+                if (elect_one()) {
+                    if (j < nx) {
                         // O_x += P_x(j) V(j): A from TMEM (lane = row, two bf16 keys per column), V in place as MN-major B
                         const uint32_t d_tmem = tmem_base + C::O_COL + x * 128, a_tmem = tmem_base + C::S_COL + x * 128 + (j & 1) * 64;
                         const uint32_t vb = sV0 + stv * C::VTILE;
@@ -230,13 +230,13 @@ attn_prefill_tc_kernel(const __grid_constant__ FaMaps tm, AttnParams p, long lon
                                            (j | kk) ? 1u : 0u);
                         tc_commit(o_done(x, j));
                         // S_x(j+2) reuses the buffer whose P the PV above consumes (UMMAs execute in issue order)
-                        if (j + 2 < n_x[x]) { issue_s(x, j + 2); release_k(x, j + 2); }
+                        if (j + 2 < nx) issue_s(j + 2);
                     }
-                    __syncwarp();
-                    FA_T(2 + x, j, 1);
+                    tc_commit(v_empty(stv));
+                    if (j + 2 < n_max) tc_commit(k_empty((j + 2) % ST));
                 }
-                if (elect_one()) tc_commit(v_empty(stv));
                 __syncwarp();
+                FA_T(2 + x, j, 1);
             }
         }
     } else {
