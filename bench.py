@@ -221,9 +221,8 @@ def run_cuda(args):
             alone_bytes = B * past * 2 * model.n_kv * model.hd * 2
             roof['alone'] = {'avg_us': round(us, 2), 'achieved': round(alone_bytes / us / 1e3, 1),
                              'frac': round(alone_bytes / us / 1e3 / peak, 4),
-                             'note': 'same kernel, 128 back-to-back launches over the 32 layers\' pages, one event pair, no o_proj prefetch'}
-            roof['note'] = ('in-step figure: one CUDA-event pair per launch inside an eager decode pass; the launch also pulls the '
-                            'next kernel\'s 18.9 MB of o_proj weights into L2, which is not counted in the algorithmic bytes')
+                             'note': 'same kernel, 128 back-to-back launches over the 32 layers\' pages, one event pair'}
+            roof['note'] = 'in-step figure: one CUDA-event pair per launch inside an eager decode pass (no PDL overlap across the events)'
         if sk:
             byts = sum(m for _, m in sk)
             ms = sum(t for t, _ in sk)

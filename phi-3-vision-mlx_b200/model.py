@@ -184,6 +184,7 @@ class Phi3B200:
         self._skip = set(filter(None, _os.environ.get('P3_SKIP', '').split(',')))   # timing ablation only (tools/ablate.py)
         # decode: RMSNorm as its own tiny PDL kernel instead of fused into every 32-row CTA of the following skinny GEMM.
         # Neutral for the bf16 weight stream (2.797 vs 2.788 ms/token on the bench), -8 % for the instruction-bound 4-bit one.
+        self._opf_in_qkv = _os.environ.get('P3_OPF', 'qkv') != 'attn'
         self.prenorm = _os.environ.get('P3_PRENORM', '1' if self.quantize_model else '0') != '0'
         self.profile = None      # bench.py: list of (kind, ev0, ev1, algorithmic_bytes) when instrumenting
 
@@ -398,17 +399,24 @@ class Phi3B200:
                 pass
             elif T <= 16:                                   # decode: qkv_proj + rope + KV write in one launch
                 hq, nq, sq = (self._prenorm(h, lw['ln1']), None, None) if self.prenorm else (h, lw['ln1'], ss_cur)
+                # the qkv kernel parks the whole o_proj stream (18.9 MB bf16) in L2 before it waits on its predecessor; it
+                # survives the evict-first KV stream of the attention kernel, which then carries no prefetch duty (A/B on the
+                # bench: 2.851 -> 2.814 ms/token, attention in-step roofline 0.776 -> 0.816; P3_OPF=attn restores the old split)
+                qo_pf, qo_bytes = (None, 0)
+                if self._opf_in_qkv:
+                    qo_pf, _ = self._prefetch_target(lw['o'])
+                    qo_bytes = qo_pf.numel() * qo_pf.element_size()
                 ev = self._ev()
                 q4 = self._w4.get(lw['qkv'].data_ptr())
                 if q4 is not None:
                     call('p3_gemm_skinny_qkv_rope_w4', ptr(hq), hq.stride(0), ptr(nq), self.eps, ptr(q4[0]), ptr(q4[1]),
                          ptr(qkv), ptr(sq), 0 if sq is None else sq.shape[0], ptr(cosT), ptr(sinT), tbs, B, L,
-                         self.n_heads, self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, None, 0, st)
+                         self.n_heads, self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, ptr(qo_pf), qo_bytes, st)
                     self._ev(ev, 'skinny', q4[0].numel() + q4[1].numel() * 2)
                 else:
                     call('p3_gemm_skinny_qkv_rope', ptr(hq), hq.stride(0), ptr(nq), self.eps, ptr(lw['qkv']), ptr(qkv),
                          ptr(sq), 0 if sq is None else sq.shape[0], ptr(cosT), ptr(sinT), tbs, B, L, self.n_heads,
-                         self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, None, 0, st)
+                         self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, ptr(qo_pf), qo_bytes, st)
                     self._ev(ev, 'skinny', self.qkv_dim * H * 2)
             else:
                 self.linear(h, lw['qkv'], qkv, _lib.EPI_NONE, norm_w=lw['ln1'], ss_in=ss_cur)
@@ -419,6 +427,8 @@ class Phi3B200:
             o_pf, pf_bytes = self._prefetch_target(lw['o']) if T <= 16 else (None, 0)   # o_proj weights ride into L2 behind the KV stream
             if T <= 16:
                 pf_bytes = o_pf.numel() * o_pf.element_size()
+                if self._opf_in_qkv:
+                    o_pf, pf_bytes = None, 0
             if use_decode_attn and 'attn' in self._skip:
                 pass
             elif use_decode_attn:
