@@ -314,3 +314,32 @@ def test_lora_adapter_folded_at_load_matches_loralinear_oracle(dev, layers, tmp_
     lo, co = ora(tok[:, None], cache=co)
     l1, c1 = m1(tok[:, None], cache=c1)
     assert rel(l1, lo) < 2e-2
+
+
+def test_quantize_model_and_quantize_cache_together(dev):
+    """both 4-bit flags at once (the reference's smallest-memory configuration): 4-bit g64 weights at decode through the W4
+    skinny GEMMs while the prompt KV is read from the 4-bit g32 cache; logits stay within tolerance of the oracle that
+    applies the same two quantisers."""
+    import phi3_b200  # noqa
+    from phi3_b200 import configs, weights, api
+    from phi3_b200.processor import ByteTokenizer
+    from oracle.phi3_oracle import Phi3Oracle, quantize_model_weights
+    cfg = configs.tiny(vision=False, use_quantized_cache=True)
+    w = weights.random_weights(cfg, seed=5)
+    model, proc = api.load(blind_model=True, quantize_model=True, quantize_cache=True, cfg=cfg, weights=w, tokenizer=ByteTokenizer())
+    assert model.quantize_model and model.use_quantized_cache
+    ora = Phi3Oracle(model.cfg, quantize_model_weights(w), prec='b200')
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(3, 32000, (2, 70), generator=g); ids[:, 0] = 1
+    lo, co = ora(ids, max_tokens=6)
+    lg, cg = model(ids, max_tokens=6)
+    rel = lambda a, b: ((a.float().cpu() - b.float().cpu()).abs().max() / b.float().abs().max()).item()
+    assert rel(lg, lo) < 2e-2
+    tok = lo[:, -1].argmax(-1)
+    for _ in range(3):
+        lo, co = ora(tok[:, None], cache=co)
+        lg, cg = model(tok[:, None], cache=cg)
+        assert rel(lg, lo) < 3e-2
+        tok = lo[:, -1].argmax(-1)
+    txt = api.generate(['abc def ghi', 'short'], preload=(model, proc), max_tokens=6, verbose=False, stream=False)
+    assert len(txt) == 2
