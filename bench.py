@@ -174,7 +174,8 @@ def run_cuda(args):
         torch.cuda.synchronize()
         peak, peak_src = peaks()
         att = [(a.elapsed_time(b), meta) for kind, a, b, meta in model.profile if kind == 'attn']
-        sk = [(a.elapsed_time(b), meta) for kind, a, b, meta in model.profile if kind == 'skinny']
+        sk = [(a.elapsed_time(b), meta) for kind, a, b, meta in model.profile if kind in ('skinny', 'mega')]
+        sk_kernel = 'decode_mega_kernel (persistent layer weight stream)' if any(k == 'mega' for k, *_ in model.profile) else 'gemm_skinny_kernel (weight stream)'
         model.profile = None
         if att:
             byts = sum(m for _, m in att)
@@ -227,7 +228,7 @@ def run_cuda(args):
             byts = sum(m for _, m in sk)
             ms = sum(t for t, _ in sk)
             ach = byts / (ms * 1e-3) / 1e9
-            gemv = {'kernel': 'gemm_skinny_kernel (weight stream)', 'bound': 'hbm', 'achieved': round(ach, 1),
+            gemv = {'kernel': sk_kernel, 'bound': 'hbm', 'achieved': round(ach, 1),
                     'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4), 'launches': len(sk)}
 
     # ---- BASELINE configs[1]: single-image VQA prefill at batch 1

@@ -181,6 +181,58 @@ int p3_clip_embed(const float* patches, const void* cls, const void* pos, float*
 int p3_gn_assemble(const float* feats, const void* sub_GN, const void* glb_GN, void* out, int hc, int wc, int C,
                    cudaStream_t st);
 
+/* ------------------------------------------------------------------------------------------------
+ * Persistent decode-layer kernel (decode_mega.cu): for M <= 8 decode rows, ONE launch of n_ctas (<= #SM,
+ * co-resident) persistent CTAs runs up to 4 chained weight-stream phases with grid barriers in between,
+ * e.g. o_proj(+residual) -> RMSNorm+gate_up(+SwiGLU) -> down_proj(+residual) -> RMSNorm+qkv_proj(+SuRoPE
+ * +paged KV write) of the next layer, or ... -> RMSNorm+lm_head. Replaces nn.Linear / nn.RMSNorm /
+ * _rotate_half / KVCache slice-assign at decode: phi:437-438, 442-453, 460, 465-471, 478-485, 604-608.
+ * Arguments travel in a plain-old-data struct (device pointers + sizes), as SURVEY.md par. 8b asks. */
+#define P3_MEGA_RESID 0     /* out[M,N] bf16 = bf16(out + bf16(x W^T)) in place; ss_out[tile][16] = sum of squares of the 16 new columns */
+#define P3_MEGA_SWIGLU 1    /* W = [gate rows | up rows] (phi:470); out[M,N/2] bf16 = silu(gate) * up */
+#define P3_MEGA_QKV_ROPE 2  /* out[M,N] bf16 = qkv with q,k rotated (phi:418-423) + K,V written to the page pool at `past` */
+#define P3_MEGA_F32 3       /* out[M,N] fp32 logits */
+#define P3_MEGA_MAX_PHASES 4
+
+typedef struct {
+    const void* wp;             /* weights in stream order (p3_mega_pack), N*K bf16 */
+    int32_t kind, N, K;         /* N = rows of W (output features, SWIGLU: gate+up), K = input features */
+    int32_t max_tiles_per_cta;  /* max over CTAs of the schedule below (checked against the smem partial buffer when K > 4096) */
+    const void* x;              /* input activations bf16 [M, ldx] */
+    int64_t ldx;
+    const void* norm_w;         /* RMSNorm gain applied to x on load (bf16 [K]) or NULL */
+    const float* ss_in;         /* per-row sum-of-squares partials of x: fp32 [n_ss_in][16]; NULL = recompute from x */
+    int32_t n_ss_in, _pad;
+    float* ss_out;              /* RESID: partials [N/16][16] of the rows written, or NULL */
+    void* out;
+    int64_t ldo;
+    const int32_t* cta_off;     /* schedule: CTA c owns tile_ids[cta_off[c] .. cta_off[c+1]) of this phase (int32 [n_ctas+1]) */
+    const int32_t* tile_ids;    /* tile = 16 (RESID) or 2x16 (other kinds) rows of W */
+} p3_mega_phase;
+
+typedef struct {
+    p3_mega_phase ph[P3_MEGA_MAX_PHASES];
+    int32_t n_phases, M;
+    float eps;                  /* RMSNorm eps */
+    int32_t n_ctas;             /* grid size the schedule was built for (<= #SM) */
+    uint32_t* sync;             /* 2 words of device memory, zero before the first launch (grid barrier state) */
+    /* P3_MEGA_QKV_ROPE: one new token per row at position *past_dev (or `past` when NULL) */
+    const float* cosT;
+    const float* sinT;          /* fp32 [Bt, L_all, hd/2]; row b uses table row b (tab_bstride elements apart, 0 = shared) */
+    int64_t tab_bstride;
+    int32_t n_heads, n_kv, hd, past;
+    const int32_t* past_dev;
+    void* pool;                 /* this layer's page pool [page][2][n_kv][64][hd] bf16 */
+    const int32_t* block_table; /* int32 [M, bt_stride] */
+    int32_t bt_stride, _pad2;
+} p3_mega_args;
+
+/* W [N,K] bf16 (nn.Linear layout; SWIGLU: the checkpoint's [gate | up] row order) -> stream order for `kind` */
+int p3_mega_pack(const void* W, void* out, int kind, int N, int K, int n_heads, int n_kv, int hd, cudaStream_t st);
+/* number of SMs of the current device = the largest valid n_ctas */
+int p3_decode_mega_ctas(void);
+int p3_decode_mega(const p3_mega_args* args, cudaStream_t st);
+
 #ifdef __cplusplus
 }
 #endif

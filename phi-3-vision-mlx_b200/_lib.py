@@ -38,6 +38,7 @@ _SIGS = {
     'p3_patch_im2col': [_p, _p, _i, _i, _p],
     'p3_clip_embed': [_p, _p, _p, _p, _i, _i, _p],
     'p3_gn_assemble': [_p, _p, _p, _p, _i, _i, _i, _p],
+    'p3_mega_pack': [_p, _p, _i, _i, _i, _i, _i, _i, _p],
 }
 
 _lib = None
@@ -45,7 +46,8 @@ launches = 0          # number of p3_* kernel-launching calls issued (bench.py r
 
 
 def exported_symbols():
-    return sorted(list(_SIGS) + ['p3_last_error', 'p3_version', 'p3_attention_decode_workspace'])
+    return sorted(list(_SIGS) + ['p3_last_error', 'p3_version', 'p3_attention_decode_workspace', 'p3_decode_mega',
+                                 'p3_decode_mega_ctas'])
 
 
 def lib():
@@ -62,6 +64,8 @@ def lib():
         L.p3_version.restype = C.c_int
         L.p3_attention_decode_workspace.argtypes = [_i, _i, _i, _i, _i]
         L.p3_attention_decode_workspace.restype = C.c_int64
+        L.p3_decode_mega.argtypes, L.p3_decode_mega.restype = [_p, _p], C.c_int      # (const p3_mega_args*, stream)
+        L.p3_decode_mega_ctas.argtypes, L.p3_decode_mega_ctas.restype = [], C.c_int
         _lib = L
     return _lib
 
@@ -77,6 +81,16 @@ def call(name, *args):
     if len(args) != len(_SIGS[name]):
         raise TypeError(f'{name}: expected {len(_SIGS[name])} arguments, got {len(args)}')
     rc = getattr(L, name)(*args)
+    launches += 1
+    if rc != 0:
+        raise RuntimeError(f'{name} failed ({rc}): {L.p3_last_error().decode()}')
+
+
+def call_struct(name, args_struct, stream):
+    """Entries that take one plain-old-data argument struct (include/phi3_b200.h) + the stream."""
+    global launches
+    L = lib()
+    rc = getattr(L, name)(C.byref(args_struct), stream)
     launches += 1
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {L.p3_last_error().decode()}')

@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
                     bool ok;
                     if (present) {
                         int qi = past + ((e & 2) ? g + 8 : g);
-                        ok = (j < s_total) && (j <= qi);
+                        ok = (j >= kv0) && (j < s_total) && (j <= qi);   // left-pad keys of a short first call (past == 0)
                     } else {
                         ok = (j >= kv0) && (j < past);
                     }

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128, 3) attn_decode_q4_kernel(AttnParams p) {
                 for (int e = 0; e < 4; e++) {
                     int j = j0 + nt * 8 + 2 * t + (e & 1);
                     bool ok;
-                    if (present) { int qi = past + ((e & 2) ? g + 8 : g); ok = (j < s_total) && (j <= qi); }
+                    if (present) { int qi = past + ((e & 2) ? g + 8 : g); ok = (j >= kv0) && (j < s_total) && (j <= qi); }
                     else ok = (j >= kv0) && (j < past);
                     if (!ok) s[nt][e] = -INFINITY;
                 }

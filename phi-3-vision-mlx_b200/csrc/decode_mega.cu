@@ -1,0 +1,424 @@
+// Persistent decode-layer kernel: the weight stream of a whole decoder layer in ONE launch.
+//
+// Replaces, for M <= 8 decode rows, the chain of per-matrix skinny GEMMs
+//     o_proj (+residual) -> RMSNorm -> gate_up_proj (+SwiGLU) -> down_proj (+residual) -> RMSNorm -> qkv_proj
+//     (+SuRoPE, +paged KV write)   |   ... -> RMSNorm -> lm_head
+// (phi.py:437-438, 442-453, 460, 465-471, 478-485, 604-608) by one launch of <#SM> persistent CTAs that walk the
+// phases with grid-wide barriers in between. The op is a pure HBM weight stream (7.4 GB per decode step), so the
+// design goal is that HBM never idles at an op boundary:
+//
+//   * weights are re-packed once at load time (p3_mega_pack) into "stream order": for every 16-row tile, K-block and
+//     consumer warp one contiguous segment whose 512-byte pieces are exactly the per-lane A fragments of
+//     mma.sync.m16n8k16 (rows of W are the MMA "M", the <= 8 tokens are "N"), so a warp consumes its stream with
+//     conflict-free 16-byte ld.shared and no transposes;
+//   * every consumer warp owns a private ring of MG_RSLOTS x 4 KB shared-memory slots filled by cp.async.bulk
+//     (mbarrier complete_tx, L2 evict-first) that it issues itself one ring ahead of its read position. The ring
+//     position runs through ALL phases of the launch, i.e. while a warp waits at a grid barrier (or, under
+//     programmatic dependent launch, for the previous kernel to finish) 192 KB per SM = 28 MB per GPU of the NEXT
+//     phase's weights are already in flight — more than HBM delivers during the barrier;
+//   * tiles are mapped to CTAs by a host-built schedule that balances CUMULATIVE bytes per CTA at every phase
+//     boundary (so all CTAs reach each barrier together) instead of per-matrix tile counts;
+//   * activations (<= 8 x 8192 bf16) live in L2: x fragments are loaded once per phase into registers
+//     (ld.global.cg, after the barrier), RMSNorm is applied to them in registers from per-tile sum-of-squares
+//     partials written by the producing phase (fixed summation order: deterministic).
+//
+// Roofline: HBM. Algorithmic bytes per launch = sum over phases of N*K*2 (226.5 MB per Phi-3.5 layer).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/phi3_b200.h"
+
+#define MG_WARPS 8
+#define MG_THREADS (MG_WARPS * 32)
+#define MG_SLOT 4096
+#define MG_RSLOTS 6
+#define MG_XF 32                       // max 16-wide k blocks per warp and K-block  (K-block <= 8 * 32 * 16 = 4096)
+#define MG_KBLOCK 4096
+#define MG_MAX_PART 8                  // tiles per CTA of a multi-K-block phase (partial sums parked in smem)
+#define MG_RED_STRIDE 136              // floats per (warp, m-tile) in the reduction scratch: n * 17 + r
+
+#define MG_RING_BYTES (MG_WARPS * MG_RSLOTS * MG_SLOT)
+#define MG_RED_BYTES (2 * MG_WARPS * 2 * MG_RED_STRIDE * 4)
+#define MG_PART_BYTES (MG_MAX_PART * 2 * 128 * 4)
+#define MG_SMEM (MG_RING_BYTES + MG_RED_BYTES + MG_PART_BYTES + MG_WARPS * MG_RSLOTS * 8)
+
+__host__ __device__ __forceinline__ int mg_mt(int kind) { return kind == P3_MEGA_RESID ? 1 : 2; }
+
+// first W row of m-tile `mt` of tile `ti` (the same map drives p3_mega_pack and the epilogues)
+__host__ __device__ __forceinline__ int mg_tile_row(int kind, int ti, int mt, int N, int n_heads, int n_kv, int hd) {
+    if (kind == P3_MEGA_RESID) return 16 * ti;
+    if (kind == P3_MEGA_SWIGLU) return mt * (N / 2) + 16 * ti;                  // gate rows | up rows (phi.py:470)
+    if (kind == P3_MEGA_QKV_ROPE) {
+        const int gpr = hd / 32, n_rope = (n_heads + n_kv) * gpr;
+        if (ti < n_rope) return (ti / gpr) * hd + 16 * (ti % gpr) + mt * (hd / 2);   // a rotary pair (d, d + hd/2) meets in one tile
+        return (n_heads + n_kv) * hd + 32 * (ti - n_rope) + 16 * mt;
+    }
+    return 32 * ti + 16 * mt;                                                   // P3_MEGA_F32
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// p3_mega_pack: W [N, K] bf16 (nn.Linear layout) -> stream order [kb][tile][warp][j][mt][lane][8 bf16]
+// lane (g, t) of k block j holds {W[g][4t,4t+1], W[g+8][4t,4t+1], W[g][4t+2,4t+3], W[g+8][4t+2,4t+3]} = a0..a3 of the
+// m16n8k16 A fragment under the k permutation (logical 2t+e -> 4t+e, logical 2t+8+e -> 4t+2+e) that lets the X operand
+// be fetched with one 8-byte load per lane and k block.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void mega_pack_kernel(const bf16* __restrict__ W, uint4* __restrict__ out, int kind, int N, int K, int n_heads,
+                                 int n_kv, int hd, int64_t total) {
+    const int MT = mg_mt(kind), T = N / (16 * MT);
+    const int n_kblk = (K + MG_KBLOCK - 1) / MG_KBLOCK, nkb_w = K / (n_kblk * 128);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i;
+        const int lane = r % 32; r /= 32;
+        const int mt = r % MT; r /= MT;
+        const int j = r % nkb_w; r /= nkb_w;
+        const int warp = r % MG_WARPS; r /= MG_WARPS;
+        const int ti = r % T; r /= T;
+        const int kb = (int)r;
+        const int g = lane >> 2, t = lane & 3;
+        const int row0 = mg_tile_row(kind, ti, mt, N, n_heads, n_kv, hd) + g;
+        const int k0 = ((kb * MG_WARPS + warp) * nkb_w + j) * 16 + 4 * t;
+        const uint2 lo = *reinterpret_cast<const uint2*>(W + (size_t)row0 * K + k0);          // W[g][4t..4t+3]
+        const uint2 hi = *reinterpret_cast<const uint2*>(W + (size_t)(row0 + 8) * K + k0);    // W[g+8][4t..4t+3]
+        out[i] = make_uint4(lo.x, hi.x, lo.y, hi.y);
+    }
+}
+
+static int mega_dims_ok(int kind, int N, int K, int n_heads, int n_kv, int hd) {
+    const int MT = mg_mt(kind);
+    if (N <= 0 || K <= 0 || N % (16 * MT) != 0) return 0;
+    const int n_kblk = (K + MG_KBLOCK - 1) / MG_KBLOCK;
+    if (K % (n_kblk * 128) != 0 || K / (n_kblk * 128) > MG_XF) return 0;
+    if (kind == P3_MEGA_QKV_ROPE && (hd % 32 != 0 || N != (n_heads + 2 * n_kv) * hd)) return 0;
+    return 1;
+}
+
+extern "C" int p3_mega_pack(const void* W, void* out, int kind, int N, int K, int n_heads, int n_kv, int hd, cudaStream_t st) {
+    P3_CHECK_ARG(kind >= P3_MEGA_RESID && kind <= P3_MEGA_F32, "mega_pack: unknown phase kind %d", kind);
+    P3_CHECK_ARG(mega_dims_ok(kind, N, K, n_heads, n_kv, hd), "mega_pack: unsupported shape N=%d K=%d kind=%d", N, K, kind);
+    const int64_t total = (int64_t)N * K / 8;
+    mega_pack_kernel<<<(unsigned)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192), 256, 0, st>>>(
+        (const bf16*)W, (uint4*)out, kind, N, K, n_heads, n_kv, hd, total);
+    P3_CHECK_LAUNCH("mega_pack");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the persistent kernel
+// ------------------------------------------------------------------------------------------------------------------
+static_assert(sizeof(p3_mega_phase) == 104 && sizeof(p3_mega_args) == 512, "p3_mega_args layout is mirrored by ctypes in mega.py");
+struct MgDerived { int MT, T, n_kblk, nkb_w; uint32_t seg; };
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float mg_silu(float x) { return x / (1.f + __expf(-x)); }
+
+// grid-wide barrier over a monotonic counter (all CTAs are co-resident: grid <= #SM, 1 CTA/SM)
+__device__ __forceinline__ void mg_grid_barrier(unsigned* ctr, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned v, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            if (v < target && ++spins > (1u << 26)) __trap();      // a CTA never arrived: fail loudly instead of hanging the GPU
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct MgCursor { int p, kb, li; uint32_t off; };          // li: index into this CTA's tile list of phase p
+
+__global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid_constant__ p3_mega_args P) {
+    extern __shared__ __align__(1024) uint8_t mg_smem[];
+    __shared__ MgDerived s_d[P3_MEGA_MAX_PHASES];
+    __shared__ int s_first[P3_MEGA_MAX_PHASES], s_cnt[P3_MEGA_MAX_PHASES];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int cta = blockIdx.x;
+    const int M = P.M;
+
+    uint8_t* ring_g = mg_smem + (size_t)warp * (MG_RSLOTS * MG_SLOT);
+    const uint32_t ring = smem_u32(ring_g);
+    float* red = reinterpret_cast<float*>(mg_smem + MG_RING_BYTES);
+    float* part = reinterpret_cast<float*>(mg_smem + MG_RING_BYTES + MG_RED_BYTES);
+    const uint32_t bars = smem_u32(mg_smem + MG_RING_BYTES + MG_RED_BYTES + MG_PART_BYTES) + warp * (MG_RSLOTS * 8);
+
+    if (tid < P.n_phases) {
+        const p3_mega_phase& ph = P.ph[tid];
+        MgDerived d;
+        d.MT = mg_mt(ph.kind); d.T = ph.N / (16 * d.MT);
+        d.n_kblk = (ph.K + MG_KBLOCK - 1) / MG_KBLOCK; d.nkb_w = ph.K / (d.n_kblk * 128);
+        d.seg = (uint32_t)d.nkb_w * d.MT * 512u;
+        s_d[tid] = d;
+        s_first[tid] = ph.cta_off[cta];
+        s_cnt[tid] = ph.cta_off[cta + 1] - ph.cta_off[cta];
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < MG_RSLOTS; s++) mbar_init(bars + s * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_trigger();
+
+    // ---- producer side of this warp's ring: walks (phase, K-block, tile) exactly like the consumer below
+    const uint64_t pol = l2_evict_first_policy();
+    MgCursor pc{0, 0, 0, 0};
+    uint32_t pn = 0;                                            // slot loads issued so far
+    auto issue_next = [&]() {                                   // all lanes walk the cursor; lane 0 issues the copy
+        while (pc.p < P.n_phases) {
+            const MgDerived d = s_d[pc.p];
+            if (pc.li >= s_cnt[pc.p]) {                         // this K-block of this phase is exhausted
+                pc.li = 0; pc.off = 0;
+                if (++pc.kb >= d.n_kblk) { pc.kb = 0; pc.p++; }
+                continue;
+            }
+            const p3_mega_phase& ph = P.ph[pc.p];
+            const int ti = ph.tile_ids[s_first[pc.p] + pc.li];
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(ph.wp) +
+                                 ((size_t)((size_t)pc.kb * d.T + ti) * MG_WARPS + warp) * d.seg + pc.off;
+            const uint32_t bytes = min((uint32_t)MG_SLOT, d.seg - pc.off);
+            if (lane == 0) {
+                const uint32_t slot = pn % MG_RSLOTS;
+                mbar_expect_tx(bars + slot * 8, bytes);
+                bulk_g2s(ring + slot * MG_SLOT, src, bytes, bars + slot * 8, pol);
+            }
+            pn++;
+            pc.off += bytes;
+            if (pc.off >= d.seg) { pc.off = 0; pc.li++; }
+            return;
+        }
+    };
+#pragma unroll 1
+    for (int s = 0; s < MG_RSLOTS; s++) issue_next();           // weights are immutable: stream them before the dependency wait
+    pdl_wait();
+
+    const int past = P.past_dev ? *P.past_dev : P.past;
+    uint32_t cn = 0;                                            // slot loads consumed so far
+    unsigned n_bar = 0;
+    int red_buf = 0;
+
+    for (int p = 0; p < P.n_phases; p++) {
+        if (p > 0) mg_grid_barrier(P.sync, ++n_bar * gridDim.x);
+        const p3_mega_phase& ph = P.ph[p];
+        const MgDerived d = s_d[p];
+        const int n_mine = s_cnt[p];
+        if (n_mine == 0) continue;
+        const bf16* X = reinterpret_cast<const bf16*>(ph.x);
+        const bf16* NW = reinterpret_cast<const bf16*>(ph.norm_w);
+
+        // ---- RMSNorm scale of row g (phi.py:478-479): from the producer's per-tile partial sums, fixed order
+        float rs = 1.f;
+        if (NW) {
+            float s = 0.f;
+            if (g < M) {
+                if (ph.ss_in) {
+                    for (int c = t; c < ph.n_ss_in; c += 4) s += __ldcg(ph.ss_in + (size_t)c * 16 + g);
+                } else {
+                    const uint2* xr = reinterpret_cast<const uint2*>(X + (size_t)g * ph.ldx);
+                    for (int c = t; c < ph.K / 4; c += 4) {
+                        const uint2 v = __ldcg(xr + c);
+                        const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y);
+                        s += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+                    }
+                }
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            rs = rsqrtf(s / (float)ph.K + P.eps);
+        }
+
+        for (int kb = 0; kb < d.n_kblk; kb++) {
+            // ---- this warp's X fragments for the K-block: [kbase, kbase + 16 nkb_w), (RMSNorm applied), in registers
+            uint32_t xf[MG_XF][2];
+            const int kbase = (kb * MG_WARPS + warp) * d.nkb_w * 16 + 4 * t;
+#pragma unroll
+            for (int j = 0; j < MG_XF; j++) {
+                uint2 v = make_uint2(0u, 0u);
+                if (j < d.nkb_w && g < M) v = __ldcg(reinterpret_cast<const uint2*>(X + (size_t)g * ph.ldx + kbase + 16 * j));
+                xf[j][0] = v.x; xf[j][1] = v.y;
+            }
+            if (NW) {
+#pragma unroll
+                for (int j = 0; j < MG_XF; j++) {
+                    if (j < d.nkb_w) {
+                        const uint2 w = *reinterpret_cast<const uint2*>(NW + kbase + 16 * j);
+                        float2 a = unpack_bf16(xf[j][0]), b = unpack_bf16(xf[j][1]);
+                        const float2 wa = unpack_bf16(w.x), wb = unpack_bf16(w.y);
+                        xf[j][0] = pack_bf16(a.x * rs * wa.x, a.y * rs * wa.y);
+                        xf[j][1] = pack_bf16(b.x * rs * wb.x, b.y * rs * wb.y);
+                    }
+                }
+            }
+            const bool last_kb = (kb == d.n_kblk - 1);
+
+            for (int li = 0; li < n_mine; li++) {
+                const int ti = ph.tile_ids[s_first[p] + li];
+                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                const int F = d.nkb_w * d.MT;                   // 512-byte fragments of this item
+                // ---- stream the item: one ld.shared.v4 + one MMA per fragment
+                auto release = [&]() {                          // slot drained by every lane: refill it one ring ahead
+                    __syncwarp();
+                    cn++;
+                    issue_next();
+                };
+                auto frag = [&](int f, int j, int mt) {         // f, j, mt are compile-time after unrolling
+                    const uint32_t slot = cn % MG_RSLOTS;
+                    if ((f & 7) == 0) mbar_wait(bars + slot * 8, (cn / MG_RSLOTS) & 1);
+                    // plain load: free to be scheduled ahead of the MMAs, fenced by the memory clobbers of the mbarrier ops
+                    const uint4 a = *reinterpret_cast<const uint4*>(ring_g + slot * MG_SLOT + (f & 7) * 512 + lane * 16);
+                    const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+                    mma_bf16_16816(acc[mt], av, xf[j][0], xf[j][1]);
+                    if ((f & 7) == 7) release();
+                };
+                if (d.MT == 1) {
+#pragma unroll
+                    for (int j = 0; j < MG_XF; j++)
+                        if (j < d.nkb_w) frag(j, j, 0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < MG_XF; j++)
+                        if (j < d.nkb_w) { frag(2 * j, j, 0); frag(2 * j + 1, j, 1); }
+                }
+                if (F & 7) release();                           // partial last slot of the item (segments never share a slot)
+                // ---- cross-warp reduction (K is split over the 8 warps) + epilogue by warps 0-3
+                float* rb = red + (size_t)red_buf * (MG_WARPS * 2 * MG_RED_STRIDE) + (size_t)warp * (2 * MG_RED_STRIDE);
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    if (mt < d.MT) {
+                        float* r2 = rb + mt * MG_RED_STRIDE;
+                        r2[(2 * t) * 17 + g] = acc[mt][0];
+                        r2[(2 * t + 1) * 17 + g] = acc[mt][1];
+                        r2[(2 * t) * 17 + g + 8] = acc[mt][2];
+                        r2[(2 * t + 1) * 17 + g + 8] = acc[mt][3];
+                    }
+                }
+                __syncthreads();
+                if (tid < 128) {
+                    const int r = tid & 15, n = tid >> 4;
+                    const float* r0 = red + (size_t)red_buf * (MG_WARPS * 2 * MG_RED_STRIDE) + n * 17 + r;
+                    float s[2] = {0.f, 0.f};
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++)
+                        if (mt < d.MT) {
+#pragma unroll
+                            for (int w = 0; w < MG_WARPS; w++) s[mt] += r0[(size_t)w * (2 * MG_RED_STRIDE) + mt * MG_RED_STRIDE];
+                            float* pp = part + ((size_t)li * 2 + mt) * 128 + tid;
+                            if (kb > 0) s[mt] += *pp;
+                            if (!last_kb) *pp = s[mt];
+                        }
+                    if (last_kb) {
+                        if (ph.kind == P3_MEGA_RESID) {                       // phi.py:483,485: h = bf16(h + bf16(y)); + sum of squares
+                            bf16* out = reinterpret_cast<bf16*>(ph.out);
+                            float sq = 0.f;
+                            if (n < M) {
+                                const size_t off = (size_t)n * ph.ldo + 16 * ti + r;
+                                const unsigned short raw = __ldcg(reinterpret_cast<const unsigned short*>(out) + off);
+                                const float rv = __bfloat162float(__ushort_as_bfloat16(raw));
+                                const bf16 hv = __float2bfloat16_rn(rv + bf16_round(s[0]));
+                                out[off] = hv;
+                                sq = __bfloat162float(hv) * __bfloat162float(hv);
+                            }
+#pragma unroll
+                            for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                            if (r == 0 && ph.ss_out) ph.ss_out[(size_t)ti * 16 + n] = sq;
+                        } else if (ph.kind == P3_MEGA_SWIGLU) {               // phi.py:470-471
+                            if (n < M) {
+                                const float gb = bf16_round(s[0]), ub = bf16_round(s[1]);
+                                const float a = bf16_round(mg_silu(gb));
+                                reinterpret_cast<bf16*>(ph.out)[(size_t)n * ph.ldo + 16 * ti + r] = __float2bfloat16_rn(a * ub);
+                            }
+                        } else if (ph.kind == P3_MEGA_F32) {                  // lm_head logits, phi.py:608
+                            if (n < M) {
+                                float* o = reinterpret_cast<float*>(ph.out) + (size_t)n * ph.ldo + 32 * ti + r;
+                                o[0] = s[0]; o[16] = s[1];
+                            }
+                        } else if (n < M) {                                   // P3_MEGA_QKV_ROPE: phi.py:442-453, one new token per row
+                            const int hd = P.hd, half = hd / 2, gpr = hd / 32, n_rope = (P.n_heads + P.n_kv) * gpr;
+                            bf16* row = reinterpret_cast<bf16*>(ph.out) + (size_t)n * ph.ldo;
+                            const int page = P.block_table[(size_t)n * P.bt_stride + past / P3_PAGE];
+                            bf16* kd = reinterpret_cast<bf16*>(P.pool) + (size_t)page * kv_page_elems(P.n_kv, hd) + (size_t)(past % P3_PAGE) * hd;
+                            bf16* vd = kd + (size_t)P.n_kv * P3_PAGE * hd;
+                            if (ti < n_rope) {
+                                const int head = ti / gpr, dd = (ti % gpr) * 16 + r;
+                                const float x1 = bf16_round(s[0]), x2 = bf16_round(s[1]);   // qkv_proj output is bf16 in the reference flow
+                                const size_t tix = (size_t)n * P.tab_bstride + (size_t)past * half + dd;
+                                const float cs = P.cosT[tix], sn = P.sinT[tix];
+                                const bf16 o1 = __float2bfloat16_rn(x1 * cs - x2 * sn), o2 = __float2bfloat16_rn(x2 * cs + x1 * sn);
+                                row[head * hd + dd] = o1;
+                                row[head * hd + half + dd] = o2;
+                                if (head >= P.n_heads) {
+                                    bf16* k = kd + (size_t)(head - P.n_heads) * P3_PAGE * hd;
+                                    k[dd] = o1; k[half + dd] = o2;
+                                }
+                            } else {
+                                const int c0 = 32 * (ti - n_rope);
+#pragma unroll
+                                for (int mt = 0; mt < 2; mt++) {
+                                    const bf16 v = __float2bfloat16_rn(s[mt]);
+                                    const int c = c0 + 16 * mt + r;
+                                    row[(P.n_heads + P.n_kv) * hd + c] = v;
+                                    vd[(size_t)(c / hd) * P3_PAGE * hd + c % hd] = v;
+                                }
+                            }
+                        }
+                    }
+                }
+                red_buf ^= 1;
+            }
+        }
+    }
+
+    // ---- leave the barrier words clean for the next launch (every CTA has passed the last barrier by now)
+    __syncthreads();
+    if (tid == 0 && gridDim.x > 1) {
+        __threadfence();
+        const unsigned old = atomicAdd(P.sync + 1, 1u);
+        if (old == gridDim.x - 1) { P.sync[0] = 0u; P.sync[1] = 0u; __threadfence(); }
+    }
+}
+
+extern "C" int p3_decode_mega_ctas(void) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return sms;
+}
+
+extern "C" int p3_decode_mega(const p3_mega_args* a, cudaStream_t st) {
+    P3_CHECK_ARG(a && a->n_phases >= 1 && a->n_phases <= P3_MEGA_MAX_PHASES, "decode_mega: 1..%d phases", P3_MEGA_MAX_PHASES);
+    P3_CHECK_ARG(a->M >= 1 && a->M <= 8, "decode_mega: M must be in [1,8] (got %d)", a->M);
+    P3_CHECK_ARG(a->sync, "decode_mega: sync words are required");
+    const int sms = p3_decode_mega_ctas();
+    P3_CHECK_ARG(a->n_ctas >= 1 && a->n_ctas <= sms, "decode_mega: n_ctas %d must be in [1, #SM = %d] (all CTAs must be co-resident)", a->n_ctas, sms);
+    for (int i = 0; i < a->n_phases; i++) {
+        const p3_mega_phase& ph = a->ph[i];
+        P3_CHECK_ARG(ph.kind >= P3_MEGA_RESID && ph.kind <= P3_MEGA_F32, "decode_mega: phase %d: unknown kind %d", i, ph.kind);
+        P3_CHECK_ARG(mega_dims_ok(ph.kind, ph.N, ph.K, a->n_heads, a->n_kv, a->hd), "decode_mega: phase %d: unsupported shape N=%d K=%d", i, ph.N, ph.K);
+        P3_CHECK_ARG(ph.wp && ph.x && ph.out && ph.cta_off && ph.tile_ids, "decode_mega: phase %d: null pointer", i);
+        P3_CHECK_ARG(ph.ldx % 4 == 0, "decode_mega: phase %d: ldx must be a multiple of 4", i);
+        P3_CHECK_ARG(ph.max_tiles_per_cta >= 0 && (ph.K <= MG_KBLOCK || ph.max_tiles_per_cta <= MG_MAX_PART),
+                     "decode_mega: phase %d: at most %d tiles per CTA when K > %d", i, MG_MAX_PART, MG_KBLOCK);
+        if (ph.kind == P3_MEGA_QKV_ROPE)
+            P3_CHECK_ARG(a->cosT && a->sinT && a->pool && a->block_table, "decode_mega: QKV phase needs rope tables, pool and block table");
+    }
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
+        P3_CHECK_ARG(e == cudaSuccess, "decode_mega: smem attribute: %s", cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)a->n_ctas); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = MG_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = p3_pdl_enabled() ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, decode_mega_kernel, *a);
+    if (e != cudaSuccess) { p3_set_error("decode_mega: %s", cudaGetErrorString(e)); return -2; }
+    return 0;
+}

@@ -173,6 +173,16 @@ class Phi3B200:
                 gu=lin(w[p + 'mlp.gate_up_proj.weight'], interleave_gate_up), down=lin(w[p + 'mlp.down_proj.weight'])))
         self.norm = d(w['model.norm.weight'])
         self.lm_head = lin(w['lm_head.weight'])
+        # persistent decode-layer kernel (mega.py / decode_mega.cu): a second, stream-order copy of the decoder weights
+        # (7.4 GB at Phi-3.5 sizes; HBM has 180 GB). bf16 weights only; P3_MEGA=0 keeps the per-matrix skinny kernels.
+        self.mega = None
+        import os as _os0
+        if not self.quantize_model and _os0.environ.get('P3_MEGA', '1') != '0':
+            from .mega import MegaDecoder
+            try:
+                self.mega = MegaDecoder(self, w)
+            except ValueError:
+                self.mega = None                      # shapes the kernel does not tile (K not a multiple of 128, ...)
         self.vision = None
         if any(k.startswith('model.vision_embed_tokens') for k in w):
             self._load_vision(w, d)
@@ -358,7 +368,7 @@ class Phi3B200:
 
     # ------------------------------------------------------------------ one decoder pass
     def _forward_tokens(self, ids_dev, B, L, cache, n_beam, write_cache, past, logits_rows, past_dev=None,
-                        n_splits=None, h=None):
+                        n_splits=None, h=None, ws=None):
         """ids_dev int32 [B*L] on device. Returns fp32 logits [B, R, V] (R = L or 1)."""
         st = _stream()
         T, H = B * L, self.H
@@ -379,11 +389,10 @@ class Phi3B200:
         att = torch.empty((T, self.n_heads * self.hd), dtype=torch.bfloat16, device=dev)
         act = torch.empty((T, self.I), dtype=torch.bfloat16, device=dev)
         use_decode_attn = L <= 16 and cache is not None
-        ws = None
         if use_decode_attn:
             if n_splits is None:
                 n_splits = self._splits(cache, B, max(1, (past + PAGE - 1) // PAGE))
-            if n_splits > 1:
+            if n_splits > 1 and ws is None:
                 ws = torch.zeros(_lib.lib().p3_attention_decode_workspace(B, L, self.n_heads, self.hd, n_splits) // 4,
                                  dtype=torch.float32, device=dev)        # zero: holds the split-arrival counters
         qoff, koff, voff = 0, self.n_heads * self.hd * 2, (self.n_heads + self.n_kv) * self.hd * 2
@@ -576,8 +585,10 @@ class DecodeSession:
             # recycled slab: same buffers, same graph -> just reset the device-side state
             self.hist, self.tok, self.step_dev, self.past_dev, self.eos = st['hist'], st['tok'], st['step'], st['past'], st['eos']
             self.n_splits, self.graph, self.launches_per_step = st['n_splits'], st['graph'], st['lps']
+            self.mega_ses, self.ws = st['mega'], st['ws']
             self._reset(first_token)
             return
+        self.mega_ses = None
         self.hist = torch.zeros((B, max_steps + 1), dtype=torch.int32, device=dev)
         self.tok = first_token.clone()
         self.step_dev = torch.ones(1, dtype=torch.int32, device=dev)
@@ -590,6 +601,15 @@ class DecodeSession:
             raise ValueError('KV cache overflow: decode session longer than the cache was sized for')
         tiles = (cache.offset + max_steps + PAGE - 1) // PAGE
         self.n_splits = model._splits(cache, B, tiles)
+        # decode scratch lives outside the captured step: split-KV partials + arrival counters (the kernel leaves the
+        # counters at zero), and the static activation buffers / argument structs of the persistent layer kernel
+        self.ws = None
+        if self.n_splits > 1:
+            self.ws = torch.zeros(_lib.lib().p3_attention_decode_workspace(B, 1, model.n_heads, model.hd, self.n_splits) // 4,
+                                  dtype=torch.float32, device=dev)
+        if model.mega is not None and B <= 8:
+            self.mega_ses = model.mega.session(cache, B)
+            self.mega_ses.bind(self.past_dev)
         if use_graph and B <= 16:
             cur = torch.cuda.current_stream()
             s = torch.cuda.Stream()
@@ -607,7 +627,7 @@ class DecodeSession:
             if sampler is None:
                 cache.slab.session = dict(max_steps=max_steps, offset0=cache.offset, hist=self.hist, tok=self.tok,
                                           step=self.step_dev, past=self.past_dev, eos=self.eos, n_splits=self.n_splits,
-                                          graph=self.graph, lps=self.launches_per_step)
+                                          graph=self.graph, lps=self.launches_per_step, mega=self.mega_ses, ws=self.ws)
 
     def _reset(self, first_token):
         self.hist[:, 0] = first_token
@@ -616,10 +636,45 @@ class DecodeSession:
         self.past_dev.fill_(self.cache.offset)
         self.eos.copy_((first_token == 32007).to(torch.int32))
 
+    def _mega_step(self):
+        """embed -> [qkv] -> 32 x (decode attention -> [o_proj, gate_up, down, next qkv | lm_head]): 2 launches per layer"""
+        m, ms, c, B = self.m, self.mega_ses, self.cache, self.B
+        st = _stream()
+        past = c.offset + self.steps_run
+        call('p3_embed_gather', ptr(m.embed), ptr(self.tok), ptr(ms.h), B, m.H, m.V, ptr(ms.ss0), st)
+        ev = m._ev()
+        ms.launch(0, st)
+        m._ev(ev, 'mega', ms.mega.shapes['qkv'][1] * ms.mega.shapes['qkv'][2] * 2)
+        qp, hb = ms.qkv.data_ptr(), m.n_heads * m.hd * 2
+        koff, voff = hb, (m.n_heads + m.n_kv) * m.hd * 2
+        bt, bts = c.block_table, c.block_table.stride(0)
+        nl = len(m.layers)
+        per_layer = sum(N * K for k, (_, N, K) in ms.mega.shapes.items() if k != 'lm') * 2
+        for li in range(nl):
+            ev = m._ev()
+            if c.quantized and c.n_quant > 0:
+                call('p3_attention_decode_q4', qp, qp + koff, qp + voff, m.qkv_dim, m.qkv_dim, m.qkv_dim, ptr(ms.att),
+                     ms.att.stride(0), B, 1, m.n_heads, m.n_kv, m.hd, m.scale, past, c.n_quant, ptr(c.kv_start), ptr(c.pool[li]),
+                     ptr(c.qcodes[li]), ptr(c.qmeta[li]), ptr(bt), bts, 1, self.n_splits, ptr(self.ws), ptr(self.past_dev),
+                     None, 0, st)
+            else:
+                call('p3_attention_decode', qp, qp + koff, qp + voff, m.qkv_dim, m.qkv_dim, m.qkv_dim, ptr(ms.att),
+                     ms.att.stride(0), B, 1, m.n_heads, m.n_kv, m.hd, m.scale, past, ptr(c.kv_start), ptr(c.pool[li]), ptr(bt),
+                     bts, 1, self.n_splits, ptr(self.ws), ptr(self.past_dev), None, 0, st)
+            m._ev(ev, 'attn', B * past * 2 * m.n_kv * m.hd * 2)
+            ev = m._ev()
+            ms.launch(li + 1, st)
+            qkv_b = ms.mega.shapes['qkv'][1] * ms.mega.shapes['qkv'][2] * 2
+            m._ev(ev, 'mega', per_layer if li + 1 < nl else per_layer - qkv_b + m.V * m.H * 2)
+        return ms.logits.view(B, 1, m.V)
+
     def _one_step(self):
         m = self.m
-        logits = m._forward_tokens(self.tok, self.B, 1, self.cache, 1, True, self.cache.offset + self.steps_run, 'last',
-                                   past_dev=self.past_dev, n_splits=self.n_splits)
+        if self.mega_ses is not None:
+            logits = self._mega_step()
+        else:
+            logits = m._forward_tokens(self.tok, self.B, 1, self.cache, 1, True, self.cache.offset + self.steps_run, 'last',
+                                       past_dev=self.past_dev, n_splits=self.n_splits, ws=self.ws)
         if self.sampler is None:
             call('p3_row_stats', ptr(logits), self.B, m.V, m.V, ptr(self.tok), None, None, 0, None, None, 0, None, None,
                  _stream())

@@ -51,13 +51,25 @@ def _names(cfg, clip_cfg, vision):
     return out
 
 
-def random_weights(cfg, seed=0, device='cpu', clip_cfg=None, vision=None):
+PEAK_ALPHA = 0.01
+
+
+def random_weights(cfg, seed=0, device='cpu', clip_cfg=None, vision=None, init='gpt2'):
     """N(0,sigma) bf16 tensors, GPT-2-style: linear 0.02, residual-writing projections (o_proj,
     down_proj, CLIP out_proj/fc2) 0.02/sqrt(2*n_layers), embedding 1.0, norm gains 1+0.1*N,
     biases/pos 0.1*N, GN separators N(0,1). With the residual scaling the residual stream stays
     O(1) over 32 layers and the random network is not chaotic (a plain 0.02 init amplifies a 1e-3
     perturbation ~25x by layer 32, which says nothing about kernel accuracy); logits have O(1)
-    spread (SURVEY.md §7 hard part 1)."""
+    spread (SURVEY.md §7 hard part 1).
+
+    init='peaked' (the parity checkpoint): identical tensors, except that lm_head is TIED to the embedding through a
+    fixed seeded permutation, lm_head[t] = PEAK_ALPHA * embed[perm[t]]. The residual stream of this init keeps a cosine
+    of ~0.68 with the input embedding through all 32 layers, so every position has ONE logit of ~20 over a N(0, 0.6)
+    background: the top-1 / top-2 margin (~17) is far above the bf16 noise of any correct implementation (~2e-2 of the
+    peak), which makes "greedy ids agree on >= 99 % of positions" a property of the kernels instead of a coin flip at
+    the noise floor. Greedy generation walks the permutation (x -> perm^-1(x)), so the rollout is not a repeated
+    token. The flat 'gpt2' init (median margin 0.18) stays available to measure the noise floor itself."""
+    assert init in ('gpt2', 'peaked')
     if vision is None:
         vision = 'V' in cfg.architectures[0]
     clip_cfg = clip_cfg or CLIP_VIT_L14_336
@@ -76,4 +88,8 @@ def random_weights(cfg, seed=0, device='cpu', clip_cfg=None, vision=None):
         elif kind == 'b':
             t.mul_(0.1)
         w[name] = t.to(torch.bfloat16)
+    if init == 'peaked':
+        perm = torch.randperm(cfg.vocab_size, generator=torch.Generator().manual_seed(seed + 12345))
+        emb = w['model.embed_tokens.weight'].to(torch.float32)
+        w['lm_head.weight'] = (PEAK_ALPHA * emb[perm.to(emb.device)]).to(torch.bfloat16)
     return w

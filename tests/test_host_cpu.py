@@ -186,3 +186,47 @@ def test_weight_quantiser_matches_oracle_and_pack_roundtrip():
                         rec[:, k], rec[:, k + 1] = (wv >> (4 * j)) & 0xF, (wv >> (4 * j + 16)) & 0xF
     assert (rec == c.to(torch.int64)).all()
     assert (meta[..., 0] == s).all() and (meta[..., 1] == b).all()
+
+
+# ------------------------------------------------------------------ persistent decode-layer kernel: host logic
+@pytest.mark.parametrize('kind,N,K,nh,nkv,hd', [(0, 384, 384, 0, 0, 0), (1, 2048, 384, 0, 0, 0), (0, 64, 8192, 0, 0, 0),
+                                                (2, 1152, 384, 4, 4, 96), (3, 640, 384, 0, 0, 0)])
+def test_mega_stream_order_reproduces_the_matmul(kind, N, K, nh, nkv, hd):
+    """pack_reference (mirror of p3_mega_pack) consumed in the kernel's order (mega.emulate_phase: CTA -> K-block -> tile ->
+    warp -> fragment, lane (g,t) pairing a0..a3 with x[n][kbase+16j+4t..]) gives x @ W^T for every tile kind."""
+    import torch
+    import phi3_b200  # noqa
+    from phi3_b200 import mega
+    g = torch.Generator().manual_seed(N + K)
+    W = torch.randn(N, K, generator=g).to(torch.bfloat16)
+    x = torch.randn(5, K, generator=g).to(torch.bfloat16)
+    pk = mega.pack_reference(W, kind, nh, nkv, hd)
+    assert pk.numel() == W.numel()
+    (off, ids, mx), = mega.build_schedule([(kind, N, K)], 7)
+    y = mega.emulate_phase(pk, kind, N, K, x, off, ids, nh, nkv, hd)
+    assert torch.allclose(y, x.float() @ W.float().T, atol=1e-3)
+
+
+def test_mega_schedule_balances_cumulative_bytes():
+    import phi3_b200  # noqa
+    from phi3_b200 import mega
+    phases = [(mega.RESID, 3072, 3072), (mega.SWIGLU, 16384, 3072), (mega.RESID, 3072, 8192), (mega.QKV_ROPE, 9216, 3072)]
+    sched = mega.build_schedule(phases, 148)
+    load = [0] * 148
+    for (kind, N, K), (off, ids, mx) in zip(phases, sched):
+        MT, T, n_kblk, nkb_w = mega.dims(kind, N, K)
+        assert sorted(ids.tolist()) == list(range(T)) and off[-1] == T          # every tile exactly once
+        cost = MT * 16 * K * 2
+        for c in range(148):
+            load[c] += (int(off[c + 1]) - int(off[c])) * cost
+        assert max(load) - min(load) <= cost                                    # within one tile at every phase boundary
+        assert K <= mega.KBLOCK or mx <= mega.MAX_PART
+    assert sum(load) == sum(N * K * 2 for _, N, K in phases)
+    assert max(load) / (sum(load) / 148) < 1.06
+
+
+def test_mega_args_layout_matches_header():
+    import ctypes
+    import phi3_b200  # noqa
+    from phi3_b200 import mega
+    assert ctypes.sizeof(mega.MegaPhase) == 104 and ctypes.sizeof(mega.MegaArgs) == 512    # static_assert in decode_mega.cu
