@@ -105,6 +105,15 @@ extern "C" int p3_mega_pack(const void* W, void* out, int kind, int N, int K, in
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------------------------
 static_assert(sizeof(p3_mega_phase) == 104 && sizeof(p3_mega_args) == 512, "p3_mega_args layout is mirrored by ctypes in mega.py");
+#include <type_traits>
+#include <utility>
+template <int N, typename Fn, int... Is>
+__device__ __forceinline__ void mg_for_slots_impl(Fn&& fn, std::integer_sequence<int, Is...>) {
+    (fn(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, typename Fn>
+__device__ __forceinline__ void mg_for_slots(Fn&& fn) { mg_for_slots_impl<N>(fn, std::make_integer_sequence<int, N>{}); }
+
 struct MgDerived { int MT, T, n_kblk, nkb_w; uint32_t seg; };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
@@ -129,12 +138,17 @@ __device__ __forceinline__ void mg_grid_barrier(unsigned* ctr, unsigned target) 
     __syncthreads();
 }
 
-struct MgCursor { int p, kb, li; uint32_t off; };          // li: index into this CTA's tile list of phase p
+#define MG_TILE_CACHE 32               // per-phase tile ids of this CTA kept in shared memory (more: read from global)
+
+struct MgCursor { int p, kb, li; uint32_t rem; const uint8_t* src; };     // li: index into this CTA's tile list of phase p
 
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid_constant__ p3_mega_args P) {
     extern __shared__ __align__(1024) uint8_t mg_smem[];
     __shared__ MgDerived s_d[P3_MEGA_MAX_PHASES];
     __shared__ int s_first[P3_MEGA_MAX_PHASES], s_cnt[P3_MEGA_MAX_PHASES];
+    __shared__ int s_tiles[P3_MEGA_MAX_PHASES][MG_TILE_CACHE];
+    __shared__ const uint8_t* s_wp[P3_MEGA_MAX_PHASES];
+    __shared__ float s_ss[MG_WARPS][8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int cta = blockIdx.x;
     const int M = P.M;
@@ -145,15 +159,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     float* part = reinterpret_cast<float*>(mg_smem + MG_RING_BYTES + MG_RED_BYTES);
     const uint32_t bars = smem_u32(mg_smem + MG_RING_BYTES + MG_RED_BYTES + MG_PART_BYTES) + warp * (MG_RSLOTS * 8);
 
-    if (tid < P.n_phases) {
-        const p3_mega_phase& ph = P.ph[tid];
-        MgDerived d;
-        d.MT = mg_mt(ph.kind); d.T = ph.N / (16 * d.MT);
-        d.n_kblk = (ph.K + MG_KBLOCK - 1) / MG_KBLOCK; d.nkb_w = ph.K / (d.n_kblk * 128);
-        d.seg = (uint32_t)d.nkb_w * d.MT * 512u;
-        s_d[tid] = d;
-        s_first[tid] = ph.cta_off[cta];
-        s_cnt[tid] = ph.cta_off[cta + 1] - ph.cta_off[cta];
+    if (warp < P.n_phases) {                                    // warp w caches the schedule of phase w
+        const p3_mega_phase& ph = P.ph[warp];
+        const int first = ph.cta_off[cta], cnt = ph.cta_off[cta + 1] - first;
+        if (lane == 0) {
+            MgDerived d;
+            d.MT = mg_mt(ph.kind); d.T = ph.N / (16 * d.MT);
+            d.n_kblk = (ph.K + MG_KBLOCK - 1) / MG_KBLOCK; d.nkb_w = ph.K / (d.n_kblk * 128);
+            d.seg = (uint32_t)d.nkb_w * d.MT * 512u;
+            s_d[warp] = d;
+            s_first[warp] = first;
+            s_cnt[warp] = cnt;
+            s_wp[warp] = reinterpret_cast<const uint8_t*>(ph.wp);
+        }
+        if (lane < cnt && lane < MG_TILE_CACHE) s_tiles[warp][lane] = ph.tile_ids[first + lane];
     }
     if (lane == 0) {
 #pragma unroll
@@ -162,41 +181,41 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     }
     __syncthreads();
     pdl_trigger();
+    auto tile_of = [&](int p, int li) -> int {
+        return li < MG_TILE_CACHE ? s_tiles[p][li] : P.ph[p].tile_ids[s_first[p] + li];
+    };
 
     // ---- producer side of this warp's ring: walks (phase, K-block, tile) exactly like the consumer below
     const uint64_t pol = l2_evict_first_policy();
-    MgCursor pc{0, 0, 0, 0};
-    uint32_t pn = 0;                                            // slot loads issued so far
+    MgCursor pc{0, 0, -1, 0u, nullptr};
+    uint32_t pslot = 0;                                         // ring slot of the next load
     auto issue_next = [&]() {                                   // all lanes walk the cursor; lane 0 issues the copy
-        while (pc.p < P.n_phases) {
+        if (pc.rem == 0) {                                      // next segment = next tile of this K-block / next K-block / next phase
+            for (;;) {
+                if (pc.p >= P.n_phases) return;
+                if (++pc.li < s_cnt[pc.p]) break;
+                pc.li = -1;
+                if (++pc.kb >= s_d[pc.p].n_kblk) { pc.kb = 0; pc.p++; }
+            }
             const MgDerived d = s_d[pc.p];
-            if (pc.li >= s_cnt[pc.p]) {                         // this K-block of this phase is exhausted
-                pc.li = 0; pc.off = 0;
-                if (++pc.kb >= d.n_kblk) { pc.kb = 0; pc.p++; }
-                continue;
-            }
-            const p3_mega_phase& ph = P.ph[pc.p];
-            const int ti = ph.tile_ids[s_first[pc.p] + pc.li];
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(ph.wp) +
-                                 ((size_t)((size_t)pc.kb * d.T + ti) * MG_WARPS + warp) * d.seg + pc.off;
-            const uint32_t bytes = min((uint32_t)MG_SLOT, d.seg - pc.off);
-            if (lane == 0) {
-                const uint32_t slot = pn % MG_RSLOTS;
-                mbar_expect_tx(bars + slot * 8, bytes);
-                bulk_g2s(ring + slot * MG_SLOT, src, bytes, bars + slot * 8, pol);
-            }
-            pn++;
-            pc.off += bytes;
-            if (pc.off >= d.seg) { pc.off = 0; pc.li++; }
-            return;
+            pc.src = s_wp[pc.p] + ((size_t)(pc.kb * d.T + tile_of(pc.p, pc.li)) * MG_WARPS + warp) * d.seg;
+            pc.rem = d.seg;
         }
+        const uint32_t bytes = min((uint32_t)MG_SLOT, pc.rem);
+        if (lane == 0) {
+            mbar_expect_tx(bars + pslot * 8, bytes);
+            bulk_g2s(ring + pslot * MG_SLOT, pc.src, bytes, bars + pslot * 8, pol);
+        }
+        pslot = (pslot + 1 == MG_RSLOTS) ? 0 : pslot + 1;
+        pc.src += bytes;
+        pc.rem -= bytes;
     };
 #pragma unroll 1
     for (int s = 0; s < MG_RSLOTS; s++) issue_next();           // weights are immutable: stream them before the dependency wait
     pdl_wait();
 
     const int past = P.past_dev ? *P.past_dev : P.past;
-    uint32_t cn = 0;                                            // slot loads consumed so far
+    uint32_t cslot = 0, cpar = 0;                               // consumer ring position: slot and its phase parity
     unsigned n_bar = 0;
     int red_buf = 0;
 
@@ -205,29 +224,46 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
         const p3_mega_phase& ph = P.ph[p];
         const MgDerived d = s_d[p];
         const int n_mine = s_cnt[p];
-        if (n_mine == 0) continue;
+        if (n_mine == 0) continue;                              // (uniform per CTA)
         const bf16* X = reinterpret_cast<const bf16*>(ph.x);
         const bf16* NW = reinterpret_cast<const bf16*>(ph.norm_w);
 
-        // ---- RMSNorm scale of row g (phi.py:478-479): from the producer's per-tile partial sums, fixed order
+        // ---- RMSNorm scale of row g (phi.py:478-479) from the producer's per-tile partial sums; the CTA sums them
+        // cooperatively in a fixed order (deterministic): thread -> partial c = tid/2 (+128 i), rows 4q..4q+3
         float rs = 1.f;
         if (NW) {
-            float s = 0.f;
-            if (g < M) {
-                if (ph.ss_in) {
-                    for (int c = t; c < ph.n_ss_in; c += 4) s += __ldcg(ph.ss_in + (size_t)c * 16 + g);
-                } else {
-                    const uint2* xr = reinterpret_cast<const uint2*>(X + (size_t)g * ph.ldx);
-                    for (int c = t; c < ph.K / 4; c += 4) {
-                        const uint2 v = __ldcg(xr + c);
-                        const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y);
-                        s += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int q = tid & 1;
+            if (ph.ss_in) {
+                for (int c = tid >> 1; c < ph.n_ss_in; c += MG_THREADS / 2) {
+                    const float4 v = __ldcg(reinterpret_cast<const float4*>(ph.ss_in + (size_t)c * 16 + 4 * q));
+                    a4.x += v.x; a4.y += v.y; a4.z += v.z; a4.w += v.w;
+                }
+            } else {                                            // no partials: thread -> 8-element chunks of x
+                for (int c = tid >> 1; c < ph.K / 8; c += MG_THREADS / 2) {
+                    float* av = reinterpret_cast<float*>(&a4);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (4 * q + i < M) {
+                            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(X + (size_t)(4 * q + i) * ph.ldx) + c);
+                            const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) { const float2 f = unpack_bf16(u[k]); av[i] += f.x * f.x + f.y * f.y; }
+                        }
                     }
                 }
             }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            rs = rsqrtf(s / (float)ph.K + P.eps);
+#pragma unroll
+            for (int o = 2; o < 32; o <<= 1) {
+                a4.x += __shfl_xor_sync(0xffffffffu, a4.x, o); a4.y += __shfl_xor_sync(0xffffffffu, a4.y, o);
+                a4.z += __shfl_xor_sync(0xffffffffu, a4.z, o); a4.w += __shfl_xor_sync(0xffffffffu, a4.w, o);
+            }
+            if (lane < 2) *reinterpret_cast<float4*>(&s_ss[warp][4 * lane]) = a4;
+            __syncthreads();
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < MG_WARPS; w++) sum += s_ss[w][g];
+            rs = rsqrtf(sum / (float)ph.K + P.eps);
         }
 
         for (int kb = 0; kb < d.n_kblk; kb++) {
@@ -244,7 +280,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
 #pragma unroll
                 for (int j = 0; j < MG_XF; j++) {
                     if (j < d.nkb_w) {
-                        const uint2 w = *reinterpret_cast<const uint2*>(NW + kbase + 16 * j);
+                        const uint2 w = __ldg(reinterpret_cast<const uint2*>(NW + kbase + 16 * j));
                         float2 a = unpack_bf16(xf[j][0]), b = unpack_bf16(xf[j][1]);
                         const float2 wa = unpack_bf16(w.x), wb = unpack_bf16(w.y);
                         xf[j][0] = pack_bf16(a.x * rs * wa.x, a.y * rs * wa.y);
@@ -253,36 +289,60 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                 }
             }
             const bool last_kb = (kb == d.n_kblk - 1);
+            const int F = d.nkb_w * d.MT;                       // 512-byte fragments per item
 
             for (int li = 0; li < n_mine; li++) {
-                const int ti = ph.tile_ids[s_first[p] + li];
+                const int ti = tile_of(p, li);
+                // RESID epilogue: the residual value this thread will add is known up front -> fetch it under the MMAs
+                float resid_pref = 0.f;
+                if (last_kb && ph.kind == P3_MEGA_RESID && tid < 128 && (tid >> 4) < M) {
+                    const unsigned short raw = __ldcg(reinterpret_cast<const unsigned short*>(ph.out) +
+                                                      (size_t)(tid >> 4) * ph.ldo + 16 * ti + (tid & 15));
+                    resid_pref = __bfloat162float(__ushort_as_bfloat16(raw));
+                }
                 float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                const int F = d.nkb_w * d.MT;                   // 512-byte fragments of this item
-                // ---- stream the item: one ld.shared.v4 + one MMA per fragment
-                auto release = [&]() {                          // slot drained by every lane: refill it one ring ahead
-                    __syncwarp();
-                    cn++;
+                // ---- stream the item slot by slot: wait, 8 x ld.shared.v4, 8 x MMA, hand the slot back (refill one ring ahead).
+                // MT == 2: fragment f = 2j + mt feeds acc[mt]. MT == 1: fragment f = j feeds acc[j & 1] (two MMA chains).
+                auto slot_group = [&](auto S_, auto MT2_) {
+                    constexpr int S = decltype(S_)::value;
+                    constexpr bool MT2 = decltype(MT2_)::value;
+                    if (8 * S >= F) return;
+                    mbar_wait(bars + cslot * 8, cpar);
+                    const uint8_t* sb = ring_g + cslot * MG_SLOT + lane * 16;
+                    if (8 * S + 8 <= F) {                       // full slot
+                        uint4 a[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) a[i] = *reinterpret_cast<const uint4*>(sb + i * 512);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int f = 8 * S + i, j = MT2 ? f / 2 : f;
+                            const uint32_t av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+                            mma_bf16_16816(acc[f & 1], av, xf[j][0], xf[j][1]);
+                        }
+                    } else {                                    // partial last slot of the item (small K only)
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int f = 8 * S + i, j = MT2 ? f / 2 : f;
+                            if (f < F) {
+                                const uint4 a = *reinterpret_cast<const uint4*>(sb + i * 512);
+                                const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+                                mma_bf16_16816(acc[f & 1], av, xf[j][0], xf[j][1]);
+                            }
+                        }
+                    }
+                    __syncwarp();                               // every lane has its fragments in registers: slot is free
+                    if (++cslot == MG_RSLOTS) { cslot = 0; cpar ^= 1; }
                     issue_next();
                 };
-                auto frag = [&](int f, int j, int mt) {         // f, j, mt are compile-time after unrolling
-                    const uint32_t slot = cn % MG_RSLOTS;
-                    if ((f & 7) == 0) mbar_wait(bars + slot * 8, (cn / MG_RSLOTS) & 1);
-                    // plain load: free to be scheduled ahead of the MMAs, fenced by the memory clobbers of the mbarrier ops
-                    const uint4 a = *reinterpret_cast<const uint4*>(ring_g + slot * MG_SLOT + (f & 7) * 512 + lane * 16);
-                    const uint32_t av[4] = {a.x, a.y, a.z, a.w};
-                    mma_bf16_16816(acc[mt], av, xf[j][0], xf[j][1]);
-                    if ((f & 7) == 7) release();
-                };
+                if (d.MT == 1) {
+                    mg_for_slots<MG_XF / 8>([&](auto S_) { slot_group(S_, std::false_type{}); });
+                } else {
+                    mg_for_slots<MG_XF / 4>([&](auto S_) { slot_group(S_, std::true_type{}); });
+                }
                 if (d.MT == 1) {
 #pragma unroll
-                    for (int j = 0; j < MG_XF; j++)
-                        if (j < d.nkb_w) frag(j, j, 0);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < MG_XF; j++)
-                        if (j < d.nkb_w) { frag(2 * j, j, 0); frag(2 * j + 1, j, 1); }
+                    for (int e = 0; e < 4; e++) acc[0][e] += acc[1][e];
                 }
-                if (F & 7) release();                           // partial last slot of the item (segments never share a slot)
                 // ---- cross-warp reduction (K is split over the 8 warps) + epilogue by warps 0-3
                 float* rb = red + (size_t)red_buf * (MG_WARPS * 2 * MG_RED_STRIDE) + (size_t)warp * (2 * MG_RED_STRIDE);
 #pragma unroll
@@ -314,11 +374,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                             bf16* out = reinterpret_cast<bf16*>(ph.out);
                             float sq = 0.f;
                             if (n < M) {
-                                const size_t off = (size_t)n * ph.ldo + 16 * ti + r;
-                                const unsigned short raw = __ldcg(reinterpret_cast<const unsigned short*>(out) + off);
-                                const float rv = __bfloat162float(__ushort_as_bfloat16(raw));
-                                const bf16 hv = __float2bfloat16_rn(rv + bf16_round(s[0]));
-                                out[off] = hv;
+                                const bf16 hv = __float2bfloat16_rn(resid_pref + bf16_round(s[0]));
+                                out[(size_t)n * ph.ldo + 16 * ti + r] = hv;
                                 sq = __bfloat162float(hv) * __bfloat162float(hv);
                             }
 #pragma unroll
