@@ -43,6 +43,13 @@
 
 __host__ __device__ __forceinline__ int mg_mt(int kind) { return kind == P3_MEGA_RESID ? 1 : 2; }
 
+// k offset (inside a warp's K slice) of the 4 consecutive elements lane t contributes to k block j. Blocks are paired so that
+// one 16-byte load of X serves two MMAs: pair p = j/2 covers 32 k, lane t owns [32p + 8t, +8), first half -> block 2p,
+// second half -> block 2p+1; an unpaired last block (odd nkb_w) owns [16j + 4t, +4).
+__host__ __device__ __forceinline__ int mg_koff(int j, int t, int nkb_w) {
+    return (j | 1) < nkb_w ? 32 * (j >> 1) + 8 * t + 4 * (j & 1) : 16 * j + 4 * t;
+}
+
 // first W row of m-tile `mt` of tile `ti` (the same map drives p3_mega_pack and the epilogues)
 __host__ __device__ __forceinline__ int mg_tile_row(int kind, int ti, int mt, int N, int n_heads, int n_kv, int hd) {
     if (kind == P3_MEGA_RESID) return 16 * ti;
@@ -57,9 +64,9 @@ __host__ __device__ __forceinline__ int mg_tile_row(int kind, int ti, int mt, in
 
 // ------------------------------------------------------------------------------------------------------------------
 // p3_mega_pack: W [N, K] bf16 (nn.Linear layout) -> stream order [kb][tile][warp][j][mt][lane][8 bf16]
-// lane (g, t) of k block j holds {W[g][4t,4t+1], W[g+8][4t,4t+1], W[g][4t+2,4t+3], W[g+8][4t+2,4t+3]} = a0..a3 of the
-// m16n8k16 A fragment under the k permutation (logical 2t+e -> 4t+e, logical 2t+8+e -> 4t+2+e) that lets the X operand
-// be fetched with one 8-byte load per lane and k block.
+// lane (g, t) of k block j holds {W[g][k,k+1], W[g+8][k,k+1], W[g][k+2,k+3], W[g+8][k+2,k+3]}, k = mg_koff(j, t), = a0..a3 of
+// the m16n8k16 A fragment under a k permutation (logical 2t+e -> k+e, logical 2t+8+e -> k+2+e) that lets the X operand of
+// two k blocks be fetched with one 16-byte load per lane.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void mega_pack_kernel(const bf16* __restrict__ W, uint4* __restrict__ out, int kind, int N, int K, int n_heads,
                                  int n_kv, int hd, int64_t total) {
@@ -75,7 +82,7 @@ __global__ void mega_pack_kernel(const bf16* __restrict__ W, uint4* __restrict__
         const int kb = (int)r;
         const int g = lane >> 2, t = lane & 3;
         const int row0 = mg_tile_row(kind, ti, mt, N, n_heads, n_kv, hd) + g;
-        const int k0 = ((kb * MG_WARPS + warp) * nkb_w + j) * 16 + 4 * t;
+        const int k0 = (kb * MG_WARPS + warp) * nkb_w * 16 + mg_koff(j, t, nkb_w);
         const uint2 lo = *reinterpret_cast<const uint2*>(W + (size_t)row0 * K + k0);          // W[g][4t..4t+3]
         const uint2 hi = *reinterpret_cast<const uint2*>(W + (size_t)(row0 + 8) * K + k0);    // W[g+8][4t..4t+3]
         out[i] = make_uint4(lo.x, hi.x, lo.y, hi.y);
@@ -122,25 +129,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ float mg_silu(float x) { return x / (1.f + __expf(-x)); }
 
-// grid-wide barrier over a monotonic counter (all CTAs are co-resident: grid <= #SM, 1 CTA/SM)
-__device__ __forceinline__ void mg_grid_barrier(unsigned* ctr, unsigned target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        unsigned v, spins = 0;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-            if (v < target && ++spins > (1u << 26)) __trap();      // a CTA never arrived: fail loudly instead of hanging the GPU
-        } while (v < target);
-        __threadfence();
-    }
-    __syncthreads();
-}
-
 #define MG_TILE_CACHE 32               // per-phase tile ids of this CTA kept in shared memory (more: read from global)
+#define MG_PF_AHEAD 10                 // L2 prefetch runs this many 4 KB slot loads ahead of the ring (per warp: 40 KB; 47 MB per GPU)
 
 struct MgCursor { int p, kb, li; uint32_t rem; const uint8_t* src; };     // li: index into this CTA's tile list of phase p
+
+__device__ __forceinline__ void mg_arrive(unsigned* ctr) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+}
 
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid_constant__ p3_mega_args P) {
     extern __shared__ __align__(1024) uint8_t mg_smem[];
@@ -149,6 +145,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     __shared__ int s_tiles[P3_MEGA_MAX_PHASES][MG_TILE_CACHE];
     __shared__ const uint8_t* s_wp[P3_MEGA_MAX_PHASES];
     __shared__ float s_ss[MG_WARPS][8];
+    __shared__ __align__(16) bf16 s_nw[MG_WARPS][MG_XF * 16];    // next phase's RMSNorm gains, this warp's K slice
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int cta = blockIdx.x;
     const int M = P.M;
@@ -184,34 +181,66 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     auto tile_of = [&](int p, int li) -> int {
         return li < MG_TILE_CACHE ? s_tiles[p][li] : P.ph[p].tile_ids[s_first[p] + li];
     };
-
-    // ---- producer side of this warp's ring: walks (phase, K-block, tile) exactly like the consumer below
-    const uint64_t pol = l2_evict_first_policy();
-    MgCursor pc{0, 0, -1, 0u, nullptr};
-    uint32_t pslot = 0;                                         // ring slot of the next load
-    auto issue_next = [&]() {                                   // all lanes walk the cursor; lane 0 issues the copy
-        if (pc.rem == 0) {                                      // next segment = next tile of this K-block / next K-block / next phase
-            for (;;) {
-                if (pc.p >= P.n_phases) return;
-                if (++pc.li < s_cnt[pc.p]) break;
-                pc.li = -1;
-                if (++pc.kb >= s_d[pc.p].n_kblk) { pc.kb = 0; pc.p++; }
-            }
-            const MgDerived d = s_d[pc.p];
-            pc.src = s_wp[pc.p] + ((size_t)(pc.kb * d.T + tile_of(pc.p, pc.li)) * MG_WARPS + warp) * d.seg;
-            pc.rem = d.seg;
-        }
-        const uint32_t bytes = min((uint32_t)MG_SLOT, pc.rem);
-        if (lane == 0) {
-            mbar_expect_tx(bars + pslot * 8, bytes);
-            bulk_g2s(ring + pslot * MG_SLOT, pc.src, bytes, bars + pslot * 8, pol);
-        }
-        pslot = (pslot + 1 == MG_RSLOTS) ? 0 : pslot + 1;
-        pc.src += bytes;
-        pc.rem -= bytes;
+    // the RMSNorm gains of phase pn (immutable) are staged in shared memory BEFORE the barrier that opens the phase
+    auto stage_norm_w = [&](int pn) {
+        if (pn >= P.n_phases || !P.ph[pn].norm_w || s_d[pn].n_kblk != 1) return;
+        const int kpw = s_d[pn].nkb_w * 16;
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.ph[pn].norm_w) + warp * kpw);
+        for (int i = lane; i < kpw / 8; i += 32) reinterpret_cast<uint4*>(s_nw[warp])[i] = __ldg(src + i);
+        __syncwarp();
     };
+
+    // ---- producer side of this warp's ring: two cursors walk (phase, K-block, tile) exactly like the consumer below:
+    // `pc` issues the bulk copies into the ring, `lc` runs MG_PF_AHEAD slot loads further ahead and only pulls lines into L2,
+    // so HBM keeps streaming (into L2) while the consumers sit in a grid barrier with a full ring.
+    const uint64_t pol = l2_evict_first_policy();
+    auto advance = [&](MgCursor& c, uint32_t& bytes) -> const uint8_t* {     // next <= 4 KB piece of this warp's stream (or nullptr)
+        if (c.rem == 0) {                                       // next segment = next tile of this K-block / next K-block / next phase
+            for (;;) {
+                if (c.p >= P.n_phases) return nullptr;
+                if (++c.li < s_cnt[c.p]) break;
+                c.li = -1;
+                if (++c.kb >= s_d[c.p].n_kblk) { c.kb = 0; c.p++; }
+            }
+            const MgDerived d = s_d[c.p];
+            c.src = s_wp[c.p] + ((size_t)(c.kb * d.T + tile_of(c.p, c.li)) * MG_WARPS + warp) * d.seg;
+            c.rem = d.seg;
+        }
+        bytes = min((uint32_t)MG_SLOT, c.rem);
+        const uint8_t* src = c.src;
+        c.src += bytes;
+        c.rem -= bytes;
+        return src;
+    };
+    MgCursor pc{0, 0, -1, 0u, nullptr}, lc{0, 0, -1, 0u, nullptr};
+    uint32_t pslot = 0;                                         // ring slot of the next load
+    auto issue_next = [&]() {                                   // all lanes walk the cursors; lane 0 issues
+        uint32_t bytes;
+        const uint8_t* src = advance(pc, bytes);
+        if (src) {
+            if (lane == 0) {
+                mbar_expect_tx(bars + pslot * 8, bytes);
+                bulk_g2s(ring + pslot * MG_SLOT, src, bytes, bars + pslot * 8, pol);
+            }
+            pslot = (pslot + 1 == MG_RSLOTS) ? 0 : pslot + 1;
+        }
+        const uint8_t* l2 = advance(lc, bytes);
+        if (l2 && lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(l2), "r"(bytes) : "memory");
+    };
+    {   // put lc MG_PF_AHEAD loads ahead: the first MG_RSLOTS pieces go straight to the ring, the next MG_PF_AHEAD to L2
+        uint32_t bytes;
 #pragma unroll 1
-    for (int s = 0; s < MG_RSLOTS; s++) issue_next();           // weights are immutable: stream them before the dependency wait
+        for (int s = 0; s < MG_RSLOTS; s++) advance(lc, bytes);
+#pragma unroll 1
+        for (int s = 0; s < MG_PF_AHEAD; s++) {
+            const uint8_t* l2 = advance(lc, bytes);
+            if (l2 && lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(l2), "r"(bytes) : "memory");
+        }
+        // weights are immutable: stream them before the dependency wait. (issue_next also moves lc by one each time.)
+#pragma unroll 1
+        for (int s = 0; s < MG_RSLOTS; s++) issue_next();
+    }
+    stage_norm_w(0);
     pdl_wait();
 
     const int past = P.past_dev ? *P.past_dev : P.past;
@@ -220,74 +249,115 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     int red_buf = 0;
 
     for (int p = 0; p < P.n_phases; p++) {
-        if (p > 0) mg_grid_barrier(P.sync, ++n_bar * gridDim.x);
+        if (p > 0) {                                            // grid barrier: everything phase p reads has been written
+            __syncthreads();
+            if (tid == 0) {
+                mg_arrive(P.sync);
+                const unsigned target = ++n_bar * gridDim.x;
+                unsigned v, spins = 0;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.sync) : "memory");
+                    if (v < target && ++spins > (1u << 26)) __trap();      // a CTA never arrived: fail loudly instead of hanging the GPU
+                } while (v < target);
+            }
+            __syncthreads();
+        }
         const p3_mega_phase& ph = P.ph[p];
         const MgDerived d = s_d[p];
         const int n_mine = s_cnt[p];
-        if (n_mine == 0) continue;                              // (uniform per CTA)
+        if (n_mine == 0) { stage_norm_w(p + 1); continue; }     // (uniform per CTA)
         const bf16* X = reinterpret_cast<const bf16*>(ph.x);
         const bf16* NW = reinterpret_cast<const bf16*>(ph.norm_w);
+        const int n_pair = d.nkb_w >> 1;
 
-        // ---- RMSNorm scale of row g (phi.py:478-479) from the producer's per-tile partial sums; the CTA sums them
-        // cooperatively in a fixed order (deterministic): thread -> partial c = tid/2 (+128 i), rows 4q..4q+3
-        float rs = 1.f;
-        if (NW) {
-            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int q = tid & 1;
-            if (ph.ss_in) {
-                for (int c = tid >> 1; c < ph.n_ss_in; c += MG_THREADS / 2) {
-                    const float4 v = __ldcg(reinterpret_cast<const float4*>(ph.ss_in + (size_t)c * 16 + 4 * q));
-                    a4.x += v.x; a4.y += v.y; a4.z += v.z; a4.w += v.w;
+        for (int kb = 0; kb < d.n_kblk; kb++) {
+            // ---- this warp's X fragments for the K-block, in registers: one 16-byte L2 load per pair of k blocks
+            uint32_t xf[MG_XF][2];
+            const int kbase = (kb * MG_WARPS + warp) * d.nkb_w * 16;
+            const bf16* xrow = X + (size_t)g * ph.ldx + kbase;
+#pragma unroll
+            for (int pr = 0; pr < MG_XF / 2; pr++) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (pr < n_pair && g < M) v = __ldcg(reinterpret_cast<const uint4*>(xrow + 32 * pr + 8 * t));
+                xf[2 * pr][0] = v.x; xf[2 * pr][1] = v.y; xf[2 * pr + 1][0] = v.z; xf[2 * pr + 1][1] = v.w;
+            }
+            if (d.nkb_w & 1) {                                  // unpaired last k block (small K only)
+                const int j = d.nkb_w - 1;
+                uint2 v = make_uint2(0u, 0u);
+                if (g < M) v = __ldcg(reinterpret_cast<const uint2*>(xrow + 16 * j + 4 * t));
+#pragma unroll
+                for (int jj = 0; jj < MG_XF; jj += 2)
+                    if (jj == j) { xf[jj][0] = v.x; xf[jj][1] = v.y; }
+            }
+            if (NW) {
+                // ---- RMSNorm (phi.py:478-479): rs of row g from the producer's per-tile partial sums, summed by the CTA in a
+                // fixed order (deterministic): thread -> partial c = tid/2 (+128 i), rows 4q..4q+3. The X loads above are in flight.
+                float rs = 1.f;
+                if (kb == 0) {
+                    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int q = tid & 1;
+                    if (ph.ss_in) {
+                        for (int c = tid >> 1; c < ph.n_ss_in; c += MG_THREADS / 2) {
+                            const float4 v = __ldcg(reinterpret_cast<const float4*>(ph.ss_in + (size_t)c * 16 + 4 * q));
+                            a4.x += v.x; a4.y += v.y; a4.z += v.z; a4.w += v.w;
+                        }
+                    } else {                                    // no partials: thread -> 8-element chunks of x
+                        for (int c = tid >> 1; c < ph.K / 8; c += MG_THREADS / 2) {
+                            float* av = reinterpret_cast<float*>(&a4);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                if (4 * q + i < M) {
+                                    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(X + (size_t)(4 * q + i) * ph.ldx) + c);
+                                    const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+                                    for (int k = 0; k < 4; k++) { const float2 f = unpack_bf16(u[k]); av[i] += f.x * f.x + f.y * f.y; }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 2; o < 32; o <<= 1) {
+                        a4.x += __shfl_xor_sync(0xffffffffu, a4.x, o); a4.y += __shfl_xor_sync(0xffffffffu, a4.y, o);
+                        a4.z += __shfl_xor_sync(0xffffffffu, a4.z, o); a4.w += __shfl_xor_sync(0xffffffffu, a4.w, o);
+                    }
+                    if (lane < 2) *reinterpret_cast<float4*>(&s_ss[warp][4 * lane]) = a4;
+                    __syncthreads();
                 }
-            } else {                                            // no partials: thread -> 8-element chunks of x
-                for (int c = tid >> 1; c < ph.K / 8; c += MG_THREADS / 2) {
-                    float* av = reinterpret_cast<float*>(&a4);
+                float sum = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        if (4 * q + i < M) {
-                            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(X + (size_t)(4 * q + i) * ph.ldx) + c);
-                            const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+                for (int w = 0; w < MG_WARPS; w++) sum += s_ss[w][g];
+                rs = rsqrtf(sum / (float)ph.K + P.eps);
+                const bool staged = (d.n_kblk == 1);
+                const bf16* nwg = NW + kbase;
 #pragma unroll
-                            for (int k = 0; k < 4; k++) { const float2 f = unpack_bf16(u[k]); av[i] += f.x * f.x + f.y * f.y; }
+                for (int pr = 0; pr < MG_XF / 2; pr++) {
+                    if (pr < n_pair) {
+                        const uint4 w = staged ? *reinterpret_cast<const uint4*>(&s_nw[warp][32 * pr + 8 * t])
+                                               : __ldg(reinterpret_cast<const uint4*>(nwg + 32 * pr + 8 * t));
+                        const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            uint32_t& xr = xf[2 * pr + (e >> 1)][e & 1];
+                            const float2 a = unpack_bf16(xr), ww = unpack_bf16(wv[e]);
+                            xr = pack_bf16(a.x * rs * ww.x, a.y * rs * ww.y);
                         }
                     }
                 }
-            }
+                if (d.nkb_w & 1) {
+                    const int j = d.nkb_w - 1;
+                    const uint2 w = staged ? *reinterpret_cast<const uint2*>(&s_nw[warp][16 * j + 4 * t])
+                                           : __ldg(reinterpret_cast<const uint2*>(nwg + 16 * j + 4 * t));
 #pragma unroll
-            for (int o = 2; o < 32; o <<= 1) {
-                a4.x += __shfl_xor_sync(0xffffffffu, a4.x, o); a4.y += __shfl_xor_sync(0xffffffffu, a4.y, o);
-                a4.z += __shfl_xor_sync(0xffffffffu, a4.z, o); a4.w += __shfl_xor_sync(0xffffffffu, a4.w, o);
-            }
-            if (lane < 2) *reinterpret_cast<float4*>(&s_ss[warp][4 * lane]) = a4;
-            __syncthreads();
-            float sum = 0.f;
-#pragma unroll
-            for (int w = 0; w < MG_WARPS; w++) sum += s_ss[w][g];
-            rs = rsqrtf(sum / (float)ph.K + P.eps);
-        }
-
-        for (int kb = 0; kb < d.n_kblk; kb++) {
-            // ---- this warp's X fragments for the K-block: [kbase, kbase + 16 nkb_w), (RMSNorm applied), in registers
-            uint32_t xf[MG_XF][2];
-            const int kbase = (kb * MG_WARPS + warp) * d.nkb_w * 16 + 4 * t;
-#pragma unroll
-            for (int j = 0; j < MG_XF; j++) {
-                uint2 v = make_uint2(0u, 0u);
-                if (j < d.nkb_w && g < M) v = __ldcg(reinterpret_cast<const uint2*>(X + (size_t)g * ph.ldx + kbase + 16 * j));
-                xf[j][0] = v.x; xf[j][1] = v.y;
-            }
-            if (NW) {
-#pragma unroll
-                for (int j = 0; j < MG_XF; j++) {
-                    if (j < d.nkb_w) {
-                        const uint2 w = __ldg(reinterpret_cast<const uint2*>(NW + kbase + 16 * j));
-                        float2 a = unpack_bf16(xf[j][0]), b = unpack_bf16(xf[j][1]);
-                        const float2 wa = unpack_bf16(w.x), wb = unpack_bf16(w.y);
-                        xf[j][0] = pack_bf16(a.x * rs * wa.x, a.y * rs * wa.y);
-                        xf[j][1] = pack_bf16(b.x * rs * wb.x, b.y * rs * wb.y);
-                    }
+                    for (int jj = 0; jj < MG_XF; jj += 2)
+                        if (jj == j) {
+                            const float2 a = unpack_bf16(xf[jj][0]), b = unpack_bf16(xf[jj][1]);
+                            const float2 wa = unpack_bf16(w.x), wb = unpack_bf16(w.y);
+                            xf[jj][0] = pack_bf16(a.x * rs * wa.x, a.y * rs * wa.y);
+                            xf[jj][1] = pack_bf16(b.x * rs * wb.x, b.y * rs * wb.y);
+                        }
                 }
             }
+            if (kb == d.n_kblk - 1) { __syncwarp(); stage_norm_w(p + 1); }    // s_nw is free again: stage the next phase's gains
             const bool last_kb = (kb == d.n_kblk - 1);
             const int F = d.nkb_w * d.MT;                       // 512-byte fragments per item
 

@@ -70,12 +70,23 @@ def tile_rows(kind, N, n_heads=0, n_kv=0, hd=0):
     return base[:, :, None] + torch.arange(16)[None, None, :]
 
 
+def k_offsets(nkb_w):
+    """int64 [nkb_w, 4 (t), 4]: offsets inside a warp's K slice of the 4 consecutive elements lane t feeds to k block j
+    (mirror of mg_koff): blocks are paired so one 16-byte X load serves two MMAs; an unpaired last block is plain."""
+    j = torch.arange(nkb_w)[:, None, None]
+    t = torch.arange(4)[None, :, None]
+    i = torch.arange(4)[None, None, :]
+    paired = (j | 1) < nkb_w
+    return torch.where(paired, 32 * (j >> 1) + 8 * t + 4 * (j & 1), 16 * j + 4 * t) + i
+
+
 def pack_reference(W, kind, n_heads=0, n_kv=0, hd=0):
     """CPU restatement of p3_mega_pack: [kb][tile][warp][j][mt][lane = g*4+t][a0 a1 a2 a3 pairs] (flat, same dtype)"""
     N, K = W.shape
     MT, T, n_kblk, nkb_w = dims(kind, N, K)
     rows = tile_rows(kind, N, n_heads, n_kv, hd)                         # [T, MT, 16]
-    Wt = W[rows.reshape(-1)].reshape(T, MT, 2, 8, n_kblk, WARPS, nkb_w, 4, 2, 2)   # [T, mt, hi, g, kb, warp, j, t, p, e]
+    kk = (torch.arange(n_kblk * WARPS)[:, None, None, None] * (nkb_w * 16) + k_offsets(nkb_w)[None]).reshape(-1)
+    Wt = W[rows.reshape(-1)][:, kk].reshape(T, MT, 2, 8, n_kblk, WARPS, nkb_w, 4, 2, 2)   # [T, mt, hi, g, kb, warp, j, t, p, e]
     return Wt.permute(4, 0, 5, 6, 1, 3, 7, 8, 2, 9).contiguous().reshape(-1)       # [kb, T, warp, j, mt, g, t, p, hi, e]
 
 
@@ -121,7 +132,7 @@ def emulate_phase(packed, kind, N, K, x, cta_off, tile_ids, n_heads=0, n_kv=0, h
                     s0 = ((kb * T + ti) * WARPS + w) * seg
                     fr = packed[s0:s0 + seg].to(torch.float32).reshape(nkb_w, MT, 8, 4, 2, 2, 2)    # [j, mt, g, t, p, hi, e]
                     kbase = (kb * WARPS + w) * nkb_w * 16
-                    xs = xf[:, kbase:kbase + nkb_w * 16].reshape(M, nkb_w, 4, 2, 2)               # [n, j, t, p, e]
+                    xs = xf[:, kbase + k_offsets(nkb_w).reshape(-1)].reshape(M, nkb_w, 4, 2, 2)   # [n, j, t, p, e]: the lane's X loads
                     d = torch.einsum('jmgtphe,njtpe->mhgn', fr, xs)                                # [mt, hi, g, n]
                     for mt in range(MT):
                         r = rows[ti, mt]                                                            # 16 rows: hi*8 + g
