@@ -28,7 +28,8 @@
 #include "../../include/phi3_b200.h"
 
 #define MG_WARPS 8
-#define MG_THREADS (MG_WARPS * 32)
+#define MG_THREADS (MG_WARPS * 32 + 32)      // 8 consumer warps + 1 producer warp
+#define MG_CONSUMERS (MG_WARPS * 32)
 #define MG_SLOT 4096
 #define MG_RSLOTS 6
 #define MG_XF 32                       // max 16-wide k blocks per warp and K-block  (K-block <= 8 * 32 * 16 = 4096)
@@ -39,7 +40,7 @@
 #define MG_RING_BYTES (MG_WARPS * MG_RSLOTS * MG_SLOT)
 #define MG_RED_BYTES (2 * MG_WARPS * 2 * MG_RED_STRIDE * 4)
 #define MG_PART_BYTES (MG_MAX_PART * 2 * 128 * 4)
-#define MG_SMEM (MG_RING_BYTES + MG_RED_BYTES + MG_PART_BYTES + MG_WARPS * MG_RSLOTS * 8)
+#define MG_SMEM (MG_RING_BYTES + MG_RED_BYTES + MG_PART_BYTES + 2 * MG_WARPS * MG_RSLOTS * 8)
 
 __host__ __device__ __forceinline__ int mg_mt(int kind) { return kind == P3_MEGA_RESID ? 1 : 2; }
 
@@ -130,9 +131,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ float mg_silu(float x) { return x / (1.f + __expf(-x)); }
 
 #define MG_TILE_CACHE 32               // per-phase tile ids of this CTA kept in shared memory (more: read from global)
-#define MG_PF_AHEAD 10                 // L2 prefetch runs this many 4 KB slot loads ahead of the ring (per warp: 40 KB; 47 MB per GPU)
+#define MG_PF_AHEAD 10                 // L2 prefetch runs this many 4 KB slot loads per warp ahead of the ring (320 KB per SM, 47 MB per GPU)
 
-struct MgCursor { int p, kb, li; uint32_t rem; const uint8_t* src; };     // li: index into this CTA's tile list of phase p
+struct MgCursor { int p, kb, li; uint32_t rem, seg; const uint8_t* src; };     // li: index into this CTA's tile list of phase p
 
 __device__ __forceinline__ void mg_arrive(unsigned* ctr) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
@@ -150,11 +151,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     const int cta = blockIdx.x;
     const int M = P.M;
 
-    uint8_t* ring_g = mg_smem + (size_t)warp * (MG_RSLOTS * MG_SLOT);
-    const uint32_t ring = smem_u32(ring_g);
+    uint8_t* ring_g = mg_smem + (size_t)(warp & 7) * (MG_RSLOTS * MG_SLOT);
     float* red = reinterpret_cast<float*>(mg_smem + MG_RING_BYTES);
     float* part = reinterpret_cast<float*>(mg_smem + MG_RING_BYTES + MG_RED_BYTES);
-    const uint32_t bars = smem_u32(mg_smem + MG_RING_BYTES + MG_RED_BYTES + MG_PART_BYTES) + warp * (MG_RSLOTS * 8);
+    // mbarriers: full[w][slot] (bulk copy landed) and empty[w][slot] (consumer warp w has the slot's fragments in registers)
+    const uint32_t bars_all = smem_u32(mg_smem + MG_RING_BYTES + MG_RED_BYTES + MG_PART_BYTES);
+    const uint32_t bars = bars_all + (warp & 7) * (MG_RSLOTS * 8);
+    const uint32_t ebars = bars + MG_WARPS * MG_RSLOTS * 8;
 
     if (warp < P.n_phases) {                                    // warp w caches the schedule of phase w
         const p3_mega_phase& ph = P.ph[warp];
@@ -171,9 +174,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
         }
         if (lane < cnt && lane < MG_TILE_CACHE) s_tiles[warp][lane] = ph.tile_ids[first + lane];
     }
-    if (lane == 0) {
+    if (warp < MG_WARPS && lane == 0) {
 #pragma unroll
-        for (int s = 0; s < MG_RSLOTS; s++) mbar_init(bars + s * 8, 1);
+        for (int s = 0; s < MG_RSLOTS; s++) { mbar_init(bars + s * 8, 1); mbar_init(ebars + s * 8, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -181,6 +184,60 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     auto tile_of = [&](int p, int li) -> int {
         return li < MG_TILE_CACHE ? s_tiles[p][li] : P.ph[p].tile_ids[s_first[p] + li];
     };
+
+    if (warp == MG_WARPS) {
+        // ================= producer warp: free-running weight stream (weights are immutable: no dependency wait) ===========
+        // One cursor walks (phase, K-block, tile) exactly like the consumers; the 8 warps' segments of an item are adjacent in
+        // memory (seg bytes apart), so lane w < 8 issues the piece of ring w. A second cursor runs MG_PF_AHEAD pieces further
+        // ahead and only pulls the lines into L2: HBM keeps streaming while the consumers sit in a grid barrier with full rings.
+        const uint64_t pol = l2_evict_first_policy();
+        auto advance = [&](MgCursor& c, uint32_t& bytes) -> const uint8_t* {   // next <= 4 KB piece (warp 0's copy) or nullptr
+            if (c.rem == 0) {                                   // next segment = next tile of this K-block / next K-block / next phase
+                for (;;) {
+                    if (c.p >= P.n_phases) return nullptr;
+                    if (++c.li < s_cnt[c.p]) break;
+                    c.li = -1;
+                    if (++c.kb >= s_d[c.p].n_kblk) { c.kb = 0; c.p++; }
+                }
+                const MgDerived d = s_d[c.p];
+                c.src = s_wp[c.p] + (size_t)(c.kb * d.T + tile_of(c.p, c.li)) * MG_WARPS * d.seg;
+                c.rem = c.seg = d.seg;
+            }
+            bytes = min((uint32_t)MG_SLOT, c.rem);
+            const uint8_t* src = c.src;
+            c.src += bytes;
+            c.rem -= bytes;
+            return src;
+        };
+        MgCursor pc{0, 0, -1, 0u, 0u, nullptr}, lc{0, 0, -1, 0u, 0u, nullptr};
+        uint32_t bytes, slot = 0, epar = 1;                     // a fresh empty barrier passes a parity-1 wait
+        const uint32_t my_ring = smem_u32(mg_smem) + (lane & 7) * (MG_RSLOTS * MG_SLOT);
+        const uint32_t my_full = bars_all + (lane & 7) * (MG_RSLOTS * 8), my_empty = my_full + MG_WARPS * MG_RSLOTS * 8;
+        auto l2_ahead = [&]() {
+            const uint8_t* l2 = advance(lc, bytes);
+            if (l2 && lane < MG_WARPS)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(l2 + (size_t)lane * lc.seg), "r"(bytes) : "memory");
+        };
+#pragma unroll 1
+        for (int s = 0; s < MG_RSLOTS; s++) advance(lc, bytes);   // the first ring-full goes straight to shared memory
+#pragma unroll 1
+        for (int s = 0; s < MG_PF_AHEAD; s++) l2_ahead();
+        for (;;) {
+            const uint8_t* src = advance(pc, bytes);
+            if (!src) break;
+            if (lane < MG_WARPS) {
+                mbar_wait(my_empty + slot * 8, epar);
+                mbar_expect_tx(my_full + slot * 8, bytes);
+                bulk_g2s(my_ring + slot * MG_SLOT, src + (size_t)lane * pc.seg, bytes, my_full + slot * 8, pol);
+            }
+            __syncwarp();
+            if (++slot == MG_RSLOTS) { slot = 0; epar ^= 1; }
+            l2_ahead();
+        }
+        return;
+    }
+
+    // ================= consumer warps =================
     // the RMSNorm gains of phase pn (immutable) are staged in shared memory BEFORE the barrier that opens the phase
     auto stage_norm_w = [&](int pn) {
         if (pn >= P.n_phases || !P.ph[pn].norm_w || s_d[pn].n_kblk != 1) return;
@@ -189,57 +246,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
         for (int i = lane; i < kpw / 8; i += 32) reinterpret_cast<uint4*>(s_nw[warp])[i] = __ldg(src + i);
         __syncwarp();
     };
-
-    // ---- producer side of this warp's ring: two cursors walk (phase, K-block, tile) exactly like the consumer below:
-    // `pc` issues the bulk copies into the ring, `lc` runs MG_PF_AHEAD slot loads further ahead and only pulls lines into L2,
-    // so HBM keeps streaming (into L2) while the consumers sit in a grid barrier with a full ring.
-    const uint64_t pol = l2_evict_first_policy();
-    auto advance = [&](MgCursor& c, uint32_t& bytes) -> const uint8_t* {     // next <= 4 KB piece of this warp's stream (or nullptr)
-        if (c.rem == 0) {                                       // next segment = next tile of this K-block / next K-block / next phase
-            for (;;) {
-                if (c.p >= P.n_phases) return nullptr;
-                if (++c.li < s_cnt[c.p]) break;
-                c.li = -1;
-                if (++c.kb >= s_d[c.p].n_kblk) { c.kb = 0; c.p++; }
-            }
-            const MgDerived d = s_d[c.p];
-            c.src = s_wp[c.p] + ((size_t)(c.kb * d.T + tile_of(c.p, c.li)) * MG_WARPS + warp) * d.seg;
-            c.rem = d.seg;
-        }
-        bytes = min((uint32_t)MG_SLOT, c.rem);
-        const uint8_t* src = c.src;
-        c.src += bytes;
-        c.rem -= bytes;
-        return src;
-    };
-    MgCursor pc{0, 0, -1, 0u, nullptr}, lc{0, 0, -1, 0u, nullptr};
-    uint32_t pslot = 0;                                         // ring slot of the next load
-    auto issue_next = [&]() {                                   // all lanes walk the cursors; lane 0 issues
-        uint32_t bytes;
-        const uint8_t* src = advance(pc, bytes);
-        if (src) {
-            if (lane == 0) {
-                mbar_expect_tx(bars + pslot * 8, bytes);
-                bulk_g2s(ring + pslot * MG_SLOT, src, bytes, bars + pslot * 8, pol);
-            }
-            pslot = (pslot + 1 == MG_RSLOTS) ? 0 : pslot + 1;
-        }
-        const uint8_t* l2 = advance(lc, bytes);
-        if (l2 && lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(l2), "r"(bytes) : "memory");
-    };
-    {   // put lc MG_PF_AHEAD loads ahead: the first MG_RSLOTS pieces go straight to the ring, the next MG_PF_AHEAD to L2
-        uint32_t bytes;
-#pragma unroll 1
-        for (int s = 0; s < MG_RSLOTS; s++) advance(lc, bytes);
-#pragma unroll 1
-        for (int s = 0; s < MG_PF_AHEAD; s++) {
-            const uint8_t* l2 = advance(lc, bytes);
-            if (l2 && lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(l2), "r"(bytes) : "memory");
-        }
-        // weights are immutable: stream them before the dependency wait. (issue_next also moves lc by one each time.)
-#pragma unroll 1
-        for (int s = 0; s < MG_RSLOTS; s++) issue_next();
-    }
+    auto cta_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(MG_CONSUMERS) : "memory"); };   // consumers only
     stage_norm_w(0);
     pdl_wait();
 
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
 
     for (int p = 0; p < P.n_phases; p++) {
         if (p > 0) {                                            // grid barrier: everything phase p reads has been written
-            __syncthreads();
+            cta_sync();
             if (tid == 0) {
                 mg_arrive(P.sync);
                 const unsigned target = ++n_bar * gridDim.x;
@@ -260,7 +267,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                     if (v < target && ++spins > (1u << 26)) __trap();      // a CTA never arrived: fail loudly instead of hanging the GPU
                 } while (v < target);
             }
-            __syncthreads();
+            cta_sync();
         }
         const p3_mega_phase& ph = P.ph[p];
         const MgDerived d = s_d[p];
@@ -297,12 +304,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                     float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     const int q = tid & 1;
                     if (ph.ss_in) {
-                        for (int c = tid >> 1; c < ph.n_ss_in; c += MG_THREADS / 2) {
+                        for (int c = tid >> 1; c < ph.n_ss_in; c += MG_CONSUMERS / 2) {
                             const float4 v = __ldcg(reinterpret_cast<const float4*>(ph.ss_in + (size_t)c * 16 + 4 * q));
                             a4.x += v.x; a4.y += v.y; a4.z += v.z; a4.w += v.w;
                         }
                     } else {                                    // no partials: thread -> 8-element chunks of x
-                        for (int c = tid >> 1; c < ph.K / 8; c += MG_THREADS / 2) {
+                        for (int c = tid >> 1; c < ph.K / 8; c += MG_CONSUMERS / 2) {
                             float* av = reinterpret_cast<float*>(&a4);
 #pragma unroll
                             for (int i = 0; i < 4; i++) {
@@ -321,7 +328,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                         a4.z += __shfl_xor_sync(0xffffffffu, a4.z, o); a4.w += __shfl_xor_sync(0xffffffffu, a4.w, o);
                     }
                     if (lane < 2) *reinterpret_cast<float4*>(&s_ss[warp][4 * lane]) = a4;
-                    __syncthreads();
+                    cta_sync();
                 }
                 float sum = 0.f;
 #pragma unroll
@@ -400,9 +407,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                             }
                         }
                     }
-                    __syncwarp();                               // every lane has its fragments in registers: slot is free
+                    __syncwarp();                               // every lane has its fragments in registers: hand the slot back
+                    if (lane == 0) mbar_arrive(ebars + cslot * 8);
                     if (++cslot == MG_RSLOTS) { cslot = 0; cpar ^= 1; }
-                    issue_next();
                 };
                 if (d.MT == 1) {
                     mg_for_slots<MG_XF / 8>([&](auto S_) { slot_group(S_, std::false_type{}); });
@@ -425,7 +432,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                         r2[(2 * t + 1) * 17 + g + 8] = acc[mt][3];
                     }
                 }
-                __syncthreads();
+                cta_sync();
                 if (tid < 128) {
                     const int r = tid & 15, n = tid >> 4;
                     const float* r0 = red + (size_t)red_buf * (MG_WARPS * 2 * MG_RED_STRIDE) + n * 17 + r;
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     }
 
     // ---- leave the barrier words clean for the next launch (every CTA has passed the last barrier by now)
-    __syncthreads();
+    cta_sync();
     if (tid == 0 && gridDim.x > 1) {
         __threadfence();
         const unsigned old = atomicAdd(P.sync + 1, 1u);
