@@ -225,6 +225,7 @@ typedef struct {
     void* pool;                 /* this layer's page pool [page][2][n_kv][64][hd] bf16 */
     const int32_t* block_table; /* int32 [M, bt_stride] */
     int32_t bt_stride, _pad2;
+    long long* dbg;             /* NULL, or int64 [n_ctas][4][8]: per-CTA / per-phase SM-clock stamps (tools/mega_trace.py) */
 } p3_mega_args;
 
 /* W [N,K] bf16 (nn.Linear layout; SWIGLU: the checkpoint's [gate | up] row order) -> stream order for `kind` */

@@ -112,7 +112,7 @@ extern "C" int p3_mega_pack(const void* W, void* out, int kind, int N, int K, in
 // ------------------------------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------------------------
-static_assert(sizeof(p3_mega_phase) == 104 && sizeof(p3_mega_args) == 512, "p3_mega_args layout is mirrored by ctypes in mega.py");
+static_assert(sizeof(p3_mega_phase) == 104 && sizeof(p3_mega_args) == 520, "p3_mega_args layout is mirrored by ctypes in mega.py");
 #include <type_traits>
 #include <utility>
 template <int N, typename Fn, int... Is>
@@ -131,14 +131,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ float mg_silu(float x) { return x / (1.f + __expf(-x)); }
 
 #define MG_TILE_CACHE 32               // per-phase tile ids of this CTA kept in shared memory (more: read from global)
-#define MG_PF_AHEAD 10                 // L2 prefetch runs this many 4 KB slot loads per warp ahead of the ring (320 KB per SM, 47 MB per GPU)
-
-struct MgCursor { int p, kb, li; uint32_t rem, seg; const uint8_t* src; };     // li: index into this CTA's tile list of phase p
+#define MG_PF_ITEMS 2                  // L2 prefetch runs this many items (96-192 KB each) ahead of the ring
 
 __device__ __forceinline__ void mg_arrive(unsigned* ctr) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 
+// Rule for everything below: the memory system is kept saturated with ~50 MB of outstanding weight requests, so a demand
+// load that MISSES L2 on a consumer's critical path waits for that whole queue (several microseconds). Consumers therefore
+// only ever load (a) activations written moments ago (L2 hits), (b) data that arrives through their ring in stream order
+// (weights and the RMSNorm gains), (c) values fetched at kernel start, before the flood (rope table row, page id).
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid_constant__ p3_mega_args P) {
     extern __shared__ __align__(1024) uint8_t mg_smem[];
     __shared__ MgDerived s_d[P3_MEGA_MAX_PHASES];
@@ -146,7 +148,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     __shared__ int s_tiles[P3_MEGA_MAX_PHASES][MG_TILE_CACHE];
     __shared__ const uint8_t* s_wp[P3_MEGA_MAX_PHASES];
     __shared__ float s_ss[MG_WARPS][8];
-    __shared__ __align__(16) bf16 s_nw[MG_WARPS][MG_XF * 16];    // next phase's RMSNorm gains, this warp's K slice
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int cta = blockIdx.x;
     const int M = P.M;
@@ -187,94 +188,122 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
 
     if (warp == MG_WARPS) {
         // ================= producer warp: free-running weight stream (weights are immutable: no dependency wait) ===========
-        // One cursor walks (phase, K-block, tile) exactly like the consumers; the 8 warps' segments of an item are adjacent in
-        // memory (seg bytes apart), so lane w < 8 issues the piece of ring w. A second cursor runs MG_PF_AHEAD pieces further
-        // ahead and only pulls the lines into L2: HBM keeps streaming while the consumers sit in a grid barrier with full rings.
+        // Walks (phase, K-block, tile) exactly like the consumers. The 8 warps' segments of an item are adjacent in memory
+        // (seg bytes apart), so lane w < 8 feeds ring w with 4 KB pieces. A normed phase starts with one extra piece per ring:
+        // that warp's slice of the RMSNorm gains. Whole items are pulled into L2 MG_PF_ITEMS items ahead of the ring, so HBM
+        // keeps streaming (into L2) while the consumers sit in a grid barrier with full rings.
         const uint64_t pol = l2_evict_first_policy();
-        auto advance = [&](MgCursor& c, uint32_t& bytes) -> const uint8_t* {   // next <= 4 KB piece (warp 0's copy) or nullptr
-            if (c.rem == 0) {                                   // next segment = next tile of this K-block / next K-block / next phase
-                for (;;) {
-                    if (c.p >= P.n_phases) return nullptr;
-                    if (++c.li < s_cnt[c.p]) break;
-                    c.li = -1;
-                    if (++c.kb >= s_d[c.p].n_kblk) { c.kb = 0; c.p++; }
-                }
-                const MgDerived d = s_d[c.p];
-                c.src = s_wp[c.p] + (size_t)(c.kb * d.T + tile_of(c.p, c.li)) * MG_WARPS * d.seg;
-                c.rem = c.seg = d.seg;
-            }
-            bytes = min((uint32_t)MG_SLOT, c.rem);
-            const uint8_t* src = c.src;
-            c.src += bytes;
-            c.rem -= bytes;
-            return src;
-        };
-        MgCursor pc{0, 0, -1, 0u, 0u, nullptr}, lc{0, 0, -1, 0u, 0u, nullptr};
-        uint32_t bytes, slot = 0, epar = 1;                     // a fresh empty barrier passes a parity-1 wait
         const uint32_t my_ring = smem_u32(mg_smem) + (lane & 7) * (MG_RSLOTS * MG_SLOT);
         const uint32_t my_full = bars_all + (lane & 7) * (MG_RSLOTS * 8), my_empty = my_full + MG_WARPS * MG_RSLOTS * 8;
-        auto l2_ahead = [&]() {
-            const uint8_t* l2 = advance(lc, bytes);
-            if (l2 && lane < MG_WARPS)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(l2 + (size_t)lane * lc.seg), "r"(bytes) : "memory");
-        };
-#pragma unroll 1
-        for (int s = 0; s < MG_RSLOTS; s++) advance(lc, bytes);   // the first ring-full goes straight to shared memory
-#pragma unroll 1
-        for (int s = 0; s < MG_PF_AHEAD; s++) l2_ahead();
-        for (;;) {
-            const uint8_t* src = advance(pc, bytes);
-            if (!src) break;
+        uint32_t slot = 0, epar = 1;                            // a fresh empty barrier passes a parity-1 wait
+        auto put = [&](const uint8_t* src, uint32_t bytes) {    // lanes 0-7: one piece into ring `lane`
             if (lane < MG_WARPS) {
                 mbar_wait(my_empty + slot * 8, epar);
                 mbar_expect_tx(my_full + slot * 8, bytes);
-                bulk_g2s(my_ring + slot * MG_SLOT, src + (size_t)lane * pc.seg, bytes, my_full + slot * 8, pol);
+                bulk_g2s(my_ring + slot * MG_SLOT, src, bytes, my_full + slot * 8, pol);
             }
             __syncwarp();
             if (++slot == MG_RSLOTS) { slot = 0; epar ^= 1; }
-            l2_ahead();
+        };
+        // item-granular look-ahead cursor for the L2 prefetch
+        int lp = 0, lkb = 0, lli = -1;
+        auto l2_next_item = [&]() {
+            for (;;) {
+                if (lp >= P.n_phases) return;
+                if (++lli < s_cnt[lp]) break;
+                lli = -1;
+                if (++lkb >= s_d[lp].n_kblk) { lkb = 0; lp++; }
+            }
+            const MgDerived d = s_d[lp];
+            const uint32_t item = MG_WARPS * d.seg, per = (item / 32 + 15) & ~15u;      // bytes per lane, 16-byte granular
+            const uint8_t* base = s_wp[lp] + (size_t)(lkb * d.T + tile_of(lp, lli)) * item;
+            const uint32_t off = lane * per;
+            if (off < item)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(min(per, item - off)) : "memory");
+        };
+        bool first_item = true;
+        for (int p = 0; p < P.n_phases; p++) {
+            const MgDerived d = s_d[p];
+            const int n_mine = s_cnt[p];
+            if (n_mine == 0) continue;
+            const uint8_t* nw = reinterpret_cast<const uint8_t*>(P.ph[p].norm_w);
+            const uint32_t kpw_b = d.nkb_w * 32;                // bytes of a warp's K slice of bf16 gains
+            for (int kb = 0; kb < d.n_kblk; kb++) {
+                if (nw) put(nw + (size_t)(kb * MG_WARPS + (lane & 7)) * kpw_b, kpw_b);
+                for (int li = 0; li < n_mine; li++) {
+                    const uint8_t* base = s_wp[p] + ((size_t)(kb * d.T + tile_of(p, li)) * MG_WARPS + (lane & 7)) * d.seg;
+                    if (first_item) {                           // ring first, then the look-ahead (skipping what the ring holds)
+                        first_item = false;
+                        for (uint32_t off = 0; off < d.seg; off += MG_SLOT) put(base + off, min((uint32_t)MG_SLOT, d.seg - off));
+                        lp = p; lkb = kb; lli = li;             // look-ahead starts behind this item
+#pragma unroll 1
+                        for (int i = 0; i < MG_PF_ITEMS; i++) l2_next_item();
+                        continue;
+                    }
+                    l2_next_item();
+                    for (uint32_t off = 0; off < d.seg; off += MG_SLOT) put(base + off, min((uint32_t)MG_SLOT, d.seg - off));
+                }
+            }
         }
         return;
     }
 
     // ================= consumer warps =================
-    // the RMSNorm gains of phase pn (immutable) are staged in shared memory BEFORE the barrier that opens the phase
-    auto stage_norm_w = [&](int pn) {
-        if (pn >= P.n_phases || !P.ph[pn].norm_w || s_d[pn].n_kblk != 1) return;
-        const int kpw = s_d[pn].nkb_w * 16;
-        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.ph[pn].norm_w) + warp * kpw);
-        for (int i = lane; i < kpw / 8; i += 32) reinterpret_cast<uint4*>(s_nw[warp])[i] = __ldg(src + i);
-        __syncwarp();
-    };
     auto cta_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(MG_CONSUMERS) : "memory"); };   // consumers only
-    stage_norm_w(0);
-    pdl_wait();
+    uint32_t cslot = 0, cpar = 0;                               // ring position: slot and its phase parity
+    auto release_slot = [&]() {                                 // every lane has the slot's data in registers: hand it back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ebars + cslot * 8);
+        if (++cslot == MG_RSLOTS) { cslot = 0; cpar ^= 1; }
+    };
 
-    const int past = P.past_dev ? *P.past_dev : P.past;
-    uint32_t cslot = 0, cpar = 0;                               // consumer ring position: slot and its phase parity
+    // ---- QKV phase (always the last one): this thread's rope factors and page id are requested now and used ~50 us later
+    // (they may miss L2; nothing waits on them until the epilogue of the last phase)
+    const int last_kind = P.ph[P.n_phases - 1].kind;
+    float rope_cs[3] = {1.f, 1.f, 1.f}, rope_sn[3] = {0.f, 0.f, 0.f};
+    int kv_page = 0;
+    pdl_wait();
+    const int past = P.past_dev ? __ldcg(P.past_dev) : P.past;
+    if (last_kind == P3_MEGA_QKV_ROPE && tid < 128 && (tid >> 4) < M) {
+        const int n = tid >> 4, r = tid & 15, half = P.hd / 2;
+        const size_t tix = (size_t)n * P.tab_bstride + (size_t)past * half + r;
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            if (q * 16 + r < half) { rope_cs[q] = __ldg(P.cosT + tix + q * 16); rope_sn[q] = __ldg(P.sinT + tix + q * 16); }
+        kv_page = __ldg(P.block_table + (size_t)n * P.bt_stride + past / P3_PAGE);
+    }
+
     unsigned n_bar = 0;
     int red_buf = 0;
-
+    // optional instrumentation (P.dbg, tools/mega_trace.py): per CTA and phase, SM-clock stamps
+    //   [0] phase start (barrier arrive)  [1] barrier released  [2] warp 0 has its X fragments  [3] last item done
+    //   [4] cycles warp 0 spent waiting for weight data   [5] same, warp 7
+    long long* dbg = P.dbg ? P.dbg + (size_t)cta * (P3_MEGA_MAX_PHASES * 8) : nullptr;
+    long long wait_cyc = 0;
     for (int p = 0; p < P.n_phases; p++) {
+        if (dbg && tid == 0) dbg[p * 8 + 0] = clock64();
         if (p > 0) {                                            // grid barrier: everything phase p reads has been written
             cta_sync();
             if (tid == 0) {
-                mg_arrive(P.sync);
+                mg_arrive(P.sync);                              // release: orders the CTA's writes (cumulative through bar.sync)
                 const unsigned target = ++n_bar * gridDim.x;
                 unsigned v, spins = 0;
                 do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.sync) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.sync) : "memory");
                     if (v < target && ++spins > (1u << 26)) __trap();      // a CTA never arrived: fail loudly instead of hanging the GPU
                 } while (v < target);
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
             }
             cta_sync();
         }
         const p3_mega_phase& ph = P.ph[p];
         const MgDerived d = s_d[p];
         const int n_mine = s_cnt[p];
-        if (n_mine == 0) { stage_norm_w(p + 1); continue; }     // (uniform per CTA)
+        if (dbg && tid == 0) dbg[p * 8 + 1] = clock64();
+        wait_cyc = 0;
+        if (n_mine == 0) continue;                              // (uniform per CTA)
         const bf16* X = reinterpret_cast<const bf16*>(ph.x);
-        const bf16* NW = reinterpret_cast<const bf16*>(ph.norm_w);
+        const bool normed = ph.norm_w != nullptr;
         const int n_pair = d.nkb_w >> 1;
 
         for (int kb = 0; kb < d.n_kblk; kb++) {
@@ -296,10 +325,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                 for (int jj = 0; jj < MG_XF; jj += 2)
                     if (jj == j) { xf[jj][0] = v.x; xf[jj][1] = v.y; }
             }
-            if (NW) {
+            if (normed) {
                 // ---- RMSNorm (phi.py:478-479): rs of row g from the producer's per-tile partial sums, summed by the CTA in a
                 // fixed order (deterministic): thread -> partial c = tid/2 (+128 i), rows 4q..4q+3. The X loads above are in flight.
-                float rs = 1.f;
                 if (kb == 0) {
                     float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     const int q = tid & 1;
@@ -333,14 +361,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                 float sum = 0.f;
 #pragma unroll
                 for (int w = 0; w < MG_WARPS; w++) sum += s_ss[w][g];
-                rs = rsqrtf(sum / (float)ph.K + P.eps);
-                const bool staged = (d.n_kblk == 1);
-                const bf16* nwg = NW + kbase;
+                const float rs = rsqrtf(sum / (float)ph.K + P.eps);
+                // the gains of this warp's K slice arrive through the ring, ahead of the K-block's weights
+                mbar_wait(bars + cslot * 8, cpar);
+                const bf16* nws = reinterpret_cast<const bf16*>(ring_g + cslot * MG_SLOT);
 #pragma unroll
                 for (int pr = 0; pr < MG_XF / 2; pr++) {
                     if (pr < n_pair) {
-                        const uint4 w = staged ? *reinterpret_cast<const uint4*>(&s_nw[warp][32 * pr + 8 * t])
-                                               : __ldg(reinterpret_cast<const uint4*>(nwg + 32 * pr + 8 * t));
+                        const uint4 w = *reinterpret_cast<const uint4*>(nws + 32 * pr + 8 * t);
                         const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
@@ -352,8 +380,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                 }
                 if (d.nkb_w & 1) {
                     const int j = d.nkb_w - 1;
-                    const uint2 w = staged ? *reinterpret_cast<const uint2*>(&s_nw[warp][16 * j + 4 * t])
-                                           : __ldg(reinterpret_cast<const uint2*>(nwg + 16 * j + 4 * t));
+                    const uint2 w = *reinterpret_cast<const uint2*>(nws + 16 * j + 4 * t);
 #pragma unroll
                     for (int jj = 0; jj < MG_XF; jj += 2)
                         if (jj == j) {
@@ -363,8 +390,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                             xf[jj][1] = pack_bf16(b.x * rs * wb.x, b.y * rs * wb.y);
                         }
                 }
+                release_slot();
             }
-            if (kb == d.n_kblk - 1) { __syncwarp(); stage_norm_w(p + 1); }    // s_nw is free again: stage the next phase's gains
+            if (dbg && tid == 0 && kb == 0) dbg[p * 8 + 2] = clock64();
             const bool last_kb = (kb == d.n_kblk - 1);
             const int F = d.nkb_w * d.MT;                       // 512-byte fragments per item
 
@@ -378,13 +406,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                     resid_pref = __bfloat162float(__ushort_as_bfloat16(raw));
                 }
                 float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                // ---- stream the item slot by slot: wait, 8 x ld.shared.v4, 8 x MMA, hand the slot back (refill one ring ahead).
+                // ---- stream the item slot by slot: wait, 8 x ld.shared.v4, 8 x MMA, hand the slot back.
                 // MT == 2: fragment f = 2j + mt feeds acc[mt]. MT == 1: fragment f = j feeds acc[j & 1] (two MMA chains).
                 auto slot_group = [&](auto S_, auto MT2_) {
                     constexpr int S = decltype(S_)::value;
                     constexpr bool MT2 = decltype(MT2_)::value;
                     if (8 * S >= F) return;
-                    mbar_wait(bars + cslot * 8, cpar);
+                    if (dbg) { const long long t0 = clock64(); mbar_wait(bars + cslot * 8, cpar); wait_cyc += clock64() - t0; }
+                    else mbar_wait(bars + cslot * 8, cpar);
                     const uint8_t* sb = ring_g + cslot * MG_SLOT + lane * 16;
                     if (8 * S + 8 <= F) {                       // full slot
                         uint4 a[8];
@@ -407,9 +436,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                             }
                         }
                     }
-                    __syncwarp();                               // every lane has its fragments in registers: hand the slot back
-                    if (lane == 0) mbar_arrive(ebars + cslot * 8);
-                    if (++cslot == MG_RSLOTS) { cslot = 0; cpar ^= 1; }
+                    release_slot();
                 };
                 if (d.MT == 1) {
                     mg_for_slots<MG_XF / 8>([&](auto S_) { slot_group(S_, std::false_type{}); });
@@ -472,14 +499,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                         } else if (n < M) {                                   // P3_MEGA_QKV_ROPE: phi.py:442-453, one new token per row
                             const int hd = P.hd, half = hd / 2, gpr = hd / 32, n_rope = (P.n_heads + P.n_kv) * gpr;
                             bf16* row = reinterpret_cast<bf16*>(ph.out) + (size_t)n * ph.ldo;
-                            const int page = P.block_table[(size_t)n * P.bt_stride + past / P3_PAGE];
-                            bf16* kd = reinterpret_cast<bf16*>(P.pool) + (size_t)page * kv_page_elems(P.n_kv, hd) + (size_t)(past % P3_PAGE) * hd;
+                            bf16* kd = reinterpret_cast<bf16*>(P.pool) + (size_t)kv_page * kv_page_elems(P.n_kv, hd) + (size_t)(past % P3_PAGE) * hd;
                             bf16* vd = kd + (size_t)P.n_kv * P3_PAGE * hd;
                             if (ti < n_rope) {
-                                const int head = ti / gpr, dd = (ti % gpr) * 16 + r;
+                                const int head = ti / gpr, q = ti % gpr, dd = q * 16 + r;
                                 const float x1 = bf16_round(s[0]), x2 = bf16_round(s[1]);   // qkv_proj output is bf16 in the reference flow
-                                const size_t tix = (size_t)n * P.tab_bstride + (size_t)past * half + dd;
-                                const float cs = P.cosT[tix], sn = P.sinT[tix];
+                                float cs, sn;
+                                if (gpr <= 3) {                                             // prefetched at kernel start (static register pick)
+                                    cs = q == 0 ? rope_cs[0] : (q == 1 ? rope_cs[1] : rope_cs[2]);
+                                    sn = q == 0 ? rope_sn[0] : (q == 1 ? rope_sn[1] : rope_sn[2]);
+                                } else {
+                                    const size_t tix = (size_t)n * P.tab_bstride + (size_t)past * half + dd;
+                                    cs = P.cosT[tix]; sn = P.sinT[tix];
+                                }
                                 const bf16 o1 = __float2bfloat16_rn(x1 * cs - x2 * sn), o2 = __float2bfloat16_rn(x2 * cs + x1 * sn);
                                 row[head * hd + dd] = o1;
                                 row[head * hd + half + dd] = o2;
@@ -502,6 +534,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                 }
                 red_buf ^= 1;
             }
+        }
+        if (dbg && lane == 0) {
+            if (warp == 0) { dbg[p * 8 + 3] = clock64(); dbg[p * 8 + 4] = wait_cyc; }
+            if (warp == 7) dbg[p * 8 + 5] = wait_cyc;
         }
     }
 

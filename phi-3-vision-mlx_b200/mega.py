@@ -32,7 +32,7 @@ class MegaArgs(C.Structure):
                 ('n_ctas', C.c_int32), ('sync', C.c_void_p), ('cosT', C.c_void_p), ('sinT', C.c_void_p),
                 ('tab_bstride', C.c_int64), ('n_heads', C.c_int32), ('n_kv', C.c_int32), ('hd', C.c_int32),
                 ('past', C.c_int32), ('past_dev', C.c_void_p), ('pool', C.c_void_p), ('block_table', C.c_void_p),
-                ('bt_stride', C.c_int32), ('_pad2', C.c_int32)]
+                ('bt_stride', C.c_int32), ('_pad2', C.c_int32), ('dbg', C.c_void_p)]
 
 
 def mt_of(kind):

@@ -229,4 +229,4 @@ def test_mega_args_layout_matches_header():
     import ctypes
     import phi3_b200  # noqa
     from phi3_b200 import mega
-    assert ctypes.sizeof(mega.MegaPhase) == 104 and ctypes.sizeof(mega.MegaArgs) == 512    # static_assert in decode_mega.cu
+    assert ctypes.sizeof(mega.MegaPhase) == 104 and ctypes.sizeof(mega.MegaArgs) == 520    # static_assert in decode_mega.cu
