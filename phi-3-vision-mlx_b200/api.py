@@ -229,8 +229,9 @@ class LogitStopper:
 
     def __init__(self, max_tokens, early_stop):
         self.step = 0
-        self.early_stop = early_stop if isinstance(early_stop, int) and not isinstance(early_stop, bool) \
-            and (early_stop < max_tokens) else False
+        # pv:82: `early_stop if isinstance(early_stop, int) and (early_stop < max_tokens) else False` — bool is an int there:
+        # True enables the heuristic with threshold 1, False (== 0) leaves it off
+        self.early_stop = early_stop if isinstance(early_stop, int) and (early_stop < max_tokens) else False
         self.log_prob_sum = 0.0
         self.best_eos_sofar = -float('inf')
         self.log_prob_sum_at_best_eos = 0.0

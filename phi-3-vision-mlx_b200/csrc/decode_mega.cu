@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     //   [0] phase start (barrier arrive)  [1] barrier released  [2] warp 0 has its X fragments  [3] last item done
     //   [4] cycles warp 0 spent waiting for weight data   [5] same, warp 7
     long long* dbg = P.dbg ? P.dbg + (size_t)cta * (P3_MEGA_MAX_PHASES * 8) : nullptr;
-    long long wait_cyc = 0;
+    long long wait_cyc = 0, sync_cyc = 0, epi_cyc = 0;
     for (int p = 0; p < P.n_phases; p++) {
         if (dbg && tid == 0) dbg[p * 8 + 0] = clock64();
         if (p > 0) {                                            // grid barrier: everything phase p reads has been written
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
         const MgDerived d = s_d[p];
         const int n_mine = s_cnt[p];
         if (dbg && tid == 0) dbg[p * 8 + 1] = clock64();
-        wait_cyc = 0;
+        wait_cyc = sync_cyc = epi_cyc = 0;
         if (n_mine == 0) continue;                              // (uniform per CTA)
         const bf16* X = reinterpret_cast<const bf16*>(ph.x);
         const bool normed = ph.norm_w != nullptr;
@@ -459,7 +459,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                         r2[(2 * t + 1) * 17 + g + 8] = acc[mt][3];
                     }
                 }
-                cta_sync();
+                if (dbg) { const long long t0 = clock64(); cta_sync(); sync_cyc += clock64() - t0; } else cta_sync();
+                const long long te0 = dbg ? clock64() : 0;
                 if (tid < 128) {
                     const int r = tid & 15, n = tid >> 4;
                     const float* r0 = red + (size_t)red_buf * (MG_WARPS * 2 * MG_RED_STRIDE) + n * 17 + r;
@@ -532,11 +533,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
                         }
                     }
                 }
+                if (dbg) epi_cyc += clock64() - te0;
                 red_buf ^= 1;
             }
         }
         if (dbg && lane == 0) {
-            if (warp == 0) { dbg[p * 8 + 3] = clock64(); dbg[p * 8 + 4] = wait_cyc; }
+            if (warp == 0) { dbg[p * 8 + 3] = clock64(); dbg[p * 8 + 4] = wait_cyc; dbg[p * 8 + 6] = sync_cyc; dbg[p * 8 + 7] = epi_cyc; }
             if (warp == 7) dbg[p * 8 + 5] = wait_cyc;
         }
     }

@@ -480,10 +480,11 @@ __global__ void top_p_sample_kernel(const float* __restrict__ logits, int64_t ld
     __syncthreads();
     if (tid == 0) {
         float mass = 0.f;
-        for (int t = 0; t < TP_THREADS; t++) mass += s_chunk[t];
+        int last_ne = 0;                                     // last chunk that holds a nucleus element (trailing chunks can be empty)
+        for (int t = 0; t < TP_THREADS; t++) { mass += s_chunk[t]; if (s_chunk[t] > 0.f) last_ne = t; }
         float target = u[r] * mass, acc = 0.f;
         int t = 0;
-        for (; t < TP_THREADS - 1; t++) { if (acc + s_chunk[t] > target) break; acc += s_chunk[t]; }
+        for (; t < last_ne; t++) { if (acc + s_chunk[t] > target) break; acc += s_chunk[t]; }   // u -> 1 rounds into the last non-empty chunk
         s_pick = t;
         s_chunk[0] = target - acc;                           // residual target inside the chosen chunk (slot 0 reused)
     }

@@ -83,7 +83,12 @@ class KVCacheB200:
     reference counting the moment the caller drops the cache)."""
 
     def __getitem__(self, i):
+        if not -self.n_layers <= i < self.n_layers:          # a finite sequence, like the reference's list of per-layer caches
+            raise IndexError(i)
         return self
+
+    def __iter__(self):
+        return iter([self] * self.n_layers)
 
     def __len__(self):
         return self.n_layers
@@ -174,10 +179,11 @@ class Phi3B200:
         self.norm = d(w['model.norm.weight'])
         self.lm_head = lin(w['lm_head.weight'])
         # persistent decode-layer kernel (mega.py / decode_mega.cu): a second, stream-order copy of the decoder weights
-        # (7.4 GB at Phi-3.5 sizes; HBM has 180 GB). bf16 weights only; P3_MEGA=0 keeps the per-matrix skinny kernels.
+        # (7.4 GB at Phi-3.5 sizes; HBM has 180 GB). bf16 weights only. Opt-in (P3_MEGA=1) while it is slower than the chain
+        # of per-matrix skinny kernels it replaces (profiles/r02_decode_mega.md).
         self.mega = None
         import os as _os0
-        if not self.quantize_model and _os0.environ.get('P3_MEGA', '1') != '0':
+        if not self.quantize_model and _os0.environ.get('P3_MEGA', '0') == '1':
             from .mega import MegaDecoder
             try:
                 self.mega = MegaDecoder(self, w)

@@ -214,13 +214,19 @@ def test_repeated_launches_are_deterministic(dev):
 
 
 def _tiny(layers=2, **kw):
+    import os
+    os.environ['P3_MEGA'] = '1'                                  # the kernel is opt-in (model.py)
     import phi3_b200  # noqa
     from phi3_b200 import configs, weights
     from phi3_b200.model import Phi3B200
     from oracle.phi3_oracle import Phi3Oracle
     cfg = configs.tiny(layers=layers, **kw)
     w = weights.random_weights(cfg, seed=0)
-    return cfg, w, Phi3B200(cfg, w), Phi3Oracle(cfg, w, prec='b200')
+    try:
+        m = Phi3B200(cfg, w)
+    finally:
+        os.environ.pop('P3_MEGA', None)
+    return cfg, w, m, Phi3Oracle(cfg, w, prec='b200')
 
 
 @pytest.mark.parametrize('B,quant', [(1, False), (4, False), (8, False), (3, True)])

@@ -9,6 +9,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ['P3_MEGA'] = '1'
 import phi3_b200  # noqa
 from phi3_b200 import configs, weights
 from phi3_b200.model import Phi3B200, DecodeSession

@@ -9,6 +9,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ['P3_MEGA'] = '1'
 import phi3_b200  # noqa
 from phi3_b200 import configs, weights
 from phi3_b200.model import Phi3B200, DecodeSession
@@ -55,6 +56,23 @@ def main():
                'data_wait_us_w7_med': (s[:, 5] / ghz / 1e3)[s[:, 3] > 0].median().item()}
         out['phases'].append({k: (round(v, 2) if isinstance(v, float) else v) for k, v in row.items()})
     out['total_us_med'] = round(((d[:, 3, 3] - t0) / ghz / 1e3).median().item(), 2)
+    # per-CTA detail grouped by the number of tiles the CTA owns in the phase
+    out['by_tiles'] = []
+    for p, name in enumerate(['o_proj', 'gate_up', 'down', 'qkv']):
+        off = ms.mega.sched['mid'][p][0].cpu()
+        cnt = (off[1:] - off[:-1])
+        s = d[:, p]
+        for k in sorted(set(cnt.tolist())):
+            sel = cnt == k
+            out['by_tiles'].append({'phase': name, 'tiles': k, 'ctas': int(sel.sum()),
+                                    'arrive_us': round(((s[sel, 0] - t0[sel]) / ghz / 1e3).mean().item(), 2),
+                                    'released_us': round(((s[sel, 1] - t0[sel]) / ghz / 1e3).mean().item(), 2),
+                                    'x_ready_us': round(((s[sel, 2] - t0[sel]) / ghz / 1e3).mean().item(), 2),
+                                    'done_us': round(((s[sel, 3] - t0[sel]) / ghz / 1e3).mean().item(), 2),
+                                    'stream_us': round(((s[sel, 3] - s[sel, 2]) / ghz / 1e3).mean().item(), 2),
+                                    'data_wait_w0_us': round((s[sel, 4] / ghz / 1e3).mean().item(), 2),
+                                    'item_sync_wait_w0_us': round((s[sel, 6] / ghz / 1e3).mean().item(), 2),
+                                    'epilogue_w0_us': round((s[sel, 7] / ghz / 1e3).mean().item(), 2)})
     print(json.dumps(out, indent=1))
 
 
