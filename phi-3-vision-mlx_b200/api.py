@@ -17,7 +17,14 @@ Differences a caller can see (all opt-in or forced by the offline environment):
     LoRALinear's two extra matmuls per call (phi:129-133). A LoRA over 4-bit weights cannot be folded: that combination
     raises NotImplementedError;
   * constrain(..., n_beam=3) exposes the beam width the reference hard-codes (pv:505);
-  * images may be PIL images or uint8 HWC arrays (no URL fetching offline).
+  * images may be PIL images or uint8 HWC arrays (no URL fetching offline);
+  * generate_batch(prompts, images_per_prompt, ...) is an extension: the reference raises on images + a prompt list
+    (pv:377-378), so its only way to run N image prompts is N sequential batch-1 calls. generate_batch runs them as ONE
+    left-padded batch with per-prompt batch-1 semantics (each row keeps its own positions 0..L_i-1, pad keys masked,
+    image tokens spliced per row), which is what BASELINE config 3 (64 image+text prompts) needs;
+  * load(model_path=<dir>) / load(weights=<dir>) read that directory's config.json like _get_cfg (pv:258,359-363): LM
+    hyper-parameters and rope_scaling come from the checkpoint, kwargs override; `sanitized` / `quantized` keys are honoured
+    (pv:262-264,371-374). The frozen PHI35_* configs are only used for random_init and weight dicts.
 """
 import os
 import time
@@ -46,7 +53,52 @@ class Tic:                                              # phi.py:16-24
 
 
 # ------------------------------------------------------------------------------------- load
-def _read_safetensors(path):
+def _read_config(path):
+    """_get_cfg (pv:359-369): config.json -> SimpleNamespace. None when the directory has no config.json."""
+    import json
+    from types import SimpleNamespace
+    f = os.path.join(path, 'config.json')
+    if not os.path.exists(f):
+        return None
+    try:
+        d = json.load(open(f))
+    except json.JSONDecodeError:
+        raise ValueError(f'Invalid JSON in configuration file: {f}')
+    d.setdefault('use_quantized_cache', False)
+    if 'num_key_value_heads' not in d:
+        d['num_key_value_heads'] = d['num_attention_heads']
+    return SimpleNamespace(**d)
+
+
+def _load_tokenizer(path):
+    """The reference takes AutoTokenizer.from_pretrained(model_path) (phi:230). Offline, a local tokenizer.json is enough:
+    load it through `tokenizers` directly when transformers cannot build the full tokenizer class."""
+    try:
+        from transformers import AutoTokenizer
+        return AutoTokenizer.from_pretrained(path, local_files_only=True)
+    except Exception:
+        from transformers import PreTrainedTokenizerFast
+        return PreTrainedTokenizerFast(tokenizer_file=os.path.join(path, 'tokenizer.json'))
+
+
+def dequantize_mlx(wq, scales, biases, group_size=64, bits=4):
+    """mx.dequantize layout (what `quantized_model.safetensors` holds after pv:291-305): `wq` uint32 [N, K*bits/32], element i
+    of a row in bits [bits*(i%(32/bits)), +bits) of word i/(32/bits); scales / biases [N, K/group_size]: w = q*scale + bias."""
+    per = 32 // bits
+    wq = wq.to(torch.int64) & 0xFFFFFFFF
+    sh = torch.arange(per, dtype=torch.int64, device=wq.device) * bits
+    q = ((wq[..., None] >> sh) & ((1 << bits) - 1)).reshape(wq.shape[0], -1).to(torch.float32)      # [N, K]
+    N, K = q.shape
+    w = q.reshape(N, K // group_size, group_size) * scales.to(torch.float32)[..., None] + biases.to(torch.float32)[..., None]
+    return w.reshape(N, K).to(torch.bfloat16)
+
+
+def _read_safetensors(path, sanitized=False, quantized=None):
+    """_get_wt (pv:371-374): every *.safetensors shard of the directory. Unsanitized (HF) checkpoints carry the patch conv as
+    [O,I,kh,kw] and are transposed to the reference layout [O,kh,kw,I]; `sanitized` ones already are (pv:276-289). A
+    `quantized` checkpoint (pv:291-305) stores weight/scales/biases triples; they are expanded to the bf16 image here and
+    re-quantised by Phi3B200(quantize_model=True) with the same group size (the codes are reproduced up to the bf16 rounding
+    of the image)."""
     from safetensors.torch import load_file
     w = {}
     for f in sorted(glob.glob(os.path.join(path, '*.safetensors'))):
@@ -54,9 +106,33 @@ def _read_safetensors(path):
     if not w:
         raise FileNotFoundError(f'no *.safetensors under {path}')
     key = 'model.vision_embed_tokens.img_processor.vision_model.embeddings.patch_embedding.weight'
-    if key in w and w[key].shape[1] == 3:               # HF [O,I,kh,kw] -> reference layout [O,kh,kw,I] (pv:374)
-        w[key] = w[key].permute(0, 2, 3, 1).contiguous()
+    if key in w and not sanitized and w[key].dim() == 4 and w[key].shape[1] == 3 and w[key].shape[-1] != 3:
+        w[key] = w[key].permute(0, 2, 3, 1).contiguous()   # HF [O,I,kh,kw] -> reference layout [O,kh,kw,I] (pv:374)
+    if quantized:
+        gs, bits = int(quantized.get('group_size', 64)), int(quantized.get('bits', 4))
+        for k in [k for k in w if k.endswith('.scales')]:
+            base = k[:-len('.scales')]
+            w[base + '.weight'] = dequantize_mlx(w[base + '.weight'], w.pop(k), w.pop(base + '.biases'), gs, bits)
     return w
+
+
+def sanitize(from_path, to_path):
+    """_sanitize (pv:276-289): re-save a checkpoint directory in the reference's own parameter layout (patch conv already
+    [O,kh,kw,I]) with `sanitized: true` in config.json, *.json side files copied."""
+    import json
+    import shutil
+    from safetensors.torch import save_file
+    cfg = _read_config(from_path)
+    if cfg is None:
+        raise FileNotFoundError(f'Configuration file not found: {from_path}/config.json')
+    w = _read_safetensors(from_path, sanitized=bool(getattr(cfg, 'sanitized', False)), quantized=getattr(cfg, 'quantized', None))
+    os.makedirs(to_path, exist_ok=True)
+    for f in glob.glob(os.path.join(from_path, '*.json')):
+        shutil.copy(f, to_path)
+    d = {k: v for k, v in vars(cfg).items() if k != 'quantized'}
+    d['sanitized'] = True
+    json.dump(d, open(os.path.join(to_path, 'config.json'), 'w'), indent=4)
+    save_file({k: v.contiguous() for k, v in w.items()}, os.path.join(to_path, 'sanitized_model.safetensors'))
 
 
 def load(blind_model=False, quantize_model=False, quantize_cache=False, use_adapter=False, **kwargs):
@@ -67,28 +143,42 @@ def load(blind_model=False, quantize_model=False, quantize_cache=False, use_adap
         raise NotImplementedError('a LoRA adapter over 4-bit weights cannot be folded into them (pv:264-271 wraps QuantizedLinear); '
                                   'load the bf16 model with use_adapter=True')
     device = kwargs.pop('device', 'cuda')
-    cfg = kwargs.pop('cfg', None) or (PHI35_MINI if blind_model else PHI35_VISION)
-    cfg = with_overrides(cfg, use_quantized_cache=quantize_cache)          # pv:1322 -> phi.py:512,572
+    cfg = kwargs.pop('cfg', None)
     tokenizer = kwargs.pop('tokenizer', None)
     weights = kwargs.pop('weights', None)
     clip_cfg = kwargs.pop('clip_cfg', None)
     num_crops = kwargs.pop('num_crops', 16)
+    default_path = PATH_ORIGINAL_PHI3_BLIND if blind_model else PATH_ORIGINAL_PHI3_VISION
+    if quantize_model and os.path.isdir(default_path + '_Q') and 'model_path' not in kwargs and weights is None:
+        default_path += '_Q'                                               # pv:1306-1315: the pre-quantised checkpoint directory
+    ckpt_dir = None
     if weights is None:
-        path = kwargs.pop('model_path', PATH_ORIGINAL_PHI3_BLIND if blind_model else PATH_ORIGINAL_PHI3_VISION)
+        path = kwargs.pop('model_path', default_path)
         if kwargs.pop('random_init', False):
+            cfg = cfg or (PHI35_MINI if blind_model else PHI35_VISION)
             weights = random_weights(cfg, seed=kwargs.pop('seed', 0), device=device, clip_cfg=clip_cfg)
         elif os.path.isdir(path):
-            weights = _read_safetensors(path)
+            ckpt_dir = path
         else:
             raise FileNotFoundError(f'{path} not found and no network to fetch it (reference: _setup, pv:247-255); '
                                     'pass weights=..., or random_init=True')
     elif isinstance(weights, str):
-        weights = _read_safetensors(weights)
+        ckpt_dir = weights
+    if ckpt_dir is not None:
+        file_cfg = _read_config(ckpt_dir)
+        if cfg is None and file_cfg is not None:
+            cfg = file_cfg
+        weights = _read_safetensors(ckpt_dir, sanitized=bool(getattr(cfg, 'sanitized', False)),
+                                    quantized=getattr(cfg, 'quantized', None))
+        if getattr(cfg, 'quantized', None):
+            quantize_model = True                                          # pv:264: nn.quantize(model, group_size, bits) before load_weights
+    cfg = cfg or (PHI35_MINI if blind_model else PHI35_VISION)
+    cfg = with_overrides(cfg, use_quantized_cache=quantize_cache)          # pv:1322 -> phi.py:512,572
     if tokenizer is None:
-        path = PATH_ORIGINAL_PHI3_BLIND if blind_model else PATH_ORIGINAL_PHI3_VISION
-        if os.path.isdir(path):
-            from transformers import AutoTokenizer
-            tokenizer = AutoTokenizer.from_pretrained(path)
+        path = ckpt_dir or default_path
+        if os.path.isdir(path) and (os.path.exists(os.path.join(path, 'tokenizer.json'))
+                                    or os.path.exists(os.path.join(path, 'tokenizer.model'))):
+            tokenizer = _load_tokenizer(path)
         else:
             tokenizer = ByteTokenizer()
     for k, v in kwargs.items():                                            # remaining kwargs override cfg (pv:359-363)
@@ -99,6 +189,8 @@ def load(blind_model=False, quantize_model=False, quantize_cache=False, use_adap
             adapter = _read_adapter(adapter_path)                          # pv:266-271, _get_adapter_path pv:462
         weights = merge_lora(weights, adapter['config'], adapter['weights'], cfg.num_hidden_layers)
     model = Phi3B200(cfg, weights, device=device, clip_cfg=clip_cfg, quantize_model=quantize_model)
+    if ckpt_dir is not None and getattr(cfg, 'architectures', None):       # pv:260: processor class follows the checkpoint's arch
+        blind_model = not cfg.architectures[0].startswith('Phi3V')
     processor = Phi3FProcessor(tokenizer) if blind_model else Phi3VProcessor(tokenizer, num_crops=num_crops, device=device)
     return model, processor
 
@@ -250,15 +342,53 @@ class LogitStopper:
         return False
 
 
+def _batch_inputs(processor, prompts, images):
+    """N image+text (or text-only) prompts -> ONE left-padded model input with per-prompt batch-1 semantics:
+    every prompt goes through the processor alone, exactly as the reference's batch-1 VLM path does (pv:381, phi:263-281), then
+    rows are left-padded like Phi3FProcessor._tokenize (phi:236-245: ids 0, pids 1, mask 0) and the image-token positions are
+    shifted by each row's pad. Row b keeps positions 0..L_b-1, so its logits equal the batch-1 call's."""
+    per = []
+    for i, p in enumerate(prompts):
+        im = None if images is None else images[i]
+        if im is not None and not isinstance(im, (list, tuple)):
+            im = [im]
+        per.append(processor(p, im) if im else processor(p))
+    B, L = len(per), max(d['input_ids'].shape[1] for d in per)
+    ids = torch.zeros((B, L), dtype=torch.int64)
+    pids = torch.ones((B, L), dtype=torch.int64)
+    mask = torch.zeros((B, L), dtype=torch.int64)
+    pvs, sizes, pos = [], [], []
+    for b, d in enumerate(per):
+        row = d['input_ids'][0]
+        l = row.shape[0]
+        ids[b, L - l:], pids[b, L - l:], mask[b, L - l:] = row, torch.arange(l), 1
+        if 'pixel_values' in d:
+            pvs.append(d['pixel_values'])
+            sizes.append(torch.as_tensor(d['image_sizes']))
+            pp = torch.as_tensor(d['positions']).clone()
+            pp[:, 0], pp[:, 1] = b, pp[:, 1] + (L - l)
+            pos.append(pp)
+    out = {'input_ids': ids, 'pids': pids, 'mask': mask}
+    if pvs:
+        n_crops = max(p.shape[1] for p in pvs)                               # crop axis is zero-padded (phi:311-316)
+        pvs = [p if p.shape[1] == n_crops else torch.cat([p, p.new_zeros((p.shape[0], n_crops - p.shape[1]) + p.shape[2:])], 1)
+               for p in pvs]
+        out.update(pixel_values=torch.cat(pvs, 0), image_sizes=torch.cat(sizes, 0), positions=torch.cat(pos, 0))
+    return out
+
+
 def _generate(model, processor, prompt, images=None, max_tokens=512, verbose=True, return_tps=False, early_stop=False,
-              stream=True, mute=False, return_tokens=False, eos_check_every=16, top_p=None, temperature=1.0, seed=0):
+              stream=True, mute=False, return_tokens=False, eos_check_every=16, top_p=None, temperature=1.0, seed=0,
+              dict_input=None):
     """pv:376-409. The loop body is one CUDA-graph replay per token; EOS for all rows
     (TokenStopper, pv:106-117) is polled every `eos_check_every` steps instead of twice per token —
-    rows are truncated at their first EOS afterwards exactly as the reference does (pv:73)."""
-    if images is not None and isinstance(prompt, list):
+    rows are truncated at their first EOS afterwards exactly as the reference does (pv:73).
+    `dict_input`: a prebuilt model input (generate_batch) instead of processor(prompt, images)."""
+    if dict_input is None and images is not None and isinstance(prompt, list):
         raise ValueError('Images cannot be provided when prompt is a list')
     streamer = Streamer(processor, stream, mute)
-    dict_input = processor(prompt, images)
+    if dict_input is None:
+        dict_input = processor(prompt, images)
     B = dict_input['input_ids'].shape[0]
     if B > 1:
         streamer.stream = False                                            # pv:53-56: batches are never streamed
@@ -336,6 +466,63 @@ def generate(prompt, images=None, preload=None, blind_model=False, quantize_mode
                        use_adapter=use_adapter)
     prompt, images = _apply_chat_template(prompt, images, verbose, apply_chat_template)
     return _generate(*preload, prompt, images, max_tokens, verbose, return_tps, early_stop, stream)
+
+
+def generate_batch(prompts, images=None, preload=None, blind_model=False, quantize_model=False, quantize_cache=False,
+                   use_adapter=False, max_tokens=512, verbose=False, return_tps=False, apply_chat_template=True,
+                   return_tokens=False):
+    """Extension of generate() (pv:1324) for BASELINE config 3: a LIST of prompts, each with its own image(s).
+    `images`: None, or a list with one entry per prompt (None | image | list of images). Returns a list of strings
+    (or (prompt_tps, gen_tps) / the token history). Per-prompt results equal separate batch-1 generate() calls."""
+    if isinstance(prompts, str):
+        raise ValueError('generate_batch takes a list of prompts; use generate() for a single one')
+    if images is not None and len(images) != len(prompts):
+        raise ValueError('images must hold one entry (None, an image or a list of images) per prompt')
+    if preload is None:
+        preload = load(blind_model=blind_model, quantize_model=quantize_model, quantize_cache=quantize_cache,
+                       use_adapter=use_adapter)
+    model, processor = preload
+    texts, imgs = [], []
+    for i, p in enumerate(prompts):
+        im = None if images is None else images[i]
+        t, im = _apply_chat_template(p, im, False, apply_chat_template)
+        texts.append(t)
+        imgs.append(im)
+    # static LongRoPE switch (phi:492, H7) is a per-prompt decision in the batch-1 reference: rows must agree on it
+    lens = _prompt_lengths(processor, texts, imgs)
+    orig = model.cfg.original_max_position_embeddings
+    if len({(l + max_tokens) > orig for l in lens}) > 1:
+        raise ValueError('prompts on both sides of the LongRoPE switch (prompt + max_tokens vs '
+                         f'{orig}) cannot share a batch: split them into two calls')
+    prev = model.force_long_rope
+    if prev is None:
+        model.force_long_rope = (max(lens) + max_tokens) > orig
+    try:
+        dict_input = _batch_inputs(processor, texts, imgs if any(i is not None for i in imgs) else None)
+        return _generate(model, processor, texts, None, max_tokens, verbose, return_tps, False, False, mute=not verbose,
+                         return_tokens=return_tokens, dict_input=dict_input)
+    finally:
+        model.force_long_rope = prev
+
+
+def _prompt_lengths(processor, texts, imgs):
+    """token count of every prompt (text chunks + image tokens, phi:263-277) without running the image transform"""
+    from .processor import hd_geometry
+    import re
+    out = []
+    for t, im in zip(texts, imgs):
+        if not im:
+            out.append(len(processor.tokenizer(t).input_ids))
+            continue
+        n = sum(len(c) for c in processor.tokenizer(re.split(r"<\|image_\d+\|>", t)).input_ids)
+        for x in im:
+            if hasattr(x, 'size') and not hasattr(x, 'shape'):
+                w, h = x.size
+            else:
+                h, w = x.shape[:2]
+            n += hd_geometry(w, h, processor.img_processor.num_crops)['num_img_tokens']
+        out.append(n)
+    return out
 
 
 # ------------------------------------------------------------------------------------- choose

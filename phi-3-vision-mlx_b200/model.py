@@ -333,6 +333,29 @@ class Phi3B200:
         # only crops 0..hc*wc of each image reach the output (phi:405-406); zero-pad crops are skipped
         used = [pv[b, :hw[0] * hw[1] + 1] for b, hw in enumerate(sizes)]
         px = torch.cat(used, 0).contiguous()
+        x = self.clip_features(px)
+        # token assembly + projector + splice (phi:400-415)
+        crop0, idx = 0, 0
+        for b, (hc, wc) in enumerate(sizes):
+            cnt = (hc * wc + 1) * 144 + 1 + (hc + 1) * 12
+            feats = x[crop0 * 577:(crop0 + hc * wc + 1) * 577]
+            tok = torch.empty((cnt, 4 * D), dtype=torch.bfloat16, device=self.dev)
+            call('p3_gn_assemble', ptr(feats), ptr(v['sub_GN']), ptr(v['glb_GN']), ptr(tok), hc, wc, D, st)
+            p1 = torch.empty((cnt, self.H), dtype=torch.bfloat16, device=self.dev)
+            self.gemm(tok, v['p0_w'], p1, _lib.EPI_GELU, bias=v['p0_b'])
+            r, c = positions[idx]
+            row_map = (torch.arange(cnt, dtype=torch.int32, device=self.dev) + (r * L + c)).contiguous()
+            self.gemm(p1, v['p2_w'], h, _lib.EPI_NONE, bias=v['p2_b'], row_map=row_map)
+            crop0 += hc * wc + 1
+            idx += cnt
+        return h
+
+    def clip_features(self, px):
+        """ClipVModel (phi:208-226): px fp32 [N,3,336,336] on the device -> fp32 residual stream [N*577, 1024] after the 23
+        encoder layers the reference runs (row 577*n is the CLS token, which phi:221 drops)."""
+        v, cc = self.vision, self.clip_cfg
+        D, nh = cc.hidden_size, cc.num_attention_heads
+        st = _stream()
         N = px.shape[0]
         T = N * 577
         A = torch.empty((N * 576, v['kpad']), dtype=torch.bfloat16, device=self.dev)
@@ -356,21 +379,7 @@ class Phi3B200:
             call('p3_layernorm', ptr(x), ptr(lw['ln2w']), ptr(lw['ln2b']), ptr(xn), T, D, cc.layer_norm_eps, 0, st)
             self.gemm(xn, lw['fc1_w'], mid, _lib.EPI_QGELU, bias=lw['fc1_b'])
             self.gemm(mid, lw['fc2_w'], x, _lib.EPI_RESIDUAL_F32, bias=lw['fc2_b'], resid=x)
-        # token assembly + projector + splice (phi:400-415)
-        crop0, idx = 0, 0
-        for b, (hc, wc) in enumerate(sizes):
-            cnt = (hc * wc + 1) * 144 + 1 + (hc + 1) * 12
-            feats = x[crop0 * 577:(crop0 + hc * wc + 1) * 577]
-            tok = torch.empty((cnt, 4 * D), dtype=torch.bfloat16, device=self.dev)
-            call('p3_gn_assemble', ptr(feats), ptr(v['sub_GN']), ptr(v['glb_GN']), ptr(tok), hc, wc, D, st)
-            p1 = torch.empty((cnt, self.H), dtype=torch.bfloat16, device=self.dev)
-            self.gemm(tok, v['p0_w'], p1, _lib.EPI_GELU, bias=v['p0_b'])
-            r, c = positions[idx]
-            row_map = (torch.arange(cnt, dtype=torch.int32, device=self.dev) + (r * L + c)).contiguous()
-            self.gemm(p1, v['p2_w'], h, _lib.EPI_NONE, bias=v['p2_b'], row_map=row_map)
-            crop0 += hc * wc + 1
-            idx += cnt
-        return h
+        return x
 
     # ------------------------------------------------------------------ one decoder pass
     def _forward_tokens(self, ids_dev, B, L, cache, n_beam, write_cache, past, logits_rows, past_dev=None,

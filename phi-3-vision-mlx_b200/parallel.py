@@ -52,17 +52,31 @@ def dp_map(fn, items, lengths=None, group=None):
     return out
 
 
-def dp_generate(model, processor, prompts, max_tokens=512, **kw):
-    """generate() over a prompt list sharded across ranks; rank 0 returns the texts in input order."""
-    from .api import _generate
-    lens = [len(processor.tokenizer(p).input_ids) for p in prompts]
+def dp_generate(model, processor, prompts, images=None, max_tokens=512, apply_chat_template=False, **kw):
+    """generate() over a prompt list sharded across ranks; rank 0 returns the texts in input order (other ranks None).
+    `images`: None (text-only: the reference's left-padded batch, phi:236-245) or one entry per prompt (None | image | list of
+    images): each rank then runs its shard through api.generate_batch (per-prompt batch-1 semantics, H11)."""
+    from .api import _generate, _prompt_lengths, _apply_chat_template, generate_batch
+    prompts = list(prompts)
+    if images is not None:
+        if len(images) != len(prompts):
+            raise ValueError('images must hold one entry per prompt')
+        norm = [None if im is None else (list(im) if isinstance(im, (list, tuple)) else [im]) for im in images]
+        texts = [_apply_chat_template(p, im, False, apply_chat_template)[0] for p, im in zip(prompts, norm)]
+        lens = _prompt_lengths(processor, texts, norm)
+    else:
+        lens = [len(processor.tokenizer(p).input_ids) for p in prompts]
+    prev = model.force_long_rope
     model.force_long_rope = global_rope_switch(lens, max_tokens, model.cfg.original_max_position_embeddings)
 
     def run(shard, idx):
+        if images is not None:
+            return generate_batch(shard, [images[i] for i in idx], preload=(model, processor), max_tokens=max_tokens,
+                                  verbose=False, apply_chat_template=apply_chat_template, **kw)
         out = _generate(model, processor, shard if len(shard) > 1 else shard[0], max_tokens=max_tokens, verbose=False,
                         stream=False, mute=True, **kw)
         return out if isinstance(out, list) else [out]
     try:
-        return dp_map(run, list(prompts), lens)
+        return dp_map(run, prompts, lens)
     finally:
-        model.force_long_rope = None
+        model.force_long_rope = prev

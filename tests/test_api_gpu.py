@@ -343,3 +343,66 @@ def test_quantize_model_and_quantize_cache_together(dev):
         tok = lo[:, -1].argmax(-1)
     txt = api.generate(['abc def ghi', 'short'], preload=(model, proc), max_tokens=6, verbose=False, stream=False)
     assert len(txt) == 2
+
+
+def test_generate_batch_equals_separate_batch1_calls(dev):
+    """generate_batch (extension for BASELINE config 3): N image+text prompts as one left-padded batch give, row by row, the
+    tokens of N separate batch-1 generate() calls (the only way the reference can run them, pv:377-378)."""
+    api, model, proc, ora = _setup(vision=True)
+    rs = np.random.RandomState(11)
+    imgs = [rs.randint(0, 256, (350, 500, 3), dtype=np.uint8), rs.randint(0, 256, (400, 400, 3), dtype=np.uint8), None]
+    prompts = ['What is shown here?', 'Describe the second picture in a few more words.', 'No image for this one']
+    hist = api.generate_batch(prompts, imgs, preload=(model, proc), max_tokens=6, return_tokens=True).cpu()
+    assert hist.shape == (3, 6)
+    for i, (p, im) in enumerate(zip(prompts, imgs)):
+        t, ims = api._apply_chat_template(p, None if im is None else [im], False)
+        one = api._generate(model, proc, t, ims, max_tokens=6, verbose=False, stream=False, mute=True, return_tokens=True).cpu()
+        assert (one[0] == hist[i]).float().mean() >= 0.8 and one[0, 0] == hist[i, 0], (i, one.tolist(), hist[i].tolist())
+    txt = api.generate_batch(prompts, imgs, preload=(model, proc), max_tokens=4)
+    assert isinstance(txt, list) and len(txt) == 3 and all(isinstance(t, str) for t in txt)
+    with pytest.raises(ValueError):
+        api.generate_batch(prompts, imgs[:2], preload=(model, proc), max_tokens=4)
+
+
+def test_dp_generate_with_images_single_process(dev):
+    from phi3_b200 import parallel
+    api, model, proc, ora = _setup(vision=True)
+    rs = np.random.RandomState(12)
+    imgs = [rs.randint(0, 256, (336, 336, 3), dtype=np.uint8) for _ in range(3)]
+    prompts = ['one', 'two two', 'three three three']
+    out = parallel.dp_generate(model, proc, prompts, images=imgs, max_tokens=4, apply_chat_template=True)
+    ref = api.generate_batch(prompts, imgs, preload=(model, proc), max_tokens=4)
+    assert out == ref and model.force_long_rope is None
+
+
+def test_short_left_padded_first_call_masks_pad_keys(dev):
+    """a left-padded batch with L <= 16 takes the decode-attention kernel on its FIRST call (past == 0); the
+    present tile must mask the pad keys like Mask4D does (phi:557-559)."""
+    api, model, proc, ora = _setup()
+    lens, n = [5, 9, 12], 12
+    g = torch.Generator().manual_seed(3)
+    ids = torch.zeros(3, n, dtype=torch.long)
+    pids = torch.ones(3, n, dtype=torch.long)
+    mask = torch.zeros(3, n, dtype=torch.long)
+    for b, l in enumerate(lens):
+        ids[b, n - l:] = torch.randint(3, 32000, (l,), generator=g)
+        ids[b, n - l] = 1
+        pids[b, n - l:] = torch.arange(l)
+        mask[b, n - l:] = 1
+    lo, co = ora(ids, pids=pids, mask=mask, max_tokens=3)
+    lg, cg = model(ids, pids=pids, mask=mask, max_tokens=3)
+    m = mask.bool()
+    rel = ((lg.cpu().float()[m] - lo[m]).abs().max() / lo[m].abs().max()).item()
+    assert rel < 2e-2, rel
+    tok = lo[:, -1].argmax(-1)
+    lo2, _ = ora(tok[:, None], cache=co)
+    lg2, _ = model(tok[:, None], cache=cg)
+    assert ((lg2.cpu().float() - lo2).abs().max() / lo2.abs().max()).item() < 2e-2
+
+
+def test_kv_cache_handle_is_a_finite_sequence(dev):
+    api, model, proc, ora = _setup()
+    lg, c = model(torch.randint(3, 300, (1, 20)), max_tokens=2)
+    assert len(list(c)) == model.cfg.num_hidden_layers and c[0].offset == 20
+    with pytest.raises(IndexError):
+        c[model.cfg.num_hidden_layers]

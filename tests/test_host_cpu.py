@@ -230,3 +230,89 @@ def test_mega_args_layout_matches_header():
     import phi3_b200  # noqa
     from phi3_b200 import mega
     assert ctypes.sizeof(mega.MegaPhase) == 104 and ctypes.sizeof(mega.MegaArgs) == 520    # static_assert in decode_mega.cu
+
+
+# ------------------------------------------------------------------ round 2 host logic: batching, checkpoint directories
+def _fake_vproc():
+    import torch
+    import phi3_b200  # noqa
+    from phi3_b200.processor import Phi3VProcessor, ByteTokenizer
+
+    class FakeIP:
+        num_crops = 4
+
+        def __call__(self, images):
+            n = len(images)
+            return {'pixel_values': torch.zeros(n, 5, 3, 336, 336), 'image_sizes': [[672, 672]] * n, 'num_img_tokens': [757] * n}
+    proc = Phi3VProcessor.__new__(Phi3VProcessor)
+    proc.tokenizer, proc.img_processor = ByteTokenizer(), FakeIP()
+    return proc
+
+
+def test_batch_inputs_keep_per_prompt_batch1_semantics():
+    """api._batch_inputs: every row is the batch-1 processor output, left-padded (ids 0 / pids 1 / mask 0, phi:236-245) with
+    the image-token positions shifted by the row's pad (H11)."""
+    import torch
+    from phi3_b200 import api
+    proc = _fake_vproc()
+    img = torch.zeros(672, 672, 3, dtype=torch.uint8)
+    texts = [api._apply_chat_template(t, im, False, True)[0] for t, im in (('a' * 100, [img]), ('hello', None), ('x' * 10, [img]))]
+    b = api._batch_inputs(proc, texts, [[img], None, [img]])
+    L = b['input_ids'].shape[1]
+    assert api._prompt_lengths(proc, texts, [[img], None, [img]]) == b['mask'].sum(1).tolist()
+    for r, (t, im) in enumerate(zip(texts, ([img], None, [img]))):
+        one = proc(t, im) if im else proc(t)
+        l = one['input_ids'].shape[1]
+        assert b['input_ids'][r, L - l:].tolist() == one['input_ids'][0].tolist()
+        assert b['input_ids'][r, :L - l].eq(0).all() and b['pids'][r, :L - l].eq(1).all() and b['mask'][r, :L - l].eq(0).all()
+        assert b['pids'][r, L - l:].tolist() == list(range(l))
+    pos = b['positions']
+    assert pos.shape[0] == 2 * 757 and set(pos[:, 0].tolist()) == {0, 2}
+    assert (b['input_ids'][pos[:, 0], pos[:, 1]] < 0).all() and (b['input_ids'] < 0).sum() == 2 * 757
+    assert b['pixel_values'].shape[0] == 2 and b['image_sizes'].tolist() == [[672, 672], [672, 672]]
+
+
+def test_checkpoint_directory_config_and_mlx_quantized_layout(tmp_path):
+    """_read_config mirrors _get_cfg (pv:359-369); _read_safetensors handles shards, the HF patch-conv layout (pv:374), the
+    `sanitized` flag (pv:276-289) and MLX's quantized weight/scales/biases triples (pv:291-305)."""
+    import json
+    import torch
+    from safetensors.torch import save_file
+    import phi3_b200  # noqa
+    from phi3_b200 import api
+    d = tmp_path / 'ckpt'
+    d.mkdir()
+    cfg = dict(architectures=['Phi3VForCausalLM'], hidden_size=64, num_attention_heads=2, rope_theta=12345.0,
+               rope_scaling={'type': 'su', 'short_factor': [1.0] * 16, 'long_factor': [2.0] * 16})
+    json.dump(cfg, open(d / 'config.json', 'w'))
+    key = 'model.vision_embed_tokens.img_processor.vision_model.embeddings.patch_embedding.weight'
+    conv = torch.randn(8, 3, 14, 14).to(torch.bfloat16)
+    save_file({key: conv}, str(d / 'model-00001-of-00002.safetensors'))
+    save_file({'lm_head.weight': torch.randn(4, 64).to(torch.bfloat16)}, str(d / 'model-00002-of-00002.safetensors'))
+    c = api._read_config(str(d))
+    assert c.rope_theta == 12345.0 and c.num_key_value_heads == 2 and c.use_quantized_cache is False
+    w = api._read_safetensors(str(d))
+    assert set(w) == {key, 'lm_head.weight'} and w[key].shape == (8, 14, 14, 3)
+    assert torch.equal(w[key], conv.permute(0, 2, 3, 1))
+    # sanitize(): reference layout on disk + sanitized flag; reading it back must NOT transpose again
+    api.sanitize(str(d), str(tmp_path / 'san'))
+    c2 = api._read_config(str(tmp_path / 'san'))
+    assert c2.sanitized is True
+    w2 = api._read_safetensors(str(tmp_path / 'san'), sanitized=True)
+    assert torch.equal(w2[key], w[key])
+    assert api._read_config(str(tmp_path)) is None
+    # MLX quantized triple: element i of a row sits in bits [4*(i%8), +4) of uint32 word i//8
+    q = torch.randint(0, 16, (4, 128))
+    words = (q.reshape(4, 16, 8).to(torch.int64) << (4 * torch.arange(8))).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)       # safetensors has no uint32 in torch
+    sc, bi = torch.rand(4, 2) + 0.1, torch.randn(4, 2)
+    ref = (q.reshape(4, 2, 64).float() * sc[..., None] + bi[..., None]).reshape(4, 128)
+    got = api.dequantize_mlx(words, sc, bi, 64, 4)
+    assert torch.allclose(got.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_logit_stopper_accepts_bool_like_the_reference():
+    from phi3_b200 import api
+    assert api.LogitStopper(100, True).early_stop is True            # pv:82: bool is an int -> enabled with threshold 1
+    assert api.LogitStopper(100, False).early_stop is False
+    assert api.LogitStopper(100, 5).early_stop == 5 and api.LogitStopper(4, 5).early_stop is False

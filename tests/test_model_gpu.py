@@ -164,38 +164,8 @@ def test_vision_splice(dev):
     assert rel(lg, lo) < TOL
 
 
-def test_full_size_config1(dev):
-    """BASELINE config 1 shapes: Phi-3.5-mini, 4 prompts x 32 tokens, random-init, a few decode steps."""
-    import phi3_b200  # noqa
-    from phi3_b200 import configs, weights
-    from phi3_b200.model import Phi3B200
-    from oracle.phi3_oracle import Phi3Oracle
-    cfg = configs.PHI35_MINI
-    w = weights.random_weights(cfg, seed=0)
-    m = Phi3B200(cfg, w)
-    o = Phi3Oracle(cfg, w, prec='b200')
-    ids = _ids(4, 32, seed=11)
-    lo, co = o(ids, max_tokens=4)
-    lg, cg = m(ids, max_tokens=4)
-    # bf16 pipelines decorrelate completely under any perturbation (DESIGN.md §4): the attainable
-    # agreement between two correct bf16 implementations is the bf16 noise floor, measured here as
-    # the distance between the oracle's own bf16 flow and its fp32 arithmetic on the same inputs.
-    lf, _ = Phi3Oracle(cfg, w, prec='fp32')(ids, max_tokens=0)
-    rms = lambda a, b: ((a.float().cpu() - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
-    floor = rms(lo, lf)
-    assert rms(lg, lo) < 2.5e-2 and rms(lg, lo) < 1.5 * floor, (rms(lg, lo), floor)
-    assert rms(lg, lf) < 1.5 * floor
-    top2 = lo.topk(2, -1).values
-    margin = top2[..., 0] - top2[..., 1]
-    agree = lg.argmax(-1).cpu() == lo.argmax(-1)
-    assert agree[margin > 0.1].all()                     # every position whose margin clears the noise floor agrees
-    assert agree.float().mean() >= 0.9
-    tok = lo[:, -1].argmax(-1)
-    for _ in range(2):
-        lo, co = o(tok[:, None], cache=co)
-        lg, cg = m(tok[:, None], cache=cg)
-        assert rms(lg, lo) < 2.5e-2
-        tok = lo[:, -1].argmax(-1)
+# Full-size parity (BASELINE configs 1-5 shapes, >= 99 % greedy agreement and <= 2e-2 relative logits error against the
+# oracle's REFERENCE dtype flow, on the peaked parity checkpoint) lives in tests/test_parity_fullsize_gpu.py.
 
 
 def test_slab_recycling_and_graph_reuse(dev):

