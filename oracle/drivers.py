@@ -9,21 +9,61 @@ import torch
 ID_EOS = 32007
 
 
-def generate_ids(model, inp, max_tokens):
-    """pv:385-398 without stoppers firing early: returns tokens [B, max_tokens] (rows not truncated, H12)."""
+class LogitStopper:
+    """pv:79-104, statement by statement (B = 1 early-stop heuristic on the EOS log-probability)."""
+
+    def __init__(self, max_tokens, early_stop):
+        self.step = 0
+        self.early_stop = early_stop if isinstance(early_stop, int) and (early_stop < max_tokens) else False
+        self.log_prob_sum = 0.0
+        self.best_eos_sofar = -float('inf')
+        self.log_prob_sum_at_best_eos = 0.0
+
+    def __call__(self, logits):
+        if not self.early_stop:
+            return False
+        if logits.shape[0] > 1:
+            self.early_stop = False
+            return False
+        log_prob = torch.log_softmax(logits[:, -1, :], -1)
+        log_prob_best = log_prob.max(-1).values.item()
+        log_prob_eos = log_prob[:, ID_EOS].item()
+        if log_prob_eos > self.best_eos_sofar:
+            since = self.log_prob_sum - self.log_prob_sum_at_best_eos
+            if (since < self.best_eos_sofar) and (self.step > self.early_stop):
+                return True
+            self.best_eos_sofar = log_prob_eos
+            self.log_prob_sum_at_best_eos = self.log_prob_sum
+        self.log_prob_sum += log_prob_best
+        self.step += 1
+        return False
+
+
+def generate_ids(model, inp, max_tokens, early_stop=False):
+    """pv:385-398 with both stoppers: returns tokens [B, n <= max_tokens] (rows not truncated, H12). The loop ends when every
+    row has emitted EOS at least once (TokenStopper pv:106-117: checked only on steps whose token batch contains an EOS) or the
+    LogitStopper fires (pv:395)."""
     logits, cache = model(**inp, max_tokens=max_tokens)
     token = logits[:, -1, :].argmax(-1)[:, None]
     out = [token]
     eos_rows = torch.ones(token.shape[0])
+    logit_stopper = LogitStopper(max_tokens, early_stop)
     for _ in range(max_tokens - 1):
         logits, cache = model(input_ids=token, cache=cache)
         token = logits[:, -1, :].argmax(-1)[:, None]
         out.append(token)
+        if logit_stopper(logits):                                         # pv:395
+            break
         if (token == ID_EOS).any():                                       # TokenStopper pv:112-117
             eos_rows = eos_rows * (token.squeeze(1) != ID_EOS)
             if eos_rows.sum() < 1:
                 break
     return torch.cat(out, 1)
+
+
+def truncate_rows(tokens):
+    """Streamer.end pv:73: every row is cut after its first EOS."""
+    return [(r[:r.index(ID_EOS) + 1] if ID_EOS in r else r) for r in tokens.tolist()]
 
 
 def choose_ids(model, inp, option_ids):

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libphi3b200.so')
+LIB_PATH = os.environ.get('P3_LIB') or os.path.join(_HERE, 'libphi3b200.so')     # P3_LIB: tuning builds (tools/), same ABI
 
 EPI_NONE, EPI_QGELU, EPI_GELU, EPI_RESIDUAL, EPI_SWIGLU, EPI_F32, EPI_RESIDUAL_F32 = range(7)
 PAGE = 64

@@ -30,8 +30,12 @@
 #define MG_WARPS 8
 #define MG_THREADS (MG_WARPS * 32 + 32)      // 8 consumer warps + 1 producer warp
 #define MG_CONSUMERS (MG_WARPS * 32)
+#ifndef MG_SLOT
 #define MG_SLOT 4096
+#endif
+#ifndef MG_RSLOTS
 #define MG_RSLOTS 6
+#endif
 #define MG_XF 32                       // max 16-wide k blocks per warp and K-block  (K-block <= 8 * 32 * 16 = 4096)
 #define MG_KBLOCK 4096
 #define MG_MAX_PART 8                  // tiles per CTA of a multi-K-block phase (partial sums parked in smem)
@@ -131,7 +135,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ float mg_silu(float x) { return x / (1.f + __expf(-x)); }
 
 #define MG_TILE_CACHE 32               // per-phase tile ids of this CTA kept in shared memory (more: read from global)
-#define MG_PF_ITEMS 2                  // L2 prefetch runs this many items (96-192 KB each) ahead of the ring
+#ifndef MG_PF_ITEMS
+#define MG_PF_ITEMS 0                  // L2 prefetch runs this many items (96-192 KB each) ahead of the ring
+#endif
 
 __device__ __forceinline__ void mg_arrive(unsigned* ctr) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");

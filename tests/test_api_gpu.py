@@ -406,3 +406,37 @@ def test_kv_cache_handle_is_a_finite_sequence(dev):
     assert len(list(c)) == model.cfg.num_hidden_layers and c[0].offset == 20
     with pytest.raises(IndexError):
         c[model.cfg.num_hidden_layers]
+
+
+def test_token_stopper_and_row_truncation_match_oracle(dev):
+    """A4: rows that emit EOS (32007) at different steps. The reference stops when every row has emitted EOS once
+    (TokenStopper pv:106-117) and cuts each row after its first EOS (Streamer.end pv:73). The checkpoint is the peaked one with
+    the next-token permutation patched so that row 0 reaches EOS at step 3 and row 1 at step 6."""
+    import phi3_b200  # noqa
+    from phi3_b200 import configs, weights, api
+    from phi3_b200.processor import ByteTokenizer
+    from oracle.phi3_oracle import Phi3Oracle
+    from oracle import drivers
+    cfg = configs.tiny()
+    w = weights.random_weights(cfg, seed=5, init='peaked')
+    emb = w['model.embed_tokens.weight'].float()
+    lm = w['lm_head.weight'].clone()
+    chains = [[ord('a') + 3, 400, 401, 402, 32007, 403], [ord('b') + 3, 500, 501, 502, 503, 504, 505, 32007, 506]]
+    for ch in chains:                                              # after token ch[i] the model predicts ch[i+1]
+        for a, b in zip(ch[:-1], ch[1:]):
+            lm[b] = (weights.PEAK_ALPHA * emb[a]).to(lm.dtype)
+    w['lm_head.weight'] = lm
+    model, proc = api.load(blind_model=True, cfg=cfg, weights=w, tokenizer=ByteTokenizer())
+    ora = Phi3Oracle(model.cfg, w, prec='b200')
+    prompts = ['xyz a', 'xyz b']                                  # equal lengths: no padding ambiguity
+    inp = proc(prompts)
+    ref = drivers.generate_ids(ora, inp, 12)
+    assert ref.shape[1] == 7 and ref[0, 3] == 32007 and ref[1, 6] == 32007      # the oracle loop stopped when both rows were done
+    hist = api._generate(model, proc, prompts, None, max_tokens=12, verbose=False, stream=False, mute=True, return_tokens=True,
+                         eos_check_every=1).cpu().long()
+    assert hist.shape == ref.shape and torch.equal(hist, ref)
+    txt = api._generate(model, proc, prompts, None, max_tokens=12, verbose=False, stream=False, mute=True)
+    assert txt == proc.tokenizer.batch_decode(drivers.truncate_rows(ref))
+    # polling EOS every 16 steps (the default) decodes past the stop point but returns the same truncated text
+    txt16 = api._generate(model, proc, prompts, None, max_tokens=12, verbose=False, stream=False, mute=True, eos_check_every=16)
+    assert txt16 == txt

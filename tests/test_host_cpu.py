@@ -316,3 +316,30 @@ def test_logit_stopper_accepts_bool_like_the_reference():
     assert api.LogitStopper(100, True).early_stop is True            # pv:82: bool is an int -> enabled with threshold 1
     assert api.LogitStopper(100, False).early_stop is False
     assert api.LogitStopper(100, 5).early_stop == 5 and api.LogitStopper(4, 5).early_stop is False
+
+
+def test_logit_stopper_decisions_equal_the_oracle_restatement():
+    """api.LogitStopper (fed the two scalars the device computes) against oracle.drivers.LogitStopper (pv:79-104, fed full
+    logits) on scripted sequences, including one that fires the early stop."""
+    import torch
+    from phi3_b200 import api
+    from oracle import drivers
+    V, EOS = 32064, 32007
+    g = torch.Generator().manual_seed(0)
+    n_fired = 0
+    for trial in range(6):
+        a, o = api.LogitStopper(64, 3), drivers.LogitStopper(64, 3)
+        fired = None
+        for step in range(40):
+            logits = torch.randn(1, 1, V, generator=g)
+            logits[0, 0, 5] += 8.0                                  # a clear best token
+            logits[0, 0, EOS] += (step * 0.6 if trial % 2 == 0 else -3.0)   # EOS log-prob keeps rising in even trials
+            lp = torch.log_softmax(logits[:, -1, :], -1)
+            ra = a(lp.max().item(), lp[0, EOS].item())
+            ro = o(logits)
+            assert ra == ro, (trial, step)
+            if ra:
+                fired = step
+                break
+        n_fired += fired is not None
+    assert n_fired >= 1                                             # the stop path was exercised

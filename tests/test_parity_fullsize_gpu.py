@@ -158,6 +158,10 @@ def test_clip_tower_23_layers(env):
     got = m.clip_features(px.to(m.dev).contiguous()).reshape(5, 577, -1)[:, 1:].cpu()
     rel = ((got - ref).abs().max() / ref.abs().max()).item()
     rms = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    f32 = env['Oracle'](cfg, env['wv'], prec='fp32', clip_cfg=CLIP_VIT_L14_336).clip(px)
+    print('CLIP 23 layers: cuda vs ref max/max %.3e rms %.3e | cuda vs fp32 max/max %.3e rms %.3e | ref vs fp32 max/max %.3e rms %.3e' % (
+        rel, rms, ((got - f32).abs().max() / f32.abs().max()).item(), ((got - f32).pow(2).mean().sqrt() / f32.pow(2).mean().sqrt()).item(),
+        ((ref - f32).abs().max() / f32.abs().max()).item(), ((ref - f32).pow(2).mean().sqrt() / f32.pow(2).mean().sqrt()).item()))
     assert rel <= TOL and rms <= TOL, (rel, rms)
 
 
@@ -170,7 +174,12 @@ def test_config2_single_image_vqa(env):
     inp = _vlm_inputs(env, 1, 781, 4)
     lo, co = o(**inp, max_tokens=9)
     lg, cg = m(**inp, max_tokens=9)
-    _check(lg, lo, what='config 2 prefill (781 positions)')
+    # logits tolerance at all 781 positions; greedy agreement at the positions that hold a TOKEN: the 757 image slots are fed
+    # projected CLIP features, their next-token distribution is never sampled and, without an input embedding, has no peak
+    text = (inp['input_ids'] >= 0)
+    rel = ((lg.float().cpu() - lo).abs().max() / lo.abs().max()).item()
+    assert rel <= TOL, f'config 2 prefill (781 positions): {rel:.3e}'
+    _check(lg, lo, valid=text, what='config 2 prefill (text positions)')
     tok = lo[:, -1].argmax(-1)
     for i in range(8):
         lo, co = o(tok[:, None], cache=co)
