@@ -182,6 +182,41 @@ int p3_gn_assemble(const float* feats, const void* sub_GN, const void* glb_GN, v
                    cudaStream_t st);
 
 /* ------------------------------------------------------------------------------------------------
+ * Struct-argument GEMM entry with the fused prefill epilogues (north_star: "SuRoPE fused into the QKV epilogue",
+ * "RMSNorm and residual fused with adjacent ops"); replaces nn.RMSNorm + nn.Linear + _rotate_half + KVCache slice-assign at
+ * prefill: phi:442-453, 478-485.
+ *   - ss_in / n_ss_in / eps: RMSNorm of the INPUT rows is applied as a per-row scale rsqrt(sum_c ss_in[row][c] / K + eps) on the
+ *     accumulators; the gain must already be folded into W (W'[n][k] = W[n][k] * g[k]). ss_in rows hold partial sums of
+ *     squares of X's rows (p3_row_sumsq, or the ss_out of the GEMM that produced X).
+ *   - ss_out (P3_EPI_RESIDUAL): fp32 [M][N/32], sum of squares of every 32-column chunk written.
+ *   - P3_EPI_ROPE_KV: out = qkv [M, N] bf16 with q,k rotated, K/V also written to the page pool (as p3_rope_kvwrite). The q
+ *     and k rows of W must be permuted per head to [16j..16j+15 | half+16j..half+16j+15], j = 0..hd/32-1 (so a rotary pair
+ *     meets in one 32-column chunk of the accumulator); v rows keep their order.
+ *   - w_plan: NULL, or a P3_GEMM_WPLAN_BYTES blob filled once by p3_gemm_plan_weights for this W (skips re-encoding the
+ *     weight tensor map on every call). */
+#define P3_EPI_ROPE_KV 8
+#define P3_GEMM_WPLAN_BYTES 320
+typedef struct {
+    const void* X; int64_t ldx;
+    const void* W; int64_t ldw;
+    const void* bias; void* out; int64_t ldo;
+    const void* resid; const int32_t* row_map;
+    int64_t M; int32_t N, K, epi, impl;
+    const float* ss_in; int32_t n_ss_in; float eps;
+    float* ss_out;
+    const void* w_plan;
+    /* P3_EPI_ROPE_KV (M = B*L rows, token i of row b at position past+i; table / cache row b/row_div) */
+    const float* cosT; const float* sinT; int64_t tab_bstride;
+    int32_t L, n_heads, n_kv, hd, past, row_div, write_cache, bt_stride;
+    const int32_t* past_dev;
+    void* pool; const int32_t* block_table;
+} p3_gemm_args;
+int p3_gemm_plan_weights(const void* W, int64_t ldw, int N, int K, void* plan);
+int p3_gemm_fused(const p3_gemm_args* args, cudaStream_t st);
+/* fp32 out[row] = sum of squares of bf16 x[row, 0..H) (feeds ss_in with n_ss_in = 1) */
+int p3_row_sumsq(const void* x, int64_t ldx, float* out, int64_t T, int H, cudaStream_t st);
+
+/* ------------------------------------------------------------------------------------------------
  * Persistent decode-layer kernel (decode_mega.cu): for M <= 8 decode rows, ONE launch of n_ctas (<= #SM,
  * co-resident) persistent CTAs runs up to 4 chained weight-stream phases with grid barriers in between,
  * e.g. o_proj(+residual) -> RMSNorm+gate_up(+SwiGLU) -> down_proj(+residual) -> RMSNorm+qkv_proj(+SuRoPE

@@ -11,6 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('P3_LIB') or os.path.join(_HERE, 'libphi3b200.so')     # P3_LIB: tuning builds (tools/), same ABI
 
 EPI_NONE, EPI_QGELU, EPI_GELU, EPI_RESIDUAL, EPI_SWIGLU, EPI_F32, EPI_RESIDUAL_F32 = range(7)
+EPI_ROPE_KV = 8
+GEMM_WPLAN_BYTES = 320
 PAGE = 64
 
 _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -39,6 +41,7 @@ _SIGS = {
     'p3_clip_embed': [_p, _p, _p, _p, _i, _i, _p],
     'p3_gn_assemble': [_p, _p, _p, _p, _i, _i, _i, _p],
     'p3_mega_pack': [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    'p3_row_sumsq': [_p, _l, _p, _l, _i, _p],
 }
 
 _lib = None
@@ -47,7 +50,7 @@ launches = 0          # number of p3_* kernel-launching calls issued (bench.py r
 
 def exported_symbols():
     return sorted(list(_SIGS) + ['p3_last_error', 'p3_version', 'p3_attention_decode_workspace', 'p3_decode_mega',
-                                 'p3_decode_mega_ctas'])
+                                 'p3_decode_mega_ctas', 'p3_gemm_fused', 'p3_gemm_plan_weights'])
 
 
 def lib():
@@ -66,6 +69,8 @@ def lib():
         L.p3_attention_decode_workspace.restype = C.c_int64
         L.p3_decode_mega.argtypes, L.p3_decode_mega.restype = [_p, _p], C.c_int      # (const p3_mega_args*, stream)
         L.p3_decode_mega_ctas.argtypes, L.p3_decode_mega_ctas.restype = [], C.c_int
+        L.p3_gemm_fused.argtypes, L.p3_gemm_fused.restype = [_p, _p], C.c_int        # (const p3_gemm_args*, stream)
+        L.p3_gemm_plan_weights.argtypes, L.p3_gemm_plan_weights.restype = [_p, _l, _i, _i, _p], C.c_int
         _lib = L
     return _lib
 
@@ -94,3 +99,26 @@ def call_struct(name, args_struct, stream):
     launches += 1
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {L.p3_last_error().decode()}')
+
+
+class GemmArgs(C.Structure):
+    """p3_gemm_args (include/phi3_b200.h)"""
+    _fields_ = [('X', _p), ('ldx', _l), ('W', _p), ('ldw', _l), ('bias', _p), ('out', _p), ('ldo', _l), ('resid', _p),
+                ('row_map', _p), ('M', _l), ('N', C.c_int32), ('K', C.c_int32), ('epi', C.c_int32), ('impl', C.c_int32),
+                ('ss_in', _p), ('n_ss_in', C.c_int32), ('eps', C.c_float), ('ss_out', _p), ('w_plan', _p),
+                ('cosT', _p), ('sinT', _p), ('tab_bstride', _l),
+                ('L', C.c_int32), ('n_heads', C.c_int32), ('n_kv', C.c_int32), ('hd', C.c_int32), ('past', C.c_int32),
+                ('row_div', C.c_int32), ('write_cache', C.c_int32), ('bt_stride', C.c_int32),
+                ('past_dev', _p), ('pool', _p), ('block_table', _p)]
+
+
+class WeightPlan:
+    """caller-owned, 64-byte aligned blob holding the TMA descriptors of one weight matrix (p3_gemm_plan_weights)"""
+
+    def __init__(self, w):
+        self._raw = C.create_string_buffer(GEMM_WPLAN_BYTES + 64)
+        self.addr = (C.addressof(self._raw) + 63) & ~63
+        self.w = w                                             # keeps the tensor (and its address) alive
+        rc = lib().p3_gemm_plan_weights(w.data_ptr(), w.stride(0), w.shape[0], w.shape[1], self.addr)
+        if rc != 0:
+            raise RuntimeError(f'p3_gemm_plan_weights failed ({rc}): {lib().p3_last_error().decode()}')

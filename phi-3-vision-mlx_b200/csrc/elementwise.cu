@@ -43,6 +43,35 @@ extern "C" int p3_embed_gather(const void* table, const int32_t* ids, void* out,
 }
 
 // ------------------------------------------------------------------------------------------
+// row_sumsq: sum of squares of every row (the statistics half of nn.RMSNorm, phi.py:478): one warp per row.
+// ------------------------------------------------------------------------------------------
+__global__ void row_sumsq_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t T, int H) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    pdl_trigger();
+    pdl_wait();
+    if (row >= T) return;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ldx);
+    float ss = 0.f;
+    for (int c = lane; c < H / 8; c += 32) {
+        const uint4 v = xr[c];
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const float2 f = unpack_bf16(u[j]); ss += f.x * f.x + f.y * f.y; }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) out[row] = ss;
+}
+
+extern "C" int p3_row_sumsq(const void* x, int64_t ldx, float* out, int64_t T, int H, cudaStream_t st) {
+    P3_CHECK_ARG(H % 8 == 0 && ldx % 8 == 0, "row_sumsq: H and ldx must be multiples of 8");
+    if (T == 0) return 0;
+    p3_launch_pdl(row_sumsq_kernel, dim3((unsigned)((T + 7) / 8)), dim3(256), 0, st, (const bf16*)x, ldx, out, T, H);
+    P3_CHECK_LAUNCH("row_sumsq");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // rmsnorm: nn.RMSNorm -> mx.fast.rms_norm (phi.py:478-479,571): fp32 accumulate, one rounding.
 // One warp per row, row held in registers (H <= 8192).
 // ------------------------------------------------------------------------------------------

@@ -13,6 +13,7 @@
 #include "tc_common.cuh"
 #include "../../include/phi3_b200.h"
 #include <cstdlib>
+#include <cstring>
 
 struct GemmEpi {
     const bf16* bias;
@@ -21,7 +22,19 @@ struct GemmEpi {
     const void* resid;
     const int32_t* row_map;
     int kind;
+    // fused RMSNorm (phi.py:478-479) of the INPUT rows: the gain is folded into W at load time, the per-row scale
+    // rsqrt(sum_c ss_in[row][c] / K + eps) multiplies the accumulators; ss_in = sum-of-squares partials of the rows of X
+    const float* ss_in; int n_ss_in; float eps;
+    // RESIDUAL: sum of squares of every 32-column chunk written, ss_out[row][N/32] (feeds the next GEMM's ss_in)
+    float* ss_out;
+    // P3_EPI_ROPE_KV: SuRoPE (phi.py:418-423,487-507) + paged KV write (phi.py:542-548) on the qkv projection. W rows are
+    // permuted per head so that every 32-column chunk holds 16 dims [16j,16j+16) and their rotary partners [half+16j, +16).
+    const float *cosT, *sinT; int64_t tab_bstride;
+    int L, n_heads, n_kv, hd, past, row_div, write_cache;
+    const int32_t* past_dev;
+    bf16* pool; const int32_t* block_table; int bt_stride;
 };
+#define P3_EPI_ROPE_KV 8
 
 __device__ __forceinline__ float epi_act(int kind, float x) {
     // CLIP fc1 and the projector run in fp32 in the reference (fp32 activations x bf16 weights
@@ -60,11 +73,83 @@ struct TcCfg {
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
-// epilogue for 32 consecutive accumulator columns of one output row
-__device__ __forceinline__ void epi_store32(const GemmEpi& ep, int64_t orow, int n0, int N, const uint32_t* acc) {
+// per-row RMSNorm scale from the producer's partial sums (fixed order: deterministic); 1 when the GEMM is not normed
+__device__ __forceinline__ float epi_row_scale(const GemmEpi& ep, int row, int K, bool row_ok) {
+    if (!ep.ss_in || !row_ok) return 1.f;
+    const float* p = ep.ss_in + (size_t)row * ep.n_ss_in;
+    float s = 0.f;
+    if ((ep.n_ss_in & 3) == 0) {
+        for (int c = 0; c < ep.n_ss_in; c += 4) { const float4 f = __ldcg(reinterpret_cast<const float4*>(p + c)); s += (f.x + f.y) + (f.z + f.w); }
+    } else {
+        for (int c = 0; c < ep.n_ss_in; c++) s += __ldcg(p + c);
+    }
+    return rsqrtf(s / (float)K + ep.eps);
+}
+
+// P3_EPI_ROPE_KV: one 32-column chunk of the (row-permuted) qkv projection for token `row`
+__device__ __forceinline__ void epi_rope32(const GemmEpi& ep, int row, int n0, float rs, const uint32_t* acc) {
+    const int hd = ep.hd, half = hd / 2, cph = hd / 32;
+    const int head = n0 / hd, j = (n0 % hd) / 32;
+    const int b = row / ep.L, pos = (ep.past_dev ? *ep.past_dev : ep.past) + row % ep.L;
+    bf16* qrow = reinterpret_cast<bf16*>(ep.out) + (size_t)row * ep.ldo;
+    bf16 *kd = nullptr, *vd = nullptr;
+    if (ep.write_cache) {
+        const int page = ep.block_table[(size_t)(b / ep.row_div) * ep.bt_stride + pos / P3_PAGE];
+        kd = ep.pool + (size_t)page * kv_page_elems(ep.n_kv, hd) + (size_t)(pos % P3_PAGE) * hd;
+        vd = kd + (size_t)ep.n_kv * P3_PAGE * hd;
+    }
+    uint4 o1[2], o2[2];
+    uint32_t* u1 = reinterpret_cast<uint32_t*>(o1);
+    uint32_t* u2 = reinterpret_cast<uint32_t*>(o2);
+    if (head < ep.n_heads + ep.n_kv) {                        // q or k head: rotate
+        const float* cr = ep.cosT + (size_t)(b / ep.row_div) * ep.tab_bstride + (size_t)pos * half + 16 * j;
+        const float* sr = ep.sinT + (size_t)(b / ep.row_div) * ep.tab_bstride + (size_t)pos * half + 16 * j;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cr + i)), s4 = __ldg(reinterpret_cast<const float4*>(sr + i));
+            const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+            float a1[4], a2[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {                     // the projection output is bf16 in the reference flow, rope runs in fp32
+                const float x1 = bf16_round(__uint_as_float(acc[i + e]) * rs), x2 = bf16_round(__uint_as_float(acc[16 + i + e]) * rs);
+                a1[e] = x1 * cs[e] - x2 * sn[e];
+                a2[e] = x2 * cs[e] + x1 * sn[e];
+            }
+            u1[i / 2] = pack_bf16(a1[0], a1[1]); u1[i / 2 + 1] = pack_bf16(a1[2], a1[3]);
+            u2[i / 2] = pack_bf16(a2[0], a2[1]); u2[i / 2 + 1] = pack_bf16(a2[2], a2[3]);
+        }
+        bf16* d1 = qrow + head * hd + 16 * j;
+        reinterpret_cast<uint4*>(d1)[0] = o1[0]; reinterpret_cast<uint4*>(d1)[1] = o1[1];
+        reinterpret_cast<uint4*>(d1 + half)[0] = o2[0]; reinterpret_cast<uint4*>(d1 + half)[1] = o2[1];
+        if (kd && head >= ep.n_heads) {
+            bf16* k = kd + (size_t)(head - ep.n_heads) * P3_PAGE * hd + 16 * j;
+            reinterpret_cast<uint4*>(k)[0] = o1[0]; reinterpret_cast<uint4*>(k)[1] = o1[1];
+            reinterpret_cast<uint4*>(k + half)[0] = o2[0]; reinterpret_cast<uint4*>(k + half)[1] = o2[1];
+        }
+    } else {                                                   // v head: 32 plain columns
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            u1[i] = pack_bf16(__uint_as_float(acc[2 * i]) * rs, __uint_as_float(acc[2 * i + 1]) * rs);
+            u2[i] = pack_bf16(__uint_as_float(acc[16 + 2 * i]) * rs, __uint_as_float(acc[17 + 2 * i]) * rs);
+        }
+        bf16* d = qrow + n0;
+        reinterpret_cast<uint4*>(d)[0] = o1[0]; reinterpret_cast<uint4*>(d)[1] = o1[1];
+        reinterpret_cast<uint4*>(d)[2] = o2[0]; reinterpret_cast<uint4*>(d)[3] = o2[1];
+        if (vd) {
+            bf16* v = vd + (size_t)(head - ep.n_heads - ep.n_kv) * P3_PAGE * hd + 32 * j;
+            reinterpret_cast<uint4*>(v)[0] = o1[0]; reinterpret_cast<uint4*>(v)[1] = o1[1];
+            reinterpret_cast<uint4*>(v)[2] = o2[0]; reinterpret_cast<uint4*>(v)[3] = o2[1];
+        }
+    }
+    (void)cph;
+}
+
+// epilogue for 32 consecutive accumulator columns of one output row (rs: RMSNorm row scale, 1 when not normed)
+__device__ __forceinline__ void epi_store32(const GemmEpi& ep, int64_t orow, int n0, int N, const uint32_t* acc, float rs = 1.f) {
+    if (ep.kind == P3_EPI_ROPE_KV) { epi_rope32(ep, (int)orow, n0, rs, acc); return; }
     float v[32];
 #pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(acc[i]);
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(acc[i]) * rs;
     if (ep.bias) {
         if (n0 + 32 <= N) {
             uint4 bv[4];
@@ -128,8 +213,16 @@ __device__ __forceinline__ void epi_store32(const GemmEpi& ep, int64_t orow, int
         for (int i = 0; i < 16; i++) ou[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
 #pragma unroll
         for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(o)[i] = ov[i];
+        if (ep.ss_out) {                                       // sum of squares of the bf16 values just written
+            float sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; i++) { const float2 f = unpack_bf16(ou[i]); sq += f.x * f.x + f.y * f.y; }
+            ep.ss_out[(size_t)orow * (N / 32) + n0 / 32] = sq;
+        }
     } else {
-        for (int i = 0; i < 32; i++) if (n0 + i < N) o[i] = __float2bfloat16_rn(v[i]);
+        float sq = 0.f;
+        for (int i = 0; i < 32; i++) if (n0 + i < N) { o[i] = __float2bfloat16_rn(v[i]); const float f = bf16_round(v[i]); sq += f * f; }
+        if (ep.ss_out) ep.ss_out[(size_t)orow * (N / 32) + n0 / 32] = sq;
     }
 }
 
@@ -226,11 +319,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int mt_, nt_;
             tile_coords(tile, m_tiles, n_tiles, nb, mt_, nt_);
             const int m_idx = mt_ * C::BM, n_idx = nt_ * BN;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
             const int row = m_idx + q * 32 + lane;
             const bool row_ok = row < M;
             const int64_t orow = row_ok ? (ep.row_map ? (int64_t)ep.row_map[row] : (int64_t)row) : 0;
+            const float rs = epi_row_scale(ep, row, K, row_ok);  // summed while the tile's MMAs run
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             if (ep.kind == P3_EPI_SWIGLU) {
                 // interleaved weights: columns [0,BN/2) gate, [BN/2,BN) matching up
@@ -244,8 +338,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint32_t* ou = reinterpret_cast<uint32_t*>(ov);
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
-                            float g0 = bf16_round(__uint_as_float(g[2 * i])), g1 = bf16_round(__uint_as_float(g[2 * i + 1]));
-                            float u0 = bf16_round(__uint_as_float(u[2 * i])), u1 = bf16_round(__uint_as_float(u[2 * i + 1]));
+                            float g0 = bf16_round(__uint_as_float(g[2 * i]) * rs), g1 = bf16_round(__uint_as_float(g[2 * i + 1]) * rs);
+                            float u0 = bf16_round(__uint_as_float(u[2 * i]) * rs), u1 = bf16_round(__uint_as_float(u[2 * i + 1]) * rs);
                             float a0 = bf16_round(g0 / (1.f + __expf(-g0))), a1 = bf16_round(g1 / (1.f + __expf(-g1)));
                             ou[i] = pack_bf16(a0 * u0, a1 * u1);
                         }
@@ -263,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                     uint32_t v[32];
                     tc_ld32(taddr + c0, v);
-                    if (row_ok && n_idx + c0 < N) epi_store32(ep, orow, n_idx + c0, N, v);
+                    if (row_ok && n_idx + c0 < N) epi_store32(ep, orow, n_idx + c0, N, v, rs);
                 }
             }
             tc_fence_before();
@@ -415,11 +509,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int mt_, nt_;
             tile_coords(tile, m_pairs, n_tiles, nb, mt_, nt_);
             const int m_idx = mt_ * (2 * C::BM) + (int)rank * C::BM, n_idx = nt_ * BN;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
             const int row = m_idx + q * 32 + lane;
             const bool row_ok = row < M;
             const int64_t orow = row_ok ? (ep.row_map ? (int64_t)ep.row_map[row] : (int64_t)row) : 0;
+            const float rs = epi_row_scale(ep, row, K, row_ok);  // summed while the tile's MMAs run
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             if (ep.kind == P3_EPI_SWIGLU) {
                 for (int c0 = half * (BN / 4); c0 < (half + 1) * (BN / 4); c0 += 32) {
@@ -432,8 +527,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         uint32_t* ou = reinterpret_cast<uint32_t*>(ov);
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
-                            float g0 = bf16_round(__uint_as_float(g[2 * i])), g1 = bf16_round(__uint_as_float(g[2 * i + 1]));
-                            float u0 = bf16_round(__uint_as_float(u[2 * i])), u1 = bf16_round(__uint_as_float(u[2 * i + 1]));
+                            float g0 = bf16_round(__uint_as_float(g[2 * i]) * rs), g1 = bf16_round(__uint_as_float(g[2 * i + 1]) * rs);
+                            float u0 = bf16_round(__uint_as_float(u[2 * i]) * rs), u1 = bf16_round(__uint_as_float(u[2 * i + 1]) * rs);
                             float a0 = bf16_round(g0 / (1.f + __expf(-g0))), a1 = bf16_round(g1 / (1.f + __expf(-g1)));
                             ou[i] = pack_bf16(a0 * u0, a1 * u1);
                         }
@@ -451,7 +546,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                     uint32_t v[32];
                     tc_ld32(taddr + c0, v);
-                    if (row_ok && n_idx + c0 < N) epi_store32(ep, orow, n_idx + c0, N, v);
+                    if (row_ok && n_idx + c0 < N) epi_store32(ep, orow, n_idx + c0, N, v, rs);
                 }
             }
             tc_fence_before();
@@ -559,6 +654,13 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(const bf16* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// Weight tensor maps are immutable for the life of a model: p3_gemm_plan_weights builds the three maps the kernels can ask
+// for (box rows 256 / 128 for the single-CTA tiles, 128 = half a 256-wide tile for the CTA pair) ONCE into a caller-owned
+// blob; p3_gemm_fused then skips cuTensorMapEncodeTiled for W (the X map still depends on the call's activation pointer).
+struct GemmWPlan { uint64_t magic; const void* W; int64_t ldw; int32_t N, K; CUtensorMap t256, t128; };
+static_assert(sizeof(GemmWPlan) <= P3_GEMM_WPLAN_BYTES, "p3_gemm weight plan blob too small");
+#define P3_WPLAN_MAGIC 0x5033574D41505331ull
+
 static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
     CUresult r = tc_encode_2d(tm, ptr, rows, K, ld, box_rows);
     P3_CHECK_ARG(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld", (int)r,
@@ -572,18 +674,21 @@ static int num_sms() {
     return n;
 }
 
+static int cur_dev() { int d = 0; cudaGetDevice(&d); return d < 0 || d >= 64 ? 0 : d; }
+
 template <int BN>
 static int launch_tc(const void* X, int64_t ldx, const void* W, int64_t ldw, const GemmEpi& ep, int64_t M, int N, int K,
-                     cudaStream_t st) {
+                     cudaStream_t st, const GemmWPlan* wp = nullptr) {
     using C = TcCfg<BN>;
     CUtensorMap ta, tb;
     if (make_tmap(&ta, X, M, K, ldx, C::BM)) return -1;
-    if (make_tmap(&tb, W, N, K, ldw, BN)) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (wp) memcpy(&tb, (BN == 256) ? &wp->t256 : &wp->t128, sizeof(tb));
+    else if (make_tmap(&tb, W, N, K, ldw, BN)) return -1;
+    static bool attr_set[64] = {};                             // the attribute is per device
+    if (!attr_set[cur_dev()]) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         P3_CHECK_ARG(e == cudaSuccess, "gemm: cannot set %d B dynamic smem: %s", C::SMEM, cudaGetErrorString(e));
-        attr_set = true;
+        attr_set[cur_dev()] = true;
     }
     int64_t tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
     unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
@@ -599,22 +704,41 @@ static int gemm_2cta_mode() {                  // P3_GEMM_2CTA=0 forces the sing
 }
 
 static int launch_tc2(const void* X, int64_t ldx, const void* W, int64_t ldw, const GemmEpi& ep, int64_t M, int N, int K,
-                      cudaStream_t st) {
+                      cudaStream_t st, const GemmWPlan* wp = nullptr) {
     using C = Tc2Cfg;
     CUtensorMap ta, tb;
     if (make_tmap(&ta, X, M, K, ldx, C::BM)) return -1;
-    if (make_tmap(&tb, W, N, K, ldw, C::BN / 2)) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (wp) memcpy(&tb, &wp->t128, sizeof(tb));               // half of a 256-wide W tile per CTA
+    else if (make_tmap(&tb, W, N, K, ldw, C::BN / 2)) return -1;
+    static bool attr_set[64] = {};
+    if (!attr_set[cur_dev()]) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         P3_CHECK_ARG(e == cudaSuccess, "gemm: cannot set %d B dynamic smem: %s", C::SMEM, cudaGetErrorString(e));
-        attr_set = true;
+        attr_set[cur_dev()] = true;
     }
     int64_t tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
     int64_t clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
     p3_launch_pdl(gemm_tc2_kernel, dim3((unsigned)(2 * clusters)), dim3(384), (size_t)C::SMEM, st, ta, tb, ep, (int)M, N, K);
     P3_CHECK_LAUNCH("gemm_tc2");
     return 0;
+}
+
+static int gemm_dispatch(const void* X, int64_t ldx, const void* W, int64_t ldw, const GemmEpi& ep, int64_t M, int N, int K,
+                         int impl, cudaStream_t st, const GemmWPlan* wp) {
+    if (impl == 1) {
+        P3_CHECK_ARG(ep.kind != P3_EPI_ROPE_KV && !ep.ss_in && !ep.ss_out, "gemm: the mma.sync cross-check kernel has no fused norm / rope epilogue");
+        int ncols = ep.kind == P3_EPI_SWIGLU ? N / 2 : N;
+        dim3 grid((ncols + FB_BN - 1) / FB_BN, (unsigned)((M + FB_BM - 1) / FB_BM));
+        gemm_mma_kernel<<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, ep, (int)M, N, K);
+        P3_CHECK_LAUNCH("gemm_mma");
+        return 0;
+    }
+    int64_t m_tiles = (M + 127) / 128;
+    if (impl == 0 && gemm_2cta_mode() && M > 128 && ((m_tiles + 1) / 2) * ((N + 255) / 256) >= num_sms() / 4)
+        return launch_tc2(X, ldx, W, ldw, ep, M, N, K, st, wp);
+    bool small = m_tiles * ((N + 255) / 256) < 2 * num_sms();
+    if (ep.kind == P3_EPI_SWIGLU || !small) return launch_tc<256>(X, ldx, W, ldw, ep, M, N, K, st, wp);
+    return launch_tc<128>(X, ldx, W, ldw, ep, M, N, K, st, wp);
 }
 
 extern "C" int p3_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
@@ -627,18 +751,49 @@ extern "C" int p3_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, c
     P3_CHECK_ARG(epi != P3_EPI_SWIGLU || (N % 256 == 0 && !bias), "gemm: SwiGLU needs N %% 256 == 0 and no bias");
     P3_CHECK_ARG(M < (1ll << 31), "gemm: M too large");
     if (M == 0) return 0;
-    GemmEpi ep{(const bf16*)bias, out, ldo, resid, row_map, epi};
-    if (impl == 1) {
-        int ncols = epi == P3_EPI_SWIGLU ? N / 2 : N;
-        dim3 grid((ncols + FB_BN - 1) / FB_BN, (unsigned)((M + FB_BM - 1) / FB_BM));
-        gemm_mma_kernel<<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)W, ldw, ep, (int)M, N, K);
-        P3_CHECK_LAUNCH("gemm_mma");
-        return 0;
+    GemmEpi ep{};
+    ep.bias = (const bf16*)bias; ep.out = out; ep.ldo = ldo; ep.resid = resid; ep.row_map = row_map; ep.kind = epi;
+    return gemm_dispatch(X, ldx, W, ldw, ep, M, N, K, impl, st, nullptr);
+}
+
+extern "C" int p3_gemm_plan_weights(const void* W, int64_t ldw, int N, int K, void* plan) {
+    P3_CHECK_ARG(W && plan && ldw % 8 == 0 && ((uintptr_t)W & 15) == 0, "gemm_plan_weights: bad arguments");
+    P3_CHECK_ARG(((uintptr_t)plan & 63) == 0, "gemm_plan_weights: the plan blob must be 64-byte aligned");
+    GemmWPlan* p = reinterpret_cast<GemmWPlan*>(plan);
+    p->W = W; p->ldw = ldw; p->N = N; p->K = K;
+    if (make_tmap(&p->t256, W, N, K, ldw, 256)) return -1;
+    if (make_tmap(&p->t128, W, N, K, ldw, 128)) return -1;
+    p->magic = P3_WPLAN_MAGIC;
+    return 0;
+}
+
+// struct-argument entry (SURVEY.md par. 8b): everything p3_gemm does + the fused prefill epilogues
+extern "C" int p3_gemm_fused(const p3_gemm_args* a, cudaStream_t st) {
+    P3_CHECK_ARG(a, "gemm_fused: null args");
+    const int epi = a->epi;
+    P3_CHECK_ARG((epi >= P3_EPI_NONE && epi <= P3_EPI_RESIDUAL_F32) || epi == P3_EPI_ROPE_KV, "gemm_fused: unknown epilogue %d", epi);
+    P3_CHECK_ARG(a->ldx % 8 == 0 && a->ldw % 8 == 0, "gemm_fused: ldx/ldw must be multiples of 8 elements (16 B)");
+    P3_CHECK_ARG(((uintptr_t)a->X & 15) == 0 && ((uintptr_t)a->W & 15) == 0, "gemm_fused: X/W must be 16-byte aligned");
+    P3_CHECK_ARG((epi != P3_EPI_RESIDUAL && epi != P3_EPI_RESIDUAL_F32) || a->resid, "gemm_fused: residual epilogue needs resid");
+    P3_CHECK_ARG(epi != P3_EPI_SWIGLU || (a->N % 256 == 0 && !a->bias), "gemm_fused: SwiGLU needs N %% 256 == 0 and no bias");
+    P3_CHECK_ARG(!a->ss_out || (epi == P3_EPI_RESIDUAL && a->N % 32 == 0 && !a->row_map), "gemm_fused: ss_out needs the bf16 residual epilogue, N %% 32 == 0");
+    P3_CHECK_ARG(!a->ss_in || (a->n_ss_in >= 1 && !a->row_map), "gemm_fused: ss_in needs n_ss_in >= 1 and no row map");
+    P3_CHECK_ARG(a->M < (1ll << 31), "gemm_fused: M too large");
+    if (a->M == 0) return 0;
+    GemmEpi ep{};
+    ep.bias = (const bf16*)a->bias; ep.out = a->out; ep.ldo = a->ldo; ep.resid = a->resid; ep.row_map = a->row_map; ep.kind = epi;
+    ep.ss_in = a->ss_in; ep.n_ss_in = a->n_ss_in; ep.eps = a->eps; ep.ss_out = a->ss_out;
+    if (epi == P3_EPI_ROPE_KV) {
+        P3_CHECK_ARG(a->hd % 32 == 0 && a->N == (a->n_heads + 2 * a->n_kv) * a->hd && a->ldo % 8 == 0 && !a->bias && !a->row_map,
+                     "gemm_fused: ROPE_KV needs head_dim %% 32 == 0, N = (n_heads + 2 n_kv) * head_dim, no bias / row map");
+        P3_CHECK_ARG(a->cosT && a->sinT && a->L >= 1 && a->row_div >= 1 && a->M % a->L == 0, "gemm_fused: ROPE_KV needs rope tables and M = B * L");
+        P3_CHECK_ARG(!a->write_cache || (a->pool && a->block_table), "gemm_fused: cache write needs pool and block table");
+        ep.cosT = a->cosT; ep.sinT = a->sinT; ep.tab_bstride = a->tab_bstride; ep.L = a->L; ep.n_heads = a->n_heads; ep.n_kv = a->n_kv;
+        ep.hd = a->hd; ep.past = a->past; ep.row_div = a->row_div; ep.write_cache = a->write_cache; ep.past_dev = a->past_dev;
+        ep.pool = (bf16*)a->pool; ep.block_table = a->block_table; ep.bt_stride = a->bt_stride;
     }
-    int64_t m_tiles = (M + 127) / 128;
-    if (impl == 0 && gemm_2cta_mode() && M > 128 && ((m_tiles + 1) / 2) * ((N + 255) / 256) >= num_sms() / 4)
-        return launch_tc2(X, ldx, W, ldw, ep, M, N, K, st);
-    bool small = m_tiles * ((N + 255) / 256) < 2 * num_sms();
-    if (epi == P3_EPI_SWIGLU || !small) return launch_tc<256>(X, ldx, W, ldw, ep, M, N, K, st);
-    return launch_tc<128>(X, ldx, W, ldw, ep, M, N, K, st);
+    const GemmWPlan* wp = reinterpret_cast<const GemmWPlan*>(a->w_plan);
+    if (wp) P3_CHECK_ARG(wp->magic == P3_WPLAN_MAGIC && wp->W == a->W && wp->ldw == a->ldw && wp->N == a->N && wp->K == a->K,
+                         "gemm_fused: weight plan does not describe this W");
+    return gemm_dispatch(a->X, a->ldx, a->W, a->ldw, ep, a->M, a->N, a->K, a->impl, st, wp);
 }

@@ -178,6 +178,18 @@ class Phi3B200:
                 gu=lin(w[p + 'mlp.gate_up_proj.weight'], interleave_gate_up), down=lin(w[p + 'mlp.down_proj.weight'])))
         self.norm = d(w['model.norm.weight'])
         self.lm_head = lin(w['lm_head.weight'])
+        # fused prefill (north_star: SuRoPE + KV write in the QKV epilogue, RMSNorm fused with the adjacent GEMM): second copies of
+        # qkv_proj / gate_up_proj with the RMSNorm gain folded in (W' = bf16(W * g), the per-row rsqrt is applied to the
+        # accumulators) and, for qkv, q/k rows permuted per head so a rotary pair meets in one 32-column accumulator chunk
+        import os as _os1
+        self.pf_fused = _os1.environ.get('P3_PF_FUSED', '1') != '0' and self.hd % 32 == 0
+        if self.pf_fused:
+            perm = self._rope_row_perm()
+            for lw in self.layers:
+                g1, g2 = lw['ln1'].to(torch.float32)[None, :], lw['ln2'].to(torch.float32)[None, :]
+                lw['qkv_pf'] = (lw['qkv'].to(torch.float32)[perm] * g1).to(torch.bfloat16).contiguous()
+                lw['gu_pf'] = (lw['gu'].to(torch.float32) * g2).to(torch.bfloat16).contiguous()
+                lw['plans'] = {k: _lib.WeightPlan(lw[k]) for k in ('qkv_pf', 'o', 'gu_pf', 'down')}
         # persistent decode-layer kernel (mega.py / decode_mega.cu): a second, stream-order copy of the decoder weights
         # (7.4 GB at Phi-3.5 sizes; HBM has 180 GB). bf16 weights only. Opt-in (P3_MEGA=1) while it is slower than the chain
         # of per-matrix skinny kernels it replaces (profiles/r02_decode_mega.md).
@@ -231,6 +243,33 @@ class Phi3B200:
                  p0_w=ql(w[Vp + 'img_projection.0.weight']), p0_b=d(w[Vp + 'img_projection.0.bias']),
                  p2_w=ql(w[Vp + 'img_projection.2.weight']), p2_b=d(w[Vp + 'img_projection.2.bias']))
         self.vision = v
+
+    def _rope_row_perm(self):
+        """row order of the prefill copy of qkv_proj: per q/k head [16j..16j+15 | half+16j..half+16j+15] for j = 0..hd/32-1
+        (P3_EPI_ROPE_KV, include/phi3_b200.h); v rows unchanged"""
+        hd, half = self.hd, self.hd // 2
+        idx = []
+        for h in range(self.n_heads + self.n_kv):
+            for j in range(hd // 32):
+                idx += [h * hd + 16 * j + i for i in range(16)] + [h * hd + half + 16 * j + i for i in range(16)]
+        idx += list(range((self.n_heads + self.n_kv) * hd, self.qkv_dim))
+        return torch.tensor(idx, dtype=torch.int64, device=self.dev)
+
+    def gemm_fused(self, x, w, out, epi, plan=None, resid=None, ss_in=None, ss_out=None, rope=None):
+        """p3_gemm_fused: tensor-core GEMM with the RMSNorm row scale / sum-of-squares / rope + KV-write epilogues"""
+        a = _lib.GemmArgs()
+        a.X, a.ldx, a.W, a.ldw = ptr(x), x.stride(0), ptr(w), w.stride(0)
+        a.out, a.ldo, a.resid = ptr(out), out.stride(0), ptr(resid)
+        a.M, a.N, a.K, a.epi, a.impl = x.shape[0], w.shape[0], x.shape[1], epi, self.gemm_impl
+        if ss_in is not None:
+            a.ss_in, a.n_ss_in, a.eps = ptr(ss_in), ss_in.shape[1], self.eps
+        a.ss_out = ptr(ss_out)
+        a.w_plan = None if plan is None else plan.addr
+        if rope is not None:
+            for k, v in rope.items():
+                setattr(a, k, v)
+        _lib.call_struct('p3_gemm_fused', a, _stream())
+        return out
 
     # ------------------------------------------------------------------ thin kernel wrappers
     def gemm(self, x, w, out, epi=_lib.EPI_NONE, bias=None, resid=None, row_map=None, N=None):
@@ -396,10 +435,14 @@ class Phi3B200:
             ssA = torch.zeros((n_part, 16), dtype=torch.float32, device=dev)
             ssB = torch.zeros((n_part, 16), dtype=torch.float32, device=dev)
         ss_cur = None
+        fused = T > 16 and self.pf_fused and self.gemm_impl == 0
+        ss0 = torch.empty((T, 1), dtype=torch.float32, device=dev) if fused else None
         if h is None:
             h = torch.empty((T, H), dtype=torch.bfloat16, device=dev)
-            call('p3_embed_gather', ptr(self.embed), ptr(ids_dev), ptr(h), T, H, self.V, ptr(ssA), st)
+            call('p3_embed_gather', ptr(self.embed), ptr(ids_dev), ptr(h), T, H, self.V, ptr(ss0 if fused else ssA), st)
             ss_cur = None if ssA is None else ssA[:1]
+        elif fused:
+            call('p3_row_sumsq', ptr(h), h.stride(0), ptr(ss0), T, H, st)
         qkv = torch.empty((T, self.qkv_dim), dtype=torch.bfloat16, device=dev)
         att = torch.empty((T, self.n_heads * self.hd), dtype=torch.bfloat16, device=dev)
         act = torch.empty((T, self.I), dtype=torch.bfloat16, device=dev)
@@ -416,9 +459,30 @@ class Phi3B200:
             bt, bts, kvs = cache.block_table, cache.block_table.stride(0), cache.kv_start
         else:
             cosT, sinT, tbs, bt, bts, kvs = self._nc_cos, self._nc_sin, self._nc_tbs, None, 0, self._nc_kvs
+        if fused:
+            # per-row sum-of-squares partials travel with the residual stream: [T,1] for the input rows (embed_gather or one
+            # pass over the spliced h), then [T, H/32] written by every residual epilogue; the normed GEMMs turn them into the
+            # RMSNorm row scale
+            ssA = torch.empty((T, H // 32), dtype=torch.float32, device=dev)
+            ssB = torch.empty((T, H // 32), dtype=torch.float32, device=dev)
+            ss_cur = ss0
         for li, lw in enumerate(self.layers):
             pool = cache.pool[li] if cache is not None else None
             wc = 1 if (write_cache and cache is not None) else 0
+            if fused:
+                rope = dict(cosT=ptr(cosT), sinT=ptr(sinT), tab_bstride=tbs, L=L, n_heads=self.n_heads, n_kv=self.n_kv, hd=self.hd,
+                            past=past, row_div=n_beam, write_cache=wc, bt_stride=bts, past_dev=ptr(past_dev), pool=ptr(pool),
+                            block_table=ptr(bt))
+                self.gemm_fused(h, lw['qkv_pf'], qkv, _lib.EPI_ROPE_KV, lw['plans']['qkv_pf'], ss_in=ss_cur, rope=rope)
+                qp = qkv.data_ptr()
+                call('p3_attention_prefill', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim, self.qkv_dim,
+                     ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale, 1, past, ptr(kvs),
+                     ptr(pool), ptr(bt), bts, n_beam, st)
+                self.gemm_fused(att, lw['o'], h, _lib.EPI_RESIDUAL, lw['plans']['o'], resid=h, ss_out=ssB)
+                self.gemm_fused(h, lw['gu_pf'], act, _lib.EPI_SWIGLU, lw['plans']['gu_pf'], ss_in=ssB)
+                self.gemm_fused(act, lw['down'], h, _lib.EPI_RESIDUAL, lw['plans']['down'], resid=h, ss_out=ssA)
+                ss_cur = ssA
+                continue
             if 'qkv' in self._skip and T <= 16:
                 pass
             elif T <= 16:                                   # decode: qkv_proj + rope + KV write in one launch

@@ -599,3 +599,95 @@ def test_top_p_sample_matches_torch_restatement(dev, top_p, temp):
         if got != want:                                   # fp32 vs fp64 cdf: only a neighbour inside the nucleus is acceptable
             idx = torch.nonzero(nucleus).flatten().tolist()
             assert abs(idx.index(got) - idx.index(min(want, idx[-1]))) <= 1
+
+
+# ------------------------------------------------------------------ round 2: fused prefill epilogues of the tensor-core GEMM
+def _gemm_fused(dev, x, w, out, epi, **kw):
+    import ctypes
+    import phi3_b200  # noqa
+    from phi3_b200 import _lib
+    a = _lib.GemmArgs()
+    a.X, a.ldx, a.W, a.ldw, a.out, a.ldo = x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0)
+    a.M, a.N, a.K, a.epi, a.impl = x.shape[0], w.shape[0], x.shape[1], epi, 0
+    for k, v in kw.items():
+        setattr(a, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+    _lib.call_struct('p3_gemm_fused', a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize('M', [40, 781, 2100])
+def test_gemm_fused_rmsnorm_scale_and_sumsq(dev, M):
+    """RMSNorm folded into the GEMM (gain in W, per-row rsqrt on the accumulators) == rmsnorm kernel + GEMM up to the
+    rounding of the folded weights; the residual epilogue's sum-of-squares partials describe the bf16 values written."""
+    import phi3_b200  # noqa
+    from phi3_b200 import _lib
+    H, N = 384, 768
+    g = torch.Generator().manual_seed(M)
+    x = (torch.randn(M, H, generator=g) * 2).to(torch.bfloat16).to(dev)
+    gain = (1 + 0.1 * torch.randn(H, generator=g)).to(torch.bfloat16).to(dev)
+    W = (torch.randn(N, H, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+    Wf = (W.float() * gain.float()[None]).to(torch.bfloat16).contiguous()
+    ss = torch.empty(M, 1, device=dev)
+    _lib.call('p3_row_sumsq', x.data_ptr(), x.stride(0), ss.data_ptr(), M, H, torch.cuda.current_stream().cuda_stream)
+    assert torch.allclose(ss[:, 0], x.float().pow(2).sum(1), rtol=1e-5)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
+    plan = _lib.WeightPlan(Wf)
+    _gemm_fused(dev, x, Wf, out, _lib.EPI_NONE, ss_in=ss, n_ss_in=1, eps=1e-5, w_plan=plan.addr)
+    xf = x.float()
+    xn = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * gain.float()).to(torch.bfloat16).float()
+    ref = xn @ W.float().T
+    assert ((out.float() - ref).abs().max() / ref.abs().max()).item() < 1e-2
+    # residual epilogue + ss_out, then a second normed GEMM fed by those partials
+    h0 = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev)
+    h = h0.clone()
+    ssp = torch.full((M, N // 32), -1.0, device=dev)
+    _gemm_fused(dev, x, W, h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssp)
+    assert torch.allclose(ssp.sum(1), h.float().pow(2).sum(1), rtol=1e-4)
+    assert ((h.float() - (h0.float() + (x.float() @ W.float().T).to(torch.bfloat16).float())).abs().max() / h.float().abs().max()).item() < 1e-2
+    W2 = (torch.randn(256, N, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+    out2 = torch.zeros(M, 256, dtype=torch.bfloat16, device=dev)
+    _gemm_fused(dev, h, W2, out2, _lib.EPI_NONE, ss_in=ssp, n_ss_in=N // 32, eps=1e-5)
+    hf = h.float()
+    ref2 = (hf * torch.rsqrt(hf.pow(2).mean(-1, keepdim=True) + 1e-5)) @ W2.float().T
+    assert ((out2.float() - ref2).abs().max() / ref2.abs().max()).item() < 1e-2
+
+
+@pytest.mark.parametrize('B,L,nh,past,row_div,wc', [(2, 40, 4, 0, 1, 1), (1, 781, 32, 0, 1, 1), (3, 70, 4, 64, 1, 1), (6, 5, 4, 130, 3, 0)])
+def test_gemm_fused_rope_kvwrite_matches_separate_kernels(dev, B, L, nh, past, row_div, wc):
+    """P3_EPI_ROPE_KV (permuted W, rope + paged KV write in the epilogue) == p3_gemm + p3_rope_kvwrite bit for bit"""
+    import phi3_b200  # noqa
+    from phi3_b200 import _lib
+    hd, H = 96, 384
+    N, M = 3 * nh * hd, B * L
+    g = torch.Generator().manual_seed(B * 100 + L)
+    x = torch.randn(M, H, generator=g).to(torch.bfloat16).to(dev)
+    W = (torch.randn(N, H, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+    n_seq = B // row_div
+    S = past + L
+    pages = (S + 63) // 64
+    cos = torch.randn(n_seq, S, hd // 2, generator=g).to(dev)
+    sin = torch.randn(n_seq, S, hd // 2, generator=g).to(dev)
+    bt = torch.randperm(n_seq * pages, generator=g).to(torch.int32).reshape(n_seq, pages).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    # reference: plain GEMM then the separate rope + KV-write kernel
+    qkv_ref = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
+    pool_ref = torch.zeros(n_seq * pages, 2, nh, 64, hd, dtype=torch.bfloat16, device=dev)
+    _lib.call('p3_gemm', x.data_ptr(), x.stride(0), W.data_ptr(), W.stride(0), None, qkv_ref.data_ptr(), qkv_ref.stride(0), None,
+              None, M, N, H, _lib.EPI_NONE, 0, st)
+    _lib.call('p3_rope_kvwrite', qkv_ref.data_ptr(), cos.data_ptr(), sin.data_ptr(), cos.stride(0), B, L, nh, nh, hd, past, row_div,
+              pool_ref.data_ptr(), bt.data_ptr(), bt.stride(0), wc, None, st)
+    # fused: permuted weights
+    idx = []
+    for h in range(2 * nh):
+        for j in range(hd // 32):
+            idx += [h * hd + 16 * j + i for i in range(16)] + [h * hd + hd // 2 + 16 * j + i for i in range(16)]
+    idx += list(range(2 * nh * hd, N))
+    Wp = W[torch.tensor(idx, device=dev)].contiguous()
+    qkv = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
+    pool = torch.zeros_like(pool_ref)
+    _gemm_fused(dev, x, Wp, qkv, _lib.EPI_ROPE_KV, cosT=cos, sinT=sin, tab_bstride=cos.stride(0), L=L, n_heads=nh, n_kv=nh, hd=hd,
+                past=past, row_div=row_div, write_cache=wc, bt_stride=bt.stride(0), pool=pool, block_table=bt)
+    assert torch.equal(qkv, qkv_ref)
+    assert torch.equal(pool, pool_ref)
+    if not wc:
+        assert pool.abs().sum() == 0
