@@ -11,14 +11,14 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _setup(vision=False, **kw):
+def _setup(vision=False, init='gpt2', **kw):
     import phi3_b200  # noqa
     from phi3_b200 import configs, weights, api
     from phi3_b200.processor import ByteTokenizer
     from oracle.phi3_oracle import Phi3Oracle
     cfg = configs.tiny(vision=vision, **kw)
     clip = configs.tiny_clip(3) if vision else None
-    w = weights.random_weights(cfg, seed=3, clip_cfg=clip)
+    w = weights.random_weights(cfg, seed=3, clip_cfg=clip, init=init)
     model, proc = api.load(blind_model=not vision, cfg=cfg, weights=w, tokenizer=ByteTokenizer(), clip_cfg=clip,
                            num_crops=4, quantize_cache=bool(kw.get('use_quantized_cache', False)))
     return api, model, proc, Phi3Oracle(model.cfg, w, prec='b200', clip_cfg=clip)
@@ -348,7 +348,7 @@ def test_quantize_model_and_quantize_cache_together(dev):
 def test_generate_batch_equals_separate_batch1_calls(dev):
     """generate_batch (extension for BASELINE config 3): N image+text prompts as one left-padded batch give, row by row, the
     tokens of N separate batch-1 generate() calls (the only way the reference can run them, pv:377-378)."""
-    api, model, proc, ora = _setup(vision=True)
+    api, model, proc, ora = _setup(vision=True, init='peaked')       # peaked logits: token equality is not a coin flip
     rs = np.random.RandomState(11)
     imgs = [rs.randint(0, 256, (350, 500, 3), dtype=np.uint8), rs.randint(0, 256, (400, 400, 3), dtype=np.uint8), None]
     prompts = ['What is shown here?', 'Describe the second picture in a few more words.', 'No image for this one']
@@ -357,7 +357,7 @@ def test_generate_batch_equals_separate_batch1_calls(dev):
     for i, (p, im) in enumerate(zip(prompts, imgs)):
         t, ims = api._apply_chat_template(p, None if im is None else [im], False)
         one = api._generate(model, proc, t, ims, max_tokens=6, verbose=False, stream=False, mute=True, return_tokens=True).cpu()
-        assert (one[0] == hist[i]).float().mean() >= 0.8 and one[0, 0] == hist[i, 0], (i, one.tolist(), hist[i].tolist())
+        assert torch.equal(one[0], hist[i]), (i, one.tolist(), hist[i].tolist())
     txt = api.generate_batch(prompts, imgs, preload=(model, proc), max_tokens=4)
     assert isinstance(txt, list) and len(txt) == 3 and all(isinstance(t, str) for t in txt)
     with pytest.raises(ValueError):
@@ -366,7 +366,7 @@ def test_generate_batch_equals_separate_batch1_calls(dev):
 
 def test_dp_generate_with_images_single_process(dev):
     from phi3_b200 import parallel
-    api, model, proc, ora = _setup(vision=True)
+    api, model, proc, ora = _setup(vision=True, init='peaked')
     rs = np.random.RandomState(12)
     imgs = [rs.randint(0, 256, (336, 336, 3), dtype=np.uint8) for _ in range(3)]
     prompts = ['one', 'two two', 'three three three']
