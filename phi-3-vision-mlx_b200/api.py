@@ -557,7 +557,7 @@ def choose(prompt, choices='ABCDE', images=None, preload=None, blind_model=False
 
 # ------------------------------------------------------------------------------------- constrain
 def _constrain(model, processor, prompt, constraints, return_full_text=False, mute=False, use_beam=False, verbose=True,
-               log_norm=False, n_beam=3, return_ids=False):
+               log_norm=False, n_beam=3, return_ids=False, alive_check_every=8, sync_timing=False):
     """pv:500-619. Scores are means of log-probs over [tokens so far + constraint]; only the
     gathered log-probs are ever materialised (p3_row_stats) instead of full-vocab log-softmax."""
     import math
@@ -575,21 +575,23 @@ def _constrain(model, processor, prompt, constraints, return_full_text=False, mu
     V = model.V
     ids_trace = []
 
-    def beam_step(row_logits, cache, ids_c):
-        """_get_beam pv:505-517 on logits rows [B,V] of the position that predicts the beam token."""
-        C = len(ids_c)
+    dev = model.dev
+
+    def beam_step(row_logits, cache, idc):
+        """_get_beam pv:505-517 on logits rows [B,V] of the position that predicts the beam token (all on the device)."""
+        C = idc.shape[0]
         st = _row_stats(model, row_logits, n_top=n_beam)
         cand, cand_lp = st['top_ids'], st['top_lp']                          # [B,nb]
-        seq = torch.cat([cand.reshape(-1, 1).long().cpu(), torch.tensor(ids_c).repeat(B * n_beam, 1)], 1)   # [B*nb,1+C]
+        seq = torch.cat([cand.reshape(-1, 1).long(), idc.repeat(B * n_beam, 1)], 1)              # [B*nb,1+C]
         lg, _ = model(seq, cache=cache, n_beam=n_beam, advance_offset=0)
-        g = torch.full((B * n_beam, 1 + C), -1, dtype=torch.int32)
+        g = torch.full((B * n_beam, 1 + C), -1, dtype=torch.int32, device=dev)
         g[:, :C] = seq[:, 1:].to(torch.int32)
         s2 = _row_stats(model, lg.reshape(-1, V), gather=g.reshape(-1, 1))
         rest = s2['gather_lp'].reshape(B * n_beam, 1 + C)[:, :C]
-        bs = torch.cat([cand_lp.reshape(-1, 1), rest], 1).cpu()              # [B*nb, 1+C]
+        bs = torch.cat([cand_lp.reshape(-1, 1), rest], 1)                    # [B*nb, 1+C]
         k = torch.argmax(bs.mean(1).reshape(B, n_beam), dim=-1)
-        ar = torch.arange(B)
-        return st['argmax'].cpu().long(), cand.cpu().long()[ar, k], bs.reshape(B, n_beam, -1)[ar, k]
+        ar = torch.arange(B, device=dev)
+        return st['argmax'].long(), cand.long()[ar, k], bs.reshape(B, n_beam, -1)[ar, k]
 
     for constraint in constraints:
         if isinstance(constraint, str):                                      # pv:531-536
@@ -600,68 +602,74 @@ def _constrain(model, processor, prompt, constraints, return_full_text=False, mu
         max_new, text = constraint
         ids_c = list(processor.tokenizer.encode(text, add_special_tokens=False)[1:])   # pv:538
         C = len(ids_c)
+        idc = torch.tensor(ids_c, dtype=torch.int64, device=dev)
         dict_input = processor(prompt)
         S = dict_input['input_ids'].shape[1]
         logits, cache = model(**dict_input, max_tokens=max_new + C + 10, logits_rows='last')
         last = logits[:, -1, :]
-        st = _row_stats(model, last, gather=torch.full((B, 1), ids_c[0]))
-        s0 = st['gather_lp'].cpu()                                           # [B,1]
-        running = (st['max'] - st['lse']).cpu()[:, None]                     # pv:548
-        tiled = torch.tensor(ids_c).repeat(B, 1)
+        st = _row_stats(model, last, gather=torch.full((B, 1), ids_c[0], dtype=torch.int32, device=dev))
+        s0 = st['gather_lp']                                                 # [B,1]
+        running = (st['max'] - st['lse'])[:, None]                           # pv:548
+        tiled = idc.repeat(B, 1)
         lr, _ = model(tiled, cache=cache, advance_offset=0)                  # peek, pv:545
-        g = torch.full((B, C), -1, dtype=torch.int32)
+        g = torch.full((B, C), -1, dtype=torch.int32, device=dev)
         g[:, :C - 1] = tiled[:, 1:].to(torch.int32)
-        s1 = _row_stats(model, lr.reshape(-1, V), gather=g.reshape(-1, 1))['gather_lp'].reshape(B, C)[:, :C - 1].cpu()
-        eos_col = torch.full((B, 1), ID_EOS, dtype=torch.long)
+        s1 = _row_stats(model, lr.reshape(-1, V), gather=g.reshape(-1, 1))['gather_lp'].reshape(B, C)[:, :C - 1]
+        eos_col = torch.full((B, 1), ID_EOS, dtype=torch.int64, device=dev)
         pre_score = mean_lp(torch.cat([s0, s1], 1))
         pre_synth = torch.cat([tiled, eos_col], 1)
         if use_beam and max_new > 0:                                         # pv:551-557
-            token, beam_tok, beam_sc = beam_step(last, cache, ids_c)
+            token, beam_tok, beam_sc = beam_step(last, cache, idc)
             post_score = mean_lp(beam_sc)
             post_synth = torch.cat([beam_tok[:, None], tiled], 1)
             win = pre_score > post_score
             score_sofar = torch.where(win, pre_score, post_score)
             synth_sofar = torch.where(win[:, None], pre_synth, post_synth)
         else:
-            token = st['argmax'].cpu().long()
+            token = st['argmax'].long()
             score_sofar, synth_sofar = pre_score, pre_synth
         tokens = []
-        alive = torch.ones(B)
+        alive = torch.ones(B, device=dev)
+        if sync_timing:
+            torch.cuda.synchronize()
         prompt_time += tic()
-        for i in range(max_new):                                             # pv:567-597
+        # pv:567-597. Every tensor of the loop lives on the device and nothing is read back per step (the reference syncs at
+        # mx.eval pv:572,597 and in `_already`); the "no row alive" exit (pv:594-595) is polled every `alive_check_every` steps —
+        # extra steps after it only append EOS columns behind the cut point of pv:601.
+        for i in range(max_new):
             tokens.append(token[:, None])
             tp = torch.cat([token[:, None], tiled], 1)                       # [B,1+C]
             lg, cache = model(tp, cache=cache, advance_offset=1)
-            g = torch.full((B, 1 + C), -1, dtype=torch.int32)
+            g = torch.full((B, 1 + C), -1, dtype=torch.int32, device=dev)
             g[:, :C] = tp[:, 1:].to(torch.int32)
             stp = _row_stats(model, lg.reshape(-1, V), gather=g.reshape(-1, 1))
-            glp = stp['gather_lp'].reshape(B, 1 + C)[:, :C].cpu()
+            glp = stp['gather_lp'].reshape(B, 1 + C)[:, :C]
             pre_score = mean_lp(torch.cat([running, glp], 1))
             pre_synth = torch.cat(tokens + [tiled, eos_col], 1)
-            first_max_lp = (stp['max'] - stp['lse']).reshape(B, 1 + C)[:, 0].cpu()
+            first_max_lp = (stp['max'] - stp['lse']).reshape(B, 1 + C)[:, 0]
             if use_beam:
-                token, beam_tok, beam_sc = beam_step(lg[:, 0, :], cache, ids_c)
+                token, beam_tok, beam_sc = beam_step(lg[:, 0, :], cache, idc)
                 post_score = mean_lp(torch.cat([running, beam_sc], 1))
                 post_synth = torch.cat(tokens + [beam_tok[:, None], tiled], 1)
                 win = pre_score > post_score
                 score = torch.where(win, pre_score, post_score)
                 synth = torch.where(win[:, None], pre_synth, post_synth)
             else:
-                token = stp['argmax'].reshape(B, 1 + C)[:, 0].cpu().long()
+                token = stp['argmax'].reshape(B, 1 + C)[:, 0].long()
                 score, synth = pre_score, pre_synth
             synth_sofar = torch.cat([synth_sofar, eos_col], 1)
             toks = torch.cat(tokens, 1)
             if toks.shape[1] >= C:                                           # _already pv:495-498
-                alive = alive * (~(toks[:, -C:] == torch.tensor(ids_c)).all(1)).float()
+                alive = alive * (~(toks[:, -C:] == idc).all(1)).float()
             upd = (score > score_sofar) & (alive > 0)
             synth_sofar = torch.where(upd[:, None], synth, synth_sofar)
             score_sofar = torch.where(upd, score, score_sofar)
             running = torch.cat([running, first_max_lp[:, None]], 1)         # lp of the greedy token (pv:592)
             alive = alive * (token != ID_EOS).float()
-            if alive.sum() < 1:
+            if (i + 1) % alive_check_every == 0 and float(alive.sum().item()) < 1:
                 break
         constrain_time += tic()
-        out_ids = torch.cat([dict_input['input_ids'], synth_sofar], 1).tolist()
+        out_ids = torch.cat([dict_input['input_ids'].to(dev), synth_sofar], 1).tolist()        # the one read-back per constraint
         out_ids = [(r[:r.index(ID_EOS, S)] if ID_EOS in r[S:] else r) for r in out_ids]
         out_ids = [[t for t in r if t not in (0, 1)] for r in out_ids]
         ids_trace.append(out_ids)
