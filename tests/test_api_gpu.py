@@ -411,7 +411,7 @@ def test_kv_cache_handle_is_a_finite_sequence(dev):
 def test_token_stopper_and_row_truncation_match_oracle(dev):
     """A4: rows that emit EOS (32007) at different steps. The reference stops when every row has emitted EOS once
     (TokenStopper pv:106-117) and cuts each row after its first EOS (Streamer.end pv:73). The checkpoint is the peaked one with
-    the next-token permutation patched so that row 0 reaches EOS at step 3 and row 1 at step 6."""
+    the next-token permutation patched so that row 0 emits EOS as its 4th token and row 1 as its 8th."""
     import phi3_b200  # noqa
     from phi3_b200 import configs, weights, api
     from phi3_b200.processor import ByteTokenizer
@@ -421,7 +421,8 @@ def test_token_stopper_and_row_truncation_match_oracle(dev):
     w = weights.random_weights(cfg, seed=5, init='peaked')
     emb = w['model.embed_tokens.weight'].float()
     lm = w['lm_head.weight'].clone()
-    chains = [[ord('a') + 3, 400, 401, 402, 32007, 403], [ord('b') + 3, 500, 501, 502, 503, 504, 505, 32007, 506]]
+    # (every token has ONE lm_head row, i.e. one predecessor: row 1's chain joins row 0's at the token 'a')
+    chains = [[ord('a') + 3, 400, 401, 402, 32007, 403], [ord('b') + 3, 500, 501, 502, ord('a') + 3]]
     for ch in chains:                                              # after token ch[i] the model predicts ch[i+1]
         for a, b in zip(ch[:-1], ch[1:]):
             target = (weights.PEAK_ALPHA * emb[a]).to(lm.dtype)
@@ -433,7 +434,7 @@ def test_token_stopper_and_row_truncation_match_oracle(dev):
     prompts = ['xyz a', 'xyz b']                                  # equal lengths: no padding ambiguity
     inp = proc(prompts)
     ref = drivers.generate_ids(ora, inp, 12)
-    assert ref.shape[1] == 7 and ref[0, 3] == 32007 and ref[1, 6] == 32007      # the oracle loop stopped when both rows were done
+    assert ref.shape[1] == 8 and ref[0, 3] == 32007 and ref[1, 7] == 32007 and (ref[1, :7] != 32007).all()      # the oracle loop stopped when both rows were done
     hist = api._generate(model, proc, prompts, None, max_tokens=12, verbose=False, stream=False, mute=True, return_tokens=True,
                          eos_check_every=1).cpu().long()
     assert hist.shape == ref.shape and torch.equal(hist, ref)
