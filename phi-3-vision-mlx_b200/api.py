@@ -440,6 +440,7 @@ def _generate(model, processor, prompt, images=None, max_tokens=512, verbose=Tru
             break
     hist = ses.finish()
     torch.cuda.synchronize()
+    cache.release()                                                        # slab + captured graph go back to the model
     result, gen_len = streamer.end(hist)
     gen_time = tic()
     prompt_len = dict_input['input_ids'].numel()

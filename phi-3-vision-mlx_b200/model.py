@@ -118,14 +118,24 @@ class KVCacheB200:
         sl.kv_start.copy_(kvs)
         self.cos, self.sin, self.tab_bstride = sl.cos, sl.sin, tbs
 
+    def release(self):
+        """Hand the slab (page pool, tables, captured decode graph) back to the model for the next cache of this shape.
+        The drivers call this when a generation is finished; `__del__` is only the safety net for callers that drop the
+        handle without releasing it. The handle must not be used afterwards."""
+        slab, self.slab = self.slab, None
+        if slab is None:
+            return
+        if self._key not in self._slabs and len(self._slabs) >= 6:          # bound the recycled memory
+            self._slabs.pop(next(iter(self._slabs)))
+        lst = self._slabs.setdefault(self._key, [])
+        if len(lst) < 2:
+            slab.qcodes, slab.qmeta = self.qcodes, self.qmeta
+            lst.append(slab)
+        self.pool = self.block_table = self.kv_start = self.cos = self.sin = self.qcodes = self.qmeta = None
+
     def __del__(self):
         try:
-            if self._key not in self._slabs and len(self._slabs) >= 6:      # bound the recycled memory
-                self._slabs.pop(next(iter(self._slabs)))
-            lst = self._slabs.setdefault(self._key, [])
-            if len(lst) < 2 and self.slab is not None:
-                self.slab.qcodes, self.slab.qmeta = self.qcodes, self.qmeta
-                lst.append(self.slab)
+            self.release()
         except Exception:
             pass
 

@@ -179,7 +179,7 @@ def test_slab_recycling_and_graph_reuse(dev):
         first = lg[:, -1].argmax(-1)
         hist = m.greedy_decode(first, c, 11)
         outs.append(hist.cpu())
-        del c                                   # returns the slab to the pool
+        c.release()                             # returns the slab to the pool (`del c` does the same through __del__)
     assert torch.equal(outs[0], outs[2]) and not torch.equal(outs[0], outs[1])
     assert len(m._slabs[(2, 70, 12, False)]) == 1 and m._slabs[(2, 70, 12, False)][0].session is not None
     # held cache is not clobbered by a second cache of the same shape

@@ -22,14 +22,16 @@ def main():
     ap.add_argument('--layers', type=int, default=32)
     ap.add_argument('--steps', type=int, default=16)
     ap.add_argument('--gen', type=int, default=96)
+    ap.add_argument('--init', default='peaked', choices=['peaked', 'gpt2'],
+                    help="'peaked' = the parity checkpoint (lm_head tied to the embedding); 'gpt2' = flat logits, measures the bf16 noise floor")
     a = ap.parse_args()
     cfg = configs.with_overrides(configs.PHI35_MINI, num_hidden_layers=a.layers)
-    w = weights.random_weights(cfg, seed=0)
+    w = weights.random_weights(cfg, seed=0, init=a.init)
     m = Phi3B200(cfg, w)
     g = torch.Generator().manual_seed(11)
     ids = torch.randint(3, 32000, (4, 32), generator=g)
     ids[:, 0] = 1
-    rep = {'config': f'Phi-3.5-mini {a.layers} layers, 4x32 prompt, random-init seed 0', 'modes': {}}
+    rep = {'config': f'Phi-3.5-mini {a.layers} layers, 4x32 prompt, random-init seed 0, init={a.init}', 'modes': {}}
     # greedy continuation from the CUDA path (device-resident loop), then teacher-force everything
     lg, cg = m(ids, max_tokens=a.gen, logits_rows='last')
     first = lg[:, -1].argmax(-1)
@@ -67,8 +69,8 @@ def main():
             'rms_over_rms': (d.pow(2).mean().sqrt() / keep[b_].pow(2).mean().sqrt()).item(),
             'max_abs_over_max_abs': (d.abs().max() / keep[b_].abs().max()).item(),
             'greedy_agreement': (keep[a_].argmax(-1) == keep[b_].argmax(-1)).float().mean().item()}
-    # step-wise decode through the skinny kernels, teacher-forced on the b200 oracle's tokens
-    o = Phi3Oracle(cfg, w, prec='b200')
+    # step-wise decode through the skinny kernels, teacher-forced on the reference-flow oracle's tokens
+    o = Phi3Oracle(cfg, w, prec='ref')
     lo, co = o(ids, max_tokens=a.steps + 1)
     lg, cg = m(ids, max_tokens=a.steps + 1)
     tok = lo[:, -1].argmax(-1)
