@@ -6,14 +6,14 @@ math) works without the CUDA extension; anything that computes raises if it is m
 """
 from . import configs  # noqa: F401
 
-__all__ = ['load', 'generate', 'choose', 'constrain', 'configs']
+__all__ = ['load', 'generate', 'choose', 'constrain', 'generate_batch', 'sanitize', 'configs']
 
 
 def __getattr__(name):
-    if name in ('load', 'generate', 'choose', 'constrain', '_generate', '_choose_from', '_constrain'):
+    if name in ('load', 'generate', 'choose', 'constrain', 'generate_batch', 'sanitize', '_generate', '_choose_from', '_constrain'):
         from . import api
         return getattr(api, name)
-    if name in ('api', 'model', 'processor', 'weights', '_lib'):
+    if name in ('api', 'model', 'processor', 'weights', '_lib', 'parallel', 'mega', 'quant'):
         import importlib
         return importlib.import_module(f'{__name__}.{name}')
     raise AttributeError(name)
