@@ -213,6 +213,10 @@ typedef struct {
 } p3_gemm_args;
 int p3_gemm_plan_weights(const void* W, int64_t ldw, int N, int K, void* plan);
 int p3_gemm_fused(const p3_gemm_args* args, cudaStream_t st);
+/* SuRoPE cos/sin table phi:487-507 on the device: cosT/sinT fp32 [Bt, L_all, half]; positions 0..L_all-1 (pids NULL) or per row
+ * cat[pids[b, 0..Lp), pids[b, Lp-1] + 1 + arange] (phi:493-497); inv_freq fp32 [half] = 1 / (factor * theta^(2i/dim)). */
+int p3_rope_table(const int32_t* pids, int64_t pid_stride, int Lp, const float* inv_freq, float* cosT, float* sinT, int Bt,
+                  int L_all, int half, float scale, cudaStream_t st);
 /* fp32 out[row] = sum of squares of bf16 x[row, 0..H) (feeds ss_in with n_ss_in = 1) */
 int p3_row_sumsq(const void* x, int64_t ldx, float* out, int64_t T, int H, cudaStream_t st);
 

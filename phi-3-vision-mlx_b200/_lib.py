@@ -42,6 +42,7 @@ _SIGS = {
     'p3_gn_assemble': [_p, _p, _p, _p, _i, _i, _i, _p],
     'p3_mega_pack': [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     'p3_row_sumsq': [_p, _l, _p, _l, _i, _p],
+    'p3_rope_table': [_p, _l, _i, _p, _p, _p, _i, _i, _i, _f, _p],
 }
 
 _lib = None

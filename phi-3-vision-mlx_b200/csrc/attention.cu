@@ -585,11 +585,11 @@ extern "C" int p3_attention_prefill(const void* q, const void* k, const void* v,
     dim3 grid((L + 127) / 128, n_heads, B);
     int smem = (2 + 2 * PF_STAGES) * 64 * hd * 2;
     if (hd == 96) {
-        static bool set = false;
+        static P3DevFlags flags; bool& set = flags.cur();
         if (!set) { cudaFuncSetAttribute(attn_prefill_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
         attn_prefill_kernel<96><<<grid, PF_THREADS, smem, st>>>(p);
     } else {
-        static bool set = false;
+        static P3DevFlags flags; bool& set = flags.cur();
         if (!set) { cudaFuncSetAttribute(attn_prefill_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
         attn_prefill_kernel<64><<<grid, PF_THREADS, smem, st>>>(p);
     }
@@ -608,7 +608,7 @@ template <int D>
 static int launch_decode(AttnParams& p, cudaStream_t st) {
     dim3 grid(p.n_splits, p.n_heads, p.B);
     int smem = 16 * D * 2 + DEC_STAGES * 2 * 64 * D * 2;
-    static bool set = false;
+    static P3DevFlags flags; bool& set = flags.cur();
     if (!set) {
         cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         P3_CHECK_ARG(e == cudaSuccess, "attention_decode: smem attribute: %s", cudaGetErrorString(e));

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(128, 3) attn_decode_q4_kernel(AttnParams p) {
 int launch_decode_q4_d96(AttnParams& p, cudaStream_t st) {
     dim3 grid(p.n_splits, p.n_heads, p.B);
     const int smem = 16 * Q4_D * 2 + QA_STAGES * QA_STAGE;          // = QB_STAGES * 24576: both phases share it
-    static bool set = false;
+    static P3DevFlags flags; bool& set = flags.cur();
     if (!set) {
         cudaError_t e = cudaFuncSetAttribute(attn_decode_q4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         P3_CHECK_ARG(e == cudaSuccess, "attention_decode_q4: smem attribute: %s", cudaGetErrorString(e));

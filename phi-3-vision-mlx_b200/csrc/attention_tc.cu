@@ -423,7 +423,7 @@ static int launch_tc_d(const AttnParams& p, cudaStream_t st) {
     }
     if (!C::TWO) { tm.q[1] = tm.q[0]; tm.k[1] = tm.k[0]; tm.pool[1] = tm.pool[0]; }
     P3_CHECK_ARG(r == CUDA_SUCCESS, "attention_prefill: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    static bool set = false;
+    static P3DevFlags flags; bool& set = flags.cur();
     if (!set) {
         cudaError_t e = cudaFuncSetAttribute(attn_prefill_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         P3_CHECK_ARG(e == cudaSuccess, "attention_prefill: cannot set %d B dynamic smem: %s", C::SMEM, cudaGetErrorString(e));

@@ -123,6 +123,12 @@ inline cudaError_t p3_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: remember it per device, not per process
+struct P3DevFlags {
+    bool set[64] = {};
+    bool& cur() { int d = 0; cudaGetDevice(&d); return set[(d < 0 || d >= 64) ? 0 : d]; }
+};
+
 // Paged KV pool addressing. One pool per layer:
 //   pool[page][kv(0=K,1=V)][head][slot(0..PAGE-1)][head_dim]   bf16
 #define P3_PAGE 64

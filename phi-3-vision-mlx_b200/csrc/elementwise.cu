@@ -43,6 +43,34 @@ extern "C" int p3_embed_gather(const void* table, const int32_t* ids, void* out,
 }
 
 // ------------------------------------------------------------------------------------------
+// rope_table: SuRoPE cos/sin table (phi.py:487-507) built on the device. f = fp32(pos) * inv_freq (one fp32 multiply, as the
+// reference), full-range cosf / sinf, times the LongRoPE scale. Positions: 0..L_all-1, or per row cat[pids, pids[-1]+1+arange]
+// (phi.py:493-497; pad slots carry pid 1). A 128K table is 50 MB: it never crosses PCIe.
+// ------------------------------------------------------------------------------------------
+__global__ void rope_table_kernel(const int32_t* __restrict__ pids, int64_t pid_stride, int Lp, const float* __restrict__ inv_freq,
+                                  float* __restrict__ cosT, float* __restrict__ sinT, int64_t total, int L_all, int half, float sf) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int d = (int)(idx % half);
+    const int i = (int)((idx / half) % L_all);
+    const int64_t b = idx / ((int64_t)half * L_all);
+    int pos = i;
+    if (pids) pos = i < Lp ? pids[b * pid_stride + i] : pids[b * pid_stride + Lp - 1] + 1 + (i - Lp);
+    const float f = __fmul_rn((float)pos, inv_freq[d]);
+    cosT[idx] = __fmul_rn(cosf(f), sf);
+    sinT[idx] = __fmul_rn(sinf(f), sf);
+}
+
+extern "C" int p3_rope_table(const int32_t* pids, int64_t pid_stride, int Lp, const float* inv_freq, float* cosT, float* sinT, int Bt,
+                             int L_all, int half, float scale, cudaStream_t st) {
+    P3_CHECK_ARG(Bt >= 1 && L_all >= 1 && half >= 1 && (!pids || (Lp >= 1 && Lp <= L_all)), "rope_table: bad sizes");
+    const int64_t total = (int64_t)Bt * L_all * half;
+    rope_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pids, pid_stride, Lp, inv_freq, cosT, sinT, total, L_all, half, scale);
+    P3_CHECK_LAUNCH("rope_table");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // row_sumsq: sum of squares of every row (the statistics half of nn.RMSNorm, phi.py:478): one warp per row.
 // ------------------------------------------------------------------------------------------
 __global__ void row_sumsq_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t T, int H) {

@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
 template <int NT, int MT, int DEPTH, bool W4 = false>
 static int launch_skinny_d(const SkParams& p, unsigned grid, cudaStream_t st) {
     using C = SkCfg<NT, MT, DEPTH, W4>;
-    static bool set = false;
+    static P3DevFlags flags; bool& set = flags.cur();
     if (!set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel<NT, MT, DEPTH, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         P3_CHECK_ARG(e == cudaSuccess, "gemm_skinny: smem attribute: %s", cudaGetErrorString(e));

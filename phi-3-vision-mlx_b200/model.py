@@ -358,17 +358,20 @@ class Phi3B200:
                        / math.log(cfg.original_max_position_embeddings))
         use_long = L_all > cfg.original_max_position_embeddings if self.force_long_rope is None else self.force_long_rope
         fac = cfg.rope_scaling['long_factor'] if use_long else cfg.rope_scaling['short_factor']   # static switch (H7)
+        # inv_freq: 48 values, fp32 on the host exactly as phi:498; the [Bt, L_all, 48] table itself is built by p3_rope_table on
+        # the device (a 128K-token table is 2 x 25 MB — round 1 built it with CPU torch and copied it over PCIe per call)
+        inv_freq = (1.0 / (torch.tensor(fac, dtype=torch.float32)
+                           * cfg.rope_theta ** (torch.arange(0, self.hd, 2, dtype=torch.float32) / self.hd))).to(self.dev)
+        half = self.hd // 2
         if pids is None:
-            pos = torch.arange(L_all, dtype=torch.float32)[None]
+            Bt, pid_dev, Lp, stride = 1, None, 0, 0
         else:
-            pids = torch.as_tensor(pids).to('cpu', torch.float32)
-            ext = pids[:, -1][:, None] + 1 + torch.arange(L_all - pids.shape[1], dtype=torch.float32)[None, :]
-            pos = torch.cat([pids, ext], dim=1)                                    # pad slots carry pid 1 (H8)
-        inv_freq = 1.0 / (torch.tensor(fac, dtype=torch.float32)
-                          * cfg.rope_theta ** (torch.arange(0, self.hd, 2, dtype=torch.float32) / self.hd))
-        freqs = pos[:, :, None] * inv_freq[None, None, :]
-        cos = (torch.cos(freqs) * sf).contiguous().to(self.dev)
-        sin = (torch.sin(freqs) * sf).contiguous().to(self.dev)
+            pid_dev = torch.as_tensor(pids).to(self.dev, torch.int32).contiguous()
+            Bt, Lp = pid_dev.shape
+            stride = pid_dev.stride(0)
+        cos = torch.empty((Bt, L_all, half), dtype=torch.float32, device=self.dev)
+        sin = torch.empty((Bt, L_all, half), dtype=torch.float32, device=self.dev)
+        call('p3_rope_table', ptr(pid_dev), stride, Lp, ptr(inv_freq), ptr(cos), ptr(sin), Bt, L_all, half, float(sf), _stream())
         return cos, sin, (0 if cos.shape[0] == 1 else cos.shape[1] * cos.shape[2])
 
     # ------------------------------------------------------------------ vision tower (phi:135-226, 393-416)
@@ -431,31 +434,45 @@ class Phi3B200:
         return x
 
     # ------------------------------------------------------------------ one decoder pass
+    def decode_scratch(self, B):
+        """activation buffers of one decode step for B rows, allocated once per decode session (outside the captured graph).
+        The sum-of-squares partials need no initialisation: every slot a consumer reads is written by its producer."""
+        dev, n_part = self.dev, (self.H + 15) // 16
+        e = lambda *s, dt=torch.bfloat16: torch.empty(s, dtype=dt, device=dev)
+        return dict(h=e(B, self.H), qkv=e(B, self.qkv_dim), att=e(B, self.n_heads * self.hd), act=e(B, self.I),
+                    ssA=e(n_part, 16, dt=torch.float32), ssB=e(n_part, 16, dt=torch.float32), logits=e(B, self.V, dt=torch.float32))
+
     def _forward_tokens(self, ids_dev, B, L, cache, n_beam, write_cache, past, logits_rows, past_dev=None,
-                        n_splits=None, h=None, ws=None):
-        """ids_dev int32 [B*L] on device. Returns fp32 logits [B, R, V] (R = L or 1)."""
+                        n_splits=None, h=None, ws=None, scratch=None):
+        """ids_dev int32 [B*L] on device. Returns fp32 logits [B, R, V] (R = L or 1).
+        `scratch`: preallocated buffers of a decode session (decode_scratch), L == 1 only."""
         st = _stream()
         T, H = B * L, self.H
         dev = self.dev
         # decode (T <= 16): per-token sum-of-squares partials travel with the residual stream so the
         # RMSNorm fused into the next skinny GEMM never re-reads X: ss[c][16] written by the producer
         ssA = ssB = None
-        if T <= 16:
+        if scratch is not None:
+            ssA, ssB = scratch['ssA'], scratch['ssB']
+        elif T <= 16:
             n_part = (H + 15) // 16
-            ssA = torch.zeros((n_part, 16), dtype=torch.float32, device=dev)
-            ssB = torch.zeros((n_part, 16), dtype=torch.float32, device=dev)
+            ssA = torch.empty((n_part, 16), dtype=torch.float32, device=dev)
+            ssB = torch.empty((n_part, 16), dtype=torch.float32, device=dev)
         ss_cur = None
         fused = T > 16 and self.pf_fused and self.gemm_impl == 0
         ss0 = torch.empty((T, 1), dtype=torch.float32, device=dev) if fused else None
         if h is None:
-            h = torch.empty((T, H), dtype=torch.bfloat16, device=dev)
+            h = scratch['h'] if scratch is not None else torch.empty((T, H), dtype=torch.bfloat16, device=dev)
             call('p3_embed_gather', ptr(self.embed), ptr(ids_dev), ptr(h), T, H, self.V, ptr(ss0 if fused else ssA), st)
             ss_cur = None if ssA is None else ssA[:1]
         elif fused:
             call('p3_row_sumsq', ptr(h), h.stride(0), ptr(ss0), T, H, st)
-        qkv = torch.empty((T, self.qkv_dim), dtype=torch.bfloat16, device=dev)
-        att = torch.empty((T, self.n_heads * self.hd), dtype=torch.bfloat16, device=dev)
-        act = torch.empty((T, self.I), dtype=torch.bfloat16, device=dev)
+        if scratch is not None:
+            qkv, att, act = scratch['qkv'], scratch['att'], scratch['act']
+        else:
+            qkv = torch.empty((T, self.qkv_dim), dtype=torch.bfloat16, device=dev)
+            att = torch.empty((T, self.n_heads * self.hd), dtype=torch.bfloat16, device=dev)
+            act = torch.empty((T, self.I), dtype=torch.bfloat16, device=dev)
         use_decode_attn = L <= 16 and cache is not None
         if use_decode_attn:
             if n_splits is None:
@@ -563,7 +580,7 @@ class Phi3B200:
         else:
             hl, R = h, L
         hl = hl.reshape(B * R, H) if hl.is_contiguous() else hl.contiguous().reshape(B * R, H)
-        logits = torch.empty((B * R, self.V), dtype=torch.float32, device=dev)
+        logits = scratch['logits'] if scratch is not None else torch.empty((B * R, self.V), dtype=torch.float32, device=dev)
         self.linear(hl, self.lm_head, logits, _lib.EPI_F32, norm_w=self.norm, ss_in=ss_cur if (R == L) else None)
         return logits.view(B, R, self.V)
 
@@ -674,10 +691,10 @@ class DecodeSession:
             # recycled slab: same buffers, same graph -> just reset the device-side state
             self.hist, self.tok, self.step_dev, self.past_dev, self.eos = st['hist'], st['tok'], st['step'], st['past'], st['eos']
             self.n_splits, self.graph, self.launches_per_step = st['n_splits'], st['graph'], st['lps']
-            self.mega_ses, self.ws = st['mega'], st['ws']
+            self.mega_ses, self.ws, self.scratch = st['mega'], st['ws'], st['scratch']
             self._reset(first_token)
             return
-        self.mega_ses = None
+        self.mega_ses = self.ws = self.scratch = None
         self.hist = torch.zeros((B, max_steps + 1), dtype=torch.int32, device=dev)
         self.tok = first_token.clone()
         self.step_dev = torch.ones(1, dtype=torch.int32, device=dev)
@@ -696,9 +713,12 @@ class DecodeSession:
         if self.n_splits > 1:
             self.ws = torch.zeros(_lib.lib().p3_attention_decode_workspace(B, 1, model.n_heads, model.hd, self.n_splits) // 4,
                                   dtype=torch.float32, device=dev)
+        self.scratch = None
         if model.mega is not None and B <= 8:
             self.mega_ses = model.mega.session(cache, B)
             self.mega_ses.bind(self.past_dev)
+        elif B <= 16:
+            self.scratch = model.decode_scratch(B)
         if use_graph and B <= 16:
             cur = torch.cuda.current_stream()
             s = torch.cuda.Stream()
@@ -716,7 +736,8 @@ class DecodeSession:
             if sampler is None:
                 cache.slab.session = dict(max_steps=max_steps, offset0=cache.offset, hist=self.hist, tok=self.tok,
                                           step=self.step_dev, past=self.past_dev, eos=self.eos, n_splits=self.n_splits,
-                                          graph=self.graph, lps=self.launches_per_step, mega=self.mega_ses, ws=self.ws)
+                                          graph=self.graph, lps=self.launches_per_step, mega=self.mega_ses, ws=self.ws,
+                                          scratch=self.scratch)
 
     def _reset(self, first_token):
         self.hist[:, 0] = first_token
@@ -763,7 +784,7 @@ class DecodeSession:
             logits = self._mega_step()
         else:
             logits = m._forward_tokens(self.tok, self.B, 1, self.cache, 1, True, self.cache.offset + self.steps_run, 'last',
-                                       past_dev=self.past_dev, n_splits=self.n_splits, ws=self.ws)
+                                       past_dev=self.past_dev, n_splits=self.n_splits, ws=self.ws, scratch=self.scratch)
         if self.sampler is None:
             call('p3_row_stats', ptr(logits), self.B, m.V, m.V, ptr(self.tok), None, None, 0, None, None, 0, None, None,
                  _stream())

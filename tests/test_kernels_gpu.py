@@ -691,3 +691,34 @@ def test_gemm_fused_rope_kvwrite_matches_separate_kernels(dev, B, L, nh, past, r
     assert torch.equal(pool, pool_ref)
     if not wc:
         assert pool.abs().sum() == 0
+
+
+@pytest.mark.parametrize('L_all,use_pids', [(200, False), (4300, False), (140, True), (131072, False)])
+def test_rope_table_on_device(dev, L_all, use_pids):
+    """p3_rope_table vs the reference formula in torch fp32 on the CPU (phi:493-504): same fp32 product, cos / sin within 2 ulp
+    of the scale (CUDA cosf/sinf vs the host libm), also at 128K positions (arguments up to 1.3e5 rad)."""
+    import math
+    import phi3_b200  # noqa
+    from phi3_b200 import _lib, configs
+    cfg = configs.PHI35_MINI
+    hd, half = 96, 48
+    sf = math.sqrt(1 + math.log(cfg.max_position_embeddings / cfg.original_max_position_embeddings) / math.log(cfg.original_max_position_embeddings))
+    fac = cfg.rope_scaling['long_factor'] if L_all > 4096 else cfg.rope_scaling['short_factor']
+    inv_freq = 1.0 / (torch.tensor(fac, dtype=torch.float32) * cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
+    if use_pids:
+        Lp = 100
+        pids = torch.stack([torch.arange(Lp), torch.cat([torch.ones(30, dtype=torch.long), torch.arange(70)])])
+        ext = pids[:, -1][:, None] + 1 + torch.arange(L_all - Lp)[None, :]
+        pos = torch.cat([pids, ext], 1).float()
+        pid_dev = pids.to(dev, torch.int32).contiguous()
+        Bt = 2
+    else:
+        pos, pid_dev, Lp, Bt = torch.arange(L_all, dtype=torch.float32)[None], None, 0, 1
+    fr = pos[:, :, None] * inv_freq[None, None, :]
+    ref_c, ref_s = torch.cos(fr) * sf, torch.sin(fr) * sf
+    cos = torch.empty(Bt, L_all, half, device=dev)
+    sin = torch.empty(Bt, L_all, half, device=dev)
+    ifd = inv_freq.to(dev)
+    _lib.call('p3_rope_table', None if pid_dev is None else pid_dev.data_ptr(), 0 if pid_dev is None else pid_dev.stride(0), Lp,
+              ifd.data_ptr(), cos.data_ptr(), sin.data_ptr(), Bt, L_all, half, float(sf), torch.cuda.current_stream().cuda_stream)
+    assert (cos.cpu() - ref_c).abs().max().item() <= 4e-7 * sf * 2 and (sin.cpu() - ref_s).abs().max().item() <= 4e-7 * sf * 2
