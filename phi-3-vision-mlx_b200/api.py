@@ -557,8 +557,84 @@ def choose(prompt, choices='ABCDE', images=None, preload=None, blind_model=False
 
 
 # ------------------------------------------------------------------------------------- constrain
+class _ConstrainStep:
+    """One constrained-decoding step (pv:567-597) as CUDA graphs: the shapes of a step are fixed for a constraint —
+    [B, 1+C] tokens for the committed forward (advance_offset=1), [B*n_beam, 1+C] for the read-only shared-prefix beam forward
+    (n_beam, advance_offset=0) — and the cache offset travels in a device int32 (`past_dev`), so the ~330 kernel launches of a
+    step replay without any Python between them. Eager first call (warm-up) is rolled back: it only writes the KV of the
+    position it is about to write again."""
+
+    def __init__(self, model, cache, B, C, n_beam, idc, use_beam, max_new):
+        self.m, self.cache, self.B, self.C, self.nb, self.use_beam = model, cache, B, C, n_beam, use_beam
+        dev = model.dev
+        self.tp = torch.zeros((B, 1 + C), dtype=torch.int64, device=dev)
+        self.tp[:, 1:] = idc
+        self.g = torch.full((B, 1 + C), -1, dtype=torch.int32, device=dev)
+        self.g[:, :C] = idc.to(torch.int32)
+        self.past_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        tiles = (cache.offset + max_new + 1 + C + 63) // 64
+        self.ns = model._splits(cache, B, tiles)
+        self.ns_beam = model._splits(cache, B * n_beam, tiles)
+        if use_beam:
+            self.seq = torch.zeros((B * n_beam, 1 + C), dtype=torch.int64, device=dev)
+            self.seq[:, 1:] = idc
+            self.gb = torch.full((B * n_beam, 1 + C), -1, dtype=torch.int32, device=dev)
+            self.gb[:, :C] = idc.to(torch.int32)
+        self.graphs = None
+
+    def _main(self):
+        lg, _ = self.m(self.tp, cache=self.cache, advance_offset=1, past_dev=self.past_dev, n_splits=self.ns)
+        self.cache.offset -= 1                                                # the caller advances the offset per replay
+        return lg, _row_stats(self.m, lg.reshape(-1, self.m.V), gather=self.g.reshape(-1, 1))
+
+    def _beam(self, lg):
+        st = _row_stats(self.m, lg[:, 0, :], n_top=self.nb)
+        self.seq[:, 0] = st['top_ids'].reshape(-1)
+        lb, _ = self.m(self.seq, cache=self.cache, n_beam=self.nb, advance_offset=0, past_dev=self.past_dev, n_splits=self.ns_beam)
+        return st, _row_stats(self.m, lb.reshape(-1, self.m.V), gather=self.gb.reshape(-1, 1))
+
+    def capture(self):
+        off = self.cache.offset
+        self.past_dev.fill_(off)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                                       # warm-up outside capture (smem attributes, allocator)
+            lg, _ = self._main()
+            if self.use_beam:
+                self.past_dev.fill_(off + 1)
+                self._beam(lg)
+                self.past_dev.fill_(off)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self.lg, self.stp = self._main()
+        g2 = None
+        if self.use_beam:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self.st_top, self.s2 = self._beam(self.lg)
+        self.graphs = (g1, g2)
+        assert self.cache.offset == off
+
+    def run_main(self, token):
+        """forward of cat[token, constraint] at the current offset; commits `token` (offset + 1)"""
+        self.tp[:, 0] = token
+        self.past_dev.fill_(self.cache.offset)
+        self.graphs[0].replay()
+        self.cache.offset += 1
+        return self.lg, self.stp
+
+    def run_beam(self):
+        """top-n_beam candidates of the first position + their read-only forwards against the shared prefix"""
+        self.past_dev.fill_(self.cache.offset)
+        self.graphs[1].replay()
+        return self.st_top, self.s2
+
+
 def _constrain(model, processor, prompt, constraints, return_full_text=False, mute=False, use_beam=False, verbose=True,
-               log_norm=False, n_beam=3, return_ids=False, alive_check_every=8, sync_timing=False):
+               log_norm=False, n_beam=3, return_ids=False, alive_check_every=8, sync_timing=False, use_graph=True):
     """pv:500-619. Scores are means of log-probs over [tokens so far + constraint]; only the
     gathered log-probs are ever materialised (p3_row_stats) instead of full-vocab log-softmax."""
     import math
@@ -631,6 +707,10 @@ def _constrain(model, processor, prompt, constraints, return_full_text=False, mu
             score_sofar, synth_sofar = pre_score, pre_synth
         tokens = []
         alive = torch.ones(B, device=dev)
+        step = None
+        if use_graph and max_new > 2 and 1 + C <= 16:
+            step = _ConstrainStep(model, cache, B, C, n_beam, idc, use_beam, max_new)
+            step.capture()
         if sync_timing:
             torch.cuda.synchronize()
         prompt_time += tic()
@@ -639,17 +719,28 @@ def _constrain(model, processor, prompt, constraints, return_full_text=False, mu
         # extra steps after it only append EOS columns behind the cut point of pv:601.
         for i in range(max_new):
             tokens.append(token[:, None])
-            tp = torch.cat([token[:, None], tiled], 1)                       # [B,1+C]
-            lg, cache = model(tp, cache=cache, advance_offset=1)
-            g = torch.full((B, 1 + C), -1, dtype=torch.int32, device=dev)
-            g[:, :C] = tp[:, 1:].to(torch.int32)
-            stp = _row_stats(model, lg.reshape(-1, V), gather=g.reshape(-1, 1))
+            if step is not None:
+                lg, stp = step.run_main(token)
+            else:
+                tp = torch.cat([token[:, None], tiled], 1)                   # [B,1+C]
+                lg, cache = model(tp, cache=cache, advance_offset=1)
+                g = torch.full((B, 1 + C), -1, dtype=torch.int32, device=dev)
+                g[:, :C] = tp[:, 1:].to(torch.int32)
+                stp = _row_stats(model, lg.reshape(-1, V), gather=g.reshape(-1, 1))
             glp = stp['gather_lp'].reshape(B, 1 + C)[:, :C]
             pre_score = mean_lp(torch.cat([running, glp], 1))
             pre_synth = torch.cat(tokens + [tiled, eos_col], 1)
             first_max_lp = (stp['max'] - stp['lse']).reshape(B, 1 + C)[:, 0]
             if use_beam:
-                token, beam_tok, beam_sc = beam_step(lg[:, 0, :], cache, idc)
+                if step is not None:
+                    sb, s2 = step.run_beam()
+                    rest = s2['gather_lp'].reshape(B * n_beam, 1 + C)[:, :C]
+                    bs = torch.cat([sb['top_lp'].reshape(-1, 1), rest], 1)
+                    kk = torch.argmax(bs.mean(1).reshape(B, n_beam), dim=-1)
+                    ar = torch.arange(B, device=dev)
+                    token, beam_tok, beam_sc = sb['argmax'].long(), sb['top_ids'].long()[ar, kk], bs.reshape(B, n_beam, -1)[ar, kk]
+                else:
+                    token, beam_tok, beam_sc = beam_step(lg[:, 0, :], cache, idc)
                 post_score = mean_lp(torch.cat([running, beam_sc], 1))
                 post_synth = torch.cat(tokens + [beam_tok[:, None], tiled], 1)
                 win = pre_score > post_score

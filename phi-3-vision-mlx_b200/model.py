@@ -502,9 +502,19 @@ class Phi3B200:
                             block_table=ptr(bt))
                 self.gemm_fused(h, lw['qkv_pf'], qkv, _lib.EPI_ROPE_KV, lw['plans']['qkv_pf'], ss_in=ss_cur, rope=rope)
                 qp = qkv.data_ptr()
-                call('p3_attention_prefill', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim, self.qkv_dim,
-                     ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale, 1, past, ptr(kvs),
-                     ptr(pool), ptr(bt), bts, n_beam, st)
+                if use_decode_attn and cache.quantized and cache.n_quant > 0:       # <= 16 new tokens per row (constrain / beam steps)
+                    call('p3_attention_decode_q4', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim,
+                         self.qkv_dim, ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale,
+                         past, cache.n_quant, ptr(kvs), ptr(pool), ptr(cache.qcodes[li]), ptr(cache.qmeta[li]), ptr(bt),
+                         bts, n_beam, n_splits, ptr(ws), ptr(past_dev), None, 0, st)
+                elif use_decode_attn:
+                    call('p3_attention_decode', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim,
+                         self.qkv_dim, ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale,
+                         past, ptr(kvs), ptr(pool), ptr(bt), bts, n_beam, n_splits, ptr(ws), ptr(past_dev), None, 0, st)
+                else:
+                    call('p3_attention_prefill', qp + qoff, qp + koff, qp + voff, self.qkv_dim, self.qkv_dim, self.qkv_dim,
+                         ptr(att), att.stride(0), B, L, self.n_heads, self.n_kv, self.hd, self.scale, 1, past, ptr(kvs),
+                         ptr(pool), ptr(bt), bts, n_beam, st)
                 self.gemm_fused(att, lw['o'], h, _lib.EPI_RESIDUAL, lw['plans']['o'], resid=h, ss_out=ssB)
                 self.gemm_fused(h, lw['gu_pf'], act, _lib.EPI_SWIGLU, lw['plans']['gu_pf'], ss_in=ssB)
                 self.gemm_fused(act, lw['down'], h, _lib.EPI_RESIDUAL, lw['plans']['down'], resid=h, ss_out=ssA)
@@ -586,7 +596,9 @@ class Phi3B200:
 
     # ------------------------------------------------------------------ reference call protocol (phi:606, 576-592)
     def __call__(self, input_ids, pixel_values=None, image_sizes=None, positions=None, cache=None, pids=None,
-                 mask=None, max_tokens=0, advance_offset=None, n_beam=1, logits_rows='all'):
+                 mask=None, max_tokens=0, advance_offset=None, n_beam=1, logits_rows='all', past_dev=None, n_splits=None):
+        """`past_dev` / `n_splits` (extensions, used by the graph-captured constrain step): the cache offset is read from a device
+        int32 at run time so that a captured call can be replayed as the cache grows (<= 16 new tokens per row)."""
         ids = torch.as_tensor(input_ids)
         if ids.dim() == 1:
             ids = ids[None]
@@ -630,7 +642,8 @@ class Phi3B200:
                                               'last' if c1 == L else 'none',
                                               h=None if h2 is None else h2[:, c0:c1].contiguous().reshape(-1, self.H))
         else:
-            logits = self._forward_tokens(ids_dev, B, L, cache, n_beam, write, past, logits_rows, h=h)
+            logits = self._forward_tokens(ids_dev, B, L, cache, n_beam, write, past, logits_rows, h=h, past_dev=past_dev,
+                                          n_splits=n_splits)
         if write:
             cache.offset = past + L                                               # phi:544-547
         if first_fill and cache.quantized:

@@ -443,3 +443,14 @@ def test_token_stopper_and_row_truncation_match_oracle(dev):
     # polling EOS every 16 steps (the default) decodes past the stop point but returns the same truncated text
     txt16 = api._generate(model, proc, prompts, None, max_tokens=12, verbose=False, stream=False, mute=True, eos_check_every=16)
     assert txt16 == txt
+
+
+@pytest.mark.parametrize('use_beam', [False, True])
+def test_constrain_graph_replay_equals_eager(dev, use_beam):
+    """the CUDA-graph constrained step (one replay per forward, cache offset in a device int) == the eager step, ids exact"""
+    api, model, proc, ora = _setup(init='peaked')
+    prompts = [api._preprocess(p) for p in api._apply_chat_template(['First question here', 'Second, longer question text here', 'q3'], None, False)[0]]
+    kw = dict(mute=True, verbose=False, use_beam=use_beam, n_beam=3, return_ids=True)
+    a = api._constrain(model, proc, prompts, [(9, ' The'), (5, ' answer')], use_graph=True, alive_check_every=4, **kw)
+    b = api._constrain(model, proc, prompts, [(9, ' The'), (5, ' answer')], use_graph=False, **kw)
+    assert a == b
