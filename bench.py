@@ -253,6 +253,41 @@ def run_cuda(args):
             gemv = {'kernel': sk_kernel, 'bound': 'hbm', 'achieved': round(ach, 1),
                     'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4), 'launches': len(sk)}
 
+    # ---- in-graph cost of the two HBM streams of a decode step: marginal step time when one of them is skipped inside the
+    # captured, PDL-chained graph (outputs are garbage, timing only). The per-launch event numbers above cannot see the overlap
+    # between neighbouring kernels; these can.
+    in_graph = None
+    if rank == 0:
+        def timed_decode(skip, steps=72, warm=8):
+            model._skip = set(skip)
+            try:
+                pv = ip([imgs_d[i] for i in range(B_PER_GPU)])['pixel_values']
+                lg, c = model(ids_d, pixel_values=pv, image_sizes=sizes, positions=positions, max_tokens=NEW, logits_rows='last')
+                c.slab.session = None                                  # capture a graph with this skip set
+                ses = model.decode_session(_row_stats(model, lg[:, -1, :])['argmax'], c, steps)
+                for _ in range(warm):
+                    ses.step()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(steps - warm):
+                    ses.step()
+                b.record()
+                torch.cuda.synchronize()
+                c.slab.session = None
+                return a.elapsed_time(b) / (steps - warm)
+            finally:
+                model._skip = set()
+        t_full, t_noattn, t_nogemm = timed_decode(()), timed_decode(('attn',)), timed_decode(('qkv', 'o', 'gu', 'down'))
+        kv_bytes = B_PER_GPU * (CTX + 40) * KV_BYTES_PER_POS * 32      # mean past over the timed steps ~ CTX + 40
+        gemm_bytes = 32 * 113_246_208 * 2                              # qkv + o + gate_up + down of 32 layers, bf16
+        peak_, _ = peaks()
+        in_graph = {'step_ms': round(t_full, 4), 'step_without_attention_ms': round(t_noattn, 4),
+                    'step_without_layer_gemms_ms': round(t_nogemm, 4),
+                    'attention_marginal_ms': round(t_full - t_noattn, 4), 'layer_gemm_marginal_ms': round(t_full - t_nogemm, 4),
+                    'attention_frac_of_hbm_peak': round(kv_bytes / ((t_full - t_noattn) * 1e-3) / 1e9 / peak_, 4),
+                    'layer_gemm_frac_of_hbm_peak': round(gemm_bytes / ((t_full - t_nogemm) * 1e-3) / 1e9 / peak_, 4),
+                    'note': 'marginal cost inside the captured graph = step time minus step time with that kernel family skipped'}
+
     # ---- BASELINE configs[1]: single-image VQA prefill at batch 1
     vqa_ms = None
     if rank == 0:
@@ -330,6 +365,7 @@ def run_cuda(args):
                     'call': 'parallel.dp_generate -> api.generate_batch(prompt strings, host uint8 images): new tokens / wall '
                             'time of the whole call incl. tokenizer, H2D, HD transform, vision tower, prefill, decode, D2H, detokenise'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_skinny_gemm': gemv,
+            'decode_step_in_graph': in_graph,
             'cpu_baseline': cpu, 'wall_s_timed_region': round(wall, 3),
         }
         _emit(line)

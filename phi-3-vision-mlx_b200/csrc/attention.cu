@@ -299,6 +299,26 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
     const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int kvh = h / (p.n_heads / p.n_kv);
     pdl_trigger();
+    if (p.past_host > 0 && p.pool && D == 96) {
+        // Before the dependency wait: pull this CTA's first KV page slices into L2. Pages below the cache offset, the block
+        // table and kv_start were written by EARLIER decode steps / the prefill, not by the kernel we are waiting for; the
+        // host-side offset (capture-time under a CUDA graph) is a lower bound of the real one, so the range is a valid
+        // subset — and a prefetch is only a hint anyway. The first tiles then hit L2 instead of paying a cold HBM access.
+        const int crow0 = b / p.row_div;
+        const int kv00 = p.kv_start ? p.kv_start[crow0] : 0;
+        const int tf = kv00 / 64, te = (p.past_host + 63) / 64, nt0 = max(te - tf, 0);
+        const int lo = tf + (int)(((long long)nt0 * split) / p.n_splits), hi = tf + (int)(((long long)nt0 * (split + 1)) / p.n_splits);
+        const size_t he = (size_t)P3_PAGE * D, pe = 2 * (size_t)p.n_kv * he;
+        for (int tix = lo; tix < min(hi, lo + DEC_STAGES - 1); tix++) {
+            const int pg = p.block_table[(size_t)crow0 * p.bt_stride + tix];
+            const uint8_t* kp = reinterpret_cast<const uint8_t*>(p.pool + (size_t)pg * pe + (size_t)kvh * he);
+            const uint8_t* vp = kp + (size_t)p.n_kv * he * sizeof(bf16);
+            for (int ln = tid; ln < (int)(he * sizeof(bf16) / 128); ln += 128) {
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(kp + (size_t)ln * 128));
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(vp + (size_t)ln * 128));
+            }
+        }
+    }
     pdl_wait();                                                 // q/k/v, past and the cache come from earlier kernels
     const int past = p.past_dev ? *p.past_dev : p.past_host;
     const int crow = b / p.row_div;

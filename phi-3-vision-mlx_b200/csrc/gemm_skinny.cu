@@ -227,6 +227,20 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
         __syncthreads();
     }
 
+    // ROPE_QKV epilogue: this thread's rope factors and page id are known up front -> request them now, use them after the K
+    // loop (they can miss L2; fetched in the epilogue they would sit on the kernel's tail)
+    float rope_cs = 1.f, rope_sn = 0.f;
+    int rope_page = 0;
+    if (p.epi == P3_EPI_ROPE_QKV && tid < 8 * NT * 16 && (tid >> 4) < p.M) {
+        const int tok = tid >> 4, r = tid & 15;
+        const int past0 = p.past_dev ? *p.past_dev : p.past;
+        const int b = tok / p.L, pos = past0 + tok % p.L;
+        if (rope_head >= 0) {
+            const size_t ti = (size_t)(b / p.row_div) * p.tab_bstride + (size_t)pos * (p.hd / 2) + rope_grp * 16 + r;
+            rope_cs = __ldg(p.cosT + ti); rope_sn = __ldg(p.sinT + ti);
+        }
+        if (p.write_cache) rope_page = __ldg(p.block_table + (size_t)(b / p.row_div) * p.bt_stride + pos / P3_PAGE);
+    }
     // RESIDUAL epilogue (MT == 1): this thread's output element is known up front -> fetch the residual now
     float resid_pref = 0.f;
     if (p.epi == P3_EPI_RESIDUAL && MT == 1 && tid < 8 * NT * 16) {
@@ -416,7 +430,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
             bf16* row = outp + (size_t)tok * p.ldo;
             bf16 *kd = nullptr, *vd = nullptr;
             if (p.write_cache) {
-                int page = p.block_table[(size_t)(b / p.row_div) * p.bt_stride + pos / P3_PAGE];
+                const int page = (o == tid) ? rope_page : p.block_table[(size_t)(b / p.row_div) * p.bt_stride + pos / P3_PAGE];
                 kd = p.pool + (size_t)page * kv_page_elems(p.n_kv, p.hd) + (size_t)(pos % P3_PAGE) * p.hd;
                 vd = kd + (size_t)p.n_kv * P3_PAGE * p.hd;
             }
@@ -424,7 +438,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
                 const float x1 = bf16_round(a0), x2 = bf16_round(a1);              // qkv_proj output is bf16 in the reference flow
                 const int d = rope_grp * 16 + r;
                 const size_t ti = (size_t)(b / p.row_div) * p.tab_bstride + (size_t)pos * half + d;
-                const float cs = p.cosT[ti], sn = p.sinT[ti];
+                const float cs = (o == tid) ? rope_cs : p.cosT[ti], sn = (o == tid) ? rope_sn : p.sinT[ti];
                 const bf16 o1 = __float2bfloat16_rn(x1 * cs - x2 * sn), o2 = __float2bfloat16_rn(x2 * cs + x1 * sn);
                 row[rope_head * p.hd + d] = o1;
                 row[rope_head * p.hd + half + d] = o2;
