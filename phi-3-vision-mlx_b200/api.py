@@ -13,9 +13,10 @@ Differences a caller can see (all opt-in or forced by the offline environment):
     `quantized_model.safetensors`;
   * use_adapter=True takes the LoRA adapter from `adapter=` ({'config': adapter_config dict, 'weights': {name: tensor}}) or
     `adapter_path=` (adapter_config.json + adapters.safetensors, the files train_lora writes, pv:1005-1013) and folds it into
-    the bf16 weights at load: W' = bf16(W + scale*alpha/rank * (A B)^T) — inference with zero extra kernels instead of
-    LoRALinear's two extra matmuls per call (phi:129-133). A LoRA over 4-bit weights cannot be folded: that combination
-    raises NotImplementedError;
+    the device weight copies: W' = bf16(W + scale*alpha/rank * (A B)^T) — inference with zero extra kernels instead of
+    LoRALinear's two extra matmuls per call (phi:129-133). `set_adapter(model, adapter)` swaps or removes it IN PLACE (the
+    reference reloads the model). With quantize_model=True the adapted matrices are base = the 4-bit image + the low-rank
+    update, i.e. LoRALinear over QuantizedLinear (phi:94-95), and stream as bf16 at decode; all other matrices stay 4-bit;
   * constrain(..., n_beam=3) exposes the beam width the reference hard-codes (pv:505);
   * images may be PIL images or uint8 HWC arrays (no URL fetching offline);
   * generate_batch(prompts, images_per_prompt, ...) is an extension: the reference raises on images + a prompt list
@@ -139,9 +140,6 @@ def load(blind_model=False, quantize_model=False, quantize_cache=False, use_adap
     """pv:1279-1322. Returns (model, processor)."""
     adapter = kwargs.pop('adapter', None)
     adapter_path = kwargs.pop('adapter_path', None)
-    if use_adapter and quantize_model:
-        raise NotImplementedError('a LoRA adapter over 4-bit weights cannot be folded into them (pv:264-271 wraps QuantizedLinear); '
-                                  'load the bf16 model with use_adapter=True')
     device = kwargs.pop('device', 'cuda')
     cfg = kwargs.pop('cfg', None)
     tokenizer = kwargs.pop('tokenizer', None)
@@ -183,12 +181,13 @@ def load(blind_model=False, quantize_model=False, quantize_cache=False, use_adap
             tokenizer = ByteTokenizer()
     for k, v in kwargs.items():                                            # remaining kwargs override cfg (pv:359-363)
         setattr(cfg, k, v)
+    lora = None
     if use_adapter:
         if adapter is None:
             adapter_path = adapter_path or f'{PATH_ADAPTERS}/{os.path.basename(PATH_ORIGINAL_PHI3_BLIND if blind_model else PATH_ORIGINAL_PHI3_VISION)}'
             adapter = _read_adapter(adapter_path)                          # pv:266-271, _get_adapter_path pv:462
-        weights = merge_lora(weights, adapter['config'], adapter['weights'], cfg.num_hidden_layers)
-    model = Phi3B200(cfg, weights, device=device, clip_cfg=clip_cfg, quantize_model=quantize_model)
+        lora = lora_modules(adapter['config'], adapter['weights'], cfg.num_hidden_layers)
+    model = Phi3B200(cfg, weights, device=device, clip_cfg=clip_cfg, quantize_model=quantize_model, lora=lora)
     if ckpt_dir is not None and getattr(cfg, 'architectures', None):       # pv:260: processor class follows the checkpoint's arch
         blind_model = not cfg.architectures[0].startswith('Phi3V')
     processor = Phi3FProcessor(tokenizer) if blind_model else Phi3VProcessor(tokenizer, num_crops=num_crops, device=device)
@@ -202,6 +201,37 @@ def _read_adapter(path):
     from safetensors.torch import load_file
     return {'config': json.load(open(os.path.join(path, 'adapter_config.json'))),
             'weights': load_file(os.path.join(path, 'adapters.safetensors'))}
+
+
+def lora_modules(lora_cfg, lora_weights, n_layers):
+    """_linear_to_lora_layers (pv:234-245): which Linear modules carry a LoRALinear and with what scale (phi:121: scale * alpha
+    / rank). Returns {module name: (lora_a [in, r], lora_b [r, out], scale)} — the `lora` argument of Phi3B200 / set_adapter."""
+    layers = lora_cfg['lora_layers']
+    if isinstance(layers, int):
+        layers = list(range(n_layers))[-layers:]
+    elif not isinstance(layers, list):
+        raise ValueError('Invalid type for lora_layers. Expected int (number of layers) or list (layer indices or names).')
+    lp = lora_cfg['lora_parameters']
+    sc = float(lp['scale']) * (float(lp['alpha']) / float(lp['rank']))
+    out = {}
+    for i in layers:
+        for t in lora_cfg['lora_targets']:
+            key = f'model.layers.{i}.{t}'
+            a, b = lora_weights.get(key + '.lora_a'), lora_weights.get(key + '.lora_b')
+            if a is None or b is None:
+                raise KeyError(f'adapter has no {key}.lora_a / .lora_b')
+            out[key] = (a, b, sc)
+    return out
+
+
+def set_adapter(model, adapter=None, adapter_path=None):
+    """Swap (or remove, adapter=None) the LoRA adapter of a loaded model without reloading it: the reference has to call load()
+    again (pv:266-271). `adapter` = {'config': adapter_config dict, 'weights': {name: tensor}} or a directory via adapter_path."""
+    if adapter is None and adapter_path is not None:
+        adapter = _read_adapter(adapter_path)
+    lora = None if adapter is None else lora_modules(adapter['config'], adapter['weights'], model.cfg.num_hidden_layers)
+    model.set_adapter(lora)
+    return model
 
 
 def merge_lora(weights, lora_cfg, lora_weights, n_layers):

@@ -166,6 +166,7 @@ class MegaDecoder:
             out = torch.empty(N * K, dtype=torch.bfloat16, device=dev)
             _lib.call('p3_mega_pack', ptr(w), ptr(out), kind, N, K, model.n_heads, model.n_kv, model.hd, st)
             return out
+        self._pack = pack
         self.layers = []
         for i in range(nl):
             p = f'model.layers.{i}.'
@@ -185,6 +186,10 @@ class MegaDecoder:
             self.sched[name] = [(off.to(dev), ids.to(dev), mx) for off, ids, mx in sc]
         self.sync = torch.zeros(2, dtype=torch.int32, device=dev)
         self.stream_bytes_per_step = 2 * (nl * sum(N * K for k, (_, N, K) in self.shapes.items() if k != 'lm') + V * H)
+
+    def repack(self, li, key, w):
+        """rewrite the stream-order copy of one matrix in place (Phi3B200.set_adapter)"""
+        self.layers[li][key].copy_(self._pack(w, key))
 
     def session(self, cache, B):
         return MegaSession(self, cache, B)

@@ -141,7 +141,11 @@ class KVCacheB200:
 
 
 class Phi3B200:
-    def __init__(self, cfg, weights, device='cuda', clip_cfg=None, gemm_impl=0, quantize_model=False):
+    _LAYER_KEYS = {'self_attn.qkv_proj': 'qkv', 'self_attn.o_proj': 'o', 'mlp.gate_up_proj': 'gu', 'mlp.down_proj': 'down'}
+
+    def __init__(self, cfg, weights, device='cuda', clip_cfg=None, gemm_impl=0, quantize_model=False, lora=None):
+        """`lora`: None or {module name ('model.layers.3.self_attn.qkv_proj'): (lora_a [in, r], lora_b [r, out], scale*alpha/r)}
+        — LoRALinear (phi:84-133) folded into the decode / prefill weight copies on the device; swap with set_adapter()."""
         if not torch.cuda.is_available():
             raise RuntimeError('Phi3B200 needs a CUDA device (sm_100a); there is no CPU fallback')
         _lib.lib()
@@ -169,8 +173,20 @@ class Phi3B200:
         self.quantize_model = bool(quantize_model)
         self._w4 = {}
 
-        def lin(t, row_perm=None):
+        self._lora = dict(lora or {})
+        self._raw = {}                # pristine checkpoint tensors of every matrix that ever carried an adapter (for hot swaps)
+
+        def lin(t, row_perm=None, name=None):
             t = d(t)
+            ad = self._lora.get(name)
+            if ad is not None:
+                # LoRALinear over a Linear / QuantizedLinear (phi:94-95,129-133): base output + scale * (x A) B. Folded:
+                # W' = bf16(base + scale (A B)^T) with base = the 4-bit image when the model is quantised. Such a matrix streams
+                # as bf16 at decode (it is no longer a 4-bit code).
+                self._raw[name] = t
+                base = fake_quant(t) if self.quantize_model else t
+                t = self._fold(base, ad)
+                return t if row_perm is None else row_perm(t)
             if not self.quantize_model:
                 return t if row_perm is None else row_perm(t)
             q = W4(t, pack=True, row_perm=row_perm)
@@ -183,9 +199,11 @@ class Phi3B200:
         for i in range(cfg.num_hidden_layers):
             p = f'model.layers.{i}.'
             self.layers.append(dict(
-                ln1=d(w[p + 'input_layernorm.weight']), qkv=lin(w[p + 'self_attn.qkv_proj.weight']),
-                o=lin(w[p + 'self_attn.o_proj.weight']), ln2=d(w[p + 'post_attention_layernorm.weight']),
-                gu=lin(w[p + 'mlp.gate_up_proj.weight'], interleave_gate_up), down=lin(w[p + 'mlp.down_proj.weight'])))
+                ln1=d(w[p + 'input_layernorm.weight']), qkv=lin(w[p + 'self_attn.qkv_proj.weight'], None, p + 'self_attn.qkv_proj'),
+                o=lin(w[p + 'self_attn.o_proj.weight'], None, p + 'self_attn.o_proj'),
+                ln2=d(w[p + 'post_attention_layernorm.weight']),
+                gu=lin(w[p + 'mlp.gate_up_proj.weight'], interleave_gate_up, p + 'mlp.gate_up_proj'),
+                down=lin(w[p + 'mlp.down_proj.weight'], None, p + 'mlp.down_proj')))
         self.norm = d(w['model.norm.weight'])
         self.lm_head = lin(w['lm_head.weight'])
         # fused prefill (north_star: SuRoPE + KV write in the QKV epilogue, RMSNorm fused with the adjacent GEMM): second copies of
@@ -194,12 +212,11 @@ class Phi3B200:
         import os as _os1
         self.pf_fused = _os1.environ.get('P3_PF_FUSED', '1') != '0' and self.hd % 32 == 0
         if self.pf_fused:
-            perm = self._rope_row_perm()
+            self._rope_perm = self._rope_row_perm()
             for lw in self.layers:
-                g1, g2 = lw['ln1'].to(torch.float32)[None, :], lw['ln2'].to(torch.float32)[None, :]
-                lw['qkv_pf'] = (lw['qkv'].to(torch.float32)[perm] * g1).to(torch.bfloat16).contiguous()
-                lw['gu_pf'] = (lw['gu'].to(torch.float32) * g2).to(torch.bfloat16).contiguous()
+                lw['qkv_pf'], lw['gu_pf'] = self._prefill_copy(lw, 'qkv'), self._prefill_copy(lw, 'gu')
                 lw['plans'] = {k: _lib.WeightPlan(lw[k]) for k in ('qkv_pf', 'o', 'gu_pf', 'down')}
+        self._raw_src = w             # names only looked up for adapter targets (set_adapter); the dict stays the caller's
         # persistent decode-layer kernel (mega.py / decode_mega.cu): a second, stream-order copy of the decoder weights
         # (7.4 GB at Phi-3.5 sizes; HBM has 180 GB). bf16 weights only. Opt-in (P3_MEGA=1) while it is slower than the chain
         # of per-matrix skinny kernels it replaces (profiles/r02_decode_mega.md).
@@ -253,6 +270,48 @@ class Phi3B200:
                  p0_w=ql(w[Vp + 'img_projection.0.weight']), p0_b=d(w[Vp + 'img_projection.0.bias']),
                  p2_w=ql(w[Vp + 'img_projection.2.weight']), p2_b=d(w[Vp + 'img_projection.2.bias']))
         self.vision = v
+
+    # ------------------------------------------------------------------ LoRA adapters (phi:84-133, pv:234-245, 266-271)
+    def _fold(self, base, ad):
+        a, b, sc = ad
+        delta = (a.to(self.dev, torch.float32) @ b.to(self.dev, torch.float32)).T                  # [out, in]
+        return (base.to(torch.float32) + float(sc) * delta).to(torch.bfloat16).contiguous()
+
+    def _prefill_copy(self, lw, key):
+        """prefill copy of qkv / gate_up: RMSNorm gain folded in (+ rope row permutation for qkv), see __init__"""
+        if key == 'qkv':
+            return (lw['qkv'].to(torch.float32)[self._rope_perm] * lw['ln1'].to(torch.float32)[None, :]).to(torch.bfloat16).contiguous()
+        return (lw['gu'].to(torch.float32) * lw['ln2'].to(torch.float32)[None, :]).to(torch.bfloat16).contiguous()
+
+    def set_adapter(self, lora=None):
+        """Swap the LoRA adapter WITHOUT reloading the model (`lora` as in __init__, None = base weights). Every matrix that
+        carries the old or the new adapter is rebuilt from its pristine checkpoint tensor and written IN PLACE into the device
+        copies the kernels read (decode stream, prefill copy, stream-order copy of the persistent kernel), so weight TMA plans,
+        KV slabs and captured decode graphs stay valid. Result is identical to constructing the model with `lora`."""
+        lora = dict(lora or {})
+        names = set(self._lora) | set(lora)
+        for name in sorted(names):
+            li = int(name.split('.')[2])
+            key = self._LAYER_KEYS.get(name.split('.', 3)[3])
+            if key is None:
+                raise KeyError(f'adapter target {name} is not a decoder-layer projection')
+            lw = self.layers[li]
+            if name not in self._raw:
+                if self.quantize_model and lw[key].data_ptr() in self._w4:
+                    raise NotImplementedError('adding an adapter to a matrix that was loaded as a 4-bit stream needs a reload '
+                                              '(load with use_adapter=True so that the targeted matrices stream as bf16)')
+                self._raw[name] = self._raw_src[name + '.weight'].to(self.dev, torch.bfloat16).contiguous()
+            base = fake_quant(self._raw[name]) if self.quantize_model else self._raw[name]
+            t = self._fold(base, lora[name]) if name in lora else base
+            if key == 'gu':
+                t = interleave_gate_up(t)
+            lw[key].copy_(t)
+            if self.pf_fused and key in ('qkv', 'gu'):
+                lw[key + '_pf'].copy_(self._prefill_copy(lw, key))
+            if self.mega is not None:
+                src = t if key != 'gu' else (self._fold(base, lora[name]) if name in lora else base)   # checkpoint row order
+                self.mega.repack(li, key, src)
+        self._lora = lora
 
     def _rope_row_perm(self):
         """row order of the prefill copy of qkv_proj: per q/k head [16j..16j+15 | half+16j..half+16j+15] for j = 0..hd/32-1
