@@ -34,7 +34,7 @@ import torch
 from . import _lib
 from ._lib import call, ptr
 from .configs import PHI35_MINI, PHI35_VISION, ID_EOS, with_overrides
-from .model import Phi3B200, _stream
+from .model import Phi3B200, _stream, capture_graph
 from .processor import Phi3FProcessor, Phi3VProcessor, ByteTokenizer
 from .weights import random_weights
 
@@ -638,12 +638,12 @@ class _ConstrainStep:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
+        with capture_graph(g1):
             self.lg, self.stp = self._main()
         g2 = None
         if self.use_beam:
             g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
+            with capture_graph(g2):
                 self.st_top, self.s2 = self._beam(self.lg)
         self.graphs = (g1, g2)
         assert self.cache.offset == off

@@ -27,6 +27,26 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def capture_graph(graph):
+    """torch.cuda.graph(graph) with the Python cycle collector out of the way: a dead reference cycle may own CUDA graphs or
+    device memory of an earlier model / cache, and destroying one of those WHILE this stream is capturing invalidates the
+    capture (cudaErrorStreamCaptureInvalidated). Collect before, keep the collector off during the capture."""
+    import gc
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph):
+            yield
+    finally:
+        if was:
+            gc.enable()
+
+
 def pick_splits(n_bh, tiles, slots=2 * 148, max_splits=32):
     """Split-KV factor for decode attention from a cost model fitted to tools/microbench.py on B200:
         T(s) = 2 us + 2.5 us * waves + bytes / min(5.95 TB/s, concurrent_CTAs * 34 GB/s)
@@ -802,7 +822,7 @@ class DecodeSession:
             self._reset(first_token)                          # the warm-up step really executed: roll back
             self.graph = torch.cuda.CUDAGraph()
             n0 = _lib.launches
-            with torch.cuda.graph(self.graph):
+            with capture_graph(self.graph):
                 self._one_step()
             self.launches_per_step = _lib.launches - n0
             if sampler is None:
