@@ -192,6 +192,7 @@ int p3_gn_assemble(const float* feats, const void* sub_GN, const void* glb_GN, v
  *   - P3_EPI_ROPE_KV: out = qkv [M, N] bf16 with q,k rotated, K/V also written to the page pool (as p3_rope_kvwrite). The q
  *     and k rows of W must be permuted per head to [16j..16j+15 | half+16j..half+16j+15], j = 0..hd/32-1 (so a rotary pair
  *     meets in one 32-column chunk of the accumulator); v rows keep their order.
+ *   - splitk_ws: see the field comment (deterministic split-K: partials are summed in slice order by the last CTA of a tile).
  *   - w_plan: NULL, or a P3_GEMM_WPLAN_BYTES blob filled once by p3_gemm_plan_weights for this W (skips re-encoding the
  *     weight tensor map on every call). */
 #define P3_EPI_ROPE_KV 8
@@ -210,6 +211,10 @@ typedef struct {
     int32_t L, n_heads, n_kv, hd, past, row_div, write_cache, bt_stride;
     const int32_t* past_dev;
     void* pool; const int32_t* block_table;
+    /* split-K for shapes with few output tiles (M <= 128 ...): NULL, or a caller-owned device workspace whose first 4 KB are
+     * zero before the first use (per-tile arrival counters, left at zero by every launch) followed by room for the fp32
+     * partial tiles (32 MB covers Phi-3.5 shapes). Without it such shapes run on as many SMs as they have tiles. */
+    void* splitk_ws; int64_t splitk_ws_bytes;
 } p3_gemm_args;
 int p3_gemm_plan_weights(const void* W, int64_t ldw, int N, int K, void* plan);
 int p3_gemm_fused(const p3_gemm_args* args, cudaStream_t st);

@@ -33,7 +33,12 @@ struct GemmEpi {
     int L, n_heads, n_kv, hd, past, row_div, write_cache;
     const int32_t* past_dev;
     bf16* pool; const int32_t* block_table; int bt_stride;
+    // split-K (small M: few output tiles, the GEMM is a weight stream and one SM ingests only ~1/148 of HBM bandwidth, so every
+    // SM must stream): `ksplit` CTAs share an output tile, each accumulates a K slice, dumps fp32 partials to `ws`
+    // [tile][ksplit][128][BN]; the last one to arrive (per-tile counter) sums them in slice order and runs the epilogue.
+    int ksplit; float* ws; int* counters; int64_t ws_bytes;
 };
+#define P3_SPLITK_COUNTER_BYTES 4096
 #define P3_EPI_ROPE_KV 8
 
 __device__ __forceinline__ float epi_act(int kind, float x) {
@@ -244,8 +249,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (M + C::BM - 1) / C::BM, n_tiles = (N + BN - 1) / BN;
-    const int total = m_tiles * n_tiles, kb = (K + C::BK - 1) / C::BK;
+    const int ksplit = ep.ksplit > 1 ? ep.ksplit : 1;
+    const int total = m_tiles * n_tiles * ksplit, kb_all = (K + C::BK - 1) / C::BK;   // work item = (tile, K slice)
     const int nb = band_width(K, BN, n_tiles);
+    __shared__ int s_last;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -272,11 +279,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < total; item += gridDim.x) {
+                const int tile = item / ksplit, ks = item - tile * ksplit;
                 int mt_, nt_;
                 tile_coords(tile, m_tiles, n_tiles, nb, mt_, nt_);
                 const int m_idx = mt_ * C::BM, n_idx = nt_ * BN;
-                for (int k = 0; k < kb; k++) {
+                const int k0 = (int)((long long)kb_all * ks / ksplit), k1 = (int)((long long)kb_all * (ks + 1) / ksplit);
+                for (int k = k0; k < k1; k++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -291,11 +300,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // descriptors in vector registers and wraps every UTCHMMA in an ELECT / R2UR loop (~70 cycles per issue).
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            const int ks = item % ksplit;
+            const int k0 = (int)((long long)kb_all * ks / ksplit), k1 = (int)((long long)kb_all * (ks + 1) / ksplit);
             mbar_wait(tempty_bar(acc), acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-            for (int k = 0; k < kb; k++) {
+            for (int k = k0; k < k1; k++) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -303,9 +314,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < C::BK / 16; kk++)   // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
-                        tc_mma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, C::IDESC, (k | kk) ? 1u : 0u);
+                        tc_mma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, C::IDESC, ((k - k0) | kk) ? 1u : 0u);
                     tc_commit(empty_bar(stage));
-                    if (k == kb - 1) tc_commit(tfull_bar(acc));
+                    if (k == k1 - 1) tc_commit(tfull_bar(acc));
                 }
                 __syncwarp();
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -315,7 +326,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp >= 4) {
         const int q = warp & 3, half = (warp - 4) >> 2;       // TMEM lane quarter, column half
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            const int tile = item / ksplit, ks = item - tile * ksplit;
             int mt_, nt_;
             tile_coords(tile, m_tiles, n_tiles, nb, mt_, nt_);
             const int m_idx = mt_ * C::BM, n_idx = nt_ * BN;
@@ -326,12 +338,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            // chunk loader: 32 accumulator columns of this thread's row — straight from TMEM, or (split-K, last CTA of the
+            // tile) the sum of all K slices' partials in slice order
+            float* wsrow = ep.ws + ((size_t)tile * ksplit * C::BM + (size_t)(q * 32 + lane)) * BN;   // slice 0, this row
+            bool from_ws = false;
+            if (ksplit > 1) {
+                float* mine = wsrow + (size_t)ks * C::BM * BN;
+                for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + c0, v);                                     // (warp-collective: every lane loads)
+                    if (!row_ok) continue;
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        reinterpret_cast<float4*>(mine + c0)[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                               __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(acc));                                   // the accumulator stage is free again
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __threadfence();
+                asm volatile("bar.sync 2, 256;" ::: "memory");                  // the 8 epilogue warps
+                if (threadIdx.x == 128) s_last = (atomicAdd(ep.counters + tile, 1) == ksplit - 1);
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (!s_last) continue;
+                __threadfence();
+                if (threadIdx.x == 128) ep.counters[tile] = 0;                  // ready for the next launch
+                from_ws = true;
+            }
+            auto load32 = [&](int c, uint32_t* v) {
+                if (!from_ws) { tc_ld32(taddr + c, v); return; }
+                if (!row_ok) return;
+                float a[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) a[i] = 0.f;
+                for (int s2 = 0; s2 < ksplit; s2++) {
+                    const float4* src = reinterpret_cast<const float4*>(wsrow + (size_t)s2 * C::BM * BN + c);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { const float4 f = __ldcg(src + i); a[4 * i] += f.x; a[4 * i + 1] += f.y; a[4 * i + 2] += f.z; a[4 * i + 3] += f.w; }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i++) v[i] = __float_as_uint(a[i]);
+            };
             if (ep.kind == P3_EPI_SWIGLU) {
                 // interleaved weights: columns [0,BN/2) gate, [BN/2,BN) matching up
                 for (int c0 = half * (BN / 4); c0 < (half + 1) * (BN / 4); c0 += 32) {
                     uint32_t g[32], u[32];
-                    tc_ld32(taddr + c0, g);
-                    tc_ld32(taddr + BN / 2 + c0, u);
+                    load32(c0, g);
+                    load32(BN / 2 + c0, u);
                     const int on0 = n_idx / 2 + c0;
                     if (row_ok && on0 < N / 2) {
                         uint4 ov[4];
@@ -356,13 +409,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
                 for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                     uint32_t v[32];
-                    tc_ld32(taddr + c0, v);
+                    load32(c0, v);
                     if (row_ok && n_idx + c0 < N) epi_store32(ep, orow, n_idx + c0, N, v, rs);
                 }
             }
-            tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (ksplit == 1) {
+                tc_fence_before();
+                mbar_arrive(tempty_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
         }
     }
     tc_fence_before();
@@ -691,8 +746,24 @@ static int launch_tc(const void* X, int64_t ldx, const void* W, int64_t ldw, con
         attr_set[cur_dev()] = true;
     }
     int64_t tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
-    unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
-    p3_launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(384), (size_t)C::SMEM, st, ta, tb, ep, (int)M, N, K);
+    GemmEpi e2 = ep;
+    e2.ksplit = 1;
+    if (ep.ws && tiles * 4 < num_sms() * 3) {
+        // few output tiles = a weight stream that must run on every SM: split K so that tiles * ksplit ~ #SM (>= 4 k-blocks each)
+        const int kb = (K + C::BK - 1) / C::BK;
+        int ks = (int)(num_sms() / tiles);
+        if (ks > 8) ks = 8;
+        if (ks > kb / 4) ks = kb / 4;
+        const int64_t need = P3_SPLITK_COUNTER_BYTES + tiles * ks * (int64_t)C::BM * BN * 4;
+        if (ks >= 2 && tiles * 4 <= P3_SPLITK_COUNTER_BYTES && need <= ep.ws_bytes) {
+            e2.ksplit = ks;
+            e2.counters = reinterpret_cast<int*>(ep.ws);
+            e2.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ep.ws) + P3_SPLITK_COUNTER_BYTES);
+        }
+    }
+    const int64_t items = tiles * e2.ksplit;
+    unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
+    p3_launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(384), (size_t)C::SMEM, st, ta, tb, e2, (int)M, N, K);
     P3_CHECK_LAUNCH("gemm_tc");
     return 0;
 }
@@ -792,6 +863,7 @@ extern "C" int p3_gemm_fused(const p3_gemm_args* a, cudaStream_t st) {
         ep.hd = a->hd; ep.past = a->past; ep.row_div = a->row_div; ep.write_cache = a->write_cache; ep.past_dev = a->past_dev;
         ep.pool = (bf16*)a->pool; ep.block_table = a->block_table; ep.bt_stride = a->bt_stride;
     }
+    ep.ws = reinterpret_cast<float*>(a->splitk_ws); ep.ws_bytes = a->splitk_ws ? a->splitk_ws_bytes : 0;   // carved up by launch_tc
     const GemmWPlan* wp = reinterpret_cast<const GemmWPlan*>(a->w_plan);
     if (wp) P3_CHECK_ARG(wp->magic == P3_WPLAN_MAGIC && wp->W == a->W && wp->ldw == a->ldw && wp->N == a->N && wp->K == a->K,
                          "gemm_fused: weight plan does not describe this W");

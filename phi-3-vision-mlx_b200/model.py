@@ -252,6 +252,10 @@ class Phi3B200:
         if any(k.startswith('model.vision_embed_tokens') for k in w):
             self._load_vision(w, d)
         self._slabs = {}              # recycled KV slabs, keyed by (B, L, max_tokens, quantized)
+        self._row_maps = {}
+        # split-K workspace of p3_gemm_fused (arrival counters + fp32 partial tiles); P3_SPLITK=0 turns split-K off
+        self._splitk_ws = (torch.zeros(32 << 20, dtype=torch.uint8, device=self.dev)
+                           if _os1.environ.get('P3_SPLITK', '1') != '0' else None)
         self.force_long_rope = None   # parallel.py: LongRoPE switch decided from the global batch (H7)
         self.prefill_chunk = 8192     # long prompts are prefilled in chunks against the paged cache (config 4: 128K)
         import os as _os
@@ -354,6 +358,8 @@ class Phi3B200:
             a.ss_in, a.n_ss_in, a.eps = ptr(ss_in), ss_in.shape[1], self.eps
         a.ss_out = ptr(ss_out)
         a.w_plan = None if plan is None else plan.addr
+        if self._splitk_ws is not None:
+            a.splitk_ws, a.splitk_ws_bytes = ptr(self._splitk_ws), self._splitk_ws.numel()
         if rope is not None:
             for k, v in rope.items():
                 setattr(a, k, v)
@@ -462,8 +468,10 @@ class Phi3B200:
         positions = torch.as_tensor(positions).cpu().tolist()
         pv = torch.as_tensor(pixel_values).to(self.dev, torch.float32)
         # only crops 0..hc*wc of each image reach the output (phi:405-406); zero-pad crops are skipped
-        used = [pv[b, :hw[0] * hw[1] + 1] for b, hw in enumerate(sizes)]
-        px = torch.cat(used, 0).contiguous()
+        if all(hw[0] * hw[1] + 1 == pv.shape[1] for hw in sizes) and pv.is_contiguous():
+            px = pv.reshape(-1, *pv.shape[2:])                  # every crop slot is used: a view, no copy kernel
+        else:
+            px = torch.cat([pv[b, :hw[0] * hw[1] + 1] for b, hw in enumerate(sizes)], 0).contiguous()
         x = self.clip_features(px)
         # token assembly + projector + splice (phi:400-415)
         crop0, idx = 0, 0
@@ -475,7 +483,11 @@ class Phi3B200:
             p1 = torch.empty((cnt, self.H), dtype=torch.bfloat16, device=self.dev)
             self.gemm(tok, v['p0_w'], p1, _lib.EPI_GELU, bias=v['p0_b'])
             r, c = positions[idx]
-            row_map = (torch.arange(cnt, dtype=torch.int32, device=self.dev) + (r * L + c)).contiguous()
+            row_map = self._row_maps.get((cnt, r * L + c))     # destination rows of the splice: built once per (length, offset)
+            if row_map is None:
+                if len(self._row_maps) > 256:
+                    self._row_maps.clear()
+                row_map = self._row_maps[(cnt, r * L + c)] = (torch.arange(cnt, dtype=torch.int32, device=self.dev) + (r * L + c)).contiguous()
             self.gemm(p1, v['p2_w'], h, _lib.EPI_NONE, bias=v['p2_b'], row_map=row_map)
             crop0 += hc * wc + 1
             idx += cnt

@@ -722,3 +722,42 @@ def test_rope_table_on_device(dev, L_all, use_pids):
     _lib.call('p3_rope_table', None if pid_dev is None else pid_dev.data_ptr(), 0 if pid_dev is None else pid_dev.stride(0), Lp,
               ifd.data_ptr(), cos.data_ptr(), sin.data_ptr(), Bt, L_all, half, float(sf), torch.cuda.current_stream().cuda_stream)
     assert (cos.cpu() - ref_c).abs().max().item() <= 4e-7 * sf * 2 and (sin.cpu() - ref_s).abs().max().item() <= 4e-7 * sf * 2
+
+
+@pytest.mark.parametrize('M', [5, 80, 128, 320])
+@pytest.mark.parametrize('N,K,epi', [(3072, 3072, 'resid'), (9216, 3072, 'none'), (3072, 8192, 'resid'), (16384, 3072, 'swiglu')])
+def test_gemm_split_k_small_m(dev, M, N, K, epi):
+    """few output tiles (small M): the tensor-core GEMM splits K over CTAs (fp32 partials, summed in slice order by the last
+    CTA of a tile) so that all SMs stream weights. Same result as the unsplit kernel up to fp32 summation order; the arrival
+    counters are left at zero; repeated launches are bit-identical (deterministic reduction)."""
+    import phi3_b200  # noqa
+    from phi3_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+    W = (torch.randn(N, K, generator=g) * 0.03).to(torch.bfloat16).to(dev)
+    ws = torch.zeros(32 << 20, dtype=torch.uint8, device=dev)
+    kind = {'resid': _lib.EPI_RESIDUAL, 'none': _lib.EPI_NONE, 'swiglu': _lib.EPI_SWIGLU}[epi]
+    No = N // 2 if epi == 'swiglu' else N
+    h0 = torch.randn(M, No, generator=g).to(torch.bfloat16).to(dev)
+
+    def run(split):
+        out = h0.clone() if epi == 'resid' else torch.zeros(M, No, dtype=torch.bfloat16, device=dev)
+        kw = dict(resid=out) if epi == 'resid' else {}
+        if split:
+            kw.update(splitk_ws=ws, splitk_ws_bytes=ws.numel())
+        _gemm_fused(dev, x, W, out, kind, **kw)
+        return out
+    a, b, c = run(False), run(True), run(True)
+    assert torch.equal(b, c)
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
+    assert ((a.float() - b.float()).abs().max() / a.float().abs().max()).item() < 4e-3      # one bf16 ulp of the largest value
+    y = x.float() @ W.float().T
+    if epi == 'resid':
+        ref = h0.float() + y.to(torch.bfloat16).float()
+    elif epi == 'swiglu':
+        Wi = W.float()                                            # interleaved layout: per 256 rows [128 gate | 128 up]
+        yb = y.to(torch.bfloat16).float().reshape(M, N // 256, 2, 128)
+        ref = (torch.nn.functional.silu(yb[:, :, 0]).to(torch.bfloat16).float() * yb[:, :, 1]).reshape(M, No)
+    else:
+        ref = y
+    assert ((b.float() - ref).abs().max() / ref.abs().max()).item() < 1e-2
