@@ -317,7 +317,14 @@ def run_cuda(args):
             rs5 = _np.random.RandomState(5)
             qs = [''.join(chr(c) for c in rs5.randint(97, 123, int(n))) for n in rs5.randint(250, 451, 16)]
             p5 = _api._apply_chat_template(qs, None, False)[0]
-            fproc = Phi3FProcessor(ByteTokenizer())
+            class _Cfg5Tok(ByteTokenizer):
+                """byte tokenizer for the prompts; the two constraint strings map to id lists of the lengths the Phi-3 tokenizer
+                gives them (SURVEY par. 8d: C = 2 and C = 4 after the [1:] of pv:538), not to 4 / 22 byte tokens"""
+                FIXED = {'\nThe': [1, 29871, 13, 1576], ' The correct answer is': [1, 29871, 450, 1959, 1234, 338]}
+
+                def encode(self, text, add_special_tokens=True):
+                    return self.FIXED.get(text) or super().encode(text, add_special_tokens)
+            fproc = Phi3FProcessor(_Cfg5Tok())
             cons = [(0, '\nThe'), (100, ' The correct answer is'), 'ABCDE']
             prev_q, model.use_quantized_cache = model.use_quantized_cache, True
             model.cfg.allow_beam_with_quantized_cache = True

@@ -750,7 +750,7 @@ def test_gemm_split_k_small_m(dev, M, N, K, epi):
     a, b, c = run(False), run(True), run(True)
     assert torch.equal(b, c)
     assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
-    assert ((a.float() - b.float()).abs().max() / a.float().abs().max()).item() < 4e-3      # one bf16 ulp of the largest value
+    assert ((a.float() - b.float()).abs().max() / a.float().abs().max()).item() < 1e-2      # <= 2 bf16 ulps of the largest value (two roundings)
     y = x.float() @ W.float().T
     if epi == 'resid':
         ref = h0.float() + y.to(torch.bfloat16).float()
