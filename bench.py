@@ -320,7 +320,7 @@ def run_cuda(args):
             class _Cfg5Tok(ByteTokenizer):
                 """byte tokenizer for the prompts; the two constraint strings map to id lists of the lengths the Phi-3 tokenizer
                 gives them (SURVEY par. 8d: C = 2 and C = 4 after the [1:] of pv:538), not to 4 / 22 byte tokens"""
-                FIXED = {'\nThe': [1, 29871, 13, 1576], ' The correct answer is': [1, 29871, 450, 1959, 1234, 338]}
+                FIXED = {'\nThe': [29871, 13, 1576], ' The correct answer is': [29871, 450, 1959, 1234, 338]}
 
                 def encode(self, text, add_special_tokens=True):
                     return self.FIXED.get(text) or super().encode(text, add_special_tokens)

@@ -748,8 +748,10 @@ static int launch_tc(const void* X, int64_t ldx, const void* W, int64_t ldw, con
     int64_t tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
     GemmEpi e2 = ep;
     e2.ksplit = 1;
-    if (ep.ws && tiles * 4 < num_sms() * 3) {
-        // few output tiles = a weight stream that must run on every SM: split K so that tiles * ksplit ~ #SM (>= 4 k-blocks each)
+    if (ep.ws && tiles * 2 < num_sms() && (int64_t)BN * K * 2 > (7ll << 18)) {
+        // few output tiles AND a long K (each CTA would stream > 1.75 MB of W alone at ~45 KB/us, e.g. down_proj at M <= 320:
+        // 24 tiles x 2 MB): split K so that tiles * ksplit ~ #SM (>= 4 k-blocks each). Measured (tools/gemm_smallm.py): 43 -> 30 us
+        // at M = 80, 40 -> 21 us at M = 16; for K = 3072 shapes the partial round trip costs more than it saves, so they stay unsplit.
         const int kb = (K + C::BK - 1) / C::BK;
         int ks = (int)(num_sms() / tiles);
         if (ks > 8) ks = 8;

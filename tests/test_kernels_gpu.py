@@ -727,8 +727,8 @@ def test_rope_table_on_device(dev, L_all, use_pids):
 @pytest.mark.parametrize('M', [5, 80, 128, 320])
 @pytest.mark.parametrize('N,K,epi', [(3072, 3072, 'resid'), (9216, 3072, 'none'), (3072, 8192, 'resid'), (16384, 3072, 'swiglu')])
 def test_gemm_split_k_small_m(dev, M, N, K, epi):
-    """few output tiles (small M): the tensor-core GEMM splits K over CTAs (fp32 partials, summed in slice order by the last
-    CTA of a tile) so that all SMs stream weights. Same result as the unsplit kernel up to fp32 summation order; the arrival
+    """few output tiles and a long K (small M, K = 8192): the tensor-core GEMM splits K over CTAs (fp32 partials, summed in slice
+    order by the last CTA of a tile) so that all SMs stream weights; the other shapes must be unaffected by the workspace. Same result as the unsplit kernel up to fp32 summation order; the arrival
     counters are left at zero; repeated launches are bit-identical (deterministic reduction)."""
     import phi3_b200  # noqa
     from phi3_b200 import _lib
