@@ -293,12 +293,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
             if (tid == 0) {
                 mg_arrive(P.sync);                              // release: orders the CTA's writes (cumulative through bar.sync)
                 const unsigned target = ++n_bar * gridDim.x;
+#ifndef MG_NO_BARRIER_WAIT                                               // (timing experiment only: results are garbage without the wait)
                 unsigned v, spins = 0;
                 do {
                     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.sync) : "memory");
                     if (v < target && ++spins > (1u << 26)) __trap();      // a CTA never arrived: fail loudly instead of hanging the GPU
                 } while (v < target);
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#else
+                (void)target;
+#endif
             }
             cta_sync();
         }
