@@ -72,6 +72,14 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm)}
 
 
+def bench_config(world):
+    """the `config` object of the JSON line — identical for the b200 arm and the --impl reference arm"""
+    return {'workload': 'Phi-3.5-vision batched generation: 8 image+text prompts per GPU x 2048 context x 256 '
+                        'new tokens, 672x672 image, HD transform num_crops=4 (BASELINE configs[2], 64 prompts at 8 GPUs)',
+            'per_gpu_batch': B_PER_GPU, 'context': CTX, 'new_tokens': NEW, 'parallelism': f'dp{world}',
+            'l2_policy': 'inputs larger than L2: 7.4 GB weights + 6.8 GB KV streamed per decode step'}
+
+
 def make_inputs(seed, B, ctx, n_img_tok):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -359,10 +367,7 @@ def run_cuda(args):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(dec_ms, 3), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic (random-init bf16 weights, random uint8 images and token ids; no network)',
-            'config': {'workload': 'Phi-3.5-vision batched generation: 8 image+text prompts per GPU x 2048 context x 256 '
-                                   'new tokens, 672x672 image, HD transform num_crops=4 (BASELINE configs[2], 64 prompts at 8 GPUs)',
-                       'per_gpu_batch': B_PER_GPU, 'context': CTX, 'new_tokens': NEW, 'parallelism': f'dp{world}',
-                       'l2_policy': 'inputs larger than L2: 7.4 GB weights + 6.8 GB KV streamed per decode step'},
+            'config': bench_config(world),
             'whole_step_ms': round(step_ms, 2), 'hd_transform_ms': round(hd_ms, 3),
             'vision_prefill_ms': round(pre_ms, 2), 'decode_ms_per_token': round(dec_ms / (NEW - 1), 4),
             'vqa_prefill_ms': None if vqa_ms is None else round(vqa_ms, 3), 'constrain_cfg5': cfg5,
@@ -416,8 +421,9 @@ def cpu_baseline(steps=2, threads=None):
         ts.append(time.perf_counter() - t1)
     s = min(ts[1:])
     return {'value': round(B / s, 3), 'unit': 'tok/s', 'cores': threads, 'kind': 'port',
-            'sample': f'Phi-3.5-mini decoder, batch {B}, {steps} greedy decode steps at a {S}-token synthetic fp32 KV cache '
-                      f'(dense mask, all-position lm_head as the reference); setup {setup:.0f}s excluded',
+            'sample': f'decode phase of the bench workload on one GPU share: batch {B}, {steps} greedy decode steps at a {S}-token '
+                      f'synthetic fp32 KV cache through the 32-layer Phi-3.5 LM backbone (the same architecture in the mini and vision '
+                      f'checkpoints), reference semantics: dense mask, fp32 KV, lm_head on every position; setup {setup:.0f}s excluded',
             's_per_step': round(s, 3)}
 
 
@@ -429,8 +435,9 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': 'tok/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', 1)),
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(1e3 * cb['s_per_step'], 1),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'CPU oracle (restatement of the reference; MLX not installable offline) on the bounded '
-                                   'decode sample of the bench workload', 'sample': cb['sample']},
+            'config': bench_config(int(os.environ.get('WORLD_SIZE', 1))),
+            'reference_impl': 'CPU oracle (op-for-op restatement of the reference; MLX itself is not installable offline) on a '
+                              'bounded sample of the workload, see cpu_baseline.sample',
             'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'tok/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     _emit(line)
 
