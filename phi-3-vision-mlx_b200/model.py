@@ -429,11 +429,13 @@ class Phi3B200:
             x = xn
         return self.gemm(x, w, out, epi, resid=resid)
 
-    def _splits(self, cache, B, tiles):
+    def _splits(self, cache, B, tiles, L=1):
         n_bh = B * self.n_heads
         if cache is not None and cache.quantized:
-            # the 4-bit kernel is ALU-bound (register dequant), 3 CTAs/SM resident: fill the 444 slots
-            return max(1, min((3 * 148 + n_bh // 2) // n_bh, max(1, tiles // 4)))
+            # the 4-bit kernel is bound by per-warp instruction latency, not by bytes: fill the resident slots
+            # (4 CTAs/SM for L <= 8 query rows, 3 for the 16-row variant) in one wave
+            slots = (4 if L <= 8 else 3) * 148
+            return max(1, min((slots + n_bh // 2) // n_bh, max(1, tiles // 4)))
         return pick_splits(n_bh, tiles)
 
     # ------------------------------------------------------------------ rope table (phi:487-507)
@@ -567,7 +569,7 @@ class Phi3B200:
         use_decode_attn = L <= 16 and cache is not None
         if use_decode_attn:
             if n_splits is None:
-                n_splits = self._splits(cache, B, max(1, (past + PAGE - 1) // PAGE))
+                n_splits = self._splits(cache, B, max(1, (past + PAGE - 1) // PAGE), L)
             if n_splits > 1 and ws is None:
                 ws = torch.zeros(_lib.lib().p3_attention_decode_workspace(B, L, self.n_heads, self.hd, n_splits) // 4,
                                  dtype=torch.float32, device=dev)        # zero: holds the split-arrival counters

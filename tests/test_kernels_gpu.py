@@ -399,6 +399,64 @@ def test_kv_quant_roundtrip_matches_oracle(dev):
                 assert torch.equal(got, deq[b, :, p * 64:p * 64 + n]), (kv, b, p)
 
 
+def _dequant_pool(qc, qm):
+    """codes [pages,2,H,64,D/2] u8 (low nibble = even dim) + meta [pages,2,H,64,D/32,2] bf16 -> bf16(code*scale + bias)."""
+    lo, hi = (qc & 15).float(), (qc >> 4).float()
+    codes = torch.stack([lo, hi], -1).reshape(*qc.shape[:-1], -1)                      # [..., D]
+    sc = qm[..., 0].float().repeat_interleave(32, -1)
+    bi = qm[..., 1].float().repeat_interleave(32, -1)
+    return (codes * sc + bi).to(torch.bfloat16)
+
+
+# (B, H, L, past, kv_start, n_splits): plain decode, beam-sized L (rows 8..15 live), left padding into the quantised
+# pages, a partial bf16 tail page, only-quantised / only-bf16 histories, split merge
+_Q4_CFGS = [(2, 3, 1, 200, [0, 0], 1), (2, 2, 5, 330, [0, 37], 2), (1, 2, 16, 130, [0], 1), (3, 2, 9, 197, [0, 70, 3], 1),
+            (2, 2, 1, 256, [0, 130], 4), (1, 2, 3, 50, [7], 1), (2, 2, 8, 640, [0, 64], 3), (1, 1, 12, 64, [0], 1)]
+
+
+@pytest.mark.parametrize('cfg', _Q4_CFGS)
+def test_decode_attention_q4_matches_dequantised_reference(dev, cfg):
+    """Quantised-cache decode attention (codes through the MMA, affine map on group sums) vs fp32 attention over the
+    dequantised cache bf16(code*scale+bias) — the oracle's order of operations (phi:536-539)."""
+    L = _mods()
+    B, H, Lq, past, kv, ns = cfg
+    D = 96
+    torch.manual_seed(21)
+    qkv = bf(torch.randn(B * Lq, 3 * H * D, device=dev))
+    kc = bf(torch.randn(B, H, past, D, device=dev) * 1.5 + 0.3)
+    vc = bf(torch.randn(B, H, past, D, device=dev) + torch.linspace(-2, 2, D, device=dev))
+    pool, bt = _paged(kc, vc, dev)
+    n_quant = (past // 64) * 64
+    qc = torch.zeros(pool.shape[0], 2, H, 64, D // 2, dtype=torch.uint8, device=dev)
+    qm = torch.zeros(pool.shape[0], 2, H, 64, D // 32, 2, dtype=torch.bfloat16, device=dev)
+    if n_quant:
+        L.call('p3_kv_quantize_q4g32', pool.data_ptr(), qc.data_ptr(), qm.data_ptr(), bt.data_ptr(), bt.stride(0), B, n_quant, H, D, st())
+    kv_start = torch.tensor(kv, dtype=torch.int32, device=dev)
+    out = torch.full((B * Lq, H * D), float('nan'), device=dev, dtype=torch.bfloat16)
+    ws = torch.zeros(max(L.lib().p3_attention_decode_workspace(B, Lq, H, D, ns) // 4, 1), device=dev)
+    p = qkv.data_ptr()
+    L.call('p3_attention_decode_q4', p, p + H * D * 2, p + 2 * H * D * 2, 3 * H * D, 3 * H * D, 3 * H * D, out.data_ptr(), H * D,
+           B, Lq, H, H, D, D ** -0.5, past, n_quant, kv_start.data_ptr(), pool.data_ptr(), qc.data_ptr(), qm.data_ptr(),
+           bt.data_ptr(), bt.stride(0), 1, ns, ws.data_ptr(), None, None, 0, st())
+    torch.cuda.synchronize()
+    # what the kernel is specified to see: dequantised pages for [0, n_quant), bf16 pages after
+    deq = _dequant_pool(qc, qm)
+    kd, vd = kc.clone(), vc.clone()
+    for b in range(B):
+        for pg in range(n_quant // 64):
+            kd[b, :, pg * 64:(pg + 1) * 64] = deq[bt[b, pg], 0]
+            vd[b, :, pg * 64:(pg + 1) * 64] = deq[bt[b, pg], 1]
+    x = qkv.view(B, Lq, 3, H, D).permute(2, 0, 3, 1, 4)
+    q, k, v = x[0], torch.cat([kd, x[1]], 2), torch.cat([vd, x[2]], 2)
+    ref = _attn_ref(q, k, v, D ** -0.5, True, past, kv_start.long()).transpose(1, 2).reshape(B * Lq, H * D)
+    assert not torch.isnan(out.float()).any()
+    _check(out, ref, tol=1e-2)
+    # and the quantisation itself is visible: the un-quantised cache gives a different answer when pages were quantised
+    if n_quant:
+        ref_bf = _attn_ref(q, torch.cat([kc, x[1]], 2), torch.cat([vc, x[2]], 2), D ** -0.5, True, past, kv_start.long())
+        assert (ref_bf.transpose(1, 2).reshape(B * Lq, H * D) - ref).abs().max() > 1e-3
+
+
 def test_skinny_ss_partials_feed_fused_rmsnorm(dev):
     """RESIDUAL epilogue emits per-CTA sum-of-squares partials; a following norm-fused skinny GEMM fed
     with them must equal the one that recomputes the statistic from X."""
