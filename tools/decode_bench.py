@@ -17,10 +17,12 @@ def main():
     ap.add_argument('--B', type=int, default=8)
     ap.add_argument('--ctx', type=int, default=2048)
     ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--qm', action='store_true', help='quantize_model (4-bit g64 weights)')
+    ap.add_argument('--qc', action='store_true', help='quantize_cache (4-bit g32 KV)')
     a = ap.parse_args()
     dev = torch.device('cuda:0')
-    cfg = configs.PHI35_MINI
-    m = Phi3B200(cfg, weights.random_weights(cfg, seed=0, device=dev), device=dev)
+    cfg = configs.with_overrides(configs.PHI35_MINI, use_quantized_cache=a.qc)
+    m = Phi3B200(cfg, weights.random_weights(cfg, seed=0, device=dev), device=dev, quantize_model=a.qm)
     ids = torch.randint(3, 32000, (a.B, a.ctx))
     ids[:, 0] = 1
     lg, c = m(ids, max_tokens=a.steps + 40, logits_rows='last')
@@ -33,8 +35,8 @@ def main():
         ses.step()
     e1.record()
     torch.cuda.synchronize()
-    knobs = {k: os.environ[k] for k in ('P3_PF_CHAIN', 'P3_PF_CAP_MB', 'P3_SK_DEPTH', 'P3_MEGA', 'P3_OPF', 'P3_PRENORM', 'P3_PDL') if k in os.environ}
-    print(f'{e0.elapsed_time(e1) / a.steps:.4f} ms/step  B={a.B} ctx={a.ctx} {knobs}')
+    knobs = {k: os.environ[k] for k in ('P3_PF_CHAIN', 'P3_PF_CAP_MB', 'P3_SK_DEPTH', 'P3_MEGA', 'P3_OPF', 'P3_PRENORM', 'P3_PDL', 'P3_SKIP') if k in os.environ}
+    print(f'{e0.elapsed_time(e1) / a.steps:.4f} ms/step  B={a.B} ctx={a.ctx} qm={a.qm} qc={a.qc} {knobs}')
 
 
 if __name__ == '__main__':
