@@ -37,7 +37,14 @@ struct GemmEpi {
     // SM must stream): `ksplit` CTAs share an output tile, each accumulates a K slice, dumps fp32 partials to `ws`
     // [tile][ksplit][128][BN]; the last one to arrive (per-tile counter) sums them in slice order and runs the epilogue.
     int ksplit; float* ws; int* counters; int64_t ws_bytes;
+    // outputs larger than the L2 can keep (batched prefill): store with the streaming (evict-first) policy so that the
+    // write-allocated lines do not push the resident W band / X rows out of L2 (ncu: 2.7-3.1x DRAM over-read without it)
+    int stream_out;
+    int band_mb;                                           // rasterisation band (MB of W kept L2-resident); 0 = default
 };
+__device__ __forceinline__ void st_out16(void* p, const uint4& v, int stream) {
+    if (stream) __stcs(reinterpret_cast<uint4*>(p), v); else *reinterpret_cast<uint4*>(p) = v;
+}
 #define P3_SPLITK_COUNTER_BYTES 4096
 #define P3_EPI_ROPE_KV 8
 
@@ -49,9 +56,12 @@ __device__ __forceinline__ float epi_act(int kind, float x) {
     return x;
 }
 
-// Tile rasterisation: n-fastest inside bands of `nb` n-tiles so the band's W tiles (nb * BN * K * 2 B, sized
-// to ~48 MB) stay L2-resident while A streams through once per band. (m-fastest order re-read A once
-// per n-tile: ncu showed 2.1 GB of DRAM reads for a 157 MB problem.)
+// Tile rasterisation: n-fastest inside bands of `nb` n-tiles so the band's W tiles (nb * BN * K * 2 B) stay
+// L2-resident while A streams through once per band. (m-fastest order re-read A once per n-tile: ncu showed
+// 2.1 GB of DRAM reads for a 157 MB problem.) Band size, ncu DRAM reads in the batched prefill (M = 16384):
+// 48 MB bands -> qkv 727 MB, gate_up 733 MB; 32 MB -> 359 / 557 MB (a 48 MB band does not survive next to the X
+// stream and the write-allocated output); for K = 8192 (4 MB per W tile, 74 concurrent tiles stream 72 MB per wave)
+// nothing is retained across waves whatever the band, and the widest band that covers N (48 MB) reads least.
 __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int nb, int& mt, int& nt) {
     const int band_tiles = nb * m_tiles;
     const int band = tile / band_tiles, rem = tile - band * band_tiles;
@@ -59,9 +69,9 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
     mt = rem / nb_this;
     nt = band * nb + rem - mt * nb_this;
 }
-__host__ __device__ __forceinline__ int band_width(int K, int BN, int n_tiles) {
+__host__ __device__ __forceinline__ int band_width(int K, int BN, int n_tiles, int band_mb = 0) {
     long long per = (long long)BN * K * 2;
-    int nb = (int)((48ll << 20) / (per > 0 ? per : 1));
+    int nb = (int)(((long long)(band_mb > 0 ? band_mb : (per <= (2ll << 20) ? 32 : 48)) << 20) / (per > 0 ? per : 1));
     return nb < 1 ? 1 : (nb > n_tiles ? n_tiles : nb);
 }
 
@@ -91,24 +101,39 @@ __device__ __forceinline__ float epi_row_scale(const GemmEpi& ep, int row, int K
     return rsqrtf(s / (float)K + ep.eps);
 }
 
-// P3_EPI_ROPE_KV: one 32-column chunk of the (row-permuted) qkv projection for token `row`
-__device__ __forceinline__ void epi_rope32(const GemmEpi& ep, int row, int n0, float rs, const uint32_t* acc) {
-    const int hd = ep.hd, half = hd / 2, cph = hd / 32;
-    const int head = n0 / hd, j = (n0 % hd) / 32;
-    const int b = row / ep.L, pos = (ep.past_dev ? *ep.past_dev : ep.past) + row % ep.L;
-    bf16* qrow = reinterpret_cast<bf16*>(ep.out) + (size_t)row * ep.ldo;
-    bf16 *kd = nullptr, *vd = nullptr;
+// P3_EPI_ROPE_KV, per output row (token): everything that does not depend on the column chunk — computed once per tile,
+// not once per 32-column chunk (the integer divisions by run-time L / page / hd cost more than the rotation itself)
+struct RopeRow {
+    bf16 *qrow, *kd, *vd;
+    const float *cr, *sr;                                      // cos / sin rows of this token's position
+};
+__device__ __forceinline__ RopeRow epi_rope_row(const GemmEpi& ep, int row) {
+    RopeRow r;
+    const int hd = ep.hd, half = hd / 2;
+    const int b = row / ep.L, pos = (ep.past_dev ? *ep.past_dev : ep.past) + (row - b * ep.L);
+    const int crow = b / ep.row_div;
+    r.qrow = reinterpret_cast<bf16*>(ep.out) + (size_t)row * ep.ldo;
+    r.kd = r.vd = nullptr;
     if (ep.write_cache) {
-        const int page = ep.block_table[(size_t)(b / ep.row_div) * ep.bt_stride + pos / P3_PAGE];
-        kd = ep.pool + (size_t)page * kv_page_elems(ep.n_kv, hd) + (size_t)(pos % P3_PAGE) * hd;
-        vd = kd + (size_t)ep.n_kv * P3_PAGE * hd;
+        const int pg = pos / P3_PAGE;
+        const int page = ep.block_table[(size_t)crow * ep.bt_stride + pg];
+        r.kd = ep.pool + (size_t)page * kv_page_elems(ep.n_kv, hd) + (size_t)(pos - pg * P3_PAGE) * hd;
+        r.vd = r.kd + (size_t)ep.n_kv * P3_PAGE * hd;
     }
+    r.cr = ep.cosT + (size_t)crow * ep.tab_bstride + (size_t)pos * half;
+    r.sr = ep.sinT + (size_t)crow * ep.tab_bstride + (size_t)pos * half;
+    return r;
+}
+// one 32-column chunk of the (row-permuted) qkv projection
+__device__ __forceinline__ void epi_rope32(const GemmEpi& ep, const RopeRow& rr, int n0, float rs, const uint32_t* acc) {
+    const int hd = ep.hd, half = hd / 2;
+    const int head = n0 / hd, j = (n0 - head * hd) / 32;
     uint4 o1[2], o2[2];
     uint32_t* u1 = reinterpret_cast<uint32_t*>(o1);
     uint32_t* u2 = reinterpret_cast<uint32_t*>(o2);
     if (head < ep.n_heads + ep.n_kv) {                        // q or k head: rotate
-        const float* cr = ep.cosT + (size_t)(b / ep.row_div) * ep.tab_bstride + (size_t)pos * half + 16 * j;
-        const float* sr = ep.sinT + (size_t)(b / ep.row_div) * ep.tab_bstride + (size_t)pos * half + 16 * j;
+        const float* cr = rr.cr + 16 * j;
+        const float* sr = rr.sr + 16 * j;
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
             const float4 c4 = __ldg(reinterpret_cast<const float4*>(cr + i)), s4 = __ldg(reinterpret_cast<const float4*>(sr + i));
@@ -123,11 +148,11 @@ __device__ __forceinline__ void epi_rope32(const GemmEpi& ep, int row, int n0, f
             u1[i / 2] = pack_bf16(a1[0], a1[1]); u1[i / 2 + 1] = pack_bf16(a1[2], a1[3]);
             u2[i / 2] = pack_bf16(a2[0], a2[1]); u2[i / 2 + 1] = pack_bf16(a2[2], a2[3]);
         }
-        bf16* d1 = qrow + head * hd + 16 * j;
-        reinterpret_cast<uint4*>(d1)[0] = o1[0]; reinterpret_cast<uint4*>(d1)[1] = o1[1];
-        reinterpret_cast<uint4*>(d1 + half)[0] = o2[0]; reinterpret_cast<uint4*>(d1 + half)[1] = o2[1];
-        if (kd && head >= ep.n_heads) {
-            bf16* k = kd + (size_t)(head - ep.n_heads) * P3_PAGE * hd + 16 * j;
+        bf16* d1 = rr.qrow + head * hd + 16 * j;
+        st_out16(d1, o1[0], ep.stream_out); st_out16(d1 + 8, o1[1], ep.stream_out);
+        st_out16(d1 + half, o2[0], ep.stream_out); st_out16(d1 + half + 8, o2[1], ep.stream_out);
+        if (rr.kd && head >= ep.n_heads) {
+            bf16* k = rr.kd + (size_t)(head - ep.n_heads) * P3_PAGE * hd + 16 * j;
             reinterpret_cast<uint4*>(k)[0] = o1[0]; reinterpret_cast<uint4*>(k)[1] = o1[1];
             reinterpret_cast<uint4*>(k + half)[0] = o2[0]; reinterpret_cast<uint4*>(k + half)[1] = o2[1];
         }
@@ -137,21 +162,19 @@ __device__ __forceinline__ void epi_rope32(const GemmEpi& ep, int row, int n0, f
             u1[i] = pack_bf16(__uint_as_float(acc[2 * i]) * rs, __uint_as_float(acc[2 * i + 1]) * rs);
             u2[i] = pack_bf16(__uint_as_float(acc[16 + 2 * i]) * rs, __uint_as_float(acc[17 + 2 * i]) * rs);
         }
-        bf16* d = qrow + n0;
-        reinterpret_cast<uint4*>(d)[0] = o1[0]; reinterpret_cast<uint4*>(d)[1] = o1[1];
-        reinterpret_cast<uint4*>(d)[2] = o2[0]; reinterpret_cast<uint4*>(d)[3] = o2[1];
-        if (vd) {
-            bf16* v = vd + (size_t)(head - ep.n_heads - ep.n_kv) * P3_PAGE * hd + 32 * j;
+        bf16* d = rr.qrow + n0;
+        st_out16(d, o1[0], ep.stream_out); st_out16(d + 8, o1[1], ep.stream_out);
+        st_out16(d + 16, o2[0], ep.stream_out); st_out16(d + 24, o2[1], ep.stream_out);
+        if (rr.vd) {
+            bf16* v = rr.vd + (size_t)(head - ep.n_heads - ep.n_kv) * P3_PAGE * hd + 32 * j;
             reinterpret_cast<uint4*>(v)[0] = o1[0]; reinterpret_cast<uint4*>(v)[1] = o1[1];
             reinterpret_cast<uint4*>(v)[2] = o2[0]; reinterpret_cast<uint4*>(v)[3] = o2[1];
         }
     }
-    (void)cph;
 }
 
 // epilogue for 32 consecutive accumulator columns of one output row (rs: RMSNorm row scale, 1 when not normed)
 __device__ __forceinline__ void epi_store32(const GemmEpi& ep, int64_t orow, int n0, int N, const uint32_t* acc, float rs = 1.f) {
-    if (ep.kind == P3_EPI_ROPE_KV) { epi_rope32(ep, (int)orow, n0, rs, acc); return; }
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(acc[i]) * rs;
@@ -207,9 +230,12 @@ __device__ __forceinline__ void epi_store32(const GemmEpi& ep, int64_t orow, int
         } else {
             for (int i = 0; i < 32; i++) if (n0 + i < N) v[i] = __bfloat162float(r[i]) + bf16_round(v[i]);
         }
-    } else if (ep.kind == P3_EPI_QGELU || ep.kind == P3_EPI_GELU) {
+    } else if (ep.kind == P3_EPI_QGELU) {                     // one branch per chunk, not per element: with the kind test inside the
+#pragma unroll                                                 // loop ptxas evaluates the erf polynomial for every element and selects
+        for (int i = 0; i < 32; i++) v[i] = __fdividef(v[i], 1.f + __expf(-1.702f * v[i]));
+    } else if (ep.kind == P3_EPI_GELU) {
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] = epi_act(ep.kind, v[i]);
+        for (int i = 0; i < 32; i++) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
     }
     if (full) {
         uint4 ov[4];
@@ -217,7 +243,7 @@ __device__ __forceinline__ void epi_store32(const GemmEpi& ep, int64_t orow, int
 #pragma unroll
         for (int i = 0; i < 16; i++) ou[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
 #pragma unroll
-        for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(o)[i] = ov[i];
+        for (int i = 0; i < 4; i++) st_out16(o + 8 * i, ov[i], ep.stream_out);
         if (ep.ss_out) {                                       // sum of squares of the bf16 values just written
             float sq = 0.f;
 #pragma unroll
@@ -251,7 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m_tiles = (M + C::BM - 1) / C::BM, n_tiles = (N + BN - 1) / BN;
     const int ksplit = ep.ksplit > 1 ? ep.ksplit : 1;
     const int total = m_tiles * n_tiles * ksplit, kb_all = (K + C::BK - 1) / C::BK;   // work item = (tile, K slice)
-    const int nb = band_width(K, BN, n_tiles);
+    const int nb = band_width(K, BN, n_tiles, ep.band_mb);
     __shared__ int s_last;
 
     if (warp == 0 && lane == 0) {
@@ -399,12 +425,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         bf16* o = reinterpret_cast<bf16*>(ep.out) + orow * ep.ldo + on0;
                         if (on0 + 32 <= N / 2 && (ep.ldo & 7) == 0) {
 #pragma unroll
-                            for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(o)[i] = ov[i];
+                            for (int i = 0; i < 4; i++) st_out16(o + 8 * i, ov[i], ep.stream_out);
                         } else {
                             const bf16* ob = reinterpret_cast<const bf16*>(ov);
                             for (int i = 0; i < 32; i++) if (on0 + i < N / 2) o[i] = ob[i];
                         }
                     }
+                }
+            } else if (ep.kind == P3_EPI_ROPE_KV) {
+                RopeRow rr;
+                if (row_ok) rr = epi_rope_row(ep, (int)orow);
+                for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+                    uint32_t v[32];
+                    load32(c0, v);
+                    if (row_ok && n_idx + c0 < N) epi_rope32(ep, rr, n_idx + c0, rs, v);
                 }
             } else {
                 for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
@@ -488,7 +522,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int m_pairs = (M + 2 * C::BM - 1) / (2 * C::BM), n_tiles = (N + BN - 1) / BN;
     const int total = m_pairs * n_tiles, kb = (K + C::BK - 1) / C::BK;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int nb = band_width(K, BN, n_tiles);
+    const int nb = band_width(K, BN, n_tiles, ep.band_mb);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -590,12 +624,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         bf16* o = reinterpret_cast<bf16*>(ep.out) + orow * ep.ldo + on0;
                         if (on0 + 32 <= N / 2 && (ep.ldo & 7) == 0) {
 #pragma unroll
-                            for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(o)[i] = ov[i];
+                            for (int i = 0; i < 4; i++) st_out16(o + 8 * i, ov[i], ep.stream_out);
                         } else {
                             const bf16* ob = reinterpret_cast<const bf16*>(ov);
                             for (int i = 0; i < 32; i++) if (on0 + i < N / 2) o[i] = ob[i];
                         }
                     }
+                }
+            } else if (ep.kind == P3_EPI_ROPE_KV) {
+                RopeRow rr;
+                if (row_ok) rr = epi_rope_row(ep, (int)orow);
+                for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + c0, v);
+                    if (row_ok && n_idx + c0 < N) epi_rope32(ep, rr, n_idx + c0, rs, v);
                 }
             } else {
                 for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
@@ -807,11 +849,21 @@ static int gemm_dispatch(const void* X, int64_t ldx, const void* W, int64_t ldw,
         return 0;
     }
     int64_t m_tiles = (M + 127) / 128;
+    GemmEpi eps = ep;
+    {
+        static int mode = -1;                              // P3_GEMM_STREAM=0/1 forces the policy off/on (A/B only)
+        if (mode < 0) { const char* e = getenv("P3_GEMM_STREAM"); mode = e ? (e[0] == '0' ? 0 : 1) : 2; }
+        const int64_t out_bytes = M * (int64_t)(ep.kind == P3_EPI_SWIGLU ? N / 2 : N) * 2;
+        eps.stream_out = mode == 2 ? (out_bytes >= (64ll << 20)) : mode;
+        static int band = -1;                              // P3_GEMM_BAND_MB (A/B only)
+        if (band < 0) { const char* e = getenv("P3_GEMM_BAND_MB"); band = e ? atoi(e) : 0; }
+        eps.band_mb = band;
+    }
     if (impl == 0 && gemm_2cta_mode() && M > 128 && ((m_tiles + 1) / 2) * ((N + 255) / 256) >= num_sms() / 4)
-        return launch_tc2(X, ldx, W, ldw, ep, M, N, K, st, wp);
+        return launch_tc2(X, ldx, W, ldw, eps, M, N, K, st, wp);
     bool small = m_tiles * ((N + 255) / 256) < 2 * num_sms();
-    if (ep.kind == P3_EPI_SWIGLU || !small) return launch_tc<256>(X, ldx, W, ldw, ep, M, N, K, st, wp);
-    return launch_tc<128>(X, ldx, W, ldw, ep, M, N, K, st, wp);
+    if (ep.kind == P3_EPI_SWIGLU || !small) return launch_tc<256>(X, ldx, W, ldw, eps, M, N, K, st, wp);
+    return launch_tc<128>(X, ldx, W, ldw, eps, M, N, K, st, wp);
 }
 
 extern "C" int p3_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
