@@ -122,6 +122,12 @@ __device__ __forceinline__ RopeRow epi_rope_row(const GemmEpi& ep, int row) {
     }
     r.cr = ep.cosT + (size_t)crow * ep.tab_bstride + (size_t)pos * half;
     r.sr = ep.sinT + (size_t)crow * ep.tab_bstride + (size_t)pos * half;
+    // the rows are read chunk by chunk after the accumulators arrive: have them in L1 by then (each miss is ~1 us of
+    // exposed epilogue when a CTA has only one or two tiles)
+    for (int o = 0; o < half * 4; o += 128) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(r.cr) + o));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(r.sr) + o));
+    }
     return r;
 }
 // one 32-column chunk of the (row-permuted) qkv projection
@@ -361,6 +367,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool row_ok = row < M;
             const int64_t orow = row_ok ? (ep.row_map ? (int64_t)ep.row_map[row] : (int64_t)row) : 0;
             const float rs = epi_row_scale(ep, row, K, row_ok);  // summed while the tile's MMAs run
+            RopeRow rr;                                          // likewise: page lookup + cos/sin rows pulled into L1
+            if (ep.kind == P3_EPI_ROPE_KV && row_ok) rr = epi_rope_row(ep, (int)orow);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -602,6 +610,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const bool row_ok = row < M;
             const int64_t orow = row_ok ? (ep.row_map ? (int64_t)ep.row_map[row] : (int64_t)row) : 0;
             const float rs = epi_row_scale(ep, row, K, row_ok);  // summed while the tile's MMAs run
+            RopeRow rr;                                          // likewise: page lookup + cos/sin rows pulled into L1
+            if (ep.kind == P3_EPI_ROPE_KV && row_ok) rr = epi_rope_row(ep, (int)orow);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -632,8 +642,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
             } else if (ep.kind == P3_EPI_ROPE_KV) {
-                RopeRow rr;
-                if (row_ok) rr = epi_rope_row(ep, (int)orow);
                 for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                     uint32_t v[32];
                     tc_ld32(taddr + c0, v);

@@ -6,7 +6,11 @@ import torch
 
 dev = torch.device('cuda:0')
 SHAPES = [(23080, 4096, 1024, 1), (23080, 3072, 1024, 0), (23080, 1024, 4096, 6), (2885, 4096, 1024, 1), (2885, 1024, 4096, 6),
-          (16384, 9216, 3072, 0), (16384, 3072, 8192, 3), (787, 9216, 3072, 0), (787, 3072, 8192, 3)]
+          (2885, 3072, 1024, 0), (2885, 1024, 1024, 6), (16384, 9216, 3072, 0), (16384, 3072, 8192, 3), (787, 9216, 3072, 0),
+          (787, 3072, 3072, 3), (787, 16384, 3072, 4), (787, 3072, 8192, 3)]
+if len(sys.argv) > 3 and sys.argv[3] == 'small':
+    SHAPES = [s for s in SHAPES if s[0] < 4000]
+    del sys.argv[3]
 _p, _l, _i = C.c_void_p, C.c_int64, C.c_int32
 
 
@@ -21,14 +25,14 @@ def main():
     for M, N, K, epi in SHAPES:
         x = torch.randn(M, K, device=dev).to(torch.bfloat16)
         w = torch.randn(N, K, device=dev).to(torch.bfloat16) * 0.02
-        out = torch.zeros(M, N, device=dev, dtype=torch.float32 if epi == 6 else torch.bfloat16)
+        out = torch.zeros(M, N // 2 if epi == 4 else N, device=dev, dtype=torch.float32 if epi == 6 else torch.bfloat16)
         bias = torch.zeros(N, device=dev, dtype=torch.bfloat16) if epi in (1, 6) else None
         res = out if epi in (3, 6) else None
         line = f'M={M:6d} N={N:5d} K={K:5d} epi={epi}'
         for rep in range(2):
             for path, L in libs:
                 def fn():
-                    rc = L.p3_gemm(x.data_ptr(), K, w.data_ptr(), K, None if bias is None else bias.data_ptr(), out.data_ptr(), N,
+                    rc = L.p3_gemm(x.data_ptr(), K, w.data_ptr(), K, None if bias is None else bias.data_ptr(), out.data_ptr(), out.shape[1],
                                    None if res is None else res.data_ptr(), None, M, N, K, epi, 0, st)
                     assert rc == 0
                 for _ in range(5):
