@@ -136,6 +136,30 @@ int p3_attention_prefill(const void* q, const void* k, const void* v, int64_t ld
  * split-arrival counters, which the kernel resets itself); needed when n_splits > 1.
  * l2_prefetch (may be NULL): l2_prefetch_bytes of the NEXT kernel's weights (o_proj) that the CTAs pull into
  * L2 (prefetch.global.L2::evict_last) while the KV pages stream. */
+/* Struct-argument form of p3_gemm_skinny / p3_gemm_skinny_w4 / p3_gemm_skinny_qkv_rope(_w4) with the RMSNorm split between
+ * producer and consumer (decode over 4-bit weights, phi:478-485 with QuantizedLinear pv:264): a RESIDUAL launch with xg_out also
+ * writes xg_out[m][n] = bf16(h[m][n] * xg_gain[n]) (xg_gain = weight of the NEXT RMSNorm); the consumer takes that as X with
+ * norm_w = NULL and rs_epi = 1 and multiplies its reduced accumulators by rsqrt(sum(ss_in[.][m]) / K + eps). */
+typedef struct {
+    int32_t op;                          /* 0: out = epi(X W^T);  1: qkv projection + SuRoPE + paged KV write */
+    const void* X; int64_t ldx;
+    const void* norm_w; float eps;
+    const void* W;                       /* bf16 [N][K], or NULL when Wq / Wmeta (4-bit g64 image) are given */
+    const void* Wq; const void* Wmeta;
+    void* out; int64_t ldo; const void* resid;
+    int32_t M, N, K, epi;                /* op 1: N, M, ldo, epi are derived (M = B * L) */
+    const float* ss_in; int32_t n_ss_in; float* ss_out;
+    const void* l2_prefetch; int64_t l2_prefetch_bytes;
+    const void* xg_gain; void* xg_out; int64_t ldxg; int32_t rs_epi;
+    const float* cosT; const float* sinT; int64_t tab_bstride;          /* op 1, as p3_gemm_skinny_qkv_rope */
+    int32_t B, L, n_heads, n_kv, hd, past, row_div, bt_stride, write_cache;
+    const int32_t* past_dev; void* pool; const int32_t* block_table;
+} p3_skinny_args;
+int p3_gemm_skinny_x(const p3_skinny_args* args, cudaStream_t st);
+/* p3_embed_gather that also writes xg_out[t] = bf16(row * xg_gain) (input of the first rs_epi consumer) */
+int p3_embed_gather_xg(const void* table, const int32_t* ids, void* out, int64_t T, int H, int vocab, float* ss_out,
+                       const void* xg_gain, void* xg_out, cudaStream_t st);
+
 int64_t p3_attention_decode_workspace(int B, int L, int n_heads, int hd, int n_splits);
 int p3_attention_decode(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* out,
                         int64_t ldo, int B, int L, int n_heads, int n_kv, int hd, float scale, int past,

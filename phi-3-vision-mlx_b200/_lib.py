@@ -43,6 +43,7 @@ _SIGS = {
     'p3_mega_pack': [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     'p3_row_sumsq': [_p, _l, _p, _l, _i, _p],
     'p3_rope_table': [_p, _l, _i, _p, _p, _p, _i, _i, _i, _f, _p],
+    'p3_embed_gather_xg': [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p],
 }
 
 _lib = None
@@ -51,7 +52,7 @@ launches = 0          # number of p3_* kernel-launching calls issued (bench.py r
 
 def exported_symbols():
     return sorted(list(_SIGS) + ['p3_last_error', 'p3_version', 'p3_attention_decode_workspace', 'p3_decode_mega',
-                                 'p3_decode_mega_ctas', 'p3_gemm_fused', 'p3_gemm_plan_weights'])
+                                 'p3_decode_mega_ctas', 'p3_gemm_fused', 'p3_gemm_plan_weights', 'p3_gemm_skinny_x'])
 
 
 def lib():
@@ -72,6 +73,7 @@ def lib():
         L.p3_decode_mega_ctas.argtypes, L.p3_decode_mega_ctas.restype = [], C.c_int
         L.p3_gemm_fused.argtypes, L.p3_gemm_fused.restype = [_p, _p], C.c_int        # (const p3_gemm_args*, stream)
         L.p3_gemm_plan_weights.argtypes, L.p3_gemm_plan_weights.restype = [_p, _l, _i, _i, _p], C.c_int
+        L.p3_gemm_skinny_x.argtypes, L.p3_gemm_skinny_x.restype = [_p, _p], C.c_int        # (const p3_skinny_args*, stream)
         _lib = L
     return _lib
 
@@ -111,6 +113,18 @@ class GemmArgs(C.Structure):
                 ('L', C.c_int32), ('n_heads', C.c_int32), ('n_kv', C.c_int32), ('hd', C.c_int32), ('past', C.c_int32),
                 ('row_div', C.c_int32), ('write_cache', C.c_int32), ('bt_stride', C.c_int32),
                 ('past_dev', _p), ('pool', _p), ('block_table', _p), ('splitk_ws', _p), ('splitk_ws_bytes', _l)]
+
+
+class SkinnyArgs(C.Structure):
+    """p3_skinny_args (include/phi3_b200.h)"""
+    _fields_ = [('op', C.c_int32), ('X', _p), ('ldx', _l), ('norm_w', _p), ('eps', C.c_float), ('W', _p), ('Wq', _p), ('Wmeta', _p),
+                ('out', _p), ('ldo', _l), ('resid', _p), ('M', C.c_int32), ('N', C.c_int32), ('K', C.c_int32), ('epi', C.c_int32),
+                ('ss_in', _p), ('n_ss_in', C.c_int32), ('ss_out', _p), ('l2_prefetch', _p), ('l2_prefetch_bytes', _l),
+                ('xg_gain', _p), ('xg_out', _p), ('ldxg', _l), ('rs_epi', C.c_int32),
+                ('cosT', _p), ('sinT', _p), ('tab_bstride', _l),
+                ('B', C.c_int32), ('L', C.c_int32), ('n_heads', C.c_int32), ('n_kv', C.c_int32), ('hd', C.c_int32), ('past', C.c_int32),
+                ('row_div', C.c_int32), ('bt_stride', C.c_int32), ('write_cache', C.c_int32),
+                ('past_dev', _p), ('pool', _p), ('block_table', _p)]
 
 
 class WeightPlan:

@@ -8,7 +8,8 @@
 // out-of-range ids are clamped to row 0; those rows are overwritten by the image scatter.
 // ------------------------------------------------------------------------------------------
 __global__ void embed_gather_kernel(const bf16* __restrict__ table, const int32_t* __restrict__ ids,
-                                    bf16* __restrict__ out, int64_t T, int H, int vocab, float* __restrict__ ss_out) {
+                                    bf16* __restrict__ out, int64_t T, int H, int vocab, float* __restrict__ ss_out,
+                                    const bf16* __restrict__ xg_gain, bf16* __restrict__ xg_out) {
     __shared__ float s_part[4];
     pdl_trigger();
     pdl_wait();
@@ -24,6 +25,14 @@ __global__ void embed_gather_kernel(const bf16* __restrict__ table, const int32_
         const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
         for (int j = 0; j < 4; j++) { float2 f = unpack_bf16(u[j]); ss += f.x * f.x + f.y * f.y; }
+        if (xg_out) {                                        // gain-scaled copy for a consumer that applies rstd in its epilogue
+            const uint4 gv = __ldg(reinterpret_cast<const uint4*>(xg_gain) + i);
+            const uint32_t* gu = reinterpret_cast<const uint32_t*>(&gv);
+            uint4 ov; uint32_t* ou = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { float2 f = unpack_bf16(u[j]), w = unpack_bf16(gu[j]); ou[j] = pack_bf16(f.x * w.x, f.y * w.y); }
+            reinterpret_cast<uint4*>(xg_out + (size_t)t * H)[i] = ov;
+        }
     }
     if (ss_out) {                                            // sum of squares of the row, for the fused RMSNorm
         ss = warp_sum(ss);
@@ -37,8 +46,18 @@ extern "C" int p3_embed_gather(const void* table, const int32_t* ids, void* out,
                                float* ss_out, cudaStream_t st) {
     P3_CHECK_ARG(H % 8 == 0, "embed_gather: H must be a multiple of 8");
     if (T == 0) return 0;
-    p3_launch_pdl(embed_gather_kernel, dim3((unsigned)T), dim3(128), 0, st, (const bf16*)table, ids, (bf16*)out, T, H, vocab, ss_out);
+    p3_launch_pdl(embed_gather_kernel, dim3((unsigned)T), dim3(128), 0, st, (const bf16*)table, ids, (bf16*)out, T, H, vocab, ss_out,
+                  (const bf16*)nullptr, (bf16*)nullptr);
     P3_CHECK_LAUNCH("embed_gather");
+    return 0;
+}
+extern "C" int p3_embed_gather_xg(const void* table, const int32_t* ids, void* out, int64_t T, int H, int vocab, float* ss_out,
+                                  const void* xg_gain, void* xg_out, cudaStream_t st) {
+    P3_CHECK_ARG(H % 8 == 0 && xg_gain && xg_out, "embed_gather_xg: H must be a multiple of 8; gain and output are required");
+    if (T == 0) return 0;
+    p3_launch_pdl(embed_gather_kernel, dim3((unsigned)T), dim3(128), 0, st, (const bf16*)table, ids, (bf16*)out, T, H, vocab, ss_out,
+                  (const bf16*)xg_gain, (bf16*)xg_out);
+    P3_CHECK_LAUNCH("embed_gather_xg");
     return 0;
 }
 

@@ -38,6 +38,11 @@ struct SkParams {
     const int32_t* past_dev;
     bf16* pool; const int32_t* block_table; int bt_stride;
     const uint8_t* l2_pf; int64_t l2_pf_bytes;   // next kernel's weights, pulled into L2 while this one streams
+    // RMSNorm split between producer and consumer (used by the 4-bit weight stream, where re-normalising X in every warp costs
+    // more ALU than the stream leaves idle, and a separate norm kernel costs a launch): the RESIDUAL epilogue also writes
+    // xg_out[m][n] = bf16(h[m][n] * xg_gain[n]) (gain of the NEXT norm); a consumer with rs_epi = 1 reads that as X and applies
+    // rsqrt(mean(h^2) + eps) from ss_in to its reduced accumulators (norm_w must be null then).
+    const bf16* xg_gain; bf16* xg_out; int64_t ldxg; int rs_epi;
 };
 #define P3_EPI_ROPE_QKV 7
 
@@ -60,6 +65,13 @@ struct SkCfg {
 __device__ __forceinline__ uint32_t w4_pair(uint32_t w, int j) { return ((w >> (4 * j)) & 0x000F000Fu) | 0x43004300u; }
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ float rs_from_parts(const float (*part)[16], int tok, int K, float eps) {
+    float ss = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_WARPS; w++) ss += part[w][tok];
+    return rsqrtf(ss / (float)K + eps);
 }
 
 template <int NT, int MT, int DEPTH, bool W4>
@@ -203,13 +215,34 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
 
     // ---- RMSNorm prologue: rs[m] = rsqrt(mean(x^2) + eps), from the producer's partial sums when
     // available (fixed summation order: deterministic), else recomputed from X (L2 resident)
-    if (p.norm_w && p.ss_in) {
-        for (int m = warp; m < p.M; m += SK_WARPS) {
-            float ss = 0.f;
-            for (int c = lane; c < p.n_ss_in; c += 32) ss += p.ss_in[c * 16 + m];
-            ss = warp_sum(ss);
-            if (lane == 0) s_rs[m] = rsqrtf(ss / (float)K + p.eps);
+    // rs_epi: the scale is needed only in the epilogue -> request the partial sums now, reduce them after the K loop (reduced
+    // here they would sit on every consumer's critical path). Coalesced: a warp instruction reads 8 partial rows x 16 tokens
+    // as float4 (lane = 4 * row + token quad); the [c * 16 + m] gather of the fused-norm prologue costs 32 sectors per
+    // instruction, ~1.6 us of LSU time per CTA, which the short 4-bit kernels cannot hide.
+    constexpr int SSR = 4;
+    __shared__ float s_sspart[SK_WARPS][16];
+    float4 ss_raw[SSR];
+    const bool ss_late = p.rs_epi && p.n_ss_in <= 64 * SSR;
+    if (ss_late) {
+#pragma unroll
+        for (int j = 0; j < SSR; j++) {
+            const int c = j * 64 + warp * 8 + (lane >> 2);
+            ss_raw[j] = (c < p.n_ss_in) ? __ldcg(reinterpret_cast<const float4*>(p.ss_in + c * 16) + (lane & 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    } else if ((p.norm_w || p.rs_epi) && p.ss_in) {                              // same coalesced read, reduced now (X is scaled in the loop)
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = warp * 8 + (lane >> 2); c < p.n_ss_in; c += 8 * SK_WARPS) {
+            const float4 f = __ldcg(reinterpret_cast<const float4*>(p.ss_in + c * 16) + (lane & 3));
+            a.x += f.x; a.y += f.y; a.z += f.z; a.w += f.w;
+        }
+#pragma unroll
+        for (int sh = 4; sh < 32; sh <<= 1) {
+            a.x += __shfl_xor_sync(0xffffffffu, a.x, sh); a.y += __shfl_xor_sync(0xffffffffu, a.y, sh);
+            a.z += __shfl_xor_sync(0xffffffffu, a.z, sh); a.w += __shfl_xor_sync(0xffffffffu, a.w, sh);
+        }
+        if (lane < 4) *reinterpret_cast<float4*>(&s_sspart[warp][4 * lane]) = a;
+        __syncthreads();
+        if (tid < 16) s_rs[tid] = rs_from_parts(s_sspart, tid, K, p.eps);
         __syncthreads();
     } else if (p.norm_w) {
         for (int m = warp; m < p.M; m += SK_WARPS) {
@@ -242,10 +275,13 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
         if (p.write_cache) rope_page = __ldg(p.block_table + (size_t)(b / p.row_div) * p.bt_stride + pos / P3_PAGE);
     }
     // RESIDUAL epilogue (MT == 1): this thread's output element is known up front -> fetch the residual now
-    float resid_pref = 0.f;
+    float resid_pref = 0.f, gain_pref = 1.f;
     if (p.epi == P3_EPI_RESIDUAL && MT == 1 && tid < 8 * NT * 16) {
         int r = tid & 15, tok = tid >> 4, n = out_col0 + r;
-        if (tok < p.M && n < p.N) resid_pref = __bfloat162float(p.resid[(size_t)tok * p.ldo + n]);
+        if (tok < p.M && n < p.N) {
+            resid_pref = __bfloat162float(p.resid[(size_t)tok * p.ldo + n]);
+            if (p.xg_out) gain_pref = __bfloat162float(p.xg_gain[n]);             // immutable: could even precede pdl_wait
+        }
     }
     float acc[MT][NT][4];
 #pragma unroll
@@ -400,8 +436,19 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
                     }
                 }
     }
+    if (ss_late) {                                                               // fixed order everywhere: deterministic
+        float4 a = ss_raw[0];
+#pragma unroll
+        for (int j = 1; j < SSR; j++) { a.x += ss_raw[j].x; a.y += ss_raw[j].y; a.z += ss_raw[j].z; a.w += ss_raw[j].w; }
+#pragma unroll
+        for (int sh = 4; sh < 32; sh <<= 1) {
+            a.x += __shfl_xor_sync(0xffffffffu, a.x, sh); a.y += __shfl_xor_sync(0xffffffffu, a.y, sh);
+            a.z += __shfl_xor_sync(0xffffffffu, a.z, sh); a.w += __shfl_xor_sync(0xffffffffu, a.w, sh);
+        }
+        if (lane < 4) *reinterpret_cast<float4*>(&s_sspart[warp][4 * lane]) = a;
+    }
     cp_async_wait<0>();
-    __syncthreads();                                                             // ring -> reduction scratch
+    __syncthreads();                                                             // ring -> reduction scratch (and s_rs visible)
 
     // ---- cross-warp reduction through shared memory
     float (*s_red)[MT][8 * NT][17] = reinterpret_cast<float (*)[MT][8 * NT][17]>(sk_smem);
@@ -426,6 +473,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int w = 0; w < SK_WARPS; w++) { a0 += s_red[w][0][tok][r]; a1 += s_red[w][MT - 1][tok][r]; }
+            if (p.rs_epi) { const float rsv = ss_late ? rs_from_parts(s_sspart, tok, K, p.eps) : s_rs[tok]; a0 *= rsv; a1 *= rsv; }
             const int b = tok / p.L, pos = past + tok % p.L;
             bf16* row = outp + (size_t)tok * p.ldo;
             bf16 *kd = nullptr, *vd = nullptr;
@@ -465,6 +513,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
             float gsum = 0.f, usum = 0.f;
 #pragma unroll
             for (int w = 0; w < SK_WARPS; w++) { gsum += s_red[w][0][tok][r]; usum += s_red[w][MT - 1][tok][r]; }
+            if (p.rs_epi) { const float rsv = ss_late ? rs_from_parts(s_sspart, tok, K, p.eps) : s_rs[tok]; gsum *= rsv; usum *= rsv; }
             float gb = bf16_round(gsum), ub = bf16_round(usum);
             float a = bf16_round(silu_f(gb));
             reinterpret_cast<bf16*>(p.out)[(size_t)tok * p.ldo + out_col0 + r] = __float2bfloat16_rn(a * ub);
@@ -477,6 +526,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
             float s = 0.f, sq = 0.f;
 #pragma unroll
             for (int w = 0; w < SK_WARPS; w++) s += s_red[w][mt][tok][r];
+            if (p.rs_epi && tok < 16) s *= ss_late ? rs_from_parts(s_sspart, tok, K, p.eps) : s_rs[tok];
             size_t off = (size_t)tok * p.ldo + n;
             if (ok) {
                 if (p.epi == P3_EPI_F32) {
@@ -486,6 +536,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
                     bf16 hv = __float2bfloat16_rn(rv + bf16_round(s));
                     reinterpret_cast<bf16*>(p.out)[off] = hv;
                     sq = __bfloat162float(hv) * __bfloat162float(hv);
+                    if (p.xg_out) p.xg_out[(size_t)tok * p.ldxg + n] = __float2bfloat16_rn(__bfloat162float(hv) * ((MT == 1) ? gain_pref : __bfloat162float(p.xg_gain[n])));
                 } else {
                     reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16_rn(s);
                 }
@@ -537,8 +588,10 @@ static int launch_skinny(const SkParams& p, unsigned grid, cudaStream_t st) {
 static int skinny_impl(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, const void* Wq,
                        const void* Wmeta, void* out, int64_t ldo, const void* resid, int M, int N, int K, int epi,
                        const float* ss_in, int n_ss_in, float* ss_out, const void* l2_prefetch, int64_t l2_prefetch_bytes,
-                       cudaStream_t st) {
+                       cudaStream_t st, const void* xg_gain = nullptr, void* xg_out = nullptr, int64_t ldxg = 0, int rs_epi = 0) {
     P3_CHECK_ARG(M >= 1 && M <= 16, "gemm_skinny: M must be in [1,16] (got %d)", M);
+    P3_CHECK_ARG(!rs_epi || (ss_in && !norm_w), "gemm_skinny: rs_epi needs ss_in and no norm_w (X is already gain-scaled)");
+    P3_CHECK_ARG(!xg_out || (xg_gain && epi == P3_EPI_RESIDUAL), "gemm_skinny: xg_out needs xg_gain and the residual epilogue");
     P3_CHECK_ARG(K % 64 == 0, "gemm_skinny: K must be a multiple of 64 (got %d)", K);
     P3_CHECK_ARG(!Wq || (K % 128 == 0 && Wmeta), "gemm_skinny_w4: K must be a multiple of 128 and meta must be given");
     P3_CHECK_ARG(epi == P3_EPI_NONE || epi == P3_EPI_RESIDUAL || epi == P3_EPI_SWIGLU || epi == P3_EPI_F32,
@@ -552,6 +605,7 @@ static int skinny_impl(const void* X, int64_t ldx, const void* norm_w, float eps
     p.ldo = ldo; p.resid = (const bf16*)resid; p.M = M; p.N = N; p.K = K; p.epi = epi;
     p.ss_in = ss_in; p.n_ss_in = n_ss_in; p.ss_out = ss_out;
     p.l2_pf = (const uint8_t*)l2_prefetch; p.l2_pf_bytes = l2_prefetch_bytes;
+    p.xg_gain = (const bf16*)xg_gain; p.xg_out = (bf16*)xg_out; p.ldxg = ldxg; p.rs_epi = rs_epi;
     if (epi == P3_EPI_SWIGLU) {
         P3_CHECK_ARG(N % 256 == 0, "gemm_skinny: SwiGLU needs N (gate+up rows) to be a multiple of 256");
         unsigned grid = (unsigned)(N / 2 / 16);
@@ -589,8 +643,9 @@ static int skinny_qkv_rope_impl(const void* X, int64_t ldx, const void* norm_w, 
                                 int64_t tab_bstride, int B, int L, int n_heads, int n_kv, int hd, int K, int past,
                                 const int32_t* past_dev, int row_div, void* pool, const int32_t* block_table,
                                 int bt_stride, int write_cache, const void* l2_prefetch, int64_t l2_prefetch_bytes,
-                                cudaStream_t st) {
+                                cudaStream_t st, int rs_epi = 0) {
     const int M = B * L;
+    P3_CHECK_ARG(!rs_epi || (ss_in && !norm_w), "gemm_skinny_qkv_rope: rs_epi needs ss_in and no norm_w");
     P3_CHECK_ARG(!Wq || (K % 128 == 0 && Wmeta), "gemm_skinny_qkv_rope_w4: K must be a multiple of 128 and meta must be given");
     P3_CHECK_ARG(M >= 1 && M <= 16, "gemm_skinny_qkv_rope: B*L must be in [1,16] (got %d)", M);
     P3_CHECK_ARG(K % 64 == 0 && ldx % 8 == 0, "gemm_skinny_qkv_rope: K %% 64 and ldx %% 8 required");
@@ -605,6 +660,7 @@ static int skinny_qkv_rope_impl(const void* X, int64_t ldx, const void* norm_w, 
     p.past = past; p.past_dev = past_dev; p.row_div = row_div; p.write_cache = write_cache;
     p.pool = (bf16*)pool; p.block_table = block_table; p.bt_stride = bt_stride;
     p.l2_pf = (const uint8_t*)l2_prefetch; p.l2_pf_bytes = l2_prefetch_bytes;
+    p.rs_epi = rs_epi;
     unsigned grid = (unsigned)((n_heads + n_kv) * (hd / 32) + n_kv * hd / 32);
     return M <= 8 ? launch_skinny<1, 2>(p, grid, st) : launch_skinny<2, 2>(p, grid, st);
 }
@@ -630,4 +686,18 @@ extern "C" int p3_gemm_skinny_qkv_rope_w4(const void* X, int64_t ldx, const void
     return skinny_qkv_rope_impl(X, ldx, norm_w, eps, nullptr, Wq, Wmeta, qkv, ss_in, n_ss_in, cosT, sinT, tab_bstride, B, L,
                                 n_heads, n_kv, hd, K, past, past_dev, row_div, pool, block_table, bt_stride, write_cache,
                                 l2_prefetch, l2_prefetch_bytes, st);
+}
+
+#include <cstddef>
+static_assert(sizeof(p3_skinny_args) == 264 && offsetof(p3_skinny_args, past_dev) == 240, "p3_skinny_args layout is mirrored by _lib.SkinnyArgs");
+// Struct-argument entry for both forms (plain / qkv+rope, bf16 / 4-bit) with the producer-consumer norm split.
+extern "C" int p3_gemm_skinny_x(const p3_skinny_args* a, cudaStream_t st) {
+    P3_CHECK_ARG(a && (a->op == 0 || a->op == 1), "gemm_skinny_x: op must be 0 (linear) or 1 (qkv + rope)");
+    P3_CHECK_ARG((a->W != nullptr) != (a->Wq != nullptr), "gemm_skinny_x: exactly one of W (bf16) and Wq/Wmeta (4-bit) must be given");
+    if (a->op == 1)
+        return skinny_qkv_rope_impl(a->X, a->ldx, a->norm_w, a->eps, a->W, a->Wq, a->Wmeta, a->out, a->ss_in, a->n_ss_in, a->cosT, a->sinT,
+                                    a->tab_bstride, a->B, a->L, a->n_heads, a->n_kv, a->hd, a->K, a->past, a->past_dev, a->row_div, a->pool,
+                                    a->block_table, a->bt_stride, a->write_cache, a->l2_prefetch, a->l2_prefetch_bytes, st, a->rs_epi);
+    return skinny_impl(a->X, a->ldx, a->norm_w, a->eps, a->W, a->Wq, a->Wmeta, a->out, a->ldo, a->resid, a->M, a->N, a->K, a->epi, a->ss_in,
+                       a->n_ss_in, a->ss_out, a->l2_prefetch, a->l2_prefetch_bytes, st, a->xg_gain, a->xg_out, a->ldxg, a->rs_epi);
 }

@@ -265,6 +265,12 @@ class Phi3B200:
         # Neutral for the bf16 weight stream (2.797 vs 2.788 ms/token on the bench), -8 % for the instruction-bound 4-bit one.
         self._opf_in_qkv = _os.environ.get('P3_OPF', 'qkv') != 'attn'
         self.prenorm = _os.environ.get('P3_PRENORM', '1' if self.quantize_model else '0') != '0'
+        # decode over 4-bit weights: RMSNorm split between producer and consumer (p3_gemm_skinny_x): the residual epilogue
+        # also writes bf16(h * gain_of_next_norm), the consumer applies rstd to its accumulators -> no norm kernel, no
+        # per-warp re-normalisation: 7 -> 5 launches per layer. P3_XG=0 restores the separate norm kernels.
+        self.xg = self.quantize_model and _os.environ.get('P3_XG', '1') != '0'
+        self._xg_spacer = _os.environ.get('P3_XG_SPACER', '0') == '1'      # experiment: tiny PDL kernel in front of each consumer
+        self._spacer_buf = torch.zeros((2, self.H), dtype=torch.bfloat16, device=self.dev)
         self.profile = None      # bench.py: list of (kind, ev0, ev1, algorithmic_bytes) when instrumenting
 
     # ------------------------------------------------------------------ vision weights
@@ -376,8 +382,27 @@ class Phi3B200:
 
     L2_PF_CAP = int(__import__('os').environ.get('P3_PF_CAP_MB', '16')) << 20   # bytes of the next kernel's weights parked in L2
 
-    def skinny(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None, ss_in=None, ss_out=None, nxt=None):
+    def skinny(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None, ss_in=None, ss_out=None, nxt=None,
+               xg_gain=None, xg_out=None, rs_epi=False):
         M, K = x.shape
+        if xg_out is not None or rs_epi:                    # producer / consumer halves of the split RMSNorm
+            ev = self._ev()
+            nxt, pf = self._prefetch_target(nxt)
+            q = self._w4.get(w.data_ptr())
+            a = _lib.SkinnyArgs()
+            a.op, a.X, a.ldx, a.eps = 0, ptr(x), x.stride(0), self.eps
+            if q is not None:
+                a.Wq, a.Wmeta = ptr(q[0]), ptr(q[1])
+            else:
+                a.W = ptr(w)
+            a.out, a.ldo, a.resid = ptr(out), out.stride(0), ptr(resid)
+            a.M, a.N, a.K, a.epi = M, w.shape[0], K, epi
+            a.ss_in, a.n_ss_in, a.ss_out = ptr(ss_in), (0 if ss_in is None else ss_in.shape[0]), ptr(ss_out)
+            a.l2_prefetch, a.l2_prefetch_bytes = ptr(nxt), pf
+            a.xg_gain, a.xg_out, a.ldxg, a.rs_epi = ptr(xg_gain), ptr(xg_out), (0 if xg_out is None else xg_out.stride(0)), int(rs_epi)
+            _lib.call_struct('p3_gemm_skinny_x', a, _stream())
+            self._ev(ev, 'skinny', (q[0].numel() + q[1].numel() * 2) if q is not None else w.shape[0] * K * 2)
+            return out
         if norm_w is not None and self.prenorm:
             x, norm_w, ss_in = self._prenorm(x, norm_w), None, None
         ev = self._ev()
@@ -418,11 +443,12 @@ class Phi3B200:
             self.profile.append((kind, start, e, nbytes))
         return e
 
-    def linear(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None, ss_in=None, ss_out=None, nxt=None):
+    def linear(self, x, w, out, epi=_lib.EPI_NONE, norm_w=None, resid=None, ss_in=None, ss_out=None, nxt=None, **xg):
         """Route by token count: <=16 rows is a weight stream (skinny), else tensor-core GEMM.
-        `nxt`: weights of the kernel that follows (decode only): pulled into L2 across the kernel boundary."""
+        `nxt`: weights of the kernel that follows (decode only): pulled into L2 across the kernel boundary.
+        `xg` (xg_gain / xg_out / rs_epi): the split RMSNorm of the 4-bit decode path, see skinny()."""
         if x.shape[0] <= 16:
-            return self.skinny(x, w, out, epi, norm_w, resid, ss_in, ss_out, nxt)
+            return self.skinny(x, w, out, epi, norm_w, resid, ss_in, ss_out, nxt, **xg)
         if norm_w is not None:
             xn = torch.empty_like(x)
             call('p3_rmsnorm', ptr(x), ptr(norm_w), ptr(xn), x.shape[0], x.shape[1], self.eps, _stream())
@@ -533,7 +559,8 @@ class Phi3B200:
         dev, n_part = self.dev, (self.H + 15) // 16
         e = lambda *s, dt=torch.bfloat16: torch.empty(s, dtype=dt, device=dev)
         return dict(h=e(B, self.H), qkv=e(B, self.qkv_dim), att=e(B, self.n_heads * self.hd), act=e(B, self.I),
-                    ssA=e(n_part, 16, dt=torch.float32), ssB=e(n_part, 16, dt=torch.float32), logits=e(B, self.V, dt=torch.float32))
+                    ssA=e(n_part, 16, dt=torch.float32), ssB=e(n_part, 16, dt=torch.float32), logits=e(B, self.V, dt=torch.float32),
+                    hgA=e(B, self.H) if self.xg else None, hgB=e(B, self.H) if self.xg else None)
 
     def _forward_tokens(self, ids_dev, B, L, cache, n_beam, write_cache, past, logits_rows, past_dev=None,
                         n_splits=None, h=None, ws=None, scratch=None):
@@ -554,9 +581,18 @@ class Phi3B200:
         ss_cur = None
         fused = T > 16 and self.pf_fused and self.gemm_impl == 0
         ss0 = torch.empty((T, 1), dtype=torch.float32, device=dev) if fused else None
+        xg = self.xg and T <= 16 and h is None             # split RMSNorm (4-bit decode): gain-scaled copies of the residual stream
+        hgA = hgB = None
+        if xg:
+            hgA = scratch['hgA'] if scratch is not None else torch.empty((T, H), dtype=torch.bfloat16, device=dev)
+            hgB = scratch['hgB'] if scratch is not None else torch.empty((T, H), dtype=torch.bfloat16, device=dev)
         if h is None:
             h = scratch['h'] if scratch is not None else torch.empty((T, H), dtype=torch.bfloat16, device=dev)
-            call('p3_embed_gather', ptr(self.embed), ptr(ids_dev), ptr(h), T, H, self.V, ptr(ss0 if fused else ssA), st)
+            if xg:
+                call('p3_embed_gather_xg', ptr(self.embed), ptr(ids_dev), ptr(h), T, H, self.V, ptr(ssA), ptr(self.layers[0]['ln1']),
+                     ptr(hgA), st)
+            else:
+                call('p3_embed_gather', ptr(self.embed), ptr(ids_dev), ptr(h), T, H, self.V, ptr(ss0 if fused else ssA), st)
             ss_cur = None if ssA is None else ssA[:1]
         elif fused:
             call('p3_row_sumsq', ptr(h), h.stride(0), ptr(ss0), T, H, st)
@@ -616,7 +652,12 @@ class Phi3B200:
             if 'qkv' in self._skip and T <= 16:
                 pass
             elif T <= 16:                                   # decode: qkv_proj + rope + KV write in one launch
-                hq, nq, sq = (self._prenorm(h, lw['ln1']), None, None) if self.prenorm else (h, lw['ln1'], ss_cur)
+                if xg:
+                    hq, nq, sq = hgA, None, ss_cur
+                    if self._xg_spacer:
+                        call('p3_rmsnorm', ptr(self._spacer_buf), ptr(lw['ln1']), ptr(self._spacer_buf[1:]), 1, H, self.eps, st)
+                else:
+                    hq, nq, sq = (self._prenorm(h, lw['ln1']), None, None) if self.prenorm else (h, lw['ln1'], ss_cur)
                 # the qkv kernel parks the whole o_proj stream (18.9 MB bf16) in L2 before it waits on its predecessor; it
                 # survives the evict-first KV stream of the attention kernel, which then carries no prefetch duty (A/B on the
                 # bench: 2.851 -> 2.814 ms/token, attention in-step roofline 0.776 -> 0.816; P3_OPF=attn restores the old split)
@@ -626,7 +667,21 @@ class Phi3B200:
                     qo_bytes = qo_pf.numel() * qo_pf.element_size()
                 ev = self._ev()
                 q4 = self._w4.get(lw['qkv'].data_ptr())
-                if q4 is not None:
+                if xg:
+                    a = _lib.SkinnyArgs()
+                    a.op, a.X, a.ldx, a.eps, a.out = 1, ptr(hq), hq.stride(0), self.eps, ptr(qkv)
+                    if q4 is not None:
+                        a.Wq, a.Wmeta = ptr(q4[0]), ptr(q4[1])
+                    else:
+                        a.W = ptr(lw['qkv'])
+                    a.K, a.ss_in, a.n_ss_in, a.rs_epi = H, ptr(sq), sq.shape[0], 1
+                    a.cosT, a.sinT, a.tab_bstride = ptr(cosT), ptr(sinT), tbs
+                    a.B, a.L, a.n_heads, a.n_kv, a.hd, a.past = B, L, self.n_heads, self.n_kv, self.hd, past
+                    a.past_dev, a.row_div, a.pool, a.block_table, a.bt_stride, a.write_cache = ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc
+                    a.l2_prefetch, a.l2_prefetch_bytes = ptr(qo_pf), qo_bytes
+                    _lib.call_struct('p3_gemm_skinny_x', a, st)
+                    self._ev(ev, 'skinny', (q4[0].numel() + q4[1].numel() * 2) if q4 is not None else self.qkv_dim * H * 2)
+                elif q4 is not None:
                     call('p3_gemm_skinny_qkv_rope_w4', ptr(hq), hq.stride(0), ptr(nq), self.eps, ptr(q4[0]), ptr(q4[1]),
                          ptr(qkv), ptr(sq), 0 if sq is None else sq.shape[0], ptr(cosT), ptr(sinT), tbs, B, L,
                          self.n_heads, self.n_kv, self.hd, H, past, ptr(past_dev), n_beam, ptr(pool), ptr(bt), bts, wc, ptr(qo_pf), qo_bytes, st)
@@ -668,6 +723,20 @@ class Phi3B200:
                 self._ev(ev, 'attn', B * past * 2 * self.n_kv * self.hd * 2)
             # decode: every kernel parks (part of) its successor's weights in L2 so HBM never idles at a boundary
             nxt_qkv = self.layers[li + 1]['qkv'] if li + 1 < len(self.layers) else self.lm_head
+            if xg:
+                g_next = self.layers[li + 1]['ln1'] if li + 1 < len(self.layers) else self.norm
+                if 'o' not in self._skip:
+                    self.linear(att, lw['o'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssB, nxt=lw['gu'] if self.pf_chain else None,
+                                xg_gain=lw['ln2'], xg_out=hgB)
+                if 'gu' not in self._skip:
+                    if self._xg_spacer:
+                        call('p3_rmsnorm', ptr(self._spacer_buf), ptr(lw['ln2']), ptr(self._spacer_buf[1:]), 1, H, self.eps, st)
+                    self.linear(hgB, lw['gu'], act, _lib.EPI_SWIGLU, ss_in=ssB, nxt=lw['down'] if self.pf_chain else None, rs_epi=True)
+                if 'down' not in self._skip:
+                    self.linear(act, lw['down'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssA, nxt=nxt_qkv if self.pf_chain else None,
+                                xg_gain=g_next, xg_out=hgA)
+                ss_cur = ssA
+                continue
             if not ('o' in self._skip and T <= 16):
                 self.linear(att, lw['o'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssB, nxt=lw['gu'] if self.pf_chain else None)
             if not ('gu' in self._skip and T <= 16):
@@ -684,7 +753,10 @@ class Phi3B200:
             hl, R = h, L
         hl = hl.reshape(B * R, H) if hl.is_contiguous() else hl.contiguous().reshape(B * R, H)
         logits = scratch['logits'] if scratch is not None else torch.empty((B * R, self.V), dtype=torch.float32, device=dev)
-        self.linear(hl, self.lm_head, logits, _lib.EPI_F32, norm_w=self.norm, ss_in=ss_cur if (R == L) else None)
+        if xg and R == L:
+            self.linear(hgA, self.lm_head, logits, _lib.EPI_F32, ss_in=ss_cur, rs_epi=True)
+        else:
+            self.linear(hl, self.lm_head, logits, _lib.EPI_F32, norm_w=self.norm, ss_in=ss_cur if (R == L) else None)
         return logits.view(B, R, self.V)
 
     # ------------------------------------------------------------------ reference call protocol (phi:606, 576-592)

@@ -495,6 +495,59 @@ def test_skinny_ss_partials_feed_fused_rmsnorm(dev):
     assert (sse[:3] - tab[ids.long()].float().pow(2).sum(-1)).abs().max() < 1e-2
 
 
+@pytest.mark.parametrize('w4', [False, True])
+@pytest.mark.parametrize('M', [3, 8, 13])
+def test_skinny_split_rmsnorm_matches_fused(dev, M, w4):
+    """p3_gemm_skinny_x: producer writes bf16(h * gain) next to h (+ sum-of-squares partials), the consumer applies
+    rsqrt(mean(h^2) + eps) to its accumulators == the RMSNorm-fused skinny GEMM on h (up to the place of one bf16 rounding)."""
+    import ctypes as C
+    from phi3_b200 import quant
+    L = _mods()
+    torch.manual_seed(31 + M)
+    H, N2 = 3072, 1024
+    act = bf(torch.randn(M, H, device=dev))
+    wo = bf(torch.randn(H, H, device=dev) * H ** -0.5)
+    h0 = bf(torch.randn(M, H, device=dev))
+    gain = bf(1 + 0.2 * torch.randn(H, device=dev))
+    w2 = bf(torch.randn(N2, H, device=dev) * H ** -0.5)
+    q2 = quant.W4(w2, pack=True) if w4 else None
+
+    def args(**kw):
+        a = L.SkinnyArgs()
+        a.eps = 1e-5
+        for k, v in kw.items():
+            setattr(a, k, v)
+        return a
+    # producer: o_proj-like residual launch, also emitting hg and the statistics
+    h = h0.clone()
+    hg = torch.zeros_like(h)
+    ss = torch.zeros((H // 16, 16), device=dev)
+    L.call_struct('p3_gemm_skinny_x', args(op=0, X=act.data_ptr(), ldx=H, W=wo.data_ptr(), out=h.data_ptr(), ldo=H, resid=h.data_ptr(),
+                                           M=M, N=H, K=H, epi=3, ss_out=ss.data_ptr(), xg_gain=gain.data_ptr(), xg_out=hg.data_ptr(), ldxg=H), st())
+    torch.cuda.synchronize()
+    h_ref = (h0.float() + bf(act.float() @ wo.float().T).float()).to(torch.bfloat16)
+    assert (h.float() - h_ref.float()).abs().max() <= 2 ** -7 * h_ref.float().abs().max()
+    assert torch.equal(hg, (h.float() * gain.float()).to(torch.bfloat16))
+    # consumer: rs_epi on hg vs the fused-norm kernel on h
+    o1 = torch.zeros(M, N2, device=dev, dtype=torch.bfloat16)
+    o2 = torch.zeros_like(o1)
+    wkw = dict(Wq=q2.codes.data_ptr(), Wmeta=q2.meta.data_ptr()) if w4 else dict(W=w2.data_ptr())
+    L.call_struct('p3_gemm_skinny_x', args(op=0, X=hg.data_ptr(), ldx=H, out=o1.data_ptr(), ldo=N2, M=M, N=N2, K=H, epi=0,
+                                           ss_in=ss.data_ptr(), n_ss_in=H // 16, rs_epi=1, **wkw), st())
+    if w4:
+        L.call('p3_gemm_skinny_w4', h.data_ptr(), H, gain.data_ptr(), 1e-5, q2.codes.data_ptr(), q2.meta.data_ptr(), o2.data_ptr(), N2, None,
+               M, N2, H, 0, ss.data_ptr(), H // 16, None, None, 0, st())
+    else:
+        L.call('p3_gemm_skinny', h.data_ptr(), H, gain.data_ptr(), 1e-5, w2.data_ptr(), o2.data_ptr(), N2, None, M, N2, H, 0,
+               ss.data_ptr(), H // 16, None, None, 0, st())
+    torch.cuda.synchronize()
+    wd = q2.deq.float() if w4 else w2.float()
+    hn = h.float() * torch.rsqrt(h.float().pow(2).mean(-1, keepdim=True) + 1e-5) * gain.float()
+    ref = hn @ wd.T
+    assert (o1.float() - ref).abs().max() <= 1e-2 * ref.abs().max()
+    assert (o1.float() - o2.float()).abs().max() <= 1e-2 * ref.abs().max()
+
+
 @pytest.mark.parametrize('M', [(2, 1), (8, 1), (2, 5), (12, 1)])
 def test_fused_qkv_rope_matches_unfused(dev, M):
     """p3_gemm_skinny_qkv_rope == p3_gemm_skinny (norm fused) followed by p3_rope_kvwrite."""
