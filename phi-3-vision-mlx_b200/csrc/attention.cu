@@ -288,6 +288,15 @@ __global__ void __launch_bounds__(PF_THREADS, 2) attn_prefill_kernel(AttnParams 
 // tile t is consumed, masking runs only on boundary tiles and exp2 is a single MUFU.
 // ------------------------------------------------------------------------------------------
 #define DEC_STAGES 4
+// timeline stamps (tools/chain_trace.py): compiled in only with -DP3_TRACE_ATTN — any extra uniform-register use in this kernel
+// makes ptxas 12.9 pick the [R + UR + imm] LDGSTS form with an odd policy descriptor register (see cp_async16_stream)
+#ifdef P3_TRACE_ATTN
+#define ATTN_TRACE_STAMP(tr, cta, i) trace_stamp(tr, cta, i)
+#define ATTN_TRACE_META(tr, cta, k) trace_meta(tr, cta, k)
+#else
+#define ATTN_TRACE_STAMP(tr, cta, i)
+#define ATTN_TRACE_META(tr, cta, k)
+#endif
 
 template <int D>
 __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
@@ -298,6 +307,8 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int kvh = h / (p.n_heads / p.n_kv);
+    ATTN_TRACE_STAMP(p.trace, (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x), 0);
+    ATTN_TRACE_META(p.trace, (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x), 900);
     pdl_trigger();
     if (p.past_host > 0 && p.pool && D == 96) {
         // Before the dependency wait: pull this CTA's first KV page slices into L2. Pages below the cache offset, the block
@@ -320,6 +331,7 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
         }
     }
     pdl_wait();                                                 // q/k/v, past and the cache come from earlier kernels
+    ATTN_TRACE_STAMP(p.trace, (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x), 1);
     const int past = p.past_dev ? *p.past_dev : p.past_host;
     const int crow = b / p.row_div;
     const int kv0 = p.kv_start ? p.kv_start[crow] : 0;
@@ -495,6 +507,7 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
         }
     }
     cp_async_wait<0>();
+    ATTN_TRACE_STAMP(p.trace, (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x), 3);
     __syncthreads();                                            // ring is free: reuse it for the warp merge
 
     float* sm_o = reinterpret_cast<float*>(smem + 16 * D * 2);  // [4][16][D]
@@ -564,6 +577,7 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
             if (tid == 0) p.counters[b * p.n_heads + h] = 0;
         }
     }
+    ATTN_TRACE_STAMP(p.trace, (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x), 4);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -586,7 +600,7 @@ static int fill_params(AttnParams& p, const void* q, const void* k, const void* 
     p.pool = (const bf16*)pool; p.block_table = block_table; p.bt_stride = bt_stride; p.row_div = row_div;
     p.n_splits = 1; p.tiles_per_split = 0; p.ws_o = nullptr; p.ws_ml = nullptr; p.counters = nullptr;
     p.l2_prefetch = nullptr; p.l2_prefetch_bytes = 0; p.zero = 0;
-    p.n_quant = 0; p.qcodes = nullptr; p.qmeta = nullptr;
+    p.n_quant = 0; p.qcodes = nullptr; p.qmeta = nullptr; p.trace = nullptr;
     return 0;
 }
 
@@ -634,6 +648,9 @@ static int launch_decode(AttnParams& p, cudaStream_t st) {
         P3_CHECK_ARG(e == cudaSuccess, "attention_decode: smem attribute: %s", cudaGetErrorString(e));
         set = true;
     }
+#ifdef P3_TRACE_ATTN
+    p.trace = p3_trace_slot();
+#endif
     p3_launch_pdl(attn_decode_kernel<D>, grid, dim3(128), (size_t)smem, st, p);
     P3_CHECK_LAUNCH("attention_decode");       // split partials are merged in-kernel by the last CTA to arrive
     return 0;

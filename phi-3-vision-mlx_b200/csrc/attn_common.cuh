@@ -32,6 +32,7 @@ struct AttnParams {
     int n_quant;
     const uint8_t* qcodes;      // [page][2][n_kv][64][D/2]
     const bf16* qmeta;          // [page][2][n_kv][64][D/32][2] (scale, bias)
+    unsigned long long* trace;  // tools/chain_trace.py (null in production)
 };
 
 

@@ -21,6 +21,19 @@ void p3_set_error(const char* fmt, ...);
     do { cudaError_t e_ = cudaGetLastError();                                              \
          if (e_ != cudaSuccess) { p3_set_error("%s: %s", name, cudaGetErrorString(e_)); return -2; } } while (0)
 
+#define P3_TRACE_CTAS 1024
+unsigned long long* p3_trace_slot();                       // api.cu: next trace slot or null
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void trace_stamp(unsigned long long* tr, int cta, int i) {
+    if (tr && threadIdx.x == 0 && cta < P3_TRACE_CTAS) tr[(size_t)cta * 8 + i] = gtimer();
+}
+__device__ __forceinline__ void trace_meta(unsigned long long* tr, int cta, int kind) {
+    if (tr && threadIdx.x == 0 && cta < P3_TRACE_CTAS) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[(size_t)cta * 8 + 5] = smid; tr[(size_t)cta * 8 + 6] = (unsigned long long)kind; tr[(size_t)cta * 8 + 7] = gridDim.x * gridDim.y * gridDim.z;
+    }
+}
+
 // ---- small device utilities ---------------------------------------------------------------
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 

@@ -21,6 +21,7 @@
 
 #define SK_WARPS 8
 #define SK_THREADS (SK_WARPS * 32)
+#define SK_SMEM_2CTA (112 * 1024)            // two CTAs per SM: 2 x (dynamic + 640 B static + 1 KB reserved) <= 228 KB
 
 struct SkParams {
     const bf16* X; int64_t ldx;
@@ -43,6 +44,8 @@ struct SkParams {
     // xg_out[m][n] = bf16(h[m][n] * xg_gain[n]) (gain of the NEXT norm); a consumer with rs_epi = 1 reads that as X and applies
     // rsqrt(mean(h^2) + eps) from ss_in to its reduced accumulators (norm_w must be null then).
     const bf16* xg_gain; bf16* xg_out; int64_t ldxg; int rs_epi;
+    unsigned long long* trace;                   // tools/chain_trace.py (null in production)
+    int n_tiles;                                 // output tiles; the grid may be smaller (persistent CTAs, tile = blockIdx.x + i * gridDim.x)
 };
 #define P3_EPI_ROPE_QKV 7
 
@@ -58,7 +61,9 @@ struct SkCfg {
     static constexpr int DEPTH = DEPTH_;
     static constexpr int RING = SK_WARPS * DEPTH * STAGE;
     static constexpr int RED = SK_WARPS * MT * 8 * NT * 17 * 4;
-    static constexpr int SMEM = RING > RED ? RING : RED;
+    // ring + reduction scratch; the scratch is double buffered by tile parity when two CTAs per SM still fit with it
+    static constexpr int NRED = (RING + 2 * RED <= SK_SMEM_2CTA) ? 2 : 1;
+    static constexpr int SMEM = RING + NRED * RED;
 };
 
 // extracts the adjacent weight pair j of a packed word as bf16x2 (128 + q): nibbles j and j + 4 (quant.py::pack_w4g64)
@@ -75,7 +80,7 @@ __device__ __forceinline__ float rs_from_parts(const float (*part)[16], int tok,
 }
 
 template <int NT, int MT, int DEPTH, bool W4>
-__global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <= 112 * 1024) ? 2 : 1) gemm_skinny_kernel(SkParams p) {
+__global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <= SK_SMEM_2CTA) ? 2 : 1) gemm_skinny_kernel(SkParams p) {
     using C = SkCfg<NT, MT, DEPTH, W4>;
     extern __shared__ __align__(128) uint8_t sk_smem[];
     __shared__ float s_rs[16];
@@ -84,62 +89,79 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
     const int K = p.K, n_chunks = K / C::CHUNK;
     const uint32_t ring = smem_u32(sk_smem) + warp * (C::DEPTH * C::STAGE);
 
-    // W rows of this lane (rows g and g+8 of each 16-row tile)
-    int wr[MT][2];
-    int out_col0;
-    int rope_head = -1, rope_grp = 0;                                              // ROPE_QKV: which head / 16-col group
-    if (p.epi == P3_EPI_ROPE_QKV) {
-        // CTAs [0, (n_heads+n_kv)*hd/32): head h, group j -> tile 0 = cols h*hd + 16j.., tile 1 = the rotary
-        // partners at +hd/2 (so each (x1,x2) pair meets in one CTA); remaining CTAs: 32 V rows each
-        const int gpr = p.hd / 32, n_rope = (p.n_heads + p.n_kv) * gpr;
-        int r0;
-        if ((int)blockIdx.x < n_rope) {
-            rope_head = blockIdx.x / gpr; rope_grp = blockIdx.x % gpr;
-            r0 = rope_head * p.hd + rope_grp * 16;
-            out_col0 = r0;
+    // W rows of this lane (rows g and g+8 of each 16-row tile) for output tile `tile`; out_col0 / rope_head / rope_grp describe
+    // the tile to the epilogue. A CTA walks tiles blockIdx.x, + gridDim.x, ... with ONE continuous weight ring: with a grid of
+    // one wave (or less) no CTA ever starts a tile with an empty ring, and there is no second, partly filled wave.
+    constexpr int PAIRS = (MT == 1) ? 8 : 16;                                   // (x1, x2) / (gate, up) pairs per tile
+    auto tile_rows = [&](int tile, int (&wr)[MT][2], int& out_col0, int& rope_head, int& rope_grp) {
+        rope_head = -1; rope_grp = 0;
+        if (p.epi == P3_EPI_ROPE_QKV) {
+            // tiles [0, (n_heads+n_kv)*hd/32): head h, group j -> tile 0 = cols h*hd + 16j.., tile 1 = the rotary
+            // partners at +hd/2 (so each (x1,x2) pair meets in one CTA); remaining tiles: 32 V rows each
+            // MT == 1: PAIRS = 8 dims per tile, x1 in rows g, the partners in rows g + 8 of the one 16-row tile; V tiles 16 rows
+            const int gpr = p.hd / (2 * PAIRS), n_rope = (p.n_heads + p.n_kv) * gpr;
+            int r0;
+            if (tile < n_rope) {
+                rope_head = tile / gpr; rope_grp = tile % gpr;
+                r0 = rope_head * p.hd + rope_grp * PAIRS;
+                out_col0 = r0;
+                if (MT == 1) {
+                    wr[0][0] = r0 + g; wr[0][1] = r0 + p.hd / 2 + g;
+                } else {
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++) {
-                wr[mt][0] = r0 + mt * (p.hd / 2) + g;
-                wr[mt][1] = r0 + mt * (p.hd / 2) + g + 8;
+                    for (int mt = 0; mt < MT; mt++) {
+                        wr[mt][0] = r0 + mt * (p.hd / 2) + g;
+                        wr[mt][1] = r0 + mt * (p.hd / 2) + g + 8;
+                    }
+                }
+            } else {
+                r0 = (p.n_heads + p.n_kv) * p.hd + (tile - n_rope) * 16 * MT;
+                out_col0 = r0;
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    wr[mt][0] = r0 + mt * 16 + g;
+                    wr[mt][1] = r0 + mt * 16 + g + 8;
+                }
+            }
+        } else if (p.epi == P3_EPI_SWIGLU) {
+            // interleaved gate/up layout: [128 gate rows | 128 up rows] per 256-row block
+            int o0 = tile * PAIRS;
+            int gate0 = (o0 / 128) * 256 + (o0 % 128);
+            out_col0 = o0;
+            if (MT == 1) {                                                       // 8 gate rows (g) + their 8 up rows (g + 8)
+                wr[0][0] = gate0 + g; wr[0][1] = gate0 + 128 + g;
+            } else {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    wr[mt][0] = gate0 + mt * 128 + g;
+                    wr[mt][1] = gate0 + mt * 128 + g + 8;
+                }
             }
         } else {
-            r0 = (p.n_heads + p.n_kv) * p.hd + ((int)blockIdx.x - n_rope) * 32;
-            out_col0 = r0;
+            int n0 = tile * 16 * MT;
+            out_col0 = n0;
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
-                wr[mt][0] = r0 + mt * 16 + g;
-                wr[mt][1] = r0 + mt * 16 + g + 8;
+                wr[mt][0] = min(n0 + mt * 16 + g, p.N - 1);
+                wr[mt][1] = min(n0 + mt * 16 + g + 8, p.N - 1);
             }
         }
-    } else if (p.epi == P3_EPI_SWIGLU) {
-        // interleaved gate/up layout: [128 gate rows | 128 up rows] per 256-row block
-        int o0 = blockIdx.x * 16;
-        int gate0 = (o0 / 128) * 256 + (o0 % 128);
-        out_col0 = o0;
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) {
-            wr[mt][0] = gate0 + mt * 128 + g;
-            wr[mt][1] = gate0 + mt * 128 + g + 8;
-        }
-    } else {
-        int n0 = blockIdx.x * 16 * MT;
-        out_col0 = n0;
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) {
-            wr[mt][0] = min(n0 + mt * 16 + g, p.N - 1);
-            wr[mt][1] = min(n0 + mt * 16 + g + 8, p.N - 1);
-        }
-    }
+    };
+    const int n_tiles = p.n_tiles;
     const bf16* wrow[MT][2];                                                     // bf16 stream: 16 B (8 weights) per lane and load
     const uint8_t* qrow[MT][2]; const bf16* mrow[MT][2];                         // W4 stream: 16 B (32 weights) + 8 B (2 groups' scale, bias)
+    auto issue_rows = [&](int tile) {                                            // row pointers of the ISSUE cursor's tile
+        int wr[MT][2], oc, rh, rg;
+        tile_rows(tile, wr, oc, rh, rg);
 #pragma unroll
-    for (int mt = 0; mt < MT; mt++)
+        for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-            wrow[mt][hh] = W4 ? nullptr : p.W + (size_t)wr[mt][hh] * K + t * 8;
-            qrow[mt][hh] = W4 ? p.Wq + (size_t)wr[mt][hh] * (K / 2) + t * 16 : nullptr;
-            mrow[mt][hh] = W4 ? p.Wmeta + (size_t)wr[mt][hh] * (K / 64) * 2 : nullptr;
-        }
+            for (int hh = 0; hh < 2; hh++) {
+                wrow[mt][hh] = W4 ? nullptr : p.W + (size_t)wr[mt][hh] * K + t * 8;
+                qrow[mt][hh] = W4 ? p.Wq + (size_t)wr[mt][hh] * (K / 2) + t * 16 : nullptr;
+                mrow[mt][hh] = W4 ? p.Wmeta + (size_t)wr[mt][hh] * (K / 64) * 2 : nullptr;
+            }
+    };
     const bf16* xrow[NT];
     int xbytes[NT];
 #pragma unroll
@@ -202,15 +224,28 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
 
     // Fill the ring with weights first: they do not depend on the previous kernel, so under
     // programmatic dependent launch this HBM traffic overlaps the predecessor's tail.
+    trace_stamp(p.trace, blockIdx.x, 0);
+    trace_meta(p.trace, blockIdx.x, p.epi * 100 + MT * 10 + (W4 ? 1 : 0));
     pdl_trigger();
-#pragma unroll
-    for (int s = 0; s < C::DEPTH; s++) {
-        if (warp + s * SK_WARPS < n_chunks) issue_w(warp + s * SK_WARPS, s);
+    // issue cursor: (tile, chunk) of the next weight stage to request; runs DEPTH stages ahead of the consumer, across tiles
+    int itile = (warp < n_chunks) ? (int)blockIdx.x : n_tiles, ici = warp;
+    if (itile < n_tiles) issue_rows(itile);
+    auto issue_next = [&](int stage) {
+        if (itile < n_tiles) {
+            issue_w(ici, stage);
+            ici += SK_WARPS;
+            if (ici >= n_chunks) {
+                ici = warp; itile += gridDim.x;
+                if (itile < n_tiles) issue_rows(itile);
+            }
+        }
         cp_async_commit();
-    }
+    };
+#pragma unroll
+    for (int s = 0; s < C::DEPTH; s++) issue_next(s);
     if (p.l2_pf) l2_prefetch_slice(p.l2_pf, p.l2_pf_bytes, blockIdx.x, gridDim.x, tid, SK_THREADS);
     pdl_wait();
-    int ci_issue = warp + C::DEPTH * SK_WARPS;
+    trace_stamp(p.trace, blockIdx.x, 1);
     if (warp < n_chunks) load_x(warp);
 
     // ---- RMSNorm prologue: rs[m] = rsqrt(mean(x^2) + eps), from the producer's partial sums when
@@ -260,16 +295,24 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
         __syncthreads();
     }
 
+    float rs[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) rs[nt] = (p.norm_w && nt * 8 + g < p.M) ? s_rs[nt * 8 + g] : 1.f;
+    int stage = 0;
+    bool first_tile = true;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
+    int wr_unused[MT][2], out_col0, rope_head, rope_grp;
+    tile_rows(tile, wr_unused, out_col0, rope_head, rope_grp);
     // ROPE_QKV epilogue: this thread's rope factors and page id are known up front -> request them now, use them after the K
     // loop (they can miss L2; fetched in the epilogue they would sit on the kernel's tail)
     float rope_cs = 1.f, rope_sn = 0.f;
     int rope_page = 0;
-    if (p.epi == P3_EPI_ROPE_QKV && tid < 8 * NT * 16 && (tid >> 4) < p.M) {
-        const int tok = tid >> 4, r = tid & 15;
+    if (p.epi == P3_EPI_ROPE_QKV && tid < 8 * NT * PAIRS && (tid / PAIRS) < p.M) {
+        const int tok = tid / PAIRS, r = tid % PAIRS;
         const int past0 = p.past_dev ? *p.past_dev : p.past;
         const int b = tok / p.L, pos = past0 + tok % p.L;
         if (rope_head >= 0) {
-            const size_t ti = (size_t)(b / p.row_div) * p.tab_bstride + (size_t)pos * (p.hd / 2) + rope_grp * 16 + r;
+            const size_t ti = (size_t)(b / p.row_div) * p.tab_bstride + (size_t)pos * (p.hd / 2) + rope_grp * PAIRS + r;
             rope_cs = __ldg(p.cosT + ti); rope_sn = __ldg(p.sinT + ti);
         }
         if (p.write_cache) rope_page = __ldg(p.block_table + (size_t)(b / p.row_div) * p.bt_stride + pos / P3_PAGE);
@@ -290,14 +333,11 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
         for (int nt = 0; nt < NT; nt++)
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[mt][nt][j] = 0.f;
-    float rs[NT];
-#pragma unroll
-    for (int nt = 0; nt < NT; nt++) rs[nt] = (p.norm_w && nt * 8 + g < p.M) ? s_rs[nt * 8 + g] : 1.f;
 
-    int stage = 0;
     for (int ci = warp; ci < n_chunks; ci += SK_WARPS) {
         cp_async_wait<C::DEPTH - 1>();                                           // oldest group (this chunk) has landed
         __syncwarp();                                                            // norm gains were copied by lanes 0-7
+        if (ci == warp && first_tile) trace_stamp(p.trace, blockIdx.x, 2);
         const uint8_t* sb = sk_smem + (size_t)warp * (C::DEPTH * C::STAGE) + stage * C::STAGE;
         if constexpr (W4) {
             uint4 qc[MT][2]; uint2 qm[MT][2]; uint4 xq[NT][4];
@@ -312,7 +352,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
             for (int nt = 0; nt < NT; nt++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) xq[nt][q] = xnext[nt][q];
-            if (ci + SK_WARPS < n_chunks) load_x(ci + SK_WARPS);
+            load_x(ci + SK_WARPS < n_chunks ? ci + SK_WARPS : warp);          // next chunk's X (wraps into the next tile)
             if (p.norm_w) {
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -330,9 +370,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
                 }
             }
             __syncwarp();
-            if (ci_issue < n_chunks) issue_w(ci_issue, stage);
-            cp_async_commit();
-            ci_issue += SK_WARPS;
+            issue_next(stage);
             if (++stage == C::DEPTH) stage = 0;
             // per 64-wide group: MMA on the raw codes (as bf16 128+q) and on a matrix of ones (-> sum of x), then
             // y += scale * sum((128+q) x) + (bias - 128 scale) * sum(x)   ==  sum((scale q + bias) x)  in fp32
@@ -396,7 +434,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
                     wcur[mt][hh][kh] = *reinterpret_cast<const uint4*>(sb + ((mt * 2 + hh) * 2 + kh) * 512 + lane * 16);
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) { xf[nt][0] = xnext[nt][0]; xf[nt][1] = xnext[nt][1]; }
-        if (ci + SK_WARPS < n_chunks) load_x(ci + SK_WARPS);                      // next chunk's X, one iteration ahead
+        load_x(ci + SK_WARPS < n_chunks ? ci + SK_WARPS : warp);                  // next chunk's X, one iteration ahead (wraps into the next tile)
         if (p.norm_w) {
             uint4 nw[2];
             nw[0] = *reinterpret_cast<const uint4*>(sb + (C::W_SLOTS + C::X_SLOTS) * 512 + t * 16);
@@ -416,9 +454,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
         }
         // the stage is in registers now: refill it with the chunk DEPTH iterations ahead
         __syncwarp();
-        if (ci_issue < n_chunks) issue_w(ci_issue, stage);
-        cp_async_commit();
-        ci_issue += SK_WARPS;
+        issue_next(stage);
         if (++stage == C::DEPTH) stage = 0;
 #pragma unroll
         for (int kh = 0; kh < 2; kh++)
@@ -436,7 +472,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
                     }
                 }
     }
-    if (ss_late) {                                                               // fixed order everywhere: deterministic
+    if (ss_late && first_tile) {                                                 // fixed order everywhere: deterministic
         float4 a = ss_raw[0];
 #pragma unroll
         for (int j = 1; j < SSR; j++) { a.x += ss_raw[j].x; a.y += ss_raw[j].y; a.z += ss_raw[j].z; a.w += ss_raw[j].w; }
@@ -447,11 +483,15 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
         }
         if (lane < 4) *reinterpret_cast<float4*>(&s_sspart[warp][4 * lane]) = a;
     }
-    cp_async_wait<0>();
-    __syncthreads();                                                             // ring -> reduction scratch (and s_rs visible)
+    if (tile + (int)gridDim.x >= n_tiles) {                                      // this CTA's stream is over: its share of HBM is idle from here on
+        trace_stamp(p.trace, blockIdx.x, 3);
+    }
 
-    // ---- cross-warp reduction through shared memory
-    float (*s_red)[MT][8 * NT][17] = reinterpret_cast<float (*)[MT][8 * NT][17]>(sk_smem);
+    // ---- cross-warp reduction through shared memory. The scratch sits behind the ring and alternates between two buffers, so
+    // one barrier per tile is enough: a warp can only write buffer (i + 2) & 1 after the barrier of tile i + 1, which every warp
+    // reaches after it has finished reading buffer i & 1 in the epilogue of tile i. The ring keeps streaming meanwhile.
+    float (*s_red)[MT][8 * NT][17] = reinterpret_cast<float (*)[MT][8 * NT][17]>(
+        sk_smem + C::RING + (C::NRED == 2 ? (((tile - (int)blockIdx.x) / (int)gridDim.x) & 1) * C::RED : 0));
 #pragma unroll
     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
@@ -467,12 +507,12 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
         const int past = p.past_dev ? *p.past_dev : p.past;
         const int half = p.hd / 2, qkv_dim = (p.n_heads + 2 * p.n_kv) * p.hd;
         bf16* outp = reinterpret_cast<bf16*>(p.out);
-        for (int o = tid; o < 8 * NT * 16; o += SK_THREADS) {
-            int r = o & 15, tok = o >> 4;
+        for (int o = tid; o < 8 * NT * PAIRS; o += SK_THREADS) {
+            int r = o % PAIRS, tok = o / PAIRS;
             if (tok >= p.M) continue;
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int w = 0; w < SK_WARPS; w++) { a0 += s_red[w][0][tok][r]; a1 += s_red[w][MT - 1][tok][r]; }
+            for (int w = 0; w < SK_WARPS; w++) { a0 += s_red[w][0][tok][r]; a1 += (MT == 1) ? s_red[w][0][tok][r + 8] : s_red[w][MT - 1][tok][r]; }
             if (p.rs_epi) { const float rsv = ss_late ? rs_from_parts(s_sspart, tok, K, p.eps) : s_rs[tok]; a0 *= rsv; a1 *= rsv; }
             const int b = tok / p.L, pos = past + tok % p.L;
             bf16* row = outp + (size_t)tok * p.ldo;
@@ -484,7 +524,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
             }
             if (rope_head >= 0) {                                                  // q or k head: rotate (phi.py:418-423)
                 const float x1 = bf16_round(a0), x2 = bf16_round(a1);              // qkv_proj output is bf16 in the reference flow
-                const int d = rope_grp * 16 + r;
+                const int d = rope_grp * PAIRS + r;
                 const size_t ti = (size_t)(b / p.row_div) * p.tab_bstride + (size_t)pos * half + d;
                 const float cs = (o == tid) ? rope_cs : p.cosT[ti], sn = (o == tid) ? rope_sn : p.sinT[ti];
                 const bf16 o1 = __float2bfloat16_rn(x1 * cs - x2 * sn), o2 = __float2bfloat16_rn(x2 * cs + x1 * sn);
@@ -499,7 +539,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++) {
                     const bf16 v = __float2bfloat16_rn(mt == 0 ? a0 : a1);
-                    const int c = c0 + mt * 16 + r;
+                    const int c = c0 + mt * PAIRS + r;
                     row[(p.n_heads + p.n_kv) * p.hd + c] = v;
                     if (vd) vd[(size_t)(c / p.hd) * P3_PAGE * p.hd + c % p.hd] = v;
                 }
@@ -507,12 +547,12 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
         }
         (void)qkv_dim;
     } else if (p.epi == P3_EPI_SWIGLU) {
-        for (int o = tid; o < 8 * NT * 16; o += SK_THREADS) {
-            int r = o & 15, tok = o >> 4;
+        for (int o = tid; o < 8 * NT * PAIRS; o += SK_THREADS) {
+            int r = o % PAIRS, tok = o / PAIRS;
             if (tok >= p.M) continue;
             float gsum = 0.f, usum = 0.f;
 #pragma unroll
-            for (int w = 0; w < SK_WARPS; w++) { gsum += s_red[w][0][tok][r]; usum += s_red[w][MT - 1][tok][r]; }
+            for (int w = 0; w < SK_WARPS; w++) { gsum += s_red[w][0][tok][r]; usum += (MT == 1) ? s_red[w][0][tok][r + 8] : s_red[w][MT - 1][tok][r]; }
             if (p.rs_epi) { const float rsv = ss_late ? rs_from_parts(s_sspart, tok, K, p.eps) : s_rs[tok]; gsum *= rsv; usum *= rsv; }
             float gb = bf16_round(gsum), ub = bf16_round(usum);
             float a = bf16_round(silu_f(gb));
@@ -544,10 +584,13 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
             if (p.ss_out && MT == 1) {                                             // 16 lanes = one token's 16 new columns
 #pragma unroll
                 for (int d = 8; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
-                if (r == 0 && tok < 16) p.ss_out[(size_t)blockIdx.x * 16 + tok] = (tok < p.M) ? sq : 0.f;
+                if (r == 0 && tok < 16) p.ss_out[(size_t)tile * 16 + tok] = (tok < p.M) ? sq : 0.f;
             }
         }
     }
+    if (C::NRED == 1 && tile + (int)gridDim.x < n_tiles) __syncthreads();        // single scratch buffer: drained before the next tile's sums
+    }   // tile loop
+    trace_stamp(p.trace, blockIdx.x, 4);
 }
 
 template <int NT, int MT, int DEPTH, bool W4 = false>
@@ -570,10 +613,43 @@ static int sk_depth_override() {
     if (v < 0) { const char* e = getenv("P3_SK_DEPTH"); v = e ? atoi(e) : 0; }
     return v;
 }
+// pair tiles (qkv + rope, gate_up + SwiGLU) as ONE 16-row MMA tile (8 + 8 rows, the 4-stage ring of the plain kernels) instead of two
+static int sk_pair_mt1() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("P3_SK_MT1"); v = e ? atoi(e) : 0; }
+    return v;
+}
+// Persistent grid: at most one wave of CTAs (2 per SM) walks the output tiles. In-kernel stamps (profiles/r02_chain_trace_*.log):
+// with one CTA per tile gate_up (512 tiles) ran a second, partly filled wave whose CTAs all started with an empty ring: 20.1 us
+// for a 15.6 us stream; one wave with a continuous ring: 19.4 us, decode step -2 % (profiles/r02_skinny_persistent_ab.log).
+// P3_SK_GRID=0 restores one CTA per tile, any other value is the cap (1 CTA/SM = 148 measured 25 % slower: half the bytes in flight).
+static int sk_grid_cap() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("P3_SK_GRID");
+        if (e) v = atoi(e);
+        else { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); v = 2 * sms; }
+    }
+    return v;
+}
 template <int NT, int MT>
-static int launch_skinny(const SkParams& p, unsigned grid, cudaStream_t st) {
-    if (p.Wq) return launch_skinny_d<NT, MT, 4, true>(p, grid, st);          // 4-bit stream: 4 stages x 128 k per warp
+static int launch_skinny(const SkParams& p_, unsigned grid, cudaStream_t st) {
+    SkParams p = p_; p.trace = p3_trace_slot();
+    p.n_tiles = (int)grid;
+    const int cap = sk_grid_cap();
+    if (cap > 0 && grid > (unsigned)cap) {
+        // every CTA gets the same number of tiles (gate_up: 256 CTAs x 2 instead of 216 x 2 + 80 x 1: -0.9 % per decode step;
+        // the slots left free take the next kernel's first CTAs, which fill their rings early). P3_SK_EVEN=0: fill the cap.
+        static int even = -1;
+        if (even < 0) { const char* e = getenv("P3_SK_EVEN"); even = e ? atoi(e) : 1; }
+        const unsigned per = (grid + cap - 1) / cap;
+        grid = even ? (grid + per - 1) / per : (unsigned)cap;
+    }
+    // 4-bit stream: 4 stages x 128 k per warp; 3 for the 32-row tiles so that ring + reduction scratch keep two CTAs per SM
+    // (4 stages = 115 KB = one CTA per SM: 2.83 instead of 2.55 ms per decode step)
+    if (p.Wq) return launch_skinny_d<NT, MT, (MT == 2 ? 3 : 4), true>(p, grid, st);
     int d = sk_depth_override();
+    { static int d1 = -1; if (d1 < 0) { const char* e = getenv("P3_SK_DEPTH1"); d1 = e ? atoi(e) : 0; } if (MT == 1 && d1) d = d1; }
     if (d == 0) d = (MT == 1) ? 4 : 2;                       // measured best (tools/microbench.py): deeper rings do not pay, residency does
     switch (d) {
         case 2: return launch_skinny_d<NT, MT, 2>(p, grid, st);
@@ -608,6 +684,7 @@ static int skinny_impl(const void* X, int64_t ldx, const void* norm_w, float eps
     p.xg_gain = (const bf16*)xg_gain; p.xg_out = (bf16*)xg_out; p.ldxg = ldxg; p.rs_epi = rs_epi;
     if (epi == P3_EPI_SWIGLU) {
         P3_CHECK_ARG(N % 256 == 0, "gemm_skinny: SwiGLU needs N (gate+up rows) to be a multiple of 256");
+        if (sk_pair_mt1() && M <= 8) return launch_skinny<1, 1>(p, (unsigned)(N / 2 / 8), st);
         unsigned grid = (unsigned)(N / 2 / 16);
         return M <= 8 ? launch_skinny<1, 2>(p, grid, st) : launch_skinny<2, 2>(p, grid, st);
     }
@@ -661,6 +738,7 @@ static int skinny_qkv_rope_impl(const void* X, int64_t ldx, const void* norm_w, 
     p.pool = (bf16*)pool; p.block_table = block_table; p.bt_stride = bt_stride;
     p.l2_pf = (const uint8_t*)l2_prefetch; p.l2_pf_bytes = l2_prefetch_bytes;
     p.rs_epi = rs_epi;
+    if (sk_pair_mt1() && M <= 8) return launch_skinny<1, 1>(p, (unsigned)((n_heads + n_kv) * (hd / 16) + n_kv * hd / 16), st);
     unsigned grid = (unsigned)((n_heads + n_kv) * (hd / 32) + n_kv * hd / 32);
     return M <= 8 ? launch_skinny<1, 2>(p, grid, st) : launch_skinny<2, 2>(p, grid, st);
 }
