@@ -33,6 +33,11 @@ extern "C" {
 
 const char* p3_last_error(void);
 int p3_version(void);
+/* Diagnostics (tools/chain_trace.py), not part of the reference interface: with a device buffer of n_slots x 1024 x 8 uint64 set,
+ * every decode-path launch (skinny GEMMs, decode attention) takes the next slot and its CTAs store globaltimer stamps
+ * {start, dependency resolved, first operands ready, main loop done, exit, smid, kind, grid}. p3_trace_set(NULL, 0) turns it off. */
+int p3_trace_set(void* buf, int n_slots);
+int p3_trace_count(void);
 
 /* nn.Embedding phi:568,577 — ids<0 (image placeholders, phi:270) read row 0. ss_out (fp32 [T], may be
  * NULL) receives each row's sum of squares for the RMSNorm fused into the next p3_gemm_skinny. */

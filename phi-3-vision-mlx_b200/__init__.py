@@ -13,7 +13,7 @@ def __getattr__(name):
     if name in ('load', 'generate', 'choose', 'constrain', 'generate_batch', 'sanitize', '_generate', '_choose_from', '_constrain'):
         from . import api
         return getattr(api, name)
-    if name in ('api', 'model', 'processor', 'weights', '_lib', 'parallel', 'mega', 'quant'):
+    if name in ('api', 'model', 'processor', 'weights', '_lib', 'parallel', 'mega', 'quant', 'server'):
         import importlib
         return importlib.import_module(f'{__name__}.{name}')
     raise AttributeError(name)

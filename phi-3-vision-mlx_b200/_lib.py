@@ -52,7 +52,7 @@ launches = 0          # number of p3_* kernel-launching calls issued (bench.py r
 
 def exported_symbols():
     return sorted(list(_SIGS) + ['p3_last_error', 'p3_version', 'p3_attention_decode_workspace', 'p3_decode_mega',
-                                 'p3_decode_mega_ctas', 'p3_gemm_fused', 'p3_gemm_plan_weights', 'p3_gemm_skinny_x'])
+                                 'p3_decode_mega_ctas', 'p3_gemm_fused', 'p3_gemm_plan_weights', 'p3_gemm_skinny_x', 'p3_trace_set', 'p3_trace_count'])
 
 
 def lib():
@@ -74,6 +74,8 @@ def lib():
         L.p3_gemm_fused.argtypes, L.p3_gemm_fused.restype = [_p, _p], C.c_int        # (const p3_gemm_args*, stream)
         L.p3_gemm_plan_weights.argtypes, L.p3_gemm_plan_weights.restype = [_p, _l, _i, _i, _p], C.c_int
         L.p3_gemm_skinny_x.argtypes, L.p3_gemm_skinny_x.restype = [_p, _p], C.c_int        # (const p3_skinny_args*, stream)
+        L.p3_trace_set.argtypes, L.p3_trace_set.restype = [_p, C.c_int], C.c_int           # diagnostics (tools/chain_trace.py)
+        L.p3_trace_count.argtypes, L.p3_trace_count.restype = [], C.c_int
         _lib = L
     return _lib
 

@@ -524,3 +524,38 @@ def test_lora_over_quantized_model(dev):
     lo, co = ora(tok[:, None], cache=co)
     lg, cg = m(tok[:, None], cache=cg)
     assert rel(lg, lo) < 2e-2
+
+
+def test_server_batches_concurrent_requests_through_the_model(dev):
+    """srv:1-38 through the B200 path: concurrent HTTP clients are served by batched generate_batch calls and each gets exactly
+    what a direct call with its own prompts returns."""
+    import threading
+    import urllib.request
+    api, model, proc, _ = _setup()
+    from phi3_b200 import server
+    pre = (model, proc)
+    httpd = server.serve(server.model_generate_fn(pre), port=0, max_batch=8, window_ms=50, host='127.0.0.1',
+                         group_key=server.rope_side_key(pre))
+    port = httpd.server_address[1]
+    threading.Thread(target=httpd.serve_forever, daemon=True).start()
+
+    def post(payload):
+        req = urllib.request.Request(f'http://127.0.0.1:{port}/v1/completions', data=json.dumps(payload).encode(),
+                                     headers={'Content-Type': 'application/json'})
+        with urllib.request.urlopen(req, timeout=120) as r:
+            return json.loads(r.read().decode())['responses']
+    try:
+        prompts = ['Hello there', 'What is the capital of France?', 'abc', 'Tell me a story about a dog']
+        want = [api.generate_batch([p], preload=pre, max_tokens=6)[0] for p in prompts]
+        got = {}
+        th = [threading.Thread(target=lambda i=i: got.__setitem__(i, post({'prompt': prompts[i], 'max_tokens': 6}))) for i in range(4)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert [got[i][0] for i in range(4)] == want
+        assert httpd.batcher.calls < 4
+        assert post({'prompt': prompts[:2], 'max_tokens': 6}) == want[:2]
+    finally:
+        httpd.shutdown()
+        httpd.batcher.close()

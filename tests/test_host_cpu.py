@@ -346,3 +346,90 @@ def test_logit_stopper_decisions_equal_the_oracle_restatement():
                 break
         n_fired += fired is not None
     assert n_fired >= 1                                             # the stop path was exercised
+
+
+# ------------------------------------------------------------------ batching HTTP front end (srv:1-38)
+def _post(port, payload, path='/v1/completions'):
+    import json
+    import urllib.request
+    req = urllib.request.Request(f'http://127.0.0.1:{port}{path}', data=json.dumps(payload).encode(),
+                                 headers={'Content-Type': 'application/json'})
+    with urllib.request.urlopen(req, timeout=30) as r:
+        return r.status, json.loads(r.read().decode())
+
+
+def test_server_wire_contract_and_request_batching():
+    """Same endpoint / JSON as the reference server; concurrent requests share batched generate calls and every client gets
+    its own answers back in order; a request with another max_tokens never joins the batch; unknown paths are 404."""
+    import threading
+    import time
+    import urllib.error
+    import phi3_b200  # noqa
+    from phi3_b200 import server
+    seen = []
+
+    def fake_generate(prompts, max_tokens):
+        seen.append((list(prompts), max_tokens))
+        time.sleep(0.15)                                     # a "decode" long enough for the other clients to queue up
+        return [f'{p}|{max_tokens}' for p in prompts]
+    httpd = server.serve(fake_generate, port=0, max_batch=8, window_ms=30, host='127.0.0.1')
+    port = httpd.server_address[1]
+    t = threading.Thread(target=httpd.serve_forever, daemon=True)
+    t.start()
+    try:
+        st, body = _post(port, {'prompt': 'solo', 'max_tokens': 5})
+        assert st == 200 and body == {'model': 'phi-3-vision', 'responses': ['solo|5']}     # str in -> list of one (srv:15-16,21-22)
+        st, body = _post(port, {'prompt': ['a', 'b']})
+        assert body['responses'] == ['a|512', 'b|512']                                       # default max_tokens (srv:14)
+        n0 = len(seen)
+        results = {}
+
+        def client(i):
+            mt = 7 if i == 5 else 9
+            results[i] = _post(port, {'prompt': [f'c{i}x', f'c{i}y'] if i % 2 else f'c{i}', 'max_tokens': mt})[1]['responses']
+        th = [threading.Thread(target=client, args=(i,)) for i in range(6)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        for i in range(6):
+            mt = 7 if i == 5 else 9
+            want = [f'c{i}x|{mt}', f'c{i}y|{mt}'] if i % 2 else [f'c{i}|{mt}']
+            assert results[i] == want
+        calls = seen[n0:]
+        assert len(calls) < 6                                # coalesced
+        assert all(len(p) <= 8 for p, _ in calls)            # max_batch respected
+        assert all(len({mt}) == 1 for _, mt in calls) and any(mt == 7 and len(p) == 2 for p, mt in calls)
+        with pytest.raises(urllib.error.HTTPError) as e:
+            _post(port, {'prompt': 'x'}, path='/v1/other')
+        assert e.value.code == 404
+    finally:
+        httpd.shutdown()
+        httpd.batcher.close()
+
+
+def test_server_failure_reaches_every_waiting_client_and_worker_survives():
+    import threading
+    import urllib.error
+    import phi3_b200  # noqa
+    from phi3_b200 import server
+
+    def flaky(prompts, max_tokens):
+        if any('boom' in p for p in prompts):
+            raise RuntimeError('decode failed')
+        return [p.upper() for p in prompts]
+    httpd = server.serve(flaky, port=0, max_batch=4, window_ms=1, host='127.0.0.1')
+    port = httpd.server_address[1]
+    threading.Thread(target=httpd.serve_forever, daemon=True).start()
+    try:
+        with pytest.raises(urllib.error.HTTPError) as e:
+            _post(port, {'prompt': 'boom'})
+        assert e.value.code == 500
+        assert _post(port, {'prompt': 'ok'})[1]['responses'] == ['OK']
+        b = server.Batcher(lambda p, m: p[:-1], max_batch=4, window_ms=1)     # wrong number of answers is an error, not a mix-up
+        with pytest.raises(RuntimeError):
+            b.submit(['a', 'b'], 3)
+        b.close()
+    finally:
+        httpd.shutdown()
+        httpd.batcher.close()
