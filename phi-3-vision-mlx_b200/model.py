@@ -265,12 +265,12 @@ class Phi3B200:
         # Neutral for the bf16 weight stream (2.797 vs 2.788 ms/token on the bench), -8 % for the instruction-bound 4-bit one.
         self._opf_in_qkv = _os.environ.get('P3_OPF', 'qkv') != 'attn'
         self.prenorm = _os.environ.get('P3_PRENORM', '1' if self.quantize_model else '0') != '0'
-        # decode over 4-bit weights: RMSNorm split between producer and consumer (p3_gemm_skinny_x): the residual epilogue
-        # also writes bf16(h * gain_of_next_norm), the consumer applies rstd to its accumulators -> no norm kernel, no
-        # per-warp re-normalisation: 7 -> 5 launches per layer. P3_XG=0 restores the separate norm kernels.
-        self.xg = self.quantize_model and _os.environ.get('P3_XG', '1') != '0'
-        self._xg_spacer = _os.environ.get('P3_XG_SPACER', '0') == '1'      # experiment: tiny PDL kernel in front of each consumer
-        self._spacer_buf = torch.zeros((2, self.H), dtype=torch.bfloat16, device=self.dev)
+        # decode: RMSNorm split between producer and consumer (p3_gemm_skinny_x): the residual epilogue also writes
+        # bf16(h * gain_of_next_norm), the consumer applies rstd to its reduced accumulators -> no norm kernel, no per-warp
+        # re-normalisation inside the K loop, no statistics reduction in front of it. Built for the 4-bit stream (7 -> 5 launches
+        # per layer); on bf16 weights it replaces the fused-norm prologue and measured -3.8 % (8 x 2048), -5.3 % (16 x 448), -5.9 %
+        # (4 x 128) per decode step (profiles/r02_split_norm_bf16_ab.log). P3_XG=0 restores the fused / separate norm.
+        self.xg = _os.environ.get('P3_XG', '1') != '0'
         self.profile = None      # bench.py: list of (kind, ev0, ev1, algorithmic_bytes) when instrumenting
 
     # ------------------------------------------------------------------ vision weights
@@ -387,8 +387,8 @@ class Phi3B200:
         M, K = x.shape
         if xg_out is not None or rs_epi:                    # producer / consumer halves of the split RMSNorm
             ev = self._ev()
-            nxt, pf = self._prefetch_target(nxt)
-            q = self._w4.get(w.data_ptr())
+            nxt, pf = self._prefetch_target(nxt, M)
+            q = self._codes(w, M)
             a = _lib.SkinnyArgs()
             a.op, a.X, a.ldx, a.eps = 0, ptr(x), x.stride(0), self.eps
             if q is not None:
@@ -407,8 +407,8 @@ class Phi3B200:
             x, norm_w, ss_in = self._prenorm(x, norm_w), None, None
         ev = self._ev()
         n_ss = 0 if ss_in is None else ss_in.shape[0]
-        nxt, pf = self._prefetch_target(nxt)
-        q = self._w4.get(w.data_ptr())
+        nxt, pf = self._prefetch_target(nxt, M)
+        q = self._codes(w, M)
         if q is not None:                                   # quantize_model: stream the 4-bit codes instead of bf16
             call('p3_gemm_skinny_w4', ptr(x), x.stride(0), ptr(norm_w), self.eps, ptr(q[0]), ptr(q[1]), ptr(out), out.stride(0),
                  ptr(resid), M, w.shape[0], K, epi, ptr(ss_in), n_ss, ptr(ss_out), ptr(nxt), pf, _stream())
@@ -425,11 +425,20 @@ class Phi3B200:
         call('p3_rmsnorm', ptr(x), ptr(norm_w), ptr(xn), x.shape[0], x.shape[1], self.eps, _stream())
         return xn
 
-    def _prefetch_target(self, nxt):
+    # Rows up to which a quantised matrix is streamed as 4-bit codes. The 4-bit kernel is instruction-bound (integer unpack + an extra
+    # MMA per group for the affine term); with two 8-token groups per warp (9..16 rows) it is slower than the bf16 stream over the
+    # dequantised image that the prefill GEMMs use anyway (B = 16 x 448: 3.23 vs 2.73 ms per step), so those steps take the bf16 path.
+    W4_MAX_ROWS = int(__import__('os').environ.get('P3_W4_MAX_ROWS', '8'))
+
+    def _codes(self, w, M):
+        """(codes, meta) of a quantised matrix when an M-row stream should read the 4-bit image, else None"""
+        return self._w4.get(w.data_ptr()) if M <= self.W4_MAX_ROWS else None
+
+    def _prefetch_target(self, nxt, M=1):
         """(tensor, bytes) of the next kernel's weight stream to park in L2: the 4-bit codes when the matrix is quantised"""
         if nxt is None:
             return None, 0
-        q = self._w4.get(nxt.data_ptr())
+        q = self._codes(nxt, M)
         if q is not None:
             return q[0], min(q[0].numel(), self.L2_PF_CAP)
         return nxt, min(nxt.numel() * 2, self.L2_PF_CAP)
@@ -654,8 +663,6 @@ class Phi3B200:
             elif T <= 16:                                   # decode: qkv_proj + rope + KV write in one launch
                 if xg:
                     hq, nq, sq = hgA, None, ss_cur
-                    if self._xg_spacer:
-                        call('p3_rmsnorm', ptr(self._spacer_buf), ptr(lw['ln1']), ptr(self._spacer_buf[1:]), 1, H, self.eps, st)
                 else:
                     hq, nq, sq = (self._prenorm(h, lw['ln1']), None, None) if self.prenorm else (h, lw['ln1'], ss_cur)
                 # the qkv kernel parks the whole o_proj stream (18.9 MB bf16) in L2 before it waits on its predecessor; it
@@ -663,10 +670,10 @@ class Phi3B200:
                 # bench: 2.851 -> 2.814 ms/token, attention in-step roofline 0.776 -> 0.816; P3_OPF=attn restores the old split)
                 qo_pf, qo_bytes = (None, 0)
                 if self._opf_in_qkv:
-                    qo_pf, _ = self._prefetch_target(lw['o'])
+                    qo_pf, _ = self._prefetch_target(lw['o'], T)
                     qo_bytes = qo_pf.numel() * qo_pf.element_size()
                 ev = self._ev()
-                q4 = self._w4.get(lw['qkv'].data_ptr())
+                q4 = self._codes(lw['qkv'], T)
                 if xg:
                     a = _lib.SkinnyArgs()
                     a.op, a.X, a.ldx, a.eps, a.out = 1, ptr(hq), hq.stride(0), self.eps, ptr(qkv)
@@ -729,8 +736,6 @@ class Phi3B200:
                     self.linear(att, lw['o'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssB, nxt=lw['gu'] if self.pf_chain else None,
                                 xg_gain=lw['ln2'], xg_out=hgB)
                 if 'gu' not in self._skip:
-                    if self._xg_spacer:
-                        call('p3_rmsnorm', ptr(self._spacer_buf), ptr(lw['ln2']), ptr(self._spacer_buf[1:]), 1, H, self.eps, st)
                     self.linear(hgB, lw['gu'], act, _lib.EPI_SWIGLU, ss_in=ssB, nxt=lw['down'] if self.pf_chain else None, rs_epi=True)
                 if 'down' not in self._skip:
                     self.linear(act, lw['down'], h, _lib.EPI_RESIDUAL, resid=h, ss_out=ssA, nxt=nxt_qkv if self.pf_chain else None,

@@ -127,7 +127,7 @@ def test_quantized_cache_generate_and_beam_raises(dev):
 
 
 def test_vision_generate_end_to_end(dev):
-    api, model, proc, ora = _setup(vision=True)
+    api, model, proc, ora = _setup(vision=True, init='peaked')     # rollouts are compared token by token: margins must clear bf16 noise
     from oracle import processors as op
     from oracle import drivers
     from PIL import Image
@@ -142,8 +142,7 @@ def test_vision_generate_end_to_end(dev):
     ref_inp = {k: torch.from_numpy(np.asarray(v)) for k, v in ref_inp.items()}
     ref = drivers.generate_ids(ora, ref_inp, 6)
     hist = api._generate(model, proc, prompt, imgs, max_tokens=6, verbose=False, stream=False, mute=True, return_tokens=True)
-    assert torch.equal(hist.cpu().long()[:, :2], ref[:, :2])
-    assert (hist.cpu().long() == ref).float().mean() >= 0.8
+    assert torch.equal(hist.cpu().long(), ref)
 
 
 def test_constrain_beam_with_quantized_cache_extension(dev):

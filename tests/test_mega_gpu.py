@@ -213,7 +213,7 @@ def test_repeated_launches_are_deterministic(dev):
     assert all(torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) for o in outs[1:])
 
 
-def _tiny(layers=2, **kw):
+def _tiny(layers=2, init='gpt2', **kw):
     import os
     os.environ['P3_MEGA'] = '1'                                  # the kernel is opt-in (model.py)
     import phi3_b200  # noqa
@@ -221,7 +221,7 @@ def _tiny(layers=2, **kw):
     from phi3_b200.model import Phi3B200
     from oracle.phi3_oracle import Phi3Oracle
     cfg = configs.tiny(layers=layers, **kw)
-    w = weights.random_weights(cfg, seed=0)
+    w = weights.random_weights(cfg, seed=0, init=init)
     try:
         m = Phi3B200(cfg, w)
     finally:
@@ -233,7 +233,9 @@ def _tiny(layers=2, **kw):
 def test_decode_loop_through_mega(dev, B, quant):
     """graph-replayed decode through the persistent kernel == eager decode through it == per-matrix skinny path (tokens),
     and its logits match the oracle step by step"""
-    cfg, w, m, o = _tiny(use_quantized_cache=quant)
+    # peaked checkpoint: token rollouts of two correct bf16 paths (different rounding points: the skinny path applies the RMSNorm
+    # scale to the accumulators, the persistent kernel to X) can only be compared where top-1 margins clear the bf16 noise
+    cfg, w, m, o = _tiny(use_quantized_cache=quant, init='peaked')
     assert m.mega is not None
     g = torch.Generator().manual_seed(B)
     L = 150 if quant else 40
@@ -253,7 +255,7 @@ def test_decode_loop_through_mega(dev, B, quant):
     m.mega = mega
     del c
     assert torch.equal(hist_graph, hist_eager)
-    assert (hist_graph == hist_skinny).float().mean() > 0.9     # two correct bf16 paths on a flat random-init model
+    assert torch.equal(hist_graph, hist_skinny)
     # step-wise logits against the oracle (teacher-forced on the oracle's tokens)
     from phi3_b200.model import DecodeSession
     lo, co = o(ids, max_tokens=steps + 1)
