@@ -159,6 +159,9 @@ typedef struct {
     const float* cosT; const float* sinT; int64_t tab_bstride;          /* op 1, as p3_gemm_skinny_qkv_rope */
     int32_t B, L, n_heads, n_kv, hd, past, row_div, bt_stride, write_cache;
     const int32_t* past_dev; void* pool; const int32_t* block_table;
+    int32_t packed;                      /* op 0, bf16 W, N % 16 == 0, N < 9472, not SwiGLU: W is given in stream order
+                                          * [N/16 tiles][K/64 chunks][row half][k half][lane = 4 * (row % 8) + 16-byte quad][8 bf16]
+                                          * (one contiguous 16 x K block per tile; phi3_b200.model.pack_rows16) */
 } p3_skinny_args;
 int p3_gemm_skinny_x(const p3_skinny_args* args, cudaStream_t st);
 /* p3_embed_gather that also writes xg_out[t] = bf16(row * xg_gain) (input of the first rs_epi consumer) */

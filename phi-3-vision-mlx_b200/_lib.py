@@ -126,7 +126,7 @@ class SkinnyArgs(C.Structure):
                 ('cosT', _p), ('sinT', _p), ('tab_bstride', _l),
                 ('B', C.c_int32), ('L', C.c_int32), ('n_heads', C.c_int32), ('n_kv', C.c_int32), ('hd', C.c_int32), ('past', C.c_int32),
                 ('row_div', C.c_int32), ('bt_stride', C.c_int32), ('write_cache', C.c_int32),
-                ('past_dev', _p), ('pool', _p), ('block_table', _p)]
+                ('past_dev', _p), ('pool', _p), ('block_table', _p), ('packed', C.c_int32)]
 
 
 class WeightPlan:

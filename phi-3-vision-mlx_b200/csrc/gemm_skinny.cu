@@ -45,6 +45,11 @@ struct SkParams {
     // rsqrt(mean(h^2) + eps) from ss_in to its reduced accumulators (norm_w must be null then).
     const bf16* xg_gain; bf16* xg_out; int64_t ldxg; int rs_epi;
     unsigned long long* trace;                   // tools/chain_trace.py (null in production)
+    // 16-row tiles of W stored in stream order [tile][64-k chunk][row half][k half][lane][16 B] (model.pack_rows16): a stage is one
+    // contiguous 2 KB block and a CTA reads one contiguous 16 x K block, instead of 8 rows x 64 B per instruction at a stride of
+    // K x 2 bytes. Same bytes, same arithmetic; the memory round trip of a contiguous stream is about half (tools/sm_ingest_bench.cu),
+    // which is what bounds the 192-CTA kernels (o_proj, down_proj: a CTA streams ring / round-trip bytes per us).
+    int packed;
     int n_tiles;                                 // output tiles; the grid may be smaller (persistent CTAs, tile = blockIdx.x + i * gridDim.x)
 };
 #define P3_EPI_ROPE_QKV 7
@@ -151,6 +156,7 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
     const bf16* wrow[MT][2];                                                     // bf16 stream: 16 B (8 weights) per lane and load
     const uint8_t* qrow[MT][2]; const bf16* mrow[MT][2];                         // W4 stream: 16 B (32 weights) + 8 B (2 groups' scale, bias)
     auto issue_rows = [&](int tile) {                                            // row pointers of the ISSUE cursor's tile
+        if (MT == 1 && p.packed) { wrow[0][0] = p.W + (size_t)tile * 16 * K + lane * 8; return; }
         int wr[MT][2], oc, rh, rg;
         tile_rows(tile, wr, oc, rh, rg);
 #pragma unroll
@@ -189,6 +195,11 @@ __global__ void __launch_bounds__(SK_THREADS, (SkCfg<NT, MT, DEPTH, W4>::SMEM <=
         }
         const uint32_t sb = ring + stage * C::STAGE + lane * 16;
         const int k0 = ci * 64;
+        if (MT == 1 && p.packed) {
+            const bf16* src = wrow[0][0] + (size_t)ci * 1024;
+#pragma unroll
+            for (int sl = 0; sl < 4; sl++) cp_async16_stream(sb + sl * 512, src + sl * 256, pol);
+        } else
 #pragma unroll
         for (int mt = 0; mt < MT; mt++)
 #pragma unroll
@@ -664,8 +675,11 @@ static int launch_skinny(const SkParams& p_, unsigned grid, cudaStream_t st) {
 static int skinny_impl(const void* X, int64_t ldx, const void* norm_w, float eps, const void* W, const void* Wq,
                        const void* Wmeta, void* out, int64_t ldo, const void* resid, int M, int N, int K, int epi,
                        const float* ss_in, int n_ss_in, float* ss_out, const void* l2_prefetch, int64_t l2_prefetch_bytes,
-                       cudaStream_t st, const void* xg_gain = nullptr, void* xg_out = nullptr, int64_t ldxg = 0, int rs_epi = 0) {
+                       cudaStream_t st, const void* xg_gain = nullptr, void* xg_out = nullptr, int64_t ldxg = 0, int rs_epi = 0,
+                       int packed = 0) {
     P3_CHECK_ARG(M >= 1 && M <= 16, "gemm_skinny: M must be in [1,16] (got %d)", M);
+    P3_CHECK_ARG(!packed || (W && !Wq && N % 16 == 0 && N < 148 * 32 * 2 && epi != P3_EPI_SWIGLU),
+                 "gemm_skinny: the packed layout is for bf16 matrices streamed as 16-row tiles (N %% 16 == 0, N < 9472, no SwiGLU)");
     P3_CHECK_ARG(!rs_epi || (ss_in && !norm_w), "gemm_skinny: rs_epi needs ss_in and no norm_w (X is already gain-scaled)");
     P3_CHECK_ARG(!xg_out || (xg_gain && epi == P3_EPI_RESIDUAL), "gemm_skinny: xg_out needs xg_gain and the residual epilogue");
     P3_CHECK_ARG(K % 64 == 0, "gemm_skinny: K must be a multiple of 64 (got %d)", K);
@@ -681,7 +695,7 @@ static int skinny_impl(const void* X, int64_t ldx, const void* norm_w, float eps
     p.ldo = ldo; p.resid = (const bf16*)resid; p.M = M; p.N = N; p.K = K; p.epi = epi;
     p.ss_in = ss_in; p.n_ss_in = n_ss_in; p.ss_out = ss_out;
     p.l2_pf = (const uint8_t*)l2_prefetch; p.l2_pf_bytes = l2_prefetch_bytes;
-    p.xg_gain = (const bf16*)xg_gain; p.xg_out = (bf16*)xg_out; p.ldxg = ldxg; p.rs_epi = rs_epi;
+    p.xg_gain = (const bf16*)xg_gain; p.xg_out = (bf16*)xg_out; p.ldxg = ldxg; p.rs_epi = rs_epi; p.packed = packed;
     if (epi == P3_EPI_SWIGLU) {
         P3_CHECK_ARG(N % 256 == 0, "gemm_skinny: SwiGLU needs N (gate+up rows) to be a multiple of 256");
         if (sk_pair_mt1() && M <= 8) return launch_skinny<1, 1>(p, (unsigned)(N / 2 / 8), st);
@@ -767,15 +781,16 @@ extern "C" int p3_gemm_skinny_qkv_rope_w4(const void* X, int64_t ldx, const void
 }
 
 #include <cstddef>
-static_assert(sizeof(p3_skinny_args) == 264 && offsetof(p3_skinny_args, past_dev) == 240, "p3_skinny_args layout is mirrored by _lib.SkinnyArgs");
+static_assert(sizeof(p3_skinny_args) == 272 && offsetof(p3_skinny_args, past_dev) == 240 && offsetof(p3_skinny_args, packed) == 264, "p3_skinny_args layout is mirrored by _lib.SkinnyArgs");
 // Struct-argument entry for both forms (plain / qkv+rope, bf16 / 4-bit) with the producer-consumer norm split.
 extern "C" int p3_gemm_skinny_x(const p3_skinny_args* a, cudaStream_t st) {
     P3_CHECK_ARG(a && (a->op == 0 || a->op == 1), "gemm_skinny_x: op must be 0 (linear) or 1 (qkv + rope)");
     P3_CHECK_ARG((a->W != nullptr) != (a->Wq != nullptr), "gemm_skinny_x: exactly one of W (bf16) and Wq/Wmeta (4-bit) must be given");
+    P3_CHECK_ARG(!a->packed || a->op == 0, "gemm_skinny_x: the packed layout applies to op 0 only");
     if (a->op == 1)
         return skinny_qkv_rope_impl(a->X, a->ldx, a->norm_w, a->eps, a->W, a->Wq, a->Wmeta, a->out, a->ss_in, a->n_ss_in, a->cosT, a->sinT,
                                     a->tab_bstride, a->B, a->L, a->n_heads, a->n_kv, a->hd, a->K, a->past, a->past_dev, a->row_div, a->pool,
                                     a->block_table, a->bt_stride, a->write_cache, a->l2_prefetch, a->l2_prefetch_bytes, st, a->rs_epi);
     return skinny_impl(a->X, a->ldx, a->norm_w, a->eps, a->W, a->Wq, a->Wmeta, a->out, a->ldo, a->resid, a->M, a->N, a->K, a->epi, a->ss_in,
-                       a->n_ss_in, a->ss_out, a->l2_prefetch, a->l2_prefetch_bytes, st, a->xg_gain, a->xg_out, a->ldxg, a->rs_epi);
+                       a->n_ss_in, a->ss_out, a->l2_prefetch, a->l2_prefetch_bytes, st, a->xg_gain, a->xg_out, a->ldxg, a->rs_epi, a->packed);
 }

@@ -67,6 +67,14 @@ def pick_splits(n_bh, tiles, slots=2 * 148, max_splits=32):
     return best
 
 
+def pack_rows16(w):
+    """[N, K] -> the same elements in the stream order of the 16-row skinny tiles (csrc/gemm_skinny.cu, SkParams.packed):
+    [N/16 tiles][K/64 chunks][row half][k half][lane = 4 * (row % 8) + 16-byte quad][8 elements]; a tile is one contiguous block."""
+    N, K = w.shape
+    assert N % 16 == 0 and K % 64 == 0
+    return w.view(N // 16, 2, 8, K // 64, 2, 4, 8).permute(0, 3, 1, 4, 2, 5, 6).contiguous().view(N, K)
+
+
 def interleave_gate_up(w):
     """[2I, K] (gate rows then up rows, phi:470) -> per 256-row block [128 gate | 128 up]."""
     I = w.shape[0] // 2
@@ -236,6 +244,15 @@ class Phi3B200:
             for lw in self.layers:
                 lw['qkv_pf'], lw['gu_pf'] = self._prefill_copy(lw, 'qkv'), self._prefill_copy(lw, 'gu')
                 lw['plans'] = {k: _lib.WeightPlan(lw[k]) for k in ('qkv_pf', 'o', 'gu_pf', 'down')}
+        # decode stream of o_proj / down_proj in tile order (pack_rows16): second copies of the bf16 matrices that stream as 16-row
+        # tiles (2.2 GB at Phi-3.5 sizes). P3_SK_PACK=0: read the row-major matrices.
+        self._pk = {}
+        if _os1.environ.get('P3_SK_PACK', '1') != '0':
+            for lw in self.layers:
+                for key in ('o', 'down'):
+                    t = lw[key]
+                    if t.data_ptr() not in self._w4 and t.shape[0] % 16 == 0 and t.shape[0] < 148 * 64 and t.shape[1] % 64 == 0:
+                        lw[key + '_pk'] = self._pk[t.data_ptr()] = pack_rows16(t)
         self._raw_src = w             # names only looked up for adapter targets (set_adapter); the dict stays the caller's
         # persistent decode-layer kernel (mega.py / decode_mega.cu): a second, stream-order copy of the decoder weights
         # (7.4 GB at Phi-3.5 sizes; HBM has 180 GB). bf16 weights only. Opt-in (P3_MEGA=1) while it is slower than the chain
@@ -336,6 +353,8 @@ class Phi3B200:
             if key == 'gu':
                 t = interleave_gate_up(t)
             lw[key].copy_(t)
+            if key + '_pk' in lw:
+                lw[key + '_pk'].copy_(pack_rows16(lw[key]))
             if self.pf_fused and key in ('qkv', 'gu'):
                 lw[key + '_pf'].copy_(self._prefill_copy(lw, key))
             if self.mega is not None:
@@ -391,8 +410,11 @@ class Phi3B200:
             q = self._codes(w, M)
             a = _lib.SkinnyArgs()
             a.op, a.X, a.ldx, a.eps = 0, ptr(x), x.stride(0), self.eps
+            pk = self._pk.get(w.data_ptr()) if q is None else None
             if q is not None:
                 a.Wq, a.Wmeta = ptr(q[0]), ptr(q[1])
+            elif pk is not None:
+                a.W, a.packed = ptr(pk), 1
             else:
                 a.W = ptr(w)
             a.out, a.ldo, a.resid = ptr(out), out.stride(0), ptr(resid)
@@ -441,6 +463,8 @@ class Phi3B200:
         q = self._codes(nxt, M)
         if q is not None:
             return q[0], min(q[0].numel(), self.L2_PF_CAP)
+        if self.xg and nxt.data_ptr() in self._pk:          # the decode stream reads the tile-order copy
+            nxt = self._pk[nxt.data_ptr()]
         return nxt, min(nxt.numel() * 2, self.L2_PF_CAP)
 
     def _ev(self, start=None, kind=None, nbytes=0):

@@ -231,7 +231,7 @@ def test_mega_args_layout_matches_header():
     from phi3_b200 import mega
     assert ctypes.sizeof(mega.MegaPhase) == 104 and ctypes.sizeof(mega.MegaArgs) == 520    # static_assert in decode_mega.cu
     from phi3_b200 import _lib
-    assert ctypes.sizeof(_lib.SkinnyArgs) == 264 and _lib.SkinnyArgs.past_dev.offset == 240  # static_assert in gemm_skinny.cu
+    assert ctypes.sizeof(_lib.SkinnyArgs) == 272 and _lib.SkinnyArgs.past_dev.offset == 240 and _lib.SkinnyArgs.packed.offset == 264  # static_assert in gemm_skinny.cu
     assert ctypes.sizeof(_lib.GemmArgs) == 224
 
 

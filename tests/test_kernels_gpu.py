@@ -548,6 +548,44 @@ def test_skinny_split_rmsnorm_matches_fused(dev, M, w4):
     assert (o1.float() - o2.float()).abs().max() <= 1e-2 * ref.abs().max()
 
 
+@pytest.mark.parametrize('K', [3072, 8192])
+@pytest.mark.parametrize('M', [1, 8, 13])
+def test_skinny_packed_tile_order_is_bit_identical(dev, M, K):
+    """p3_gemm_skinny_x with W in the stream order of the 16-row tiles (model.pack_rows16) == the row-major launch, bit for bit
+    (same loads per lane, same arithmetic order): output, gain-scaled copy and the sum-of-squares partials."""
+    from phi3_b200.model import pack_rows16
+    L = _mods()
+    torch.manual_seed(K + M)
+    N = 3072
+    x = bf(torch.randn(M, K, device=dev))
+    w = bf(torch.randn(N, K, device=dev) * K ** -0.5)
+    wp = pack_rows16(w)
+    assert wp.shape == w.shape and not torch.equal(wp, w)
+    # element (n, k) sits at tile n // 16, chunk k // 64, row half (n % 16) // 8, k half (k % 64) // 32, lane 4 * (n % 8) + (k % 32) // 8
+    n, k = 37, 1000
+    flat = (((n // 16) * (K // 64) + k // 64) * 4 + ((n % 16) // 8) * 2 + (k % 64) // 32) * 256 + (4 * (n % 8) + (k % 32) // 8) * 8 + k % 8
+    assert wp.view(-1)[flat] == w[n, k]
+    h0 = bf(torch.randn(M, N, device=dev))
+    gain = bf(1 + 0.2 * torch.randn(N, device=dev))
+    outs = []
+    for W, packed in ((w, 0), (wp, 1)):
+        h, hg, ss = h0.clone(), torch.zeros(M, N, device=dev, dtype=torch.bfloat16), torch.zeros((N // 16, 16), device=dev)
+        a = L.SkinnyArgs()
+        a.op, a.X, a.ldx, a.W, a.out, a.ldo, a.resid, a.M, a.N, a.K, a.epi = 0, x.data_ptr(), K, W.data_ptr(), h.data_ptr(), N, h.data_ptr(), M, N, K, 3
+        a.ss_out, a.xg_gain, a.xg_out, a.ldxg, a.packed, a.eps = ss.data_ptr(), gain.data_ptr(), hg.data_ptr(), N, packed, 1e-5
+        L.call_struct('p3_gemm_skinny_x', a, st())
+        torch.cuda.synchronize()
+        outs.append((h, hg, ss))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
+    ref = (h0.float() + bf(x.float() @ w.float().T).float()).to(torch.bfloat16)
+    assert (outs[1][0].float() - ref.float()).abs().max() <= 2 ** -6 * ref.float().abs().max()
+    # the packed layout is refused where the kernel would not read 16-row tiles
+    a.epi = 4
+    with pytest.raises(RuntimeError):
+        L.call_struct('p3_gemm_skinny_x', a, st())
+
+
 @pytest.mark.parametrize('M', [(2, 1), (8, 1), (2, 5), (12, 1)])
 def test_fused_qkv_rope_matches_unfused(dev, M):
     """p3_gemm_skinny_qkv_rope == p3_gemm_skinny (norm fused) followed by p3_rope_kvwrite."""

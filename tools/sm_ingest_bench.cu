@@ -142,6 +142,14 @@ int main() {
     };
     for (int ctas : {1, 8, 37, 74, 111, 148}) run_l(std::integral_constant<int, 4>{}, ctas, 1);
     for (int ctas : {74, 148, 296}) run_l(std::integral_constant<int, 4>{}, ctas, 2);
+    printf("short kernels, one launch each: contiguous 256 KB per CTA vs 16 rows x 16 KB (the down_proj tile), depth 4, 2 CTAs/SM\n");
+    for (int ctas : {148, 192, 296, 592}) {
+        cudaFuncSetAttribute(ldgsts_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        float us = time_us([&](int r) { ldgsts_stream<4><<<ctas, 256, 8 * 4 * 2048>>>(buf + (size_t)r * ctas * 262144, 262144, sink); });
+        float us2 = time_us([&](int r) { ldgsts_rows<4><<<ctas, 256, 8 * 4 * 2048>>>(buf + (size_t)r * ctas * 262144, 16384, sink); });
+        printf("  CTAs %4d  contiguous %6.1f us (%5.0f GB/s)   16 rows x 16 KB %6.1f us (%5.0f GB/s)\n", ctas, us, ctas * 262144.0 / us / 1e3, us2,
+               ctas * 262144.0 / us2 / 1e3);
+    }
     printf("skinny-GEMM pattern (16 rows per CTA, 8 rows x 64 B per instruction), depth 4 = 64 KB in flight per CTA, 2 CTAs/SM\n");
     for (int row_bytes : {6144, 16384, 262144}) {
         for (int ctas : {148, 296, 592, 1184}) {
