@@ -135,10 +135,18 @@ def run_cuda(args):
         ev[2].record()
         model.profile = [] if instrument else None
         if instrument:
-            # Eager launches with an event pair around each kernel: park the GPU first so that the host stays ahead
-            # of it and an event interval is the kernel's own duration, not the host's launch gap.
-            torch.cuda._sleep(int(0.15 * 1.9e9))
-        hist = model.greedy_decode(tok, cache, NEW - 1, use_graph=not instrument)
+            # Eager launches with an event pair around each kernel: park the GPU before EVERY step (20 ms, longer than the host needs
+            # to enqueue one step's ~160 launches + 320 events) so that the host stays ahead of it and an event interval is the
+            # kernel's own duration, not the host's launch gap. (One 0.15 s park at the start was enough while a step cost the host
+            # less than the GPU; with the struct-argument entries the host is the slower side in eager mode and fell behind.)
+            from phi3_b200.model import DecodeSession
+            ses = DecodeSession(model, tok, cache, NEW - 1, False)
+            for _ in range(NEW - 1):
+                torch.cuda._sleep(int(0.02 * 1.9e9))
+                ses.step()
+            hist = ses.finish()
+        else:
+            hist = model.greedy_decode(tok, cache, NEW - 1, use_graph=True)
         ev[3].record()
         if timing is not None:
             timing.append(ev)

@@ -81,6 +81,7 @@ def main():
     lo = last_step[8]
     hi = last_step[8 + a.layers]
     report(tr, n, lo, hi - lo, f'last traced step (captured graph replay), layers 8..{8 + a.layers - 1}')
+    report(tr, n, n - 6, 6, 'end of the step: last layer, lm_head')
     gl = (tr[first:n, 0, 7] > 0)
     exits = np.array([tr[i, :min(int(tr[i, 0, 7]), 1024), 4].max() for i in range(first, n) if tr[i, 0, 7] > 0])
     starts = np.array([tr[i, :min(int(tr[i, 0, 7]), 1024), 0].min() for i in range(first, n) if tr[i, 0, 7] > 0])
