@@ -433,3 +433,19 @@ def test_server_failure_reaches_every_waiting_client_and_worker_survives():
     finally:
         httpd.shutdown()
         httpd.batcher.close()
+
+
+def test_pack_rows16_layout_matches_the_header_formula():
+    """p3_skinny_args.packed (include/phi3_b200.h): [N/16 tiles][K/64 chunks][row half][k half][lane = 4 * (row % 8) + quad][8]"""
+    import torch
+    import phi3_b200  # noqa
+    from phi3_b200.model import pack_rows16
+    N, K = 48, 192
+    w = torch.arange(N * K, dtype=torch.float32).view(N, K)
+    p = pack_rows16(w).view(-1)
+    for n, k in [(0, 0), (7, 63), (8, 0), (15, 191), (16, 64), (37, 100), (47, 191)]:
+        flat = (((n // 16) * (K // 64) + k // 64) * 4 + ((n % 16) // 8) * 2 + (k % 64) // 32) * 256 + (4 * (n % 8) + (k % 32) // 8) * 8 + k % 8
+        assert p[flat] == w[n, k]
+    assert torch.equal(p.sort().values, w.view(-1))                  # a permutation
+    with pytest.raises(AssertionError):
+        pack_rows16(torch.zeros(40, 192))
