@@ -310,48 +310,6 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
     ATTN_TRACE_STAMP(p.trace, (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x), 0);
     ATTN_TRACE_META(p.trace, (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x), 900);
     pdl_trigger();
-    if (p.past_host > 0 && p.pool && D == 96) {
-        // Before the dependency wait: pull this CTA's first KV page slices into L2. Pages below the cache offset, the block
-        // table and kv_start were written by EARLIER decode steps / the prefill, not by the kernel we are waiting for; the
-        // host-side offset (capture-time under a CUDA graph) is a lower bound of the real one, so the range is a valid
-        // subset — and a prefetch is only a hint anyway. The first tiles then hit L2 instead of paying a cold HBM access.
-        const int crow0 = b / p.row_div;
-        const int kv00 = p.kv_start ? p.kv_start[crow0] : 0;
-        const int tf = kv00 / 64, te = (p.past_host + 63) / 64, nt0 = max(te - tf, 0);
-        const int lo = tf + (int)(((long long)nt0 * split) / p.n_splits), hi = tf + (int)(((long long)nt0 * (split + 1)) / p.n_splits);
-        const size_t he = (size_t)P3_PAGE * D, pe = 2 * (size_t)p.n_kv * he;
-        for (int tix = lo; tix < min(hi, lo + DEC_STAGES - 1); tix++) {
-            const int pg = p.block_table[(size_t)crow0 * p.bt_stride + tix];
-            const uint8_t* kp = reinterpret_cast<const uint8_t*>(p.pool + (size_t)pg * pe + (size_t)kvh * he);
-            const uint8_t* vp = kp + (size_t)p.n_kv * he * sizeof(bf16);
-            for (int ln = tid; ln < (int)(he * sizeof(bf16) / 128); ln += 128) {
-                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(kp + (size_t)ln * 128));
-                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(vp + (size_t)ln * 128));
-            }
-        }
-    }
-    pdl_wait();                                                 // q/k/v, past and the cache come from earlier kernels
-    ATTN_TRACE_STAMP(p.trace, (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x), 1);
-    const int past = p.past_dev ? *p.past_dev : p.past_host;
-    const int crow = b / p.row_div;
-    const int kv0 = p.kv_start ? p.kv_start[crow] : 0;
-    const int s_total = past + p.L;
-    const int32_t* bt = p.block_table + (size_t)crow * p.bt_stride;
-
-    for (int idx = tid; idx < 16 * CPR; idx += 128) {
-        int r = idx / CPR, c = idx % CPR;
-        const bf16* src = p.q + ((size_t)b * p.L + (r < p.L ? r : 0)) * p.ldq + h * D + c * 8;
-        cp_async16(sq + tile_off<D>(r, c), src, r < p.L ? 16 : 0);
-    }
-    // balanced split of the cached tiles [t_lo, t_hi); the last split also owns the "present" tile
-    const int t_first = kv0 / 64, t_end = (past + 63) / 64;
-    const int nt_all = max(t_end - t_first, 0);
-    const int n_lo = t_first + (int)(((long long)nt_all * split) / p.n_splits);
-    const int n_hi = t_first + (int)(((long long)nt_all * (split + 1)) / p.n_splits);
-    const int n_cached = n_hi - n_lo;
-    const bool has_present = (split == p.n_splits - 1);
-    const int n_iter = n_cached + (has_present ? 1 : 0);
-
     // hoisted per-thread copy slots: chunk (tid + 128 i) of the contiguous 64 x D page slice
     uint32_t soff[NSLOT];
 #pragma unroll
@@ -378,6 +336,61 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
             }
         }
     };
+    // Before the dependency wait: fill the ring with this CTA's first DEC_STAGES-1 KV tiles. Pages below the cache offset, the block
+    // table and kv_start were written by EARLIER decode steps / the prefill, not by the kernel we are waiting for, and the
+    // host-side offset (capture-time under a CUDA graph) is a lower bound of the real one: full tiles below it are immutable for
+    // this launch. The KV stream then starts while the qkv projection drains instead of one memory round trip after the release
+    // (in-kernel stamps: the attention window of a layer was 3.5 us longer than its stream). Only without split-KV, where the
+    // first tile of the CTA does not depend on the real offset; otherwise the first tiles are at least pulled into L2.
+    bool pre = false;
+    if (p.past_host > 0 && p.pool && D == 96) {
+        const int crow0 = b / p.row_div;
+        const int kv00 = p.kv_start ? p.kv_start[crow0] : 0;
+        const int tf = kv00 / 64, te = (p.past_host + 63) / 64, nt0 = max(te - tf, 0);
+        if (p.early_fill && p.n_splits == 1 && tf + (DEC_STAGES - 1) <= p.past_host / 64) {
+            pre = true;
+            const int vz = p.zero * tid;                        // 0, but keeps the stage address in a vector register (see cp_async16_stream)
+#pragma unroll 1
+            for (int i = 0; i < DEC_STAGES - 1; i++) {
+                issue_cached(i + vz, p.block_table[(size_t)crow0 * p.bt_stride + tf + i]);
+                cp_async_commit();
+            }
+        } else {
+            const int lo = tf + (int)(((long long)nt0 * split) / p.n_splits), hi = tf + (int)(((long long)nt0 * (split + 1)) / p.n_splits);
+            const size_t he = (size_t)P3_PAGE * D, pe = 2 * (size_t)p.n_kv * he;
+            for (int tix = lo; tix < min(hi, lo + DEC_STAGES - 1); tix++) {
+                const int pg = p.block_table[(size_t)crow0 * p.bt_stride + tix];
+                const uint8_t* kp = reinterpret_cast<const uint8_t*>(p.pool + (size_t)pg * pe + (size_t)kvh * he);
+                const uint8_t* vp = kp + (size_t)p.n_kv * he * sizeof(bf16);
+                for (int ln = tid; ln < (int)(he * sizeof(bf16) / 128); ln += 128) {
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(kp + (size_t)ln * 128));
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(vp + (size_t)ln * 128));
+                }
+            }
+        }
+    }
+    pdl_wait();                                                 // q/k/v, past and the cache come from earlier kernels
+    ATTN_TRACE_STAMP(p.trace, (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x), 1);
+    const int past = p.past_dev ? *p.past_dev : p.past_host;
+    const int crow = b / p.row_div;
+    const int kv0 = p.kv_start ? p.kv_start[crow] : 0;
+    const int s_total = past + p.L;
+    const int32_t* bt = p.block_table + (size_t)crow * p.bt_stride;
+
+    for (int idx = tid; idx < 16 * CPR; idx += 128) {
+        int r = idx / CPR, c = idx % CPR;
+        const bf16* src = p.q + ((size_t)b * p.L + (r < p.L ? r : 0)) * p.ldq + h * D + c * 8;
+        cp_async16(sq + tile_off<D>(r, c), src, r < p.L ? 16 : 0);
+    }
+    // balanced split of the cached tiles [t_lo, t_hi); the last split also owns the "present" tile
+    const int t_first = kv0 / 64, t_end = (past + 63) / 64;
+    const int nt_all = max(t_end - t_first, 0);
+    const int n_lo = t_first + (int)(((long long)nt_all * split) / p.n_splits);
+    const int n_hi = t_first + (int)(((long long)nt_all * (split + 1)) / p.n_splits);
+    const int n_cached = n_hi - n_lo;
+    const bool has_present = (split == p.n_splits - 1);
+    const int n_iter = n_cached + (has_present ? 1 : 0);
+
     auto issue_present = [&](int it) {
         const uint32_t sk = skv + (it % DEC_STAGES) * 2 * TILE, sv = sk + TILE;
         for (int idx = tid; idx < 16 * CPR; idx += 128) {
@@ -389,16 +402,21 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
     };
     // page ids are fetched DEC_STAGES-1 tiles ahead of their use
     int page_next = (n_cached > 0) ? bt[n_lo] : 0;
+    if (pre) {                                                  // the first DEC_STAGES-1 tiles are already in flight (n_cached >= DEC_STAGES-1)
+        if (DEC_STAGES - 1 < n_cached) page_next = bt[n_lo + DEC_STAGES - 1];
+        cp_async_commit();                                      // the Q tile
+    } else {
 #pragma unroll
-    for (int i = 0; i < DEC_STAGES - 1; i++) {
-        if (i < n_cached) {
-            int pg = page_next;
-            if (i + 1 < n_cached) page_next = bt[n_lo + i + 1];
-            issue_cached(i, pg);
-        } else if (i == n_cached && has_present) {
-            issue_present(i);
+        for (int i = 0; i < DEC_STAGES - 1; i++) {
+            if (i < n_cached) {
+                int pg = page_next;
+                if (i + 1 < n_cached) page_next = bt[n_lo + i + 1];
+                issue_cached(i, pg);
+            } else if (i == n_cached && has_present) {
+                issue_present(i);
+            }
+            cp_async_commit();                                  // group 0 also carries the Q tile
         }
-        cp_async_commit();                                      // group 0 also carries the Q tile
     }
 
     uint32_t qf[D / 16][4];
@@ -418,7 +436,8 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(AttnParams p) {
     // CTA pulls its slice of them into L2 three quarters of the way through its KV stream.
     const int pf_iter = (n_iter * 3) / 4;
     for (int it = 0; it < n_iter; it++) {
-        cp_async_wait<DEC_STAGES - 2>();
+        if (pre && it == 0) cp_async_wait<0>();                 // early tiles + the Q group committed after them
+        else cp_async_wait<DEC_STAGES - 2>();
         __syncthreads();
         if (it == pf_iter && p.l2_prefetch) {
             const int64_t n_cta = (int64_t)gridDim.x * gridDim.y * gridDim.z;
@@ -600,7 +619,7 @@ static int fill_params(AttnParams& p, const void* q, const void* k, const void* 
     p.pool = (const bf16*)pool; p.block_table = block_table; p.bt_stride = bt_stride; p.row_div = row_div;
     p.n_splits = 1; p.tiles_per_split = 0; p.ws_o = nullptr; p.ws_ml = nullptr; p.counters = nullptr;
     p.l2_prefetch = nullptr; p.l2_prefetch_bytes = 0; p.zero = 0;
-    p.n_quant = 0; p.qcodes = nullptr; p.qmeta = nullptr; p.trace = nullptr;
+    p.n_quant = 0; p.qcodes = nullptr; p.qmeta = nullptr; p.trace = nullptr; p.early_fill = 0;
     return 0;
 }
 
@@ -651,6 +670,7 @@ static int launch_decode(AttnParams& p, cudaStream_t st) {
 #ifdef P3_TRACE_ATTN
     p.trace = p3_trace_slot();
 #endif
+    { static int v = -1; if (v < 0) { const char* e = getenv("P3_ATTN_EARLY"); v = e ? atoi(e) : 1; } p.early_fill = v; }
     p3_launch_pdl(attn_decode_kernel<D>, grid, dim3(128), (size_t)smem, st, p);
     P3_CHECK_LAUNCH("attention_decode");       // split partials are merged in-kernel by the last CTA to arrive
     return 0;

@@ -33,6 +33,7 @@ struct AttnParams {
     const uint8_t* qcodes;      // [page][2][n_kv][64][D/2]
     const bf16* qmeta;          // [page][2][n_kv][64][D/32][2] (scale, bias)
     unsigned long long* trace;  // tools/chain_trace.py (null in production)
+    int early_fill;             // decode: first KV tiles requested before the dependency wait (P3_ATTN_EARLY=0 turns it off)
 };
 
 
