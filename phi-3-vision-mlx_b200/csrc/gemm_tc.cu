@@ -78,7 +78,7 @@ __host__ __device__ __forceinline__ int band_width(int K, int BN, int n_tiles, i
 template <int BN>
 struct TcCfg {
     static constexpr int BM = 128, BK = 64;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -787,8 +787,8 @@ static int launch_tc(const void* X, int64_t ldx, const void* W, int64_t ldw, con
     using C = TcCfg<BN>;
     CUtensorMap ta, tb;
     if (make_tmap(&ta, X, M, K, ldx, C::BM)) return -1;
-    if (wp) memcpy(&tb, (BN == 256) ? &wp->t256 : &wp->t128, sizeof(tb));
-    else if (make_tmap(&tb, W, N, K, ldw, BN)) return -1;
+    if (wp && BN >= 128) memcpy(&tb, (BN == 256) ? &wp->t256 : &wp->t128, sizeof(tb));
+    else if (make_tmap(&tb, W, N, K, ldw, BN)) return -1;      // 64-row boxes are not part of the plan blob: encoded per call
     static bool attr_set[64] = {};                             // the attribute is per device
     if (!attr_set[cur_dev()]) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -798,7 +798,7 @@ static int launch_tc(const void* X, int64_t ldx, const void* W, int64_t ldw, con
     int64_t tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
     GemmEpi e2 = ep;
     e2.ksplit = 1;
-    if (ep.ws && tiles * 2 < num_sms() && (int64_t)BN * K * 2 > (7ll << 18)) {
+    if (ep.ws && tiles * 2 < num_sms() && (int64_t)BN * K * 2 > (7ll << 18) * BN / 128) {
         // few output tiles AND a long K (each CTA would stream > 1.75 MB of W alone at ~45 KB/us, e.g. down_proj at M <= 320:
         // 24 tiles x 2 MB): split K so that tiles * ksplit ~ #SM (>= 4 k-blocks each). Measured (tools/gemm_smallm.py): 43 -> 30 us
         // at M = 80, 40 -> 21 us at M = 16; for K = 3072 shapes the partial round trip costs more than it saves, so they stay unsplit.
@@ -871,6 +871,13 @@ static int gemm_dispatch(const void* X, int64_t ldx, const void* W, int64_t ldw,
         return launch_tc2(X, ldx, W, ldw, eps, M, N, K, st, wp);
     bool small = m_tiles * ((N + 255) / 256) < 2 * num_sms();
     if (ep.kind == P3_EPI_SWIGLU || !small) return launch_tc<256>(X, ldx, W, ldw, eps, M, N, K, st, wp);
+    // one row tile and fewer 128-wide column tiles than SMs (M <= 128 against the 3072..9216-row matrices: constrain steps): the GEMM
+    // is a weight stream and a CTA only pulls what its TMA ring turns over per round trip -> 64-row W tiles put twice as many CTAs
+    // on it (tools/gemm_smallm.py, M = 80: qkv 18.9 -> 16.8 us, o_proj 19.3 -> 17.2, down_proj with split-K 28.6 -> 21.8). Not for
+    // more row tiles: every CTA re-reads its X rows over the whole K, which outweighs the gain (M = 320 down_proj 36.6 -> 39.4 us).
+    static int bn64 = -1;
+    if (bn64 < 0) { const char* e = getenv("P3_GEMM_BN64"); bn64 = e ? atoi(e) : 1; }
+    if (bn64 && m_tiles == 1 && (N + 127) / 128 < num_sms()) return launch_tc<64>(X, ldx, W, ldw, eps, M, N, K, st, wp);
     return launch_tc<128>(X, ldx, W, ldw, eps, M, N, K, st, wp);
 }
 
