@@ -612,35 +612,6 @@ class _ConstrainStep:
             self.gb[:, :C] = idc.to(torch.int32)
         self.graphs = None
 
-    @classmethod
-    def get(cls, model, cache, B, C, n_beam, idc, use_beam, max_new):
-        """A captured step is kept in the cache's slab and reused by later calls whose launch parameters are identical: same
-        shapes, same offset at the start of the constrained phase (the kernels take it as their host-side lower bound), same
-        quantised prefix, same split-KV factors. Everything else a call changes lives in device buffers the graphs read (KV pool,
-        block table, rope tables, the constraint ids). Capturing costs ~0.1 s per constraint, a quarter of a config-5 call."""
-        slab = cache.slab
-        tiles = (cache.offset + max_new + 1 + C + 63) // 64
-        key = (B, C, n_beam, bool(use_beam), cache.offset, getattr(cache, 'n_quant', 0),
-               model._splits(cache, B, tiles), model._splits(cache, B * n_beam, tiles), slab.pool.data_ptr(),
-               0 if slab.cos is None else slab.cos.data_ptr())
-        store = slab.__dict__.setdefault('csteps', {})
-        st = store.get(key)
-        if st is not None:
-            st.cache = cache
-            ic = idc.to(torch.int32)
-            st.tp[:, 1:] = idc
-            st.g[:, :C] = ic
-            if use_beam:
-                st.seq[:, 1:] = idc
-                st.gb[:, :C] = ic
-            return st
-        st = cls(model, cache, B, C, n_beam, idc, use_beam, max_new)
-        st.capture()
-        if len(store) >= 8:                                                   # bound the memory held by captured graphs
-            store.pop(next(iter(store)))
-        store[key] = st
-        return st
-
     def _main(self):
         lg, _ = self.m(self.tp, cache=self.cache, advance_offset=1, past_dev=self.past_dev, n_splits=self.ns)
         self.cache.offset -= 1                                                # the caller advances the offset per replay
@@ -768,7 +739,8 @@ def _constrain(model, processor, prompt, constraints, return_full_text=False, mu
         alive = torch.ones(B, device=dev)
         step = None
         if use_graph and max_new > 2 and 1 + C <= 16:
-            step = _ConstrainStep.get(model, cache, B, C, n_beam, idc, use_beam, max_new)
+            step = _ConstrainStep(model, cache, B, C, n_beam, idc, use_beam, max_new)
+            step.capture()
         if sync_timing:
             torch.cuda.synchronize()
         prompt_time += tic()
@@ -818,10 +790,6 @@ def _constrain(model, processor, prompt, constraints, return_full_text=False, mu
             alive = alive * (token != ID_EOS).float()
             if (i + 1) % alive_check_every == 0 and float(alive.sum().item()) < 1:
                 break
-        if step is not None:
-            step.cache = None                                                # the slab keeps the step: it must not keep the cache alive
-        step = None
-        cache.release()                                                      # slab (pool, tables, captured step) back to the model
         constrain_time += tic()
         out_ids = torch.cat([dict_input['input_ids'].to(dev), synth_sofar], 1).tolist()        # the one read-back per constraint
         out_ids = [(r[:r.index(ID_EOS, S)] if ID_EOS in r[S:] else r) for r in out_ids]

@@ -141,7 +141,6 @@ class KVCacheB200:
         sl = self.slab
         if sl.cos is None or sl.cos.shape != cos.shape:
             sl.cos, sl.sin, sl.session = cos.clone(), sin.clone(), None
-            sl.__dict__.pop('csteps', None)              # captured constrain steps (api._ConstrainStep) read the old tables
         else:
             sl.cos.copy_(cos); sl.sin.copy_(sin)
         sl.kv_start.copy_(kvs)

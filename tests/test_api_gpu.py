@@ -452,28 +452,6 @@ def test_constrain_graph_replay_equals_eager(dev, use_beam):
     assert a == b
 
 
-@pytest.mark.parametrize('use_beam', [False, True])
-def test_constrain_captured_step_is_reused_across_calls(dev, use_beam):
-    """a later call with the same launch parameters replays the step captured by an earlier one (kept in the KV slab) with ITS
-    constraint ids, prompts and cache contents: ids equal the eager path; a call with another shape captures its own"""
-    api, model, proc, ora = _setup(init='peaked')
-    tmpl = lambda qs: [api._preprocess(p) for p in api._apply_chat_template(qs, None, False)[0]]
-    p1 = tmpl(['First question here', 'Second, longer question text here', 'q3'])
-    p2 = tmpl(['Other question here', 'Minute, longer question text here', 'q9'])        # same padded length, other content
-    kw = dict(mute=True, verbose=False, use_beam=use_beam, n_beam=3, return_ids=True, alive_check_every=4)
-    a1 = api._constrain(model, proc, p1, [(9, ' The')], use_graph=True, **kw)
-    slabs = [sl for lst in model._slabs.values() for sl in lst]
-    n_steps = sum(len(sl.__dict__.get('csteps', {})) for sl in slabs)
-    assert n_steps >= 1
-    a2 = api._constrain(model, proc, p2, [(9, ' Yes')], use_graph=True, **kw)              # same C: the captured step is reused
-    slabs = [sl for lst in model._slabs.values() for sl in lst]
-    assert sum(len(sl.__dict__.get('csteps', {})) for sl in slabs) == n_steps
-    assert a1 == api._constrain(model, proc, p1, [(9, ' The')], use_graph=False, **kw)
-    assert a2 == api._constrain(model, proc, p2, [(9, ' Yes')], use_graph=False, **kw)
-    a3 = api._constrain(model, proc, p1, [(9, ' The answer')], use_graph=True, **kw)       # longer constraint: another step
-    assert a3 == api._constrain(model, proc, p1, [(9, ' The answer')], use_graph=False, **kw)
-
-
 def _lora_fixture(cfg, w, seed, layers, targets=('self_attn.qkv_proj', 'mlp.gate_up_proj'), r=4):
     g = torch.Generator().manual_seed(seed)
     n = cfg.num_hidden_layers
